@@ -1,0 +1,143 @@
+/*
+ * iper_b200 — C ABI of the B200-native (sm_100a) kernels for iPERCore's motion-imitation hot path.
+ *
+ * Boundary rules: plain C, raw DEVICE pointers + sizes + a CUDA stream; no torch types; the
+ * library never allocates device memory, never synchronises and launches only on the stream it is given.
+ * Every function returns 0 on success; non-zero = error, message via iper_last_error() (thread-local).
+ * The Python shims under ipercore_b200/ keep the reference's operator API on top of these entry points; the
+ * reference-side binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Reference citations are relative to /root/reference/ (iPERDance/iPERCore @ fcf9a18).
+ */
+#ifndef IPER_B200_H
+#define IPER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* iper_stream_t; /* == cudaStream_t */
+
+const char* iper_last_error(void);
+int iper_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Seam B1 — replaces neural_renderer.rasterize_face_index_map_and_weight_map(faces, image_size, False)
+ * (third-party CUDA ext; call sites iPERCore/tools/human_digitalizer/renders/nmr.py:337 and :356).
+ * faces (B,nf,3,3) f32 NDC  ->  fim (B,S,S) i32 (-1 = background), wim (B,S,S,3) f32 (0 on background).
+ * Correct for any B (the reference loops around an upstream B==3 bug, nmr.py:892-918).
+ * ---------------------------------------------------------------------------------------------------------- */
+int iper_rasterize_faces(const float* faces, int B, int nf, int S, float near_, float far_, int32_t* fim, float* wim,
+                         iper_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Seam B2 / engine — replaces SMPLRenderer.render_fim_wim (nmr.py:319-342: orthographic projection :34-52, y flip,
+ * nr.look_at with eye=(0,0,eye_z), nr.vertices_to_faces, rasterise, f2pts) and, when tsf_inputs/Tst are given,
+ * also encode_fim (nmr.py:390-401), cal_bc_transform (nmr.py:713-757), FlowComposition.make_tsf_inputs
+ * (iPERCore/models/flowcomposition.py:206-248) and make_trans_flow (:514-582) for a batch of independent frames.
+ *   verts (B,nv,3) f32, cams (B,3) f32 [s,tx,ty], faces (nf,3) i32
+ *   optional outputs: fim (B,S,S) i32, wim (B,S,S,3) f32, f2pts (B,nf,3,2) f32
+ *   fused outputs   : tsf_inputs (B,6,S,S) f32 = cat[grid_sample(uv_img, Tuv2t), cond], Tst (B,ns,S,S,2) f32
+ *                     from map_fn (nf+1,3), f_uvs2img (nf,3,2), uv_img (3,S,S), src_f2pts (ns,nf,3,2)
+ * ---------------------------------------------------------------------------------------------------------- */
+int iper_raster_frames(const float* verts, const float* cams, const int32_t* faces, int B, int nv, int nf, int S,
+                       float eye_z, float near_, float far_, int32_t* fim, float* wim, float* f2pts,
+                       const float* map_fn, const float* f_uvs2img, const float* uv_img, const float* src_f2pts,
+                       int ns, float* tsf_inputs, float* Tst, iper_stream_t stream);
+
+/* SMPLRenderer.cal_bc_transform (nmr.py:713-757).  T (nb,nsrc,S,S,2): item (b,s) combines fim/wim[b] with
+ * f2pts[s] (f2pts_per_item=0, shape (nsrc,nf,3,2)) or f2pts[b] (f2pts_per_item=1, nsrc must be 1). */
+int iper_flow_from_fim_wim(const float* f2pts, int f2pts_per_item, const int32_t* fim, const float* wim, int nb,
+                           int nsrc, int nf, int S, float* T, iper_stream_t stream);
+
+/* SMPLRenderer.encode_fim (nmr.py:390-401): out = map_fn[fim] (fim == -1 -> row nf); transpose -> (nb,ch,S,S). */
+int iper_encode_fim(const int32_t* fim, const float* map_fn, int nb, int nf, int ch, int S, int transpose, float* out,
+                    iper_stream_t stream);
+
+/* LWB.resize_trans (iPERCore/models/networks/generators/attlwb_spade_resunet.py:175-182):
+ * bilinear align_corners=True resize of a flow field (n,S,S,2) -> (n,h,w,2). */
+int iper_flow_resize(const float* T, int n, int S, int h, int w, float* out, iper_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Seam B3 — building blocks of the AttLWB-SPADE generator (attlwb_spade_resunet.py).  Activations live in HBM
+ * as NHWC fp16 "planes": plane 0 = fp16(x), optional plane 1 = fp16(x - plane0) (split-fp16, ~22 significand
+ * bits).  With two planes a convolution is three tcgen05 MMAs per K step (hi*hi + lo*hi + hi*lo), fp32 accumulate.
+ * ---------------------------------------------------------------------------------------------------------- */
+enum { IPER_CONV_S1 = 0,    /* k x k, stride 1, pad k/2 (k = 1, 3, 5)                                     */
+       IPER_CONV_S2 = 1,    /* 3x3, stride 2, pad 1                                                        */
+       IPER_CONVT_4S2 = 2 };/* ConvTranspose2d(k=4, s=2, p=1) as four 2x2 phase convolutions               */
+
+enum { IPER_EPI_PLANES = 0, /* out = [relu](acc + bias [+ residual x]) -> NHWC fp16 planes                 */
+       IPER_EPI_F32 = 1,    /* out = acc + bias -> NHWC fp32                                               */
+       IPER_EPI_SPADE = 2,  /* rows = [gamma block | beta block]; out = IN(x)*(1+gamma)+beta -> planes     */
+       IPER_EPI_HEADS = 3 };/* rows 0..2 tanh image, row 3 sigmoid mask, + composite with background       */
+
+typedef struct {
+    /* A operand: input activations, NHWC fp16 planes */
+    const void* a; int a_planes; long long a_plane_stride;   /* stride in elements                         */
+    int N, H, W;                                             /* input spatial dims                          */
+    int a_pitch, a_coff, Cin;                                /* channels per pixel in memory, window start  */
+    int mode, ksize;
+    /* B operand: packed weights fp16 [plane][phase][rows][taps*Cin], K ordered (tap, cin), K-major          */
+    const void* w; int w_planes; long long w_plane_stride;
+    int rows;                                                /* GEMM N per phase (multiple of block_n)      */
+    int block_n;                                             /* 16, 64, 128 or 256                          */
+    /* epilogue */
+    int epi; const float* bias; int relu;
+    void* out; int out_planes; long long out_plane_stride; int out_pitch, out_coff;
+    const void* x; int x_planes; long long x_plane_stride; int x_pitch, x_coff; /* residual / SPADE input   */
+    const float* mean_rstd;                                  /* (N, C, 2) instance-norm statistics of x     */
+    int spade_C;
+    /* IPER_EPI_HEADS: NCHW fp32 outputs (N,3,H,W), (N,1,H,W), (N,3,H,W); bg (.,3,H,W) with batch stride     */
+    const float* bg; long long bg_batch_stride; float* img; float* mask; float* pred;
+    int max_ctas;                                            /* 0 = one persistent CTA per SM               */
+} iper_conv_gemm_desc;
+
+/* tcgen05/TMEM implicit-GEMM convolution with TMA im2col tile loads (conv_tc.cu). */
+int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream);
+
+/* CUDA-core direct convolution on the same operand formats — the on-device cross-check of iper_conv_gemm and
+ * the path for tensor-core-hostile shapes.  Same descriptor; `w` is ignored, weights come as fp32 in the
+ * reference's own layout: Conv2d (Cout,Cin,k,k) / ConvTranspose2d (Cin,Cout,4,4), values = hi(+lo) of planes. */
+int iper_conv_direct(const iper_conv_gemm_desc* d, const float* w_f32, int Cout, iper_stream_t stream);
+
+/* Stem: Conv2d(Cin<=8 -> Cout, 3x3, s2, p1)(+bias)+ReLU from an NCHW fp32 image to NHWC planes
+ * (tsf_net_enc.layers.0 / src_net.encoders.layers.0, attlwb_spade_resunet.py:268-271). */
+int iper_conv_stem(const float* in_nchw, int N, int Cin, int H, int W, const float* w_f32, const float* bias, int Cout,
+                   void* out, int out_planes, long long out_plane_stride, int out_pitch, int out_coff,
+                   iper_stream_t stream);
+
+/* nn.InstanceNorm2d(affine=False) statistics (attlwb_spade_resunet.py:62, eps 1e-5, biased variance):
+ * mean_rstd (N,C,2) = (mean, 1/sqrt(var+eps)) of an NHWC planes tensor. Deterministic (no atomics). */
+int iper_instnorm_stats(const void* x, int x_planes, long long x_plane_stride, int N, int HW, int C, int x_pitch,
+                        int x_coff, float eps, float* mean_rstd, iper_stream_t stream);
+
+/* Flow-guided warp + per-pixel source attention (LWB.transform :184-191, SelfAttentionBlock :102-139), using
+ * fk(warp(x)) = warp(Wk x) + bk:  kv (ns,h,w,2C) fp32 holds [Wk x | Wv x] per source (no bias);
+ * q (B,h,w,C) fp32 (bias included); T (B,ns,h,w,2) flow at this resolution.
+ * out x (B,h,w,C) planes = sum_s softmax_s(K_s.q / sqrt(C)) V_s. */
+int iper_warp_attention(const float* q, const float* kv, const float* bias_k, const float* bias_v, const float* T,
+                        int B, int ns, int h, int w, int C, void* out, int out_planes, long long out_plane_stride,
+                        int out_pitch, int out_coff, iper_stream_t stream);
+
+/* LWB.transform alone: grid_sample(src (ns,h,w,C) fp32 NHWC, T (B,ns,h,w,2)) -> (B,ns,h,w,C) fp32 (seam/debug). */
+int iper_warp_nhwc(const float* src, const float* T, int B, int ns, int h, int w, int C, float* out,
+                   iper_stream_t stream);
+
+/* layout converters between the reference's NCHW fp32 tensors and NHWC planes */
+int iper_nchw_to_planes(const float* in, int N, int C, int HW, void* out, int out_planes, long long out_plane_stride,
+                        int out_pitch, int out_coff, iper_stream_t stream);
+int iper_planes_to_nchw(const void* x, int x_planes, long long x_plane_stride, int N, int C, int HW, int x_pitch,
+                        int x_coff, float* out, iper_stream_t stream);
+int iper_nhwc_f32_to_nchw(const float* in, int N, int C, int HW, int pitch, int coff, float* out, iper_stream_t stream);
+
+/* (B,3,S,S) fp32 in [-1,1] -> (B,S,S,3) uint8 BGR, the conversion of cv_utils.save_cv2_img(normalize=True)
+ * (iPERCore/tools/utils/filesio/cv_utils.py:100-116) done on device so only 0.75 MB/frame crosses PCIe. */
+int iper_pred_to_u8(const float* pred, int B, int S, uint8_t* out, iper_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPER_B200_H */

@@ -1,0 +1,523 @@
+// HBM-bound kernels of the generator path (sm_100a): stem conv, instance-norm statistics, flow-guided warp +
+// per-pixel source attention, layout converters, and a CUDA-core direct convolution used as the on-device
+// cross-check of the tcgen05 path.  Reference line citations are in include/iper_b200.h.
+#include "common.cuh"
+#include "iper_b200.h"
+
+namespace iper {
+
+IPER_DEVINL float load_plane_val(const __half* x, int planes, long long plane_stride, size_t off) {
+    float v = __half2float(x[off]);
+    if (planes > 1) v += __half2float(x[plane_stride + off]);
+    return v;
+}
+IPER_DEVINL void store_plane_val(__half* o, int planes, long long plane_stride, size_t off, float v) {
+    __half hi, lo;
+    split_half(v, hi, lo);
+    o[off] = hi;
+    if (planes > 1) o[plane_stride + off] = lo;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// CUDA-core direct convolution on NHWC planes; one thread per (pixel, output channel), fp32 accumulate in the
+// reference's own weight layout.  Slow by design: it is the checker for conv_tc.cu and the fallback for shapes
+// the tensor-core kernel does not take.
+// ------------------------------------------------------------------------------------------------------------
+struct DirectArgs {
+    const __half* a; int a_planes; long long a_plane_stride; int N, H, W, a_pitch, a_coff, Cin;
+    int mode, ksize, Cout, oH, oW;
+    const float* w; const float* bias; int relu, epi;
+    void* out; int out_planes; long long out_plane_stride; int out_pitch, out_coff;
+    const __half* x; int x_planes; long long x_plane_stride; int x_pitch, x_coff;
+    const float* mean_rstd; int spade_C;
+};
+
+IPER_DEVINL float direct_dot(const DirectArgs& d, int n, int oy, int ox, int co) {
+    float acc = 0.f;
+    if (d.mode == IPER_CONVT_4S2) {
+        // out[oy] += in[iy] * W[ci][co][ky][kx] with oy = 2*iy - 1 + ky
+        for (int ky = 0; ky < 4; ky++) {
+            const int ty = oy + 1 - ky;
+            if (ty < 0 || (ty & 1)) continue;
+            const int iy = ty >> 1;
+            if (iy >= d.H) continue;
+            for (int kx = 0; kx < 4; kx++) {
+                const int tx = ox + 1 - kx;
+                if (tx < 0 || (tx & 1)) continue;
+                const int ix = tx >> 1;
+                if (ix >= d.W) continue;
+                const size_t base = (((size_t)n * d.H + iy) * d.W + ix) * d.a_pitch + d.a_coff;
+                for (int ci = 0; ci < d.Cin; ci++)
+                    acc += load_plane_val(d.a, d.a_planes, d.a_plane_stride, base + ci) *
+                           d.w[(((size_t)ci * d.Cout + co) * 4 + ky) * 4 + kx];
+            }
+        }
+    } else {
+        const int stride = d.mode == IPER_CONV_S2 ? 2 : 1;
+        const int k = d.mode == IPER_CONV_S2 ? 3 : d.ksize, pad = k / 2;
+        for (int ky = 0; ky < k; ky++) {
+            const int iy = oy * stride - pad + ky;
+            if (iy < 0 || iy >= d.H) continue;
+            for (int kx = 0; kx < k; kx++) {
+                const int ix = ox * stride - pad + kx;
+                if (ix < 0 || ix >= d.W) continue;
+                const size_t base = (((size_t)n * d.H + iy) * d.W + ix) * d.a_pitch + d.a_coff;
+                for (int ci = 0; ci < d.Cin; ci++)
+                    acc += load_plane_val(d.a, d.a_planes, d.a_plane_stride, base + ci) *
+                           d.w[(((size_t)co * d.Cin + ci) * k + ky) * k + kx];
+            }
+        }
+    }
+    return acc;
+}
+
+__global__ void conv_direct_kernel(const DirectArgs d) {
+    const int Cthreads = d.epi == IPER_EPI_SPADE ? d.spade_C : d.Cout;
+    const size_t total = (size_t)d.N * d.oH * d.oW * Cthreads;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cthreads);
+        const size_t pix = i / Cthreads;
+        const int ox = (int)(pix % d.oW), oy = (int)((pix / d.oW) % d.oH), n = (int)(pix / ((size_t)d.oW * d.oH));
+        float v;
+        if (d.epi == IPER_EPI_SPADE) {
+            // weights (2C, Cin, k, k): rows [0,C) gamma, [C,2C) beta (reference order: mlp_gamma then mlp_beta)
+            const float gamma = direct_dot(d, n, oy, ox, c) + d.bias[c];
+            const float beta = direct_dot(d, n, oy, ox, d.spade_C + c) + d.bias[d.spade_C + c];
+            const float xv = load_plane_val(d.x, d.x_planes, d.x_plane_stride, pix * d.x_pitch + d.x_coff + c);
+            const float* mr = d.mean_rstd + ((size_t)n * d.spade_C + c) * 2;
+            v = (xv - mr[0]) * mr[1] * (1.f + gamma) + beta;
+        } else {
+            v = direct_dot(d, n, oy, ox, c);
+            if (d.bias) v += d.bias[c];
+            if (d.x) v = load_plane_val(d.x, d.x_planes, d.x_plane_stride, pix * d.x_pitch + d.x_coff + c) + v;
+            if (d.relu) v = fmaxf(v, 0.f);
+        }
+        const size_t o = pix * d.out_pitch + d.out_coff + c;
+        if (d.epi == IPER_EPI_F32) reinterpret_cast<float*>(d.out)[o] = v;
+        else store_plane_val(reinterpret_cast<__half*>(d.out), d.out_planes, d.out_plane_stride, o, v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Stem: Conv2d(Cin<=8 -> 64, 3x3, s2, p1)(+bias)+ReLU, NCHW fp32 image -> NHWC planes.  K = 9*Cin <= 72 is
+// tensor-core hostile; 0.45 GFLOP per 512^2 frame.  Block = 16x8 output pixels; the 33x17 input halo and the
+// whole filter bank live in shared memory; each thread computes 1 pixel x 16 channels per pass.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int STEM_TW = 32, STEM_TH = 8, STEM_MAXC = 8;
+__host__ __device__ constexpr int stem_halo_floats(int cin) { return ((cin * (2 * STEM_TH + 1) * (2 * STEM_TW + 1) + 3) / 4) * 4; }
+
+template <int CIN>
+__global__ void __launch_bounds__(256) conv_stem_kernel(const float* __restrict__ in, int N, int H, int W,
+                                                        const float* __restrict__ wgt, const float* __restrict__ bias,
+                                                        int Cout, __half* __restrict__ out, int out_planes,
+                                                        long long out_plane_stride, int out_pitch, int out_coff) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int HALO_W = 2 * STEM_TW + 1, HALO_H = 2 * STEM_TH + 1;
+    float* s_in = sm;                                  // [CIN][HALO_H][HALO_W]
+    float* s_w = sm + stem_halo_floats(CIN);           // [9*CIN][Cout]  (ci,ky,kx major, cout fastest)
+    const int Ho = H / 2, Wo = W / 2;
+    const int n = blockIdx.z, oy0 = blockIdx.y * STEM_TH, ox0 = blockIdx.x * STEM_TW;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < Cout * CIN * 9; i += 256) {
+        const int co = i / (CIN * 9), r = i % (CIN * 9);        // source order (co, ci, ky, kx)
+        s_w[r * Cout + co] = wgt[i];
+    }
+    const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;
+    for (int i = tid; i < CIN * HALO_H * HALO_W; i += 256) {
+        const int c = i / (HALO_H * HALO_W), r = i % (HALO_H * HALO_W);
+        const int iy = iy0 + r / HALO_W, ix = ix0 + r % HALO_W;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = in[(((size_t)n * CIN + c) * H + iy) * W + ix];
+        s_in[i] = v;
+    }
+    __syncthreads();
+    const int lx = tid % STEM_TW, ly = tid / STEM_TW;   // 32 x 8 output pixels per block
+    const int oy = oy0 + ly, ox = ox0 + lx;
+    float patch[CIN * 9];
+#pragma unroll
+    for (int c = 0; c < CIN; c++)
+#pragma unroll
+        for (int t = 0; t < 9; t++)
+            patch[c * 9 + t] = s_in[(c * HALO_H + 2 * ly + t / 3) * HALO_W + 2 * lx + t % 3];
+    if (oy >= Ho || ox >= Wo) return;
+    const size_t obase = (((size_t)n * Ho + oy) * Wo + ox) * out_pitch + out_coff;
+    for (int co0 = 0; co0 < Cout; co0 += 8) {
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = 0.f;
+#pragma unroll
+        for (int r = 0; r < CIN * 9; r++) {
+            const float pv = patch[r];
+            const float4 w0 = *reinterpret_cast<const float4*>(&s_w[r * Cout + co0]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&s_w[r * Cout + co0 + 4]);
+            acc[0] += pv * w0.x; acc[1] += pv * w0.y; acc[2] += pv * w0.z; acc[3] += pv * w0.w;
+            acc[4] += pv * w1.x; acc[5] += pv * w1.y; acc[6] += pv * w1.z; acc[7] += pv * w1.w;
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            float v0 = acc[2 * j] + (bias ? bias[co0 + 2 * j] : 0.f);
+            float v1 = acc[2 * j + 1] + (bias ? bias[co0 + 2 * j + 1] : 0.f);
+            v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f);
+            __half h0, l0, h1, l1;
+            split_half(v0, h0, l0); split_half(v1, h1, l1);
+            hi[j] = pack_half2(h0, h1); lo[j] = pack_half2(l0, l1);
+        }
+        *reinterpret_cast<uint4*>(out + obase + co0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (out_planes > 1)
+            *reinterpret_cast<uint4*>(out + out_plane_stride + obase + co0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Instance-norm statistics over an NHWC planes tensor: grid (C/32, N); block 256 = 8 pixel-lanes x 32 channels.
+// Each warp-row walks pixels with a stride, fp32 partial sums are combined in a fixed order (deterministic).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) instnorm_stats_kernel(const __half* __restrict__ x, int x_planes,
+                                                             long long x_plane_stride, int HW, int C, int x_pitch,
+                                                             int x_coff, float eps, float* __restrict__ mean_rstd) {
+    const int n = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), lane_p = threadIdx.x >> 5;
+    __shared__ double s_sum[8][33], s_sq[8][33];
+    double sum = 0.0, sq = 0.0;
+    if (c < C) {
+        const size_t base = (size_t)n * HW * x_pitch + x_coff + c;
+        for (int p = lane_p; p < HW; p += 8) {
+            const float v = load_plane_val(x, x_planes, x_plane_stride, base + (size_t)p * x_pitch);
+            sum += (double)v;
+            sq += (double)v * (double)v;
+        }
+    }
+    s_sum[lane_p][threadIdx.x & 31] = sum;
+    s_sq[lane_p][threadIdx.x & 31] = sq;
+    __syncthreads();
+    if (lane_p == 0 && c < C) {
+        double ts = 0.0, tq = 0.0;
+        for (int i = 0; i < 8; i++) { ts += s_sum[i][threadIdx.x & 31]; tq += s_sq[i][threadIdx.x & 31]; }
+        const double mean = ts / HW;
+        double var = tq / HW - mean * mean;   // biased variance (F.instance_norm)
+        if (var < 0.0) var = 0.0;
+        mean_rstd[((size_t)n * C + c) * 2 + 0] = (float)mean;
+        mean_rstd[((size_t)n * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Flow-guided warp + per-pixel source attention.  One warp per target pixel; lanes stride the channel dimension
+// with 128-bit (4 x fp32) gathers from the precomputed [Wk x | Wv x] source maps.  Bilinear taps / zero padding
+// follow F.grid_sample(align_corners=False).  C <= 256, ns <= 8.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int ATT_MAX_NS = 8;
+struct Taps { int off[4]; float wt[4]; };
+IPER_DEVINL Taps bilinear_taps(float gx, float gy, int h, int w) {
+    Taps t;
+    const float ix = ((gx + 1.f) * w - 1.f) * 0.5f, iy = ((gy + 1.f) * h - 1.f) * 0.5f;
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    // huge/NaN coordinates: every tap out of range
+    const bool sane = fabsf(ix) < 1e8f && fabsf(iy) < 1e8f;
+    const int x0 = sane ? (int)fx0 : -10, y0 = sane ? (int)fy0 : -10, x1 = x0 + 1, y1 = y0 + 1;
+    const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix, wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
+    const int xs[4] = {x0, x1, x0, x1}, ys[4] = {y0, y0, y1, y1};
+    const float ws[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const bool ok = xs[i] >= 0 && xs[i] < w && ys[i] >= 0 && ys[i] < h;
+        t.off[i] = ok ? ys[i] * w + xs[i] : -1;
+        t.wt[i] = ok ? ws[i] : 0.f;
+    }
+    return t;
+}
+
+__global__ void __launch_bounds__(256) warp_attention_kernel(const float* __restrict__ q, const float* __restrict__ kv,
+                                                             const float* __restrict__ bias_k,
+                                                             const float* __restrict__ bias_v,
+                                                             const float* __restrict__ T, int B, int ns, int h, int w,
+                                                             int C, __half* __restrict__ out, int out_planes,
+                                                             long long out_plane_stride, int out_pitch, int out_coff) {
+    const int lane = threadIdx.x & 31;
+    const size_t hw = (size_t)h * w;
+    const size_t total = (size_t)B * hw;
+    const float inv_sqrt = 1.f / sqrtf((float)C);
+    const int nvec = C / 4;                     // float4 per pixel per map
+    for (size_t pix = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5); pix < total; pix += (size_t)gridDim.x * 8) {
+        const size_t b = pix / hw, p = pix % hw;
+        const float4* qp = reinterpret_cast<const float4*>(q + pix * C);
+        float4 qv[2];
+#pragma unroll
+        for (int j = 0; j < 2; j++) qv[j] = (lane + 32 * j < nvec) ? __ldg(qp + lane + 32 * j) : make_float4(0, 0, 0, 0);
+        float logit[ATT_MAX_NS];
+        float4 vacc[ATT_MAX_NS][2];
+#pragma unroll
+        for (int s = 0; s < ATT_MAX_NS; s++) {
+            if (s >= ns) break;
+            const float2 g = reinterpret_cast<const float2*>(T)[(b * ns + s) * hw + p];
+            const Taps t = bilinear_taps(g.x, g.y, h, w);
+            const float4* src = reinterpret_cast<const float4*>(kv + (size_t)s * hw * 2 * C);
+            float dot = 0.f;
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+                const int cv = lane + 32 * j;
+                float4 kk = make_float4(0, 0, 0, 0), vv = make_float4(0, 0, 0, 0);
+                if (cv < nvec) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        if (t.off[i] < 0) continue;
+                        const float4* px = src + (size_t)t.off[i] * (2 * nvec);
+                        const float4 a = __ldg(px + cv), c4 = __ldg(px + nvec + cv);
+                        const float wt = t.wt[i];
+                        kk.x += a.x * wt; kk.y += a.y * wt; kk.z += a.z * wt; kk.w += a.w * wt;
+                        vv.x += c4.x * wt; vv.y += c4.y * wt; vv.z += c4.z * wt; vv.w += c4.w * wt;
+                    }
+                    const float4 bk = __ldg(reinterpret_cast<const float4*>(bias_k) + cv);
+                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_v) + cv);
+                    kk.x += bk.x; kk.y += bk.y; kk.z += bk.z; kk.w += bk.w;
+                    vv.x += bv.x; vv.y += bv.y; vv.z += bv.z; vv.w += bv.w;
+                    dot += kk.x * qv[j].x + kk.y * qv[j].y + kk.z * qv[j].z + kk.w * qv[j].w;
+                }
+                vacc[s][j] = vv;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            logit[s] = dot * inv_sqrt;
+        }
+        float mx = -INFINITY;
+#pragma unroll
+        for (int s = 0; s < ATT_MAX_NS; s++) if (s < ns) mx = fmaxf(mx, logit[s]);
+        float den = 0.f;
+#pragma unroll
+        for (int s = 0; s < ATT_MAX_NS; s++) if (s < ns) { logit[s] = expf(logit[s] - mx); den += logit[s]; }
+        const float rden = 1.f / den;
+#pragma unroll
+        for (int j = 0; j < 2; j++) {
+            const int cv = lane + 32 * j;
+            if (cv >= nvec) continue;
+            float4 o = make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int s = 0; s < ATT_MAX_NS; s++) {
+                if (s >= ns) break;
+                const float al = logit[s] * rden;
+                o.x += al * vacc[s][j].x; o.y += al * vacc[s][j].y; o.z += al * vacc[s][j].z; o.w += al * vacc[s][j].w;
+            }
+            __half h0, l0, h1, l1, h2, l2, h3, l3;
+            split_half(o.x, h0, l0); split_half(o.y, h1, l1); split_half(o.z, h2, l2); split_half(o.w, h3, l3);
+            const size_t off = pix * out_pitch + out_coff + 4 * cv;
+            *reinterpret_cast<uint2*>(out + off) = make_uint2(pack_half2(h0, h1), pack_half2(h2, h3));
+            if (out_planes > 1)
+                *reinterpret_cast<uint2*>(out + out_plane_stride + off) = make_uint2(pack_half2(l0, l1), pack_half2(l2, l3));
+        }
+    }
+}
+
+// plain warp (LWB.transform) on NHWC fp32, for the seam and for debugging
+__global__ void __launch_bounds__(256) warp_nhwc_kernel(const float* __restrict__ src, const float* __restrict__ T, int B,
+                                                        int ns, int h, int w, int C, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const size_t hw = (size_t)h * w, total = (size_t)B * ns * hw;
+    const int nvec = C / 4;
+    for (size_t i = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5); i < total; i += (size_t)gridDim.x * 8) {
+        const size_t s = (i / hw) % ns;
+        const float2 g = reinterpret_cast<const float2*>(T)[i];
+        const Taps t = bilinear_taps(g.x, g.y, h, w);
+        const float4* sp = reinterpret_cast<const float4*>(src + s * hw * C);
+        for (int cv = lane; cv < nvec; cv += 32) {
+            float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (t.off[k] < 0) continue;
+                const float4 a = __ldg(sp + (size_t)t.off[k] * nvec + cv);
+                acc.x += a.x * t.wt[k]; acc.y += a.y * t.wt[k]; acc.z += a.z * t.wt[k]; acc.w += a.w * t.wt[k];
+            }
+            reinterpret_cast<float4*>(out + i * C)[cv] = acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// layout converters
+// ------------------------------------------------------------------------------------------------------------
+__global__ void nchw_to_planes_kernel(const float* __restrict__ in, int N, int C, int HW, __half* __restrict__ out,
+                                      int out_planes, long long out_plane_stride, int out_pitch, int out_coff) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = c0 + r, p = p0 + threadIdx.x;
+        tile[r][threadIdx.x] = (c < C && p < HW) ? in[((size_t)n * C + c) * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int p = p0 + r, c = c0 + threadIdx.x;
+        if (p < HW && c < C)
+            store_plane_val(out, out_planes, out_plane_stride, ((size_t)n * HW + p) * out_pitch + out_coff + c,
+                            tile[threadIdx.x][r]);
+    }
+}
+__global__ void planes_to_nchw_kernel(const __half* __restrict__ x, int x_planes, long long x_plane_stride, int N, int C,
+                                      int HW, int x_pitch, int x_coff, const float* __restrict__ xf,
+                                      float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int p = p0 + r, c = c0 + threadIdx.x;
+        float v = 0.f;
+        if (p < HW && c < C) {
+            const size_t off = ((size_t)n * HW + p) * x_pitch + x_coff + c;
+            v = xf ? xf[off] : load_plane_val(x, x_planes, x_plane_stride, off);
+        }
+        tile[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int c = c0 + r, p = p0 + threadIdx.x;
+        if (c < C && p < HW) out[((size_t)n * C + c) * HW + p] = tile[threadIdx.x][r];
+    }
+}
+
+__global__ void pred_to_u8_kernel(const float* __restrict__ pred, int B, size_t SS, uint8_t* __restrict__ out) {
+    const size_t total = (size_t)B * SS;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t b = i / SS, p = i % SS;
+        uint8_t bgr[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            float v = (pred[(b * 3 + c) * SS + p] + 1.f) / 2.0f * 255.f;   // cv_utils.py:111-113, then astype(uint8)
+            v = fminf(fmaxf(v, 0.f), 255.f);
+            bgr[2 - c] = (uint8_t)v;                                      // RGB -> BGR (cv_utils.py:104-105)
+        }
+        out[i * 3 + 0] = bgr[0]; out[i * 3 + 1] = bgr[1]; out[i * 3 + 2] = bgr[2];
+    }
+}
+
+}  // namespace iper
+
+using namespace iper;
+
+extern "C" int iper_conv_direct(const iper_conv_gemm_desc* g, const float* w_f32, int Cout, iper_stream_t stream) {
+    IPER_REQUIRE(g && w_f32 && g->a && g->out, "iper_conv_direct: null pointer");
+    IPER_REQUIRE(g->epi != IPER_EPI_HEADS, "iper_conv_direct: heads epilogue not supported; use IPER_EPI_F32 and post-process");
+    DirectArgs d = {};
+    d.a = reinterpret_cast<const __half*>(g->a); d.a_planes = g->a_planes; d.a_plane_stride = g->a_plane_stride;
+    d.N = g->N; d.H = g->H; d.W = g->W; d.a_pitch = g->a_pitch; d.a_coff = g->a_coff; d.Cin = g->Cin;
+    d.mode = g->mode; d.ksize = g->ksize; d.Cout = Cout;
+    d.oH = g->mode == IPER_CONV_S2 ? g->H / 2 : (g->mode == IPER_CONVT_4S2 ? 2 * g->H : g->H);
+    d.oW = g->mode == IPER_CONV_S2 ? g->W / 2 : (g->mode == IPER_CONVT_4S2 ? 2 * g->W : g->W);
+    d.w = w_f32; d.bias = g->bias; d.relu = g->relu; d.epi = g->epi;
+    d.out = g->out; d.out_planes = g->out_planes; d.out_plane_stride = g->out_plane_stride;
+    d.out_pitch = g->out_pitch; d.out_coff = g->out_coff;
+    d.x = reinterpret_cast<const __half*>(g->x); d.x_planes = g->x_planes; d.x_plane_stride = g->x_plane_stride;
+    d.x_pitch = g->x_pitch; d.x_coff = g->x_coff; d.mean_rstd = g->mean_rstd; d.spade_C = g->spade_C;
+    if (g->epi == IPER_EPI_SPADE)
+        IPER_REQUIRE(g->x && g->mean_rstd && g->bias && Cout == 2 * g->spade_C, "iper_conv_direct: bad SPADE arguments");
+    const size_t total = (size_t)d.N * d.oH * d.oW * (g->epi == IPER_EPI_SPADE ? d.spade_C : Cout);
+    if (total == 0) return 0;
+    const int blocks = (int)min((size_t)148 * 32, (total + 255) / 256);
+    conv_direct_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d);
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int iper_conv_stem(const float* in_nchw, int N, int Cin, int H, int W, const float* w_f32, const float* bias,
+                              int Cout, void* out, int out_planes, long long out_plane_stride, int out_pitch,
+                              int out_coff, iper_stream_t stream) {
+    IPER_REQUIRE(in_nchw && w_f32 && out, "iper_conv_stem: null pointer");
+    IPER_REQUIRE(Cin >= 1 && Cin <= STEM_MAXC, "iper_conv_stem: Cin=%d not in [1,8]", Cin);
+    IPER_REQUIRE(Cout % 8 == 0 && Cout <= 128, "iper_conv_stem: Cout=%d must be a multiple of 8, <= 128", Cout);
+    IPER_REQUIRE(H % 2 == 0 && W % 2 == 0, "iper_conv_stem: H, W must be even");
+    IPER_REQUIRE(out_pitch % 8 == 0 && out_coff % 8 == 0, "iper_conv_stem: output window must be 8-aligned");
+    const size_t smem = sizeof(float) * ((size_t)stem_halo_floats(Cin) + (size_t)9 * Cin * Cout);
+    dim3 grid((W / 2 + STEM_TW - 1) / STEM_TW, (H / 2 + STEM_TH - 1) / STEM_TH, N);
+#define IPER_STEM_CASE(CI)                                                                                              \
+    case CI:                                                                                                            \
+        IPER_CHECK_CUDA(cudaFuncSetAttribute(conv_stem_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        conv_stem_kernel<CI><<<grid, 256, smem, (cudaStream_t)stream>>>(in_nchw, N, H, W, w_f32, bias, Cout,              \
+                                                                       reinterpret_cast<__half*>(out), out_planes,     \
+                                                                       out_plane_stride, out_pitch, out_coff);         \
+        break;
+    switch (Cin) {
+        IPER_STEM_CASE(1) IPER_STEM_CASE(2) IPER_STEM_CASE(3) IPER_STEM_CASE(4)
+        IPER_STEM_CASE(5) IPER_STEM_CASE(6) IPER_STEM_CASE(7) IPER_STEM_CASE(8)
+    }
+#undef IPER_STEM_CASE
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int iper_instnorm_stats(const void* x, int x_planes, long long x_plane_stride, int N, int HW, int C,
+                                   int x_pitch, int x_coff, float eps, float* mean_rstd, iper_stream_t stream) {
+    IPER_REQUIRE(x && mean_rstd, "iper_instnorm_stats: null pointer");
+    if (N == 0) return 0;
+    dim3 grid((C + 31) / 32, N);
+    instnorm_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(x), x_planes,
+                                                                  x_plane_stride, HW, C, x_pitch, x_coff, eps, mean_rstd);
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int iper_warp_attention(const float* q, const float* kv, const float* bias_k, const float* bias_v,
+                                   const float* T, int B, int ns, int h, int w, int C, void* out, int out_planes,
+                                   long long out_plane_stride, int out_pitch, int out_coff, iper_stream_t stream) {
+    IPER_REQUIRE(q && kv && bias_k && bias_v && T && out, "iper_warp_attention: null pointer");
+    IPER_REQUIRE(ns >= 1 && ns <= ATT_MAX_NS, "iper_warp_attention: ns=%d not in [1,%d]", ns, ATT_MAX_NS);
+    IPER_REQUIRE(C % 4 == 0 && C <= 256, "iper_warp_attention: C=%d must be a multiple of 4, <= 256", C);
+    IPER_REQUIRE(out_pitch % 4 == 0 && out_coff % 4 == 0, "iper_warp_attention: output window must be 4-aligned");
+    const size_t total = (size_t)B * h * w;
+    if (total == 0) return 0;
+    const int blocks = (int)min((size_t)148 * 8, (total + 7) / 8);
+    warp_attention_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(q, kv, bias_k, bias_v, T, B, ns, h, w, C,
+                                                                   reinterpret_cast<__half*>(out), out_planes,
+                                                                   out_plane_stride, out_pitch, out_coff);
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int iper_warp_nhwc(const float* src, const float* T, int B, int ns, int h, int w, int C, float* out,
+                              iper_stream_t stream) {
+    IPER_REQUIRE(src && T && out, "iper_warp_nhwc: null pointer");
+    IPER_REQUIRE(C % 4 == 0, "iper_warp_nhwc: C must be a multiple of 4");
+    const size_t total = (size_t)B * ns * h * w;
+    if (total == 0) return 0;
+    const int blocks = (int)min((size_t)148 * 8, (total + 7) / 8);
+    warp_nhwc_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, T, B, ns, h, w, C, out);
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int iper_nchw_to_planes(const float* in, int N, int C, int HW, void* out, int out_planes,
+                                   long long out_plane_stride, int out_pitch, int out_coff, iper_stream_t stream) {
+    IPER_REQUIRE(in && out, "iper_nchw_to_planes: null pointer");
+    if (N == 0) return 0;
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
+    nchw_to_planes_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(in, N, C, HW, reinterpret_cast<__half*>(out),
+                                                                   out_planes, out_plane_stride, out_pitch, out_coff);
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int iper_planes_to_nchw(const void* x, int x_planes, long long x_plane_stride, int N, int C, int HW,
+                                   int x_pitch, int x_coff, float* out, iper_stream_t stream) {
+    IPER_REQUIRE(x && out, "iper_planes_to_nchw: null pointer");
+    if (N == 0) return 0;
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
+    planes_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(x), x_planes,
+                                                                   x_plane_stride, N, C, HW, x_pitch, x_coff, nullptr, out);
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int iper_nhwc_f32_to_nchw(const float* in, int N, int C, int HW, int pitch, int coff, float* out,
+                                     iper_stream_t stream) {
+    IPER_REQUIRE(in && out, "iper_nhwc_f32_to_nchw: null pointer");
+    if (N == 0) return 0;
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
+    planes_to_nchw_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(nullptr, 0, 0, N, C, HW, pitch, coff, in, out);
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int iper_pred_to_u8(const float* pred, int B, int S, uint8_t* out, iper_stream_t stream) {
+    IPER_REQUIRE(pred && out, "iper_pred_to_u8: null pointer");
+    const size_t total = (size_t)B * S * S;
+    if (total == 0) return 0;
+    const int blocks = (int)min((size_t)148 * 16, (total + 255) / 256);
+    pred_to_u8_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, B, (size_t)S * S, out);
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

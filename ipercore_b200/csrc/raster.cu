@@ -1,0 +1,465 @@
+// SMPL mesh rasteriser + per-frame geometry (rows a1-a8 of SURVEY.md §8a), sm_100a.
+//
+// Replaces, for the hot path:
+//   * nr.rasterize_face_index_map_and_weight_map   (reference call sites nmr.py:337,356; third-party CUDA ext)
+//   * SMPLRenderer.render_fim_wim glue              (nmr.py:319-342: projection, y flip, look_at, vertices_to_faces)
+//   * SMPLRenderer.encode_fim                       (nmr.py:390-401)
+//   * SMPLRenderer.cal_bc_transform                 (nmr.py:713-757)
+//   * FlowComposition.make_tsf_inputs / make_trans_flow (flowcomposition.py:206-248, 514-582)
+//
+// Design (B200): one CTA per 64x32 pixel tile per frame.  The frame's projected vertices are staged in shared
+// memory once per CTA (82 KB), every thread walks a strided slice of the 13 776 faces and BINS them against
+// the tile by bounding box; faces that overlap are scan-converted over (bbox ∩ tile) straight into a shared
+// memory z-buffer with a 64-bit atomicMin on (depth bits << 32 | face index) — which is exactly the upstream
+// rule "strictly smaller depth wins, lowest face index wins a tie".  A resolve pass then recomputes the winner's
+// barycentric weights (same float sequence, hence identical bits) and writes fim / wim / cond / flow / sampled
+// UV image with fully coalesced stores.  Work is proportional to covered area, not faces x pixels
+// (upstream: 262 144 px x 13 776 faces per 512^2 frame).
+//
+// Parity contract: every float operation below that feeds the inside test, the weights or the depth is an
+// explicitly rounded binary32 op (__fmul_rn/__fadd_rn/__fdiv_rn — never contracted into FMA) in the same order
+// as oracle/raster_ref.c, including the two places where upstream's double literals promote to double.
+#include "common.cuh"
+#include "iper_b200.h"
+
+namespace iper {
+
+constexpr int TILE_W = 64;
+constexpr int TILE_H = 32;
+constexpr int RASTER_THREADS = 256;
+constexpr unsigned long long ZBUF_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+
+struct FaceGeom {
+    float v[9];  // x0 y0 z0 x1 y1 z1 x2 y2 z2 (NDC, +y up after the reference's flip)
+};
+
+IPER_DEVINL bool is_backface(const float* f) {
+    return __fmul_rn(__fsub_rn(f[7], f[1]), __fsub_rn(f[3], f[0])) <
+           __fmul_rn(__fsub_rn(f[4], f[1]), __fsub_rn(f[6], f[0]));
+}
+
+// upstream kernel 1: pixel-space corners and the adjugate/determinant inverse
+IPER_DEVINL void face_inverse(const float* f, int is, float* inv) {
+    float p[3][2];
+    const float fis = (float)is;
+#pragma unroll
+    for (int n = 0; n < 3; n++)
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+            float t = __fmul_rn(f[3 * n + d], fis);
+            t = __fadd_rn(t, fis);
+            t = __fsub_rn(t, 1.0f);
+            p[n][d] = __fmul_rn(0.5f, t);  // exact
+        }
+    float a[9];
+    a[0] = __fsub_rn(p[1][1], p[2][1]);
+    a[1] = __fsub_rn(p[2][0], p[1][0]);
+    a[2] = __fsub_rn(__fmul_rn(p[1][0], p[2][1]), __fmul_rn(p[2][0], p[1][1]));
+    a[3] = __fsub_rn(p[2][1], p[0][1]);
+    a[4] = __fsub_rn(p[0][0], p[2][0]);
+    a[5] = __fsub_rn(__fmul_rn(p[2][0], p[0][1]), __fmul_rn(p[0][0], p[2][1]));
+    a[6] = __fsub_rn(p[0][1], p[1][1]);
+    a[7] = __fsub_rn(p[1][0], p[0][0]);
+    a[8] = __fsub_rn(__fmul_rn(p[0][0], p[1][1]), __fmul_rn(p[1][0], p[0][1]));
+    float den = __fmul_rn(p[2][0], __fsub_rn(p[0][1], p[1][1]));
+    den = __fadd_rn(den, __fmul_rn(p[0][0], __fsub_rn(p[1][1], p[2][1])));
+    den = __fadd_rn(den, __fmul_rn(p[1][0], __fsub_rn(p[2][1], p[0][1])));
+#pragma unroll
+    for (int k = 0; k < 9; k++) inv[k] = __fdiv_rn(a[k], den);
+}
+
+IPER_DEVINL float pixel_centre(int i, int is) {
+    // (float)((2. * i + 1 - is) / is): evaluated in double, rounded once
+    return __double2float_rn(__ddiv_rn(2.0 * (double)i + 1.0 - (double)is, (double)is));
+}
+
+IPER_DEVINL bool inside_face(const float* f, float xp, float yp) {
+    if (__fmul_rn(__fsub_rn(yp, f[1]), __fsub_rn(f[3], f[0])) < __fmul_rn(__fsub_rn(xp, f[0]), __fsub_rn(f[4], f[1])))
+        return false;
+    if (__fmul_rn(__fsub_rn(yp, f[4]), __fsub_rn(f[6], f[3])) < __fmul_rn(__fsub_rn(xp, f[3]), __fsub_rn(f[7], f[4])))
+        return false;
+    if (__fmul_rn(__fsub_rn(yp, f[7]), __fsub_rn(f[0], f[6])) < __fmul_rn(__fsub_rn(xp, f[6]), __fsub_rn(f[1], f[7])))
+        return false;
+    return true;
+}
+
+// clamped + renormalised barycentric weights and perspective-correct depth; returns false when rejected
+IPER_DEVINL bool weights_depth(const float* f, const float* inv, int xi, int yi, float near_, float far_, float* w,
+                               float& zp) {
+    const float fx = (float)xi, fy = (float)yi;
+    float ws = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float t = __fmul_rn(inv[3 * k + 0], fx);
+        t = __fadd_rn(t, __fmul_rn(inv[3 * k + 1], fy));
+        t = __fadd_rn(t, inv[3 * k + 2]);
+        double d = fmax((double)t, 0.0);  // min(max(w, 0.), 1.) — NaN -> 0 like upstream's fmax/fmin
+        d = fmin(d, 1.0);
+        w[k] = (float)d;
+        ws = __fadd_rn(ws, w[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) w[k] = __fdiv_rn(w[k], ws);
+    float s = __fdiv_rn(w[0], f[2]);
+    s = __fadd_rn(s, __fdiv_rn(w[1], f[5]));
+    s = __fadd_rn(s, __fdiv_rn(w[2], f[8]));
+    zp = __double2float_rn(__ddiv_rn(1.0, (double)s));
+    if (zp <= near_ || far_ <= zp) return false;
+    return true;
+}
+
+// F.grid_sample(img, grid) for one location, bilinear / zeros / align_corners=False, C planes of an (C,S,S) image
+template <int C>
+IPER_DEVINL void grid_sample_chw(const float* __restrict__ img, int S, float gx, float gy, float* out) {
+    const float ix = ((gx + 1.f) * S - 1.f) * 0.5f;
+    const float iy = ((gy + 1.f) * S - 1.f) * 0.5f;
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
+    const float wx1 = ix - fx0, wx0 = (fx0 + 1.f) - ix;
+    const float wy1 = iy - fy0, wy0 = (fy0 + 1.f) - iy;
+    const float nw = wx0 * wy0, ne = wx1 * wy0, sw = wx0 * wy1, se = wx1 * wy1;
+    const bool vx0 = (x0 >= 0 && x0 < S), vx1 = (x1 >= 0 && x1 < S);
+    const bool vy0 = (y0 >= 0 && y0 < S), vy1 = (y1 >= 0 && y1 < S);
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const float* p = img + (size_t)c * S * S;
+        float acc = 0.f;
+        if (vy0 && vx0) acc += p[y0 * S + x0] * nw;
+        if (vy0 && vx1) acc += p[y0 * S + x1] * ne;
+        if (vy1 && vx0) acc += p[y1 * S + x0] * sw;
+        if (vy1 && vx1) acc += p[y1 * S + x1] * se;
+        out[c] = acc;
+    }
+}
+
+struct RasterArgs {
+    // geometry source A: per-frame vertices + camera + shared topology (engine path, staged in smem)
+    const float* verts;    // (B, nv, 3) or null
+    const float* cams;     // (B, 3)
+    const int32_t* faces;  // (nf, 3)
+    // geometry source B: pre-gathered, already projected faces (neural_renderer seam)
+    const float* face_verts;  // (B, nf, 3, 3) or null
+    int B, nv, nf, S;
+    float near_, far_, eye_z;
+    // outputs (any may be null)
+    int32_t* fim;  // (B,S,S)
+    float* wim;    // (B,S,S,3)
+    float* f2pts;  // (B,nf,3,2)   image-space (x, y) of every face corner, y flipped back (nmr.py:339-340)
+    // fused per-frame generator inputs (all-or-nothing: enabled when tsf_inputs != null)
+    const float* map_fn;     // (nf+1, 3)
+    const float* f_uvs2img;  // (nf, 3, 2)
+    const float* uv_img;     // (3, S, S)
+    const float* src_f2pts;  // (ns, nf, 3, 2)
+    int ns;
+    float* tsf_inputs;  // (B, 6, S, S)  = cat[syn_img, cond]
+    float* Tst;         // (B, ns, S, S, 2)
+};
+
+template <bool FROM_VERTS>
+__global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(const RasterArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* zbuf = reinterpret_cast<unsigned long long*>(smem_raw);
+    float* sv = reinterpret_cast<float*>(smem_raw + (size_t)TILE_W * TILE_H * sizeof(unsigned long long));
+
+    const int S = a.S, nf = a.nf;
+    const int b = blockIdx.y;
+    const int tiles_x = (S + TILE_W - 1) / TILE_W;
+    const int tx0 = (blockIdx.x % tiles_x) * TILE_W;
+    const int r0 = (blockIdx.x / tiles_x) * TILE_H;  // image rows r0 .. r0+TILE_H-1
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < TILE_W * TILE_H; i += RASTER_THREADS) zbuf[i] = ZBUF_EMPTY;
+
+    if (FROM_VERTS) {
+        // a1: orthographic_proj_withz_idrot + y flip + look_at (identity rotation, z -> z - eye_z)
+        const float s = a.cams[3 * b + 0], tx = a.cams[3 * b + 1], ty = a.cams[3 * b + 2];
+        const float* v = a.verts + (size_t)b * a.nv * 3;
+        for (int i = tid; i < a.nv; i += RASTER_THREADS) {
+            const float x = v[3 * i + 0], y = v[3 * i + 1], z = v[3 * i + 2];
+            sv[3 * i + 0] = __fmul_rn(s, __fadd_rn(x, tx));
+            sv[3 * i + 1] = -__fmul_rn(s, __fadd_rn(y, ty));
+            sv[3 * i + 2] = __fsub_rn(z, a.eye_z);
+        }
+    }
+    __syncthreads();
+
+    // f2pts (a3) is per frame, not per tile: the x-tile 0 / row-tile 0 CTA of each frame writes it
+    if (FROM_VERTS && a.f2pts != nullptr && blockIdx.x == 0) {
+        float* o = a.f2pts + (size_t)b * nf * 6;
+        for (int f = tid; f < nf; f += RASTER_THREADS) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int vi = a.faces[3 * f + k];
+                o[6 * f + 2 * k + 0] = sv[3 * vi + 0];
+                o[6 * f + 2 * k + 1] = -sv[3 * vi + 1];
+            }
+        }
+    }
+
+    // pixel-index bounds of this tile in the upstream (xi, yi) frame: yi = S-1-row
+    const int xi_lo = tx0, xi_hi = min(tx0 + TILE_W, S) - 1;
+    const int yi_hi = S - 1 - r0, yi_lo = S - 1 - (min(r0 + TILE_H, S) - 1);
+    const float fS = (float)S;
+
+    // ---- binning + scan conversion into the shared z-buffer ----
+    for (int f = tid; f < nf; f += RASTER_THREADS) {
+        FaceGeom g;
+        if (FROM_VERTS) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int vi = __ldg(a.faces + 3 * f + k);
+                g.v[3 * k + 0] = sv[3 * vi + 0];
+                g.v[3 * k + 1] = sv[3 * vi + 1];
+                g.v[3 * k + 2] = sv[3 * vi + 2];
+            }
+        } else {
+            const float* src = a.face_verts + ((size_t)b * nf + f) * 9;
+#pragma unroll
+            for (int k = 0; k < 9; k++) g.v[k] = __ldg(src + k);
+        }
+        if (is_backface(g.v)) continue;
+        // conservative pixel range of the face's bounding box, grown by one pixel on every side
+        const float xmin = fminf(g.v[0], fminf(g.v[3], g.v[6])), xmax = fmaxf(g.v[0], fmaxf(g.v[3], g.v[6]));
+        const float ymin = fminf(g.v[1], fminf(g.v[4], g.v[7])), ymax = fmaxf(g.v[1], fmaxf(g.v[4], g.v[7]));
+        int x0 = xi_lo, x1 = xi_hi, y0 = yi_lo, y1 = yi_hi;
+        const bool finite = (xmin == xmin) && (xmax == xmax) && (ymin == ymin) && (ymax == ymax) &&
+                            fabsf(xmin) < 1e6f && fabsf(xmax) < 1e6f && fabsf(ymin) < 1e6f && fabsf(ymax) < 1e6f;
+        if (finite) {
+            x0 = max(x0, (int)floorf((xmin * fS + fS - 1.f) * 0.5f) - 1);
+            x1 = min(x1, (int)ceilf((xmax * fS + fS - 1.f) * 0.5f) + 1);
+            y0 = max(y0, (int)floorf((ymin * fS + fS - 1.f) * 0.5f) - 1);
+            y1 = min(y1, (int)ceilf((ymax * fS + fS - 1.f) * 0.5f) + 1);
+        }
+        if (x0 > x1 || y0 > y1) continue;  // face not binned to this tile
+        float inv[9];
+        face_inverse(g.v, S, inv);
+        for (int yi = y0; yi <= y1; yi++) {
+            const float yp = pixel_centre(yi, S);
+            for (int xi = x0; xi <= x1; xi++) {
+                const float xp = pixel_centre(xi, S);
+                if (!inside_face(g.v, xp, yp)) continue;
+                float w[3], zp;
+                if (!weights_depth(g.v, inv, xi, yi, a.near_, a.far_, w, zp)) continue;
+                const unsigned long long key = ((unsigned long long)__float_as_uint(zp) << 32) | (unsigned)f;
+                atomicMin(&zbuf[(S - 1 - yi - r0) * TILE_W + (xi - tx0)], key);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- resolve: coalesced writes of fim / wim / cond / flow / sampled UV image ----
+    const size_t SS = (size_t)S * S;
+    for (int i = tid; i < TILE_W * TILE_H; i += RASTER_THREADS) {
+        const int lx = i % TILE_W, ly = i / TILE_W;
+        const int xi = tx0 + lx, row = r0 + ly;
+        if (xi >= S || row >= S) continue;
+        const unsigned long long key = zbuf[i];
+        const int fn = (key == ZBUF_EMPTY) ? -1 : (int)(unsigned)(key & 0xFFFFFFFFull);
+        float w[3] = {0.f, 0.f, 0.f};
+        if (fn >= 0) {
+            FaceGeom g;
+            if (FROM_VERTS) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const int vi = __ldg(a.faces + 3 * fn + k);
+                    g.v[3 * k + 0] = sv[3 * vi + 0];
+                    g.v[3 * k + 1] = sv[3 * vi + 1];
+                    g.v[3 * k + 2] = sv[3 * vi + 2];
+                }
+            } else {
+                const float* src = a.face_verts + ((size_t)b * nf + fn) * 9;
+#pragma unroll
+                for (int k = 0; k < 9; k++) g.v[k] = __ldg(src + k);
+            }
+            float inv[9], zp;
+            face_inverse(g.v, S, inv);
+            weights_depth(g.v, inv, xi, S - 1 - row, a.near_, a.far_, w, zp);
+        }
+        const size_t pix = (size_t)row * S + xi;
+        if (a.fim) a.fim[(size_t)b * SS + pix] = fn;
+        if (a.wim) {
+            float* o = a.wim + ((size_t)b * SS + pix) * 3;
+            o[0] = w[0]; o[1] = w[1]; o[2] = w[2];
+        }
+        if (a.tsf_inputs) {
+            // a4: cond = map_fn[fim] (index -1 -> last row)
+            const float* mf = a.map_fn + 3 * (size_t)(fn >= 0 ? fn : nf);
+            float* ti = a.tsf_inputs + (size_t)b * 6 * SS + pix;
+            ti[3 * SS] = __ldg(mf + 0);
+            ti[4 * SS] = __ldg(mf + 1);
+            ti[5 * SS] = __ldg(mf + 2);
+            // a6/a7: Tuv2t then syn_img = grid_sample(uv_img, Tuv2t); background T = -2 samples zeros
+            float syn[3] = {0.f, 0.f, 0.f};
+            if (fn >= 0) {
+                const float* fu = a.f_uvs2img + (size_t)fn * 6;
+                const float gx = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(fu + 0), w[0]), __fmul_rn(__ldg(fu + 2), w[1])),
+                                           __fmul_rn(__ldg(fu + 4), w[2]));
+                const float gy = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(fu + 1), w[0]), __fmul_rn(__ldg(fu + 3), w[1])),
+                                           __fmul_rn(__ldg(fu + 5), w[2]));
+                grid_sample_chw<3>(a.uv_img, S, gx, gy, syn);
+            }
+            ti[0] = syn[0];
+            ti[SS] = syn[1];
+            ti[2 * SS] = syn[2];
+            // a8: Tst[b, s] from each source's f2pts
+            for (int s = 0; s < a.ns; s++) {
+                float2 t = make_float2(-2.f, -2.f);
+                if (fn >= 0) {
+                    const float* fp = a.src_f2pts + ((size_t)s * nf + fn) * 6;
+                    t.x = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(fp + 0), w[0]), __fmul_rn(__ldg(fp + 2), w[1])),
+                                    __fmul_rn(__ldg(fp + 4), w[2]));
+                    t.y = __fadd_rn(__fadd_rn(__fmul_rn(__ldg(fp + 1), w[0]), __fmul_rn(__ldg(fp + 3), w[1])),
+                                    __fmul_rn(__ldg(fp + 5), w[2]));
+                }
+                reinterpret_cast<float2*>(a.Tst)[((size_t)b * a.ns + s) * SS + pix] = t;
+            }
+        }
+    }
+}
+
+// cal_bc_transform (nmr.py:713-757): T[p] = sum_k wim[p,k] * f2pts[fim[p],k,:], background (-2,-2)
+__global__ void flow_kernel(const float* __restrict__ f2pts, int f2pts_per_item, const int32_t* __restrict__ fim,
+                            const float* __restrict__ wim, int nb, int nsrc, int nf, size_t SS, float* __restrict__ T) {
+    const size_t total = (size_t)nb * nsrc * SS;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t pix = i % SS;
+        const int s = (int)((i / SS) % nsrc);
+        const int b = (int)(i / (SS * nsrc));
+        const int fn = fim[(size_t)b * SS + pix];
+        float2 t = make_float2(-2.f, -2.f);
+        if (fn >= 0) {
+            const float* w = wim + ((size_t)b * SS + pix) * 3;
+            const float* fp = f2pts + ((size_t)(f2pts_per_item ? b : s) * nf + fn) * 6;
+            t.x = __fadd_rn(__fadd_rn(__fmul_rn(fp[0], w[0]), __fmul_rn(fp[2], w[1])), __fmul_rn(fp[4], w[2]));
+            t.y = __fadd_rn(__fadd_rn(__fmul_rn(fp[1], w[0]), __fmul_rn(fp[3], w[1])), __fmul_rn(fp[5], w[2]));
+        }
+        reinterpret_cast<float2*>(T)[i] = t;
+    }
+}
+
+// encode_fim (nmr.py:390-401): out[b, c, y, x] = map_fn[fim[b,y,x] (or last row for -1)][c]   (transpose=True)
+__global__ void encode_fim_kernel(const int32_t* __restrict__ fim, const float* __restrict__ map_fn, int nb, int nf,
+                                  int ch, size_t SS, int transpose, float* __restrict__ out) {
+    const size_t total = (size_t)nb * SS;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int fn = fim[i];
+        const float* mf = map_fn + (size_t)ch * (fn >= 0 ? fn : nf);
+        const size_t b = i / SS, pix = i % SS;
+        for (int c = 0; c < ch; c++) {
+            if (transpose) out[(b * ch + c) * SS + pix] = mf[c];
+            else out[i * ch + c] = mf[c];
+        }
+    }
+}
+
+// LWB.resize_trans (attlwb_spade_resunet.py:175-182): bilinear, align_corners=True, (N,S,S,2) -> (N,h,w,2)
+__global__ void flow_resize_kernel(const float* __restrict__ T, int n, int S, int h, int w, float* __restrict__ out) {
+    const float sy = (h > 1) ? (float)(S - 1) / (float)(h - 1) : 0.f;
+    const float sx = (w > 1) ? (float)(S - 1) / (float)(w - 1) : 0.f;
+    const size_t total = (size_t)n * h * w;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % w), y = (int)((i / w) % h);
+        const size_t b = i / ((size_t)w * h);
+        const float fy = sy * y, fx = sx * x;
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = y0 + (y0 < S - 1 ? 1 : 0), x1 = x0 + (x0 < S - 1 ? 1 : 0);
+        const float ly1 = fy - y0, ly0 = 1.f - ly1, lx1 = fx - x0, lx0 = 1.f - lx1;
+        const float2* src = reinterpret_cast<const float2*>(T) + b * S * S;
+        const float2 a = src[(size_t)y0 * S + x0], bb = src[(size_t)y0 * S + x1];
+        const float2 c = src[(size_t)y1 * S + x0], d = src[(size_t)y1 * S + x1];
+        float2 o;
+        o.x = ly0 * (lx0 * a.x + lx1 * bb.x) + ly1 * (lx0 * c.x + lx1 * d.x);
+        o.y = ly0 * (lx0 * a.y + lx1 * bb.y) + ly1 * (lx0 * c.y + lx1 * d.y);
+        reinterpret_cast<float2*>(out)[i] = o;
+    }
+}
+
+static size_t raster_smem_bytes(bool from_verts, int nv) {
+    return (size_t)TILE_W * TILE_H * sizeof(unsigned long long) + (from_verts ? (size_t)nv * 3 * sizeof(float) : 0);
+}
+
+static int launch_raster(const RasterArgs& a, bool from_verts, cudaStream_t stream) {
+    const int S = a.S;
+    const int tiles = ((S + TILE_W - 1) / TILE_W) * ((S + TILE_H - 1) / TILE_H);
+    const size_t smem = raster_smem_bytes(from_verts, a.nv);
+    IPER_REQUIRE(smem <= 227 * 1024, "rasteriser: %d vertices do not fit the shared-memory staging buffer", a.nv);
+    dim3 grid(tiles, a.B);
+    if (from_verts) {
+        IPER_CHECK_CUDA(cudaFuncSetAttribute(raster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        raster_kernel<true><<<grid, RASTER_THREADS, smem, stream>>>(a);
+    } else {
+        IPER_CHECK_CUDA(cudaFuncSetAttribute(raster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        raster_kernel<false><<<grid, RASTER_THREADS, smem, stream>>>(a);
+    }
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace iper
+
+using namespace iper;
+
+extern "C" int iper_rasterize_faces(const float* faces, int B, int nf, int S, float near_, float far_, int32_t* fim,
+                                    float* wim, iper_stream_t stream) {
+    IPER_REQUIRE(faces && fim && wim, "iper_rasterize_faces: null pointer");
+    IPER_REQUIRE(B >= 0 && nf > 0 && S > 0, "iper_rasterize_faces: bad sizes B=%d nf=%d S=%d", B, nf, S);
+    if (B == 0) return 0;
+    RasterArgs a = {};
+    a.face_verts = faces; a.B = B; a.nf = nf; a.S = S; a.near_ = near_; a.far_ = far_;
+    a.fim = fim; a.wim = wim;
+    return launch_raster(a, false, (cudaStream_t)stream);
+}
+
+extern "C" int iper_raster_frames(const float* verts, const float* cams, const int32_t* faces, int B, int nv, int nf,
+                                  int S, float eye_z, float near_, float far_, int32_t* fim, float* wim, float* f2pts,
+                                  const float* map_fn, const float* f_uvs2img, const float* uv_img,
+                                  const float* src_f2pts, int ns, float* tsf_inputs, float* Tst,
+                                  iper_stream_t stream) {
+    IPER_REQUIRE(verts && cams && faces, "iper_raster_frames: null geometry pointer");
+    IPER_REQUIRE(B >= 0 && nv > 0 && nf > 0 && S > 0, "iper_raster_frames: bad sizes");
+    if (tsf_inputs || Tst) {
+        IPER_REQUIRE(tsf_inputs && Tst && map_fn && f_uvs2img && uv_img && src_f2pts && ns > 0,
+                     "iper_raster_frames: the fused frame-input outputs need map_fn, f_uvs2img, uv_img, src_f2pts, ns");
+    }
+    if (B == 0) return 0;
+    RasterArgs a = {};
+    a.verts = verts; a.cams = cams; a.faces = faces; a.B = B; a.nv = nv; a.nf = nf; a.S = S;
+    a.near_ = near_; a.far_ = far_; a.eye_z = eye_z;
+    a.fim = fim; a.wim = wim; a.f2pts = f2pts;
+    a.map_fn = map_fn; a.f_uvs2img = f_uvs2img; a.uv_img = uv_img; a.src_f2pts = src_f2pts; a.ns = ns;
+    a.tsf_inputs = tsf_inputs; a.Tst = Tst;
+    return launch_raster(a, true, (cudaStream_t)stream);
+}
+
+extern "C" int iper_flow_from_fim_wim(const float* f2pts, int f2pts_per_item, const int32_t* fim, const float* wim,
+                                      int nb, int nsrc, int nf, int S, float* T, iper_stream_t stream) {
+    IPER_REQUIRE(f2pts && fim && wim && T, "iper_flow_from_fim_wim: null pointer");
+    IPER_REQUIRE(!f2pts_per_item || nsrc == 1, "iper_flow_from_fim_wim: per-item f2pts needs nsrc == 1");
+    const size_t total = (size_t)nb * nsrc * S * S;
+    if (total == 0) return 0;
+    const int blocks = (int)min((size_t)148 * 16, (total + 255) / 256);
+    flow_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(f2pts, f2pts_per_item, fim, wim, nb, nsrc, nf, (size_t)S * S, T);
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int iper_encode_fim(const int32_t* fim, const float* map_fn, int nb, int nf, int ch, int S, int transpose,
+                               float* out, iper_stream_t stream) {
+    IPER_REQUIRE(fim && map_fn && out, "iper_encode_fim: null pointer");
+    const size_t total = (size_t)nb * S * S;
+    if (total == 0) return 0;
+    const int blocks = (int)min((size_t)148 * 16, (total + 255) / 256);
+    encode_fim_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(fim, map_fn, nb, nf, ch, (size_t)S * S, transpose, out);
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int iper_flow_resize(const float* T, int n, int S, int h, int w, float* out, iper_stream_t stream) {
+    IPER_REQUIRE(T && out, "iper_flow_resize: null pointer");
+    const size_t total = (size_t)n * h * w;
+    if (total == 0) return 0;
+    const int blocks = (int)min((size_t)148 * 16, (total + 255) / 256);
+    flow_resize_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(T, n, S, h, w, out);
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
