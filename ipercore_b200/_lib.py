@@ -1,0 +1,82 @@
+"""ctypes binding of libiper_b200.so — the C-ABI boundary (include/iper_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a symbol is absent this module raises at
+import time, and every op raises RuntimeError with iper_last_error() on a non-zero status.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libiper_b200.so")
+
+c_void_p, c_int, c_float, c_ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
+
+IPER_CONV_S1, IPER_CONV_S2, IPER_CONVT_4S2 = 0, 1, 2
+IPER_EPI_PLANES, IPER_EPI_F32, IPER_EPI_SPADE, IPER_EPI_HEADS = 0, 1, 2, 3
+
+
+class ConvGemmDesc(ctypes.Structure):
+    """Mirror of iper_conv_gemm_desc (include/iper_b200.h) — field order and types must match exactly."""
+    _fields_ = [
+        ("a", c_void_p), ("a_planes", c_int), ("a_plane_stride", c_ll),
+        ("N", c_int), ("H", c_int), ("W", c_int),
+        ("a_pitch", c_int), ("a_coff", c_int), ("Cin", c_int),
+        ("mode", c_int), ("ksize", c_int),
+        ("w", c_void_p), ("w_planes", c_int), ("w_plane_stride", c_ll),
+        ("rows", c_int), ("block_n", c_int),
+        ("epi", c_int), ("bias", c_void_p), ("relu", c_int),
+        ("out", c_void_p), ("out_planes", c_int), ("out_plane_stride", c_ll), ("out_pitch", c_int), ("out_coff", c_int),
+        ("x", c_void_p), ("x_planes", c_int), ("x_plane_stride", c_ll), ("x_pitch", c_int), ("x_coff", c_int),
+        ("mean_rstd", c_void_p), ("spade_C", c_int),
+        ("bg", c_void_p), ("bg_batch_stride", c_ll), ("img", c_void_p), ("mask", c_void_p), ("pred", c_void_p),
+        ("max_ctas", c_int),
+    ]
+
+
+# name -> argtypes; every function returns int status except iper_last_error
+SIGNATURES = {
+    "iper_abi_version": [],
+    "iper_rasterize_faces": [c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p],
+    "iper_raster_frames": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                           c_void_p, c_void_p],
+    "iper_flow_from_fim_wim": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "iper_encode_fim": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "iper_flow_resize": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "iper_conv_gemm": [ctypes.POINTER(ConvGemmDesc), c_void_p],
+    "iper_conv_direct": [ctypes.POINTER(ConvGemmDesc), c_void_p, c_int, c_void_p],
+    "iper_conv_stem": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_ll, c_int,
+                       c_int, c_void_p],
+    "iper_instnorm_stats": [c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p],
+    "iper_warp_attention": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                            c_void_p, c_int, c_ll, c_int, c_int, c_void_p],
+    "iper_warp_nhwc": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "iper_nchw_to_planes": [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p],
+    "iper_planes_to_nchw": [c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "iper_nhwc_f32_to_nchw": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "iper_pred_to_u8": [c_void_p, c_int, c_int, c_void_p, c_void_p],
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "ipercore_b200: %s is missing — build it with `python -m ipercore_b200.build` (nvcc, sm_100a). "
+            "There is no CPU or PyTorch fallback for these kernels." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = ABI drift; fail loudly
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    lib.iper_last_error.argtypes = []
+    lib.iper_last_error.restype = ctypes.c_char_p
+    return lib
+
+
+lib = _load()
+
+
+def check(status, what=""):
+    if status != 0:
+        msg = lib.iper_last_error()
+        raise RuntimeError("iper_b200 %s failed (status %d): %s" % (what, status, msg.decode() if msg else "?"))

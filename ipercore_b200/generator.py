@@ -1,0 +1,366 @@
+"""Seam B3 — drop-in for the reference's AttLWB-SPADE generator on the B200 kernels.
+
+Mirrors ``iPERCore/models/networks/generators/attlwb_spade_resunet.py`` (class AttentionLWBGenerator :538-699,
+BaseAttentionLWBGenerator.forward_src :450-478 / forward_tsf :480-535): same constructor arguments, same method
+names and argument meaning, and the same flat ``state_dict`` (221 tensors) so existing checkpoints
+(``AttLWB-SPADE_id_G_*.pth``, ``personalized.pth``) load unchanged with ``load_state_dict``.
+
+The modules below only HOLD parameters under the reference's names; compute goes through ``ops`` (C ABI):
+tcgen05 implicit-GEMM convs with fused bias/ReLU/residual/SPADE/heads epilogues, the stem conv, instance-norm
+statistics and the fused warp+attention kernel.  There is no PyTorch compute fallback.
+
+Precision modes (``precision=``):
+  "fp16x2" (default)  activations/weights as hi+lo fp16 planes, 3 MMAs per K step, fp32 accumulate — meets the
+                      1e-3 max-abs fp32 parity target of BASELINE.json;
+  "fp16"              single fp16 plane, 1 MMA per K step (≈ TF32-grade operands; ~3e-3 max-abs on the golden case).
+
+Algebraic restructuring used (SURVEY.md §8a note): fk/fv are 1x1 convs of a bilinear warp of constant source features,
+and warp is linear, so  fk(warp(x)) = warp(Wk x) + bk.  ``forward_src`` therefore projects the source features once
+(``[Wk x | Wv x]`` per stage) and ``forward_tsf`` gathers those with the flow inside the attention kernel.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import (IPER_CONV_S1, IPER_CONV_S2, IPER_CONVT_4S2, IPER_EPI_F32, IPER_EPI_HEADS, IPER_EPI_PLANES,
+                  IPER_EPI_SPADE, Planes)
+
+
+def _bn_for(rows):
+    return 256 if rows >= 256 else rows
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# parameter holders named like the reference modules
+# ---------------------------------------------------------------------------------------------------------------------
+class _Res(nn.Module):
+    def __init__(self, c, second_idx):
+        super().__init__()
+        layers = [nn.Conv2d(c, c, 3, 1, 1)] + [nn.Identity() for _ in range(second_idx - 1)] + [nn.Conv2d(c, c, 3, 1, 1)]
+        self.main = nn.Sequential(*layers)
+
+
+def _seq_with(pairs, length):
+    mods = [nn.Identity() for _ in range(length)]
+    for i, m in pairs:
+        mods[i] = m
+    return nn.Sequential(*mods)
+
+
+class _BGNetParams(nn.Module):
+    """bg_inpaintor.py:24-60 ResNetInpaintor parameter layout: main.{0,3,6,9}, main.{12..17}.main.{0,3}, main.{18,21,24}, main.27."""
+
+    def __init__(self, c_dim, nf, n_res):
+        super().__init__()
+        pairs = [(0, nn.Conv2d(c_dim, nf[0], 7, 1, 3))]
+        idx = 3
+        for i in range(1, len(nf)):
+            pairs.append((idx, nn.Conv2d(nf[i - 1], nf[i], 3, 2, 1))); idx += 3
+        for _ in range(n_res):
+            pairs.append((idx, _Res(nf[-1], 3))); idx += 1
+        for i in range(len(nf) - 1, 0, -1):
+            pairs.append((idx, nn.ConvTranspose2d(nf[i], nf[i - 1], 4, 2, 1, bias=False))); idx += 3
+        pairs.append((idx, nn.Conv2d(nf[0], 3, 7, 1, 3, bias=False)))
+        self.main = _seq_with(pairs, idx + 2)
+
+
+class _EncParams(nn.Module):
+    def __init__(self, cin, nf, bias):
+        super().__init__()
+        chans = [cin] + list(nf)
+        self.layers = nn.Sequential(*[nn.Sequential(nn.Conv2d(chans[i], chans[i + 1], 3, 2, 1, bias=bias), nn.Identity())
+                                      for i in range(len(nf))])
+
+
+class _DecParams(nn.Module):
+    def __init__(self, cin, nf):
+        super().__init__()
+        chans = [cin] + list(nf)
+        self.layers = nn.Sequential(*[nn.Sequential(nn.ConvTranspose2d(chans[i], chans[i + 1], 4, 2, 1), nn.Identity())
+                                      for i in range(len(nf))])
+
+
+class _SIDNetParams(nn.Module):
+    def __init__(self, cin, nf, n_res):
+        super().__init__()
+        self.encoders = _EncParams(cin, nf, True)
+        self.res_blocks = nn.Sequential(*[_Res(nf[-1], 2) for _ in range(n_res)])
+        self.decoders = _DecParams(nf[-1], list(reversed(nf)))
+        self.img_reg = nn.Sequential(nn.Conv2d(nf[0], 3, 5, 1, 2, bias=False), nn.Identity())
+        self.att_reg = nn.Sequential(nn.Conv2d(nf[0], 1, 5, 1, 2, bias=False), nn.Identity())
+
+
+class _SkipDecParams(nn.Module):
+    def __init__(self, cin, enc_nf, dec_nf):
+        super().__init__()
+        n = len(dec_nf)
+        ups, skips = [], []
+        for i in range(n):
+            d_in = cin if i == 0 else dec_nf[i - 1]
+            ups.append(nn.Sequential(nn.ConvTranspose2d(d_in, dec_nf[i], 4, 2, 1), nn.Identity()))
+            if i != n - 1:
+                skips.append(nn.Sequential(nn.Conv2d(enc_nf[n - 2 - i] + dec_nf[i], dec_nf[i], 3, 1, 1), nn.Identity()))
+        self.skippers = nn.Sequential(*skips)     # registered before upconvs, as in the reference (:342-343)
+        self.upconvs = nn.Sequential(*ups)
+
+
+class _SpadeParams(nn.Module):
+    def __init__(self, norm_nc, cond_nc):
+        super().__init__()
+        self.mlp_shared = nn.Sequential(nn.Conv2d(cond_nc, 128, 3, padding=1), nn.Identity())
+        self.mlp_gamma = nn.Conv2d(128, norm_nc, 3, padding=1)
+        self.mlp_beta = nn.Conv2d(128, norm_nc, 3, padding=1)
+
+
+class _AttLWBParams(nn.Module):
+    def __init__(self, cq, cs, c):
+        super().__init__()
+        self.fq = nn.Conv2d(cq, c, 1)
+        self.fk = nn.Conv2d(cs, c, 1)
+        self.fv = nn.Conv2d(cs, c, 1)
+        self.spade = _SpadeParams(cq, c)
+
+
+def _attach(t, **attrs):
+    for k, v in attrs.items():
+        setattr(t, k, v)
+    return t
+
+
+class AttentionLWBGenerator(nn.Module):
+    """B200 drop-in for attlwb_spade_resunet.AttentionLWBGenerator(cfg, temporal=False)."""
+
+    def __init__(self, cfg, temporal=False, precision="fp16x2"):
+        super().__init__()
+        if temporal:
+            raise NotImplementedError("temporal=True (TemporalFIFO recurrence, default false in deploy.toml:40) is not "
+                                      "on the B200 hot path yet")
+        get = (lambda o, k: o[k]) if isinstance(cfg, dict) else getattr
+        self._name = get(cfg, "name") if (isinstance(cfg, dict) and "name" in cfg) or hasattr(cfg, "name") else "AttLWB-SPADE"
+        bg, sid, tsf = get(cfg, "BGNet"), get(cfg, "SIDNet"), get(cfg, "TSFNet")
+        nf = list(get(tsf, "num_filters")); n_res = get(tsf, "n_res_block")
+        self.temporal = False
+        self.num_filters, self.n_res = nf, n_res
+        self.bg_net = _BGNetParams(get(bg, "cond_nc"), list(get(bg, "num_filters")), get(bg, "n_res_block"))
+        self.src_net = _SIDNetParams(get(sid, "cond_nc"), list(get(sid, "num_filters")), get(sid, "n_res_block"))
+        self.tsf_net_enc = _EncParams(get(tsf, "cond_nc"), nf, False)
+        self.tsf_net_dec = _SkipDecParams(nf[-1], nf, list(reversed(nf)))
+        self.enc_attlwbs = nn.ModuleList([_AttLWBParams(c, c, c) for c in nf])
+        self.res_attlwbs = nn.ModuleList([_AttLWBParams(nf[-1], nf[-1], nf[-1]) for _ in range(n_res)])
+        self.res_blocks = nn.Sequential(*[_Res(nf[-1], 2) for _ in range(n_res)])
+        self.tsf_img_reg = nn.Sequential(nn.Conv2d(nf[0], 3, 5, 1, 2, bias=False), nn.Identity())
+        self.tsf_att_reg = nn.Sequential(nn.Conv2d(nf[0], 1, 5, 1, 2, bias=False), nn.Identity())
+        assert nf == [64, 128, 256] and list(get(sid, "num_filters")) == nf, \
+            "kernel tiling is specialised to the deploy config num_filters=[64,128,256] (AttLWB-SPADE.toml)"
+        self.set_precision(precision)
+        self._packed = None
+        self._packed_key = None
+        for p in self.parameters():
+            p.requires_grad_(False)
+
+    # -------------------------------------------------------------------------------------------------------------
+    def set_precision(self, precision):
+        if precision not in ("fp16x2", "fp16"):
+            raise ValueError("precision must be 'fp16x2' or 'fp16'")
+        self.precision = precision
+        self.P = 2 if precision == "fp16x2" else 1
+        self._packed_key = None
+
+    def _key(self):
+        return (self.P, tuple((p.data_ptr(), p._version) for p in self.parameters()))
+
+    def _pack(self):
+        """One-time repack of the reference-layout fp32 weights into K-major fp16 planes (redone if params change)."""
+        key = self._key()
+        if self._packed is not None and self._packed_key == key:
+            return self._packed
+        P = self.P
+        sd = {k: v.detach().float().contiguous() for k, v in self.state_dict().items()}
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("ipercore_b200.AttentionLWBGenerator runs on CUDA only; call .to('cuda') first")
+        pk = {}
+
+        def conv(name, bias=True):
+            pk[name] = (ops.pack_conv_weight(sd[name + ".weight"], P), sd.get(name + ".bias") if bias else None)
+
+        def convT(name):
+            pk[name] = (ops.pack_convT_weight(sd[name + ".weight"], P), sd.get(name + ".bias"))
+
+        def att(prefix, c):
+            wkv = torch.cat([sd[prefix + ".fk.weight"], sd[prefix + ".fv.weight"]], 0)      # (2C, C, 1, 1)
+            pk[prefix + ".kv"] = (ops.pack_conv_weight(wkv, P), None)
+            pk[prefix + ".bk"] = sd[prefix + ".fk.bias"]; pk[prefix + ".bv"] = sd[prefix + ".fv.bias"]
+            conv(prefix + ".fq")
+            conv(prefix + ".spade.mlp_shared.0")
+            pk[prefix + ".spade.gb"] = ops.pack_spade_weight(
+                sd[prefix + ".spade.mlp_gamma.weight"], sd[prefix + ".spade.mlp_gamma.bias"],
+                sd[prefix + ".spade.mlp_beta.weight"], sd[prefix + ".spade.mlp_beta.bias"], P, _bn_for(2 * c))
+
+        for net in ("src_net.encoders", "tsf_net_enc"):
+            pk[net + ".stem"] = (sd[net + ".layers.0.0.weight"], sd.get(net + ".layers.0.0.bias"))
+            for i in (1, 2):
+                conv("%s.layers.%d.0" % (net, i))
+        for i in range(self.n_res):
+            for pre in ("src_net.res_blocks", "res_blocks"):
+                conv("%s.%d.main.0" % (pre, i)); conv("%s.%d.main.2" % (pre, i))
+            att("res_attlwbs.%d" % i, 256)
+        for i, c in enumerate(self.num_filters):
+            att("enc_attlwbs.%d" % i, c)
+        for i in range(3):
+            convT("tsf_net_dec.upconvs.%d.0" % i)
+        for i in range(2):
+            conv("tsf_net_dec.skippers.%d.0" % i)
+        heads = torch.cat([sd["tsf_img_reg.0.weight"], sd["tsf_att_reg.0.weight"]], 0)     # (4, 64, 5, 5)
+        pk["tsf_heads"] = (ops.pack_conv_weight(heads, P, pad_rows_to=16), None)
+        self._packed, self._packed_key = pk, key
+        return pk
+
+    # -------------------------------------------------------------------------------------------------------------
+    def _conv(self, pk, name, a, mode, ksize, out, relu=False, x=None):
+        w, b = pk[name]
+        rows = w.shape[1] // (4 if mode == IPER_CONVT_4S2 else 1)
+        ops.conv_gemm(a, w, mode, ksize, rows, _bn_for(rows), IPER_EPI_PLANES, bias=b, relu=relu, out=out, x=x)
+        return out
+
+    def _project_kv(self, pk, prefix, feat):
+        """[Wk x | Wv x] (no bias) of source features: Planes (ns,h,w,C) -> fp32 (ns,h,w,2C)."""
+        w, _ = pk[prefix + ".kv"]
+        kv = torch.empty((feat.N, feat.H, feat.W, w.shape[1]), dtype=torch.float32, device=feat.data.device)
+        ops.conv_gemm(feat, w, IPER_CONV_S1, 1, w.shape[1], _bn_for(w.shape[1]), IPER_EPI_F32, out=kv)
+        return kv
+
+    def _stage_prefixes(self):
+        return ["enc_attlwbs.%d" % i for i in range(3)] + ["res_attlwbs.%d" % i for i in range(self.n_res)]
+
+    # -------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_src(self, src_inputs, only_enc=True):
+        """attlwb_spade_resunet.py:450-478.  src_inputs (bs, ns, 6, S, S) -> (src_enc_outs[3], src_res_outs[n_res]).
+
+        Returned tensors are NCHW fp32 like the reference's; each carries the pre-projected [Wk x | Wv x] maps
+        (``_iper_kv``) that forward_tsf consumes, so the per-frame path never re-projects constant source features."""
+        if not only_enc:
+            raise NotImplementedError("forward_src(only_enc=False) (SIDNet decoder, training-only) is not on the B200 path")
+        pk = self._pack()
+        bs, ns, _, S, _ = src_inputs.shape
+        x_in = src_inputs.reshape(bs * ns, -1, S, S).float().contiguous()
+        N, P, dev = bs * ns, self.P, src_inputs.device
+        w, b = pk["src_net.encoders.stem"]
+        feats = []
+        x = Planes.empty(P, N, S // 2, S // 2, 64, dev)
+        ops.conv_stem(x_in, w, b, x)
+        feats.append(x)
+        for i, c in ((1, 128), (2, 256)):
+            y = Planes.empty(P, N, x.H // 2, x.W // 2, c, dev)
+            x = self._conv(pk, "src_net.encoders.layers.%d.0" % i, x, IPER_CONV_S2, 3, y, relu=True)
+            feats.append(x)
+        for i in range(self.n_res):
+            y = Planes.empty(P, N, x.H, x.W, 256, dev)
+            self._conv(pk, "src_net.res_blocks.%d.main.0" % i, x, IPER_CONV_S1, 3, y, relu=True)
+            z = Planes.empty(P, N, x.H, x.W, 256, dev)
+            x = self._conv(pk, "src_net.res_blocks.%d.main.2" % i, y, IPER_CONV_S1, 3, z, x=x)
+            feats.append(x)
+        outs = []
+        for prefix, f in zip(self._stage_prefixes(), feats):
+            t = f.to_nchw()
+            outs.append(_attach(t, _iper_kv=self._project_kv(pk, prefix, f), _iper_key=self._packed_key))
+        return outs[:3], outs[3:]
+
+    def _kv_for(self, pk, prefix, src_x):
+        kv = getattr(src_x, "_iper_kv", None)
+        if kv is not None and getattr(src_x, "_iper_key", None) == self._packed_key:
+            return kv
+        # plain tensor (e.g. torch.cat of several sources' features): project now
+        return self._project_kv(pk, prefix, Planes.from_nchw(src_x, self.P))
+
+    @torch.no_grad()
+    def forward_tsf(self, tsf_inputs, src_enc_outs, src_res_outs, Tst, temp_enc_outs=None, temp_res_outs=None, Ttt=None,
+                    bg_img=None, return_pred=False):
+        """attlwb_spade_resunet.py:480-535.  tsf_inputs (bs,6,S,S), Tst (bs,ns,S,S,2) -> (tsf_img (bs,3,S,S), tsf_mask (bs,1,S,S)).
+
+        With ``bg_img`` ((1|bs),3,S,S) and ``return_pred`` the heads epilogue also writes the composite
+        ``mask*bg + (1-mask)*img`` of Imitator.forward (models/imitator.py:393) and returns it as a third value."""
+        if temp_enc_outs is not None or Ttt is not None:
+            raise NotImplementedError("temporal attention inputs are not supported on the B200 path (temporal=false)")
+        pk = self._pack()
+        B, ns, S, _, _ = Tst.shape
+        P, dev = self.P, tsf_inputs.device
+        tsf_inputs = tsf_inputs.float().contiguous(); Tst = Tst.float().contiguous()
+        nf = self.num_filters
+        # concatenation buffers of the SkipDecoder (attlwb_spade_resunet.py:353): [enc_out | upconv out]
+        cat0 = Planes.empty(P, B, S // 2, S // 2, nf[0] + nf[1], dev)      # 64 + 128 = 192
+        cat1 = Planes.empty(P, B, S // 4, S // 4, nf[1] + nf[2], dev)      # 128 + 256 = 384
+        enc_dst = [cat0.window(0, nf[0]), cat1.window(0, nf[1]), None]
+        flows = {}
+
+        def flow_at(h):
+            if h not in flows:
+                flows[h] = ops.flow_resize(Tst, h, h) if h != S else Tst
+            return flows[h]
+
+        def att_block(prefix, x, src_x, out):
+            """SelfAttentionLWB.forward (attlwb_spade_resunet.py:208-252)."""
+            C, h = x.C, x.H
+            stats = ops.instnorm_stats(x)
+            wq, bq = pk[prefix + ".fq"]
+            q = torch.empty((B, h, h, C), dtype=torch.float32, device=dev)
+            ops.conv_gemm(x, wq, IPER_CONV_S1, 1, C, _bn_for(C), IPER_EPI_F32, bias=bq, out=q)
+            a = Planes.empty(P, B, h, h, C, dev)
+            ops.warp_attention(q, self._kv_for(pk, prefix, src_x), pk[prefix + ".bk"], pk[prefix + ".bv"], flow_at(h), a)
+            actv = Planes.empty(P, B, h, h, 128, dev)
+            self._conv(pk, prefix + ".spade.mlp_shared.0", a, IPER_CONV_S1, 3, actv, relu=True)
+            wgb, bgb = pk[prefix + ".spade.gb"]
+            if out is None:
+                out = Planes.empty(P, B, h, h, C, dev)
+            ops.conv_gemm(actv, wgb, IPER_CONV_S1, 3, 2 * C, _bn_for(2 * C), IPER_EPI_SPADE, bias=bgb, out=out, x=x,
+                          mean_rstd=stats, spade_C=C)
+            return out
+
+        # 1. encoder (:507-519)
+        w, b = pk["tsf_net_enc.stem"]
+        x = Planes.empty(P, B, S // 2, S // 2, nf[0], dev)
+        ops.conv_stem(tsf_inputs, w, b, x)
+        for i in range(3):
+            if i > 0:
+                y = Planes.empty(P, B, x.H // 2, x.W // 2, nf[i], dev)
+                x = self._conv(pk, "tsf_net_enc.layers.%d.0" % i, x, IPER_CONV_S2, 3, y, relu=True)
+            x = att_block("enc_attlwbs.%d" % i, x, src_enc_outs[i], enc_dst[i])
+        # 2. residual blocks (:522-529)
+        for i in range(self.n_res):
+            y = Planes.empty(P, B, x.H, x.W, 256, dev)
+            self._conv(pk, "res_blocks.%d.main.0" % i, x, IPER_CONV_S1, 3, y, relu=True)
+            z = Planes.empty(P, B, x.H, x.W, 256, dev)
+            x = self._conv(pk, "res_blocks.%d.main.2" % i, y, IPER_CONV_S1, 3, z, x=x)
+            x = att_block("res_attlwbs.%d" % i, x, src_res_outs[i], None)
+        # 3. SkipDecoder (:348-357)
+        self._conv(pk, "tsf_net_dec.upconvs.0.0", x, IPER_CONVT_4S2, 4, cat1.window(nf[1], nf[2]), relu=True)
+        s0 = Planes.empty(P, B, S // 4, S // 4, nf[2], dev)
+        self._conv(pk, "tsf_net_dec.skippers.0.0", cat1, IPER_CONV_S1, 3, s0, relu=True)
+        self._conv(pk, "tsf_net_dec.upconvs.1.0", s0, IPER_CONVT_4S2, 4, cat0.window(nf[0], nf[1]), relu=True)
+        s1 = Planes.empty(P, B, S // 2, S // 2, nf[1], dev)
+        self._conv(pk, "tsf_net_dec.skippers.1.0", cat0, IPER_CONV_S1, 3, s1, relu=True)
+        d2 = Planes.empty(P, B, S, S, nf[0], dev)
+        self._conv(pk, "tsf_net_dec.upconvs.2.0", s1, IPER_CONVT_4S2, 4, d2, relu=True)
+        # 4. heads (:533) + composite (imitator.py:393)
+        img = torch.empty((B, 3, S, S), dtype=torch.float32, device=dev)
+        mask = torch.empty((B, 1, S, S), dtype=torch.float32, device=dev)
+        heads = dict(img=img, mask=mask)
+        pred = None
+        if return_pred:
+            if bg_img is None:
+                raise ValueError("return_pred needs bg_img")
+            bg_img = bg_img.float().contiguous()
+            pred = torch.empty((B, 3, S, S), dtype=torch.float32, device=dev)
+            heads.update(bg=bg_img, pred=pred)
+        wh, _ = pk["tsf_heads"]
+        ops.conv_gemm(d2, wh, IPER_CONV_S1, 5, 16, 16, IPER_EPI_HEADS, heads=heads)
+        return (img, mask, pred) if return_pred else (img, mask)
+
+    # -------------------------------------------------------------------------------------------------------------
+    def forward_bg(self, bg_inputs):
+        raise NotImplementedError("forward_bg (BGNet, one-time per source — SURVEY.md §8(f) rank 2) is not ported yet; "
+                                  "pass a background image (Imitator.source_setup bg_img=...)")
+
+    def forward(self, bg_inputs, src_inputs, tsf_inputs, Tst, Ttt=None, only_tsf=True):
+        raise NotImplementedError("the training-shape forward (BGNet + SIDNet decoder) is not on the B200 hot path yet")

@@ -1,0 +1,278 @@
+"""Tensor-level wrappers over the C ABI.  torch is used only as allocator and stream provider: every call passes
+raw device pointers + the current CUDA stream to libiper_b200.so (see include/iper_b200.h for reference citations).
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import (ConvGemmDesc, IPER_CONV_S1, IPER_CONV_S2, IPER_CONVT_4S2, IPER_EPI_F32, IPER_EPI_HEADS,
+                   IPER_EPI_PLANES, IPER_EPI_SPADE, check, lib)
+
+# nmr.py:225 eye z, converted to float32 inside nr.look_at
+EYE_Z = float(torch.tensor(-(1.0 / math.tan(math.radians(30.0)) + 1.0), dtype=torch.float32))
+NEAR, FAR = 0.1, 100.0   # neural_renderer defaults used by rasterize_face_index_map_and_weight_map
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _req(t, dtype, name):
+    if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise ValueError("%s must be a contiguous CUDA %s tensor (got %s, cuda=%s, contiguous=%s)" %
+                         (name, dtype, t.dtype, t.is_cuda, t.is_contiguous()))
+    return t
+
+
+class Planes:
+    """NHWC fp16 activation tensor with P planes: data (P, N, H, W, pitch); value = plane0 (+ plane1).
+
+    A `Planes` may be a channel window [coff, coff+C) of a wider buffer (used for the decoder's concatenations)."""
+
+    def __init__(self, data, C=None, coff=0):
+        assert data.dim() == 5 and data.dtype == torch.float16 and data.is_contiguous()
+        self.data = data
+        self.P, self.N, self.H, self.W, self.pitch = data.shape
+        self.C = self.pitch if C is None else C
+        self.coff = coff
+
+    @staticmethod
+    def empty(P, N, H, W, C, device, pitch=None):
+        return Planes(torch.empty((P, N, H, W, pitch or C), dtype=torch.float16, device=device), C=C)
+
+    def window(self, coff, C):
+        return Planes(self.data, C=C, coff=self.coff + coff)
+
+    @property
+    def plane_stride(self):
+        return self.N * self.H * self.W * self.pitch
+
+    def ptr(self):
+        return self.data.data_ptr()
+
+    def to_nchw(self):
+        out = torch.empty((self.N, self.C, self.H, self.W), dtype=torch.float32, device=self.data.device)
+        check(lib.iper_planes_to_nchw(self.ptr(), self.P, self.plane_stride, self.N, self.C, self.H * self.W,
+                                      self.pitch, self.coff, out.data_ptr(), _stream()), "planes_to_nchw")
+        return out
+
+    @staticmethod
+    def from_nchw(x, P, pitch=None, out=None):
+        x = _req(x.float().contiguous(), torch.float32, "x")
+        N, C, H, W = x.shape
+        if out is None:
+            out = Planes.empty(P, N, H, W, C, x.device, pitch=pitch)
+        check(lib.iper_nchw_to_planes(x.data_ptr(), N, C, H * W, out.ptr(), out.P, out.plane_stride, out.pitch,
+                                      out.coff, _stream()), "nchw_to_planes")
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# raster / flow
+# ------------------------------------------------------------------------------------------------------------------
+def rasterize_faces(faces, image_size, near=NEAR, far=FAR):
+    """neural_renderer.rasterize_face_index_map_and_weight_map(faces, image_size, False) (nmr.py:337,356)."""
+    faces = _req(faces, torch.float32, "faces")
+    B, nf = faces.shape[:2]
+    fim = torch.empty((B, image_size, image_size), dtype=torch.int32, device=faces.device)
+    wim = torch.empty((B, image_size, image_size, 3), dtype=torch.float32, device=faces.device)
+    check(lib.iper_rasterize_faces(faces.data_ptr(), B, nf, image_size, near, far, fim.data_ptr(), wim.data_ptr(),
+                                   _stream()), "rasterize_faces")
+    return fim, wim
+
+
+def raster_frames(verts, cams, faces, image_size, want_fim=True, want_f2pts=True, fused=None):
+    """render_fim_wim (nmr.py:319-342) for a batch; `fused` = dict(map_fn, f_uvs2img, uv_img, src_f2pts) additionally
+    produces tsf_inputs (B,6,S,S) and Tst (B,ns,S,S,2) in the same launch (flowcomposition.py:206-248, 514-582)."""
+    verts = _req(verts, torch.float32, "verts"); cams = _req(cams, torch.float32, "cams")
+    faces = _req(faces, torch.int32, "faces")
+    B, nv = verts.shape[:2]; nf = faces.shape[0]; S = image_size; dev = verts.device
+    fim = torch.empty((B, S, S), dtype=torch.int32, device=dev) if want_fim else None
+    wim = torch.empty((B, S, S, 3), dtype=torch.float32, device=dev) if want_fim else None
+    f2pts = torch.empty((B, nf, 3, 2), dtype=torch.float32, device=dev) if want_f2pts else None
+    tsf = Tst = None
+    map_fn = f_uv = uv_img = src_f2pts = None; ns = 0
+    if fused is not None:
+        map_fn = _req(fused["map_fn"], torch.float32, "map_fn"); f_uv = _req(fused["f_uvs2img"], torch.float32, "f_uvs2img")
+        uv_img = _req(fused["uv_img"], torch.float32, "uv_img"); src_f2pts = _req(fused["src_f2pts"], torch.float32, "src_f2pts")
+        assert map_fn.shape == (nf + 1, 3) and f_uv.shape == (nf, 3, 2) and uv_img.shape[-3:] == (3, S, S)
+        ns = src_f2pts.shape[0]
+        tsf = torch.empty((B, 6, S, S), dtype=torch.float32, device=dev)
+        Tst = torch.empty((B, ns, S, S, 2), dtype=torch.float32, device=dev)
+    check(lib.iper_raster_frames(verts.data_ptr(), cams.data_ptr(), faces.data_ptr(), B, nv, nf, S, EYE_Z, NEAR, FAR,
+                                 _ptr(fim), _ptr(wim), _ptr(f2pts), _ptr(map_fn), _ptr(f_uv), _ptr(uv_img),
+                                 _ptr(src_f2pts), ns, _ptr(tsf), _ptr(Tst), _stream()), "raster_frames")
+    return dict(fim=fim, wim=wim, f2pts=f2pts, tsf_inputs=tsf, Tst=Tst)
+
+
+def cal_bc_transform(src_f2pts, fims, wims):
+    """SMPLRenderer.cal_bc_transform (nmr.py:713-757): item i combines src_f2pts[i] with fims[i]/wims[i]."""
+    src_f2pts = _req(src_f2pts.contiguous(), torch.float32, "src_f2pts")
+    fims = _req(fims.contiguous(), torch.int32, "fims"); wims = _req(wims.contiguous(), torch.float32, "wims")
+    b, S = fims.shape[0], fims.shape[1]; nf = src_f2pts.shape[1]
+    T = torch.empty((b, S, S, 2), dtype=torch.float32, device=fims.device)
+    check(lib.iper_flow_from_fim_wim(src_f2pts.data_ptr(), 1, fims.data_ptr(), wims.data_ptr(), b, 1, nf, S,
+                                     T.data_ptr(), _stream()), "flow_from_fim_wim")
+    return T
+
+
+def encode_fim(fim, map_fn, transpose=True):
+    fim = _req(fim.contiguous(), torch.int32, "fim"); map_fn = _req(map_fn.contiguous(), torch.float32, "map_fn")
+    nb, S = fim.shape[0], fim.shape[1]; ch = map_fn.shape[1]; nf = map_fn.shape[0] - 1
+    shape = (nb, ch, S, S) if transpose else (nb, S, S, ch)
+    out = torch.empty(shape, dtype=torch.float32, device=fim.device)
+    check(lib.iper_encode_fim(fim.data_ptr(), map_fn.data_ptr(), nb, nf, ch, S, int(transpose), out.data_ptr(),
+                              _stream()), "encode_fim")
+    return out
+
+
+def flow_resize(T, h, w):
+    """LWB.resize_trans (attlwb_spade_resunet.py:175-182) on (..., S, S, 2) -> (..., h, w, 2)."""
+    T = _req(T.contiguous(), torch.float32, "T")
+    lead = T.shape[:-3]; S = T.shape[-2]
+    n = int(torch.tensor(lead).prod()) if len(lead) else 1
+    out = torch.empty((*lead, h, w, 2), dtype=torch.float32, device=T.device)
+    check(lib.iper_flow_resize(T.data_ptr(), n, S, h, w, out.data_ptr(), _stream()), "flow_resize")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# generator building blocks
+# ------------------------------------------------------------------------------------------------------------------
+def _fill_desc(a, mode, ksize, rows, block_n, epi, bias=None, relu=False, out=None, x=None, mean_rstd=None,
+               spade_C=0, heads=None, max_ctas=0):
+    d = ConvGemmDesc()
+    d.a = a.ptr(); d.a_planes = a.P; d.a_plane_stride = a.plane_stride
+    d.N, d.H, d.W = a.N, a.H, a.W
+    d.a_pitch, d.a_coff, d.Cin = a.pitch, a.coff, a.C
+    d.mode, d.ksize = mode, ksize
+    d.rows, d.block_n = rows, block_n
+    d.epi = epi; d.bias = _ptr(bias); d.relu = int(relu)
+    if out is not None:
+        if isinstance(out, Planes):
+            d.out = out.ptr(); d.out_planes = out.P; d.out_plane_stride = out.plane_stride
+            d.out_pitch = out.pitch; d.out_coff = out.coff
+        else:  # fp32 NHWC tensor (N,H,W,pitch)
+            d.out = out.data_ptr(); d.out_planes = 1; d.out_plane_stride = 0; d.out_pitch = out.shape[-1]; d.out_coff = 0
+    if x is not None:
+        d.x = x.ptr(); d.x_planes = x.P; d.x_plane_stride = x.plane_stride; d.x_pitch = x.pitch; d.x_coff = x.coff
+    d.mean_rstd = _ptr(mean_rstd); d.spade_C = spade_C
+    if heads is not None:
+        bg = heads.get("bg")
+        d.bg = _ptr(bg); d.bg_batch_stride = 0 if bg is None or bg.shape[0] == 1 else bg[0].numel()
+        d.img = _ptr(heads.get("img")); d.mask = _ptr(heads.get("mask")); d.pred = _ptr(heads.get("pred"))
+    d.max_ctas = max_ctas
+    return d
+
+
+def conv_gemm(a, wpack, mode, ksize, rows, block_n, epi, **kw):
+    """tcgen05 implicit-GEMM convolution (conv_tc.cu). `wpack` = fp16 (P, phases*rows, taps*Cin) packed weights."""
+    d = _fill_desc(a, mode, ksize, rows, block_n, epi, **kw)
+    assert wpack.dtype == torch.float16 and wpack.is_contiguous() and wpack.dim() == 3
+    d.w = wpack.data_ptr(); d.w_planes = wpack.shape[0]; d.w_plane_stride = wpack[0].numel()
+    check(lib.iper_conv_gemm(d, _stream()), "conv_gemm")
+
+
+def conv_direct(a, w_f32, mode, ksize, Cout, epi, **kw):
+    """CUDA-core cross-check convolution (ops.cu) on the reference's own fp32 weight layout."""
+    d = _fill_desc(a, mode, ksize, Cout, 64, epi, **kw)
+    w_f32 = _req(w_f32, torch.float32, "w_f32")
+    check(lib.iper_conv_direct(d, w_f32.data_ptr(), Cout, _stream()), "conv_direct")
+
+
+def conv_stem(x_nchw, w_f32, bias, out):
+    x_nchw = _req(x_nchw, torch.float32, "x"); w_f32 = _req(w_f32, torch.float32, "w")
+    N, Cin, H, W = x_nchw.shape
+    check(lib.iper_conv_stem(x_nchw.data_ptr(), N, Cin, H, W, w_f32.data_ptr(), _ptr(bias), w_f32.shape[0], out.ptr(),
+                             out.P, out.plane_stride, out.pitch, out.coff, _stream()), "conv_stem")
+
+
+def instnorm_stats(x, eps=1e-5, out=None):
+    if out is None:
+        out = torch.empty((x.N, x.C, 2), dtype=torch.float32, device=x.data.device)
+    check(lib.iper_instnorm_stats(x.ptr(), x.P, x.plane_stride, x.N, x.H * x.W, x.C, x.pitch, x.coff, eps,
+                                  out.data_ptr(), _stream()), "instnorm_stats")
+    return out
+
+
+def warp_attention(q, kv, bias_k, bias_v, T, out):
+    """q (B,h,w,C) f32; kv (ns,h,w,2C) f32; T (B,ns,h,w,2) f32 -> out Planes (B,h,w,C)."""
+    B, h, w, C = q.shape; ns = kv.shape[0]
+    check(lib.iper_warp_attention(q.data_ptr(), kv.data_ptr(), bias_k.data_ptr(), bias_v.data_ptr(), T.data_ptr(), B, ns,
+                                  h, w, C, out.ptr(), out.P, out.plane_stride, out.pitch, out.coff, _stream()),
+          "warp_attention")
+
+
+def warp_nhwc(src, T):
+    ns, h, w, C = src.shape; B = T.shape[0]
+    out = torch.empty((B, ns, h, w, C), dtype=torch.float32, device=src.device)
+    check(lib.iper_warp_nhwc(src.data_ptr(), T.data_ptr(), B, ns, h, w, C, out.data_ptr(), _stream()), "warp_nhwc")
+    return out
+
+
+def nhwc_f32_to_nchw(x):
+    N, H, W, C = x.shape
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
+    check(lib.iper_nhwc_f32_to_nchw(x.data_ptr(), N, C, H * W, C, 0, out.data_ptr(), _stream()), "nhwc_f32_to_nchw")
+    return out
+
+
+def pred_to_u8(pred, out=None):
+    B, _, S, _ = pred.shape
+    if out is None:
+        out = torch.empty((B, S, S, 3), dtype=torch.uint8, device=pred.device)
+    check(lib.iper_pred_to_u8(pred.data_ptr(), B, S, out.data_ptr(), _stream()), "pred_to_u8")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# weight packing (one-time, at load): reference layouts -> K-major fp16 planes for the tcgen05 kernel
+# ------------------------------------------------------------------------------------------------------------------
+def split_planes(w, P):
+    """fp32 -> (P, ...) fp16: plane0 = fp16(w), plane1 = fp16(w - plane0)."""
+    hi = w.to(torch.float16)
+    if P == 1:
+        return hi[None].contiguous()
+    lo = (w - hi.float()).to(torch.float16)
+    return torch.stack([hi, lo], 0).contiguous()
+
+
+def pack_conv_weight(w, P, pad_rows_to=None):
+    """Conv2d weight (Cout,Cin,k,k) -> (P, rows, k*k*Cin) with K ordered (tap=ky*k+kx, cin)."""
+    Cout, Cin, k, _ = w.shape
+    m = w.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).float()
+    if pad_rows_to is not None and pad_rows_to > Cout:
+        m = torch.cat([m, m.new_zeros(pad_rows_to - Cout, m.shape[1])], 0)
+    return split_planes(m, P)
+
+
+def pack_convT_weight(w, P):
+    """ConvTranspose2d(4,2,1) weight (Cin,Cout,4,4) -> (P, 4*Cout, 4*Cin): phase p=py*2+px, tap (ta,tb), K=(ta*2+tb, cin).
+    ky = {py=0: (1,3), py=1: (0,2)}[ta], same for kx — matches the producer's tap decode in conv_tc.cu."""
+    Cin, Cout = w.shape[:2]
+    kidx = {0: (1, 3), 1: (0, 2)}
+    phases = []
+    for py in range(2):
+        for px in range(2):
+            taps = []
+            for ta in range(2):
+                for tb in range(2):
+                    taps.append(w[:, :, kidx[py][ta], kidx[px][tb]].t())     # (Cout, Cin)
+            phases.append(torch.cat(taps, 1))                               # (Cout, 4*Cin)
+    return split_planes(torch.cat(phases, 0).float(), P)                     # (4*Cout, 4*Cin)
+
+
+def pack_spade_weight(wg, bg_, wb, bb, P, block_n):
+    """mlp_gamma / mlp_beta (C,128,3,3) -> rows interleaved per tile: [gamma cb | beta cb] with cb = block_n/2."""
+    C = wg.shape[0]; cb = block_n // 2
+    mg = wg.permute(0, 2, 3, 1).reshape(C, -1).float(); mb = wb.permute(0, 2, 3, 1).reshape(C, -1).float()
+    rows, bias = [], []
+    for t in range(C // cb):
+        rows += [mg[t * cb:(t + 1) * cb], mb[t * cb:(t + 1) * cb]]
+        bias += [bg_[t * cb:(t + 1) * cb], bb[t * cb:(t + 1) * cb]]
+    return split_planes(torch.cat(rows, 0), P), torch.cat(bias, 0).float().contiguous()

@@ -1,0 +1,74 @@
+"""CPU tests of the C-ABI boundary: the library builds/loads, exports every symbol include/iper_b200.h declares,
+argument validation reports errors (no compute is launched without a GPU), and the host-side module keeps the
+reference's checkpoint layout."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "iper_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(iper_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ipercore_b200 import _lib
+    names = _declared_symbols()
+    assert len(names) >= 15
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), "libiper_b200.so does not export %s" % n
+    assert set(_lib.SIGNATURES) | {"iper_last_error"} == set(names), "ctypes table and header drifted apart"
+    assert _lib.lib.iper_abi_version() == 1
+
+
+def test_descriptor_struct_matches_header():
+    from ipercore_b200._lib import ConvGemmDesc
+    assert ctypes.sizeof(ConvGemmDesc) == 240 and ConvGemmDesc.max_ctas.offset == 232
+
+
+def test_argument_validation_reports_errors():
+    from ipercore_b200 import _lib
+    d = _lib.ConvGemmDesc()
+    assert _lib.lib.iper_conv_gemm(ctypes.byref(d), None) != 0
+    assert b"null" in _lib.lib.iper_last_error()
+    with pytest.raises(RuntimeError, match="iper_b200"):
+        _lib.check(_lib.lib.iper_rasterize_faces(None, 1, 1, 8, 0.1, 100.0, None, None, None), "rasterize_faces")
+
+
+def test_generator_loads_reference_checkpoint_layout():
+    from ipercore_b200.generator import AttentionLWBGenerator
+    from oracle.weights import synth_state_dict
+    cfg = dict(name="AttLWB-SPADE", BGNet=dict(cond_nc=4, n_res_block=6, num_filters=[64, 128, 128, 256]),
+               SIDNet=dict(cond_nc=6, n_res_block=6, num_filters=[64, 128, 256]),
+               TSFNet=dict(cond_nc=6, n_res_block=6, num_filters=[64, 128, 256]))
+    g = AttentionLWBGenerator(cfg)
+    sd = synth_state_dict(0)
+    assert list(g.state_dict().keys()) == list(sd.keys())
+    g.load_state_dict(sd, strict=True)
+    # DDP-style "module." prefixes are stripped by the reference's loader before load_state_dict; strict=False works too
+    g.load_state_dict({k: v for k, v in list(sd.items())[:10]}, strict=False)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        g.forward_src(torch.zeros(1, 2, 6, 64, 64))
+
+
+def test_weight_packing_layouts():
+    from ipercore_b200 import ops
+    w = torch.arange(2 * 3 * 3 * 3, dtype=torch.float32).reshape(2, 3, 3, 3)
+    p = ops.pack_conv_weight(w, 2)
+    assert p.shape == (2, 2, 27)
+    # K order is (tap, cin): element (co=1, tap=4 (ky=1,kx=1), ci=2)
+    assert float(p[0, 1, 4 * 3 + 2]) + float(p[1, 1, 4 * 3 + 2]) == float(w[1, 2, 1, 1])
+    wt = torch.randn(4, 5, 4, 4)
+    pt = ops.pack_convT_weight(wt, 1)
+    assert pt.shape == (1, 4 * 5, 4 * 4)
+    # phase (py=1,px=0), tap (ta=0,tb=1): ky=0, kx=3
+    torch.testing.assert_close(pt[0, 2 * 5 + 3, (0 * 2 + 1) * 4 + 2].float(), wt[2, 3, 0, 3], atol=2e-3, rtol=2e-3)
+    hi_lo = ops.split_planes(torch.tensor([1.0001234, -3.14159265]), 2).float()
+    torch.testing.assert_close(hi_lo.sum(0), torch.tensor([1.0001234, -3.14159265]), atol=1e-6, rtol=0)

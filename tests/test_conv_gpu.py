@@ -1,0 +1,162 @@
+"""GPU parity of the tcgen05 implicit-GEMM convolution: against a plain PyTorch fp32 convolution (CPU) of the same
+operands and against the CUDA-core cross-check kernel, for every mode / epilogue / tile width the generator uses."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(shape, generator=g) * 2 - 1) * scale
+
+
+def _planes_value(p):
+    return p.to_nchw().cpu()
+
+
+def _ref_conv(x, w, mode, k):
+    if mode == 0:
+        return F.conv2d(x, w, padding=k // 2)
+    if mode == 1:
+        return F.conv2d(x, w, stride=2, padding=1)
+    return F.conv_transpose2d(x, w, stride=2, padding=1)
+
+
+# (N, H, W, Cin, Cout, mode, k): shapes cover block_n 64/128/256, multi n-tile (512 rows), partial tiles, tn>1
+CASES = [
+    (2, 16, 16, 64, 64, 0, 3), (1, 32, 32, 128, 128, 0, 3), (2, 16, 16, 256, 256, 0, 3), (3, 8, 8, 64, 256, 0, 1),
+    (1, 20, 12, 64, 64, 0, 3), (2, 32, 32, 64, 128, 1, 3), (2, 16, 16, 128, 256, 1, 3),
+    (2, 8, 8, 256, 256, 2, 4), (1, 16, 16, 256, 128, 2, 4), (1, 16, 16, 128, 64, 2, 4), (1, 16, 16, 384, 256, 0, 3),
+]
+
+
+@pytest.mark.parametrize("P", [2, 1])
+@pytest.mark.parametrize("N,H,W,Cin,Cout,mode,k", CASES)
+def test_conv_gemm_planes(N, H, W, Cin, Cout, mode, k, P):
+    from ipercore_b200 import ops
+    from ipercore_b200.ops import Planes
+    x = _rand((N, Cin, H, W), 1)
+    wshape = (Cin, Cout, 4, 4) if mode == 2 else (Cout, Cin, k, k)
+    fan = Cin * (4 if mode == 2 else k * k)
+    w = _rand(wshape, 2, scale=(3.0 / fan) ** 0.5)
+    bias = _rand((Cout,), 3, 0.1)
+    a = Planes.from_nchw(x.to(DEV), P)
+    xq = _planes_value(a)                                   # operands as the kernel sees them
+    wp = (ops.pack_convT_weight if mode == 2 else ops.pack_conv_weight)(w, P).to(DEV)
+    wq = ops.split_planes(w, P).float().sum(0)
+    oH, oW = (H // 2, W // 2) if mode == 1 else ((2 * H, 2 * W) if mode == 2 else (H, W))
+    out = Planes.empty(P, N, oH, oW, Cout, DEV)
+    rows = Cout
+    ops.conv_gemm(a, wp, mode, k, rows, 256 if rows >= 256 else rows, ops.IPER_EPI_PLANES, bias=bias.to(DEV), relu=True,
+                  out=out)
+    chk = Planes.empty(P, N, oH, oW, Cout, DEV)
+    ops.conv_direct(a, w.to(DEV), mode, k, Cout, ops.IPER_EPI_PLANES, bias=bias.to(DEV), relu=True, out=chk)
+    torch.cuda.synchronize()
+    exp = F.relu(_ref_conv(xq, wq, mode, k) + bias.view(1, -1, 1, 1))
+    got = _planes_value(out)
+    tol = 2e-5 if P == 2 else 2e-3     # P=2: fp32-grade; P=1: only the lo*x cross terms of the weights are dropped... no: both rounded
+    np.testing.assert_allclose(_planes_value(chk).numpy(), exp.numpy(), atol=2e-4 if P == 1 else 2e-5, rtol=0)
+    np.testing.assert_allclose(got.numpy(), exp.numpy(), atol=tol if P == 2 else 2e-4, rtol=0)
+
+
+def test_conv_gemm_fp32_out_residual_and_windows():
+    """EPI_F32 (q / kv projections), residual add, channel windows of wider buffers (decoder concatenations)."""
+    from ipercore_b200 import ops
+    from ipercore_b200.ops import Planes
+    P, N, H, W = 2, 2, 16, 16
+    x = _rand((N, 128, H, W), 11)
+    w = _rand((256, 128, 1, 1), 12, 0.1); b = _rand((256,), 13, 0.1)
+    buf = Planes.empty(P, N, H, W, 320, DEV); buf.data.zero_()
+    a = Planes.from_nchw(x.to(DEV), P, out=buf.window(64, 128))
+    xq = _planes_value(a)
+    out = torch.empty((N, H, W, 256), dtype=torch.float32, device=DEV)
+    ops.conv_gemm(a, ops.pack_conv_weight(w, P).to(DEV), 0, 1, 256, 256, ops.IPER_EPI_F32, bias=b.to(DEV), out=out)
+    exp = F.conv2d(xq, ops.split_planes(w, P).float().sum(0)) + b.view(1, -1, 1, 1)
+    np.testing.assert_allclose(out.permute(0, 3, 1, 2).cpu().numpy(), exp.numpy(), atol=2e-5, rtol=0)
+    # residual: y = x + conv3x3(x) written into a window
+    w3 = _rand((128, 128, 3, 3), 14, 0.03)
+    dst = Planes.empty(P, N, H, W, 384, DEV); dst.data.zero_()
+    ops.conv_gemm(a, ops.pack_conv_weight(w3, P).to(DEV), 0, 3, 128, 128, ops.IPER_EPI_PLANES, bias=None, relu=False,
+                  out=dst.window(128, 128), x=a)
+    exp = xq + F.conv2d(xq, ops.split_planes(w3, P).float().sum(0), padding=1)
+    np.testing.assert_allclose(_planes_value(dst.window(128, 128)).numpy(), exp.numpy(), atol=3e-5, rtol=0)
+    assert float(dst.window(0, 128).to_nchw().abs().max()) == 0.0 and float(dst.window(256, 128).to_nchw().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("C,P", [(64, 2), (128, 2), (256, 2), (256, 1)])
+def test_conv_gemm_spade_epilogue(C, P):
+    """mlp_gamma|mlp_beta GEMM fused with IN(x)*(1+gamma)+beta (attlwb_spade_resunet.py:80-93)."""
+    from ipercore_b200 import ops
+    from ipercore_b200.ops import Planes
+    N, H, W = 2, 16, 16
+    actv = F.relu(_rand((N, 128, H, W), 21)); x = F.relu(_rand((N, C, H, W), 22) + 0.3)
+    wg = _rand((C, 128, 3, 3), 23, 0.02); wb = _rand((C, 128, 3, 3), 24, 0.02); bg = _rand((C,), 25, 0.1); bb = _rand((C,), 26, 0.1)
+    a = Planes.from_nchw(actv.to(DEV), P); xp = Planes.from_nchw(x.to(DEV), P)
+    aq, xq = _planes_value(a), _planes_value(xp)
+    stats = ops.instnorm_stats(xp)
+    bn = 256 if 2 * C >= 256 else 2 * C
+    wpk, bpk = ops.pack_spade_weight(wg, bg, wb, bb, P, bn)
+    out = Planes.empty(P, N, H, W, C, DEV)
+    ops.conv_gemm(a, wpk.to(DEV), 0, 3, 2 * C, bn, ops.IPER_EPI_SPADE, bias=bpk.to(DEV), out=out, x=xp, mean_rstd=stats,
+                  spade_C=C)
+    q = lambda t: ops.split_planes(t, P).float().sum(0)
+    gamma = F.conv2d(aq, q(wg), bg, padding=1); beta = F.conv2d(aq, q(wb), bb, padding=1)
+    exp = F.instance_norm(xq, eps=1e-5) * (1 + gamma) + beta
+    mean = xq.mean((2, 3)); var = xq.var((2, 3), unbiased=False)
+    np.testing.assert_allclose(stats[..., 0].cpu().numpy(), mean.numpy(), atol=1e-6, rtol=0)
+    np.testing.assert_allclose(stats[..., 1].cpu().numpy(), (1 / torch.sqrt(var + 1e-5)).numpy(), rtol=2e-6, atol=0)
+    np.testing.assert_allclose(_planes_value(out).numpy(), exp.numpy(), atol=5e-5 if P == 2 else 1e-3, rtol=0)
+    chk = Planes.empty(P, N, H, W, C, DEV)
+    ops.conv_direct(a, torch.cat([wg, wb], 0).to(DEV), 0, 3, 2 * C, ops.IPER_EPI_SPADE, bias=torch.cat([bg, bb]).to(DEV),
+                    out=chk, x=xp, mean_rstd=stats, spade_C=C)
+    np.testing.assert_allclose(_planes_value(chk).numpy(), exp.numpy(), atol=5e-5 if P == 2 else 1e-3, rtol=0)
+
+
+def test_conv_gemm_heads_epilogue():
+    """5x5 heads (64->3 tanh, 64->1 sigmoid) + composite (imitator.py:393)."""
+    from ipercore_b200 import ops
+    from ipercore_b200.ops import Planes
+    P, N, S = 2, 2, 32
+    x = F.relu(_rand((N, 64, S, S), 31)); wi = _rand((3, 64, 5, 5), 32, 0.03); wm = _rand((1, 64, 5, 5), 33, 0.03)
+    bgimg = _rand((1, 3, S, S), 34)
+    a = Planes.from_nchw(x.to(DEV), P); xq = _planes_value(a)
+    wp = ops.pack_conv_weight(torch.cat([wi, wm], 0), P, pad_rows_to=16).to(DEV)
+    img = torch.empty((N, 3, S, S), device=DEV); mask = torch.empty((N, 1, S, S), device=DEV); pred = torch.empty((N, 3, S, S), device=DEV)
+    ops.conv_gemm(a, wp, 0, 5, 16, 16, ops.IPER_EPI_HEADS, heads=dict(img=img, mask=mask, pred=pred, bg=bgimg.to(DEV)))
+    q = lambda t: ops.split_planes(t, P).float().sum(0)
+    ei = torch.tanh(F.conv2d(xq, q(wi), padding=2)); em = torch.sigmoid(F.conv2d(xq, q(wm), padding=2))
+    np.testing.assert_allclose(img.cpu().numpy(), ei.numpy(), atol=2e-5, rtol=0)
+    np.testing.assert_allclose(mask.cpu().numpy(), em.numpy(), atol=2e-5, rtol=0)
+    np.testing.assert_allclose(pred.cpu().numpy(), (em * bgimg + (1 - em) * ei).numpy(), atol=3e-5, rtol=0)
+
+
+def test_stem_and_attention_kernels():
+    from ipercore_b200 import ops
+    from ipercore_b200.ops import Planes
+    import math
+    P, N, S = 2, 2, 64
+    x = _rand((N, 6, S, S), 41); w = _rand((64, 6, 3, 3), 42, 0.2); b = _rand((64,), 43, 0.1)
+    out = Planes.empty(P, N, S // 2, S // 2, 64, DEV)
+    ops.conv_stem(x.to(DEV), w.to(DEV), b.to(DEV), out)
+    exp = F.relu(F.conv2d(x, w, b, stride=2, padding=1))
+    np.testing.assert_allclose(_planes_value(out).numpy(), exp.numpy(), atol=1e-5, rtol=0)
+    # attention: K = warp(Wk x)+bk etc. against the reference formulation (warp first, then 1x1 convs)
+    B, ns, h, C = 2, 2, 16, 64
+    src = _rand((ns, C, h, h), 44); q = _rand((B, C, h, h), 45)
+    wk = _rand((C, C, 1, 1), 46, 0.2); wv = _rand((C, C, 1, 1), 47, 0.2); bk = _rand((C,), 48, 0.1); bv = _rand((C,), 49, 0.1)
+    T = _rand((B, ns, h, h, 2), 50, 1.3)                      # some samples fall outside [-1,1] -> zero padding
+    kv = torch.cat([F.conv2d(src, wk), F.conv2d(src, wv)], 1).permute(0, 2, 3, 1).contiguous()
+    att = Planes.empty(P, B, h, h, C, DEV)
+    ops.warp_attention(q.permute(0, 2, 3, 1).contiguous().to(DEV), kv.to(DEV), bk.to(DEV), bv.to(DEV), T.to(DEV), att)
+    exp = []
+    for bi in range(B):
+        warp = F.grid_sample(src, T[bi], mode="bilinear", padding_mode="zeros", align_corners=False)
+        K = F.conv2d(warp, wk, bk); V = F.conv2d(warp, wv, bv)
+        logit = (K * q[bi:bi + 1]).sum(1, keepdim=True) / math.sqrt(C)
+        exp.append((torch.softmax(logit, 0) * V).sum(0))
+    np.testing.assert_allclose(_planes_value(att).numpy(), torch.stack(exp).numpy(), atol=2e-5, rtol=0)

@@ -1,0 +1,57 @@
+"""GPU parity of the generator path (seam B3) against the golden fixtures produced by the REFERENCE's own
+AttentionLWBGenerator on CPU in fp32 (tests/golden/make_golden.py).  Tolerance: BASELINE.json north_star —
+1e-3 max-abs for the fp32-parity mode ("fp16x2")."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CFG = dict(name="AttLWB-SPADE", BGNet=dict(cond_nc=4, n_res_block=6, num_filters=[64, 128, 128, 256]),
+           SIDNet=dict(cond_nc=6, n_res_block=6, num_filters=[64, 128, 256]),
+           TSFNet=dict(cond_nc=6, n_res_block=6, num_filters=[64, 128, 256]))
+
+
+def _gen(precision):
+    from ipercore_b200.generator import AttentionLWBGenerator
+    from oracle.weights import synth_state_dict
+    g = AttentionLWBGenerator(CFG, precision=precision)
+    g.load_state_dict(synth_state_dict(0), strict=True)
+    return g.to("cuda:0").eval()
+
+
+@pytest.mark.parametrize("S,precision,tol", [(256, "fp16x2", 1e-3), (64, "fp16x2", 1e-3), (256, "fp16", 1e-2)])
+def test_forward_src_tsf_matches_reference(S, precision, tol, golden_dir):
+    import make_golden
+    g = np.load(os.path.join(golden_dir, "gen_S%d.npz" % S))
+    inp = {k: torch.from_numpy(v).to("cuda:0") for k, v in make_golden.gen_inputs(S).items()}
+    net = _gen(precision)
+    enc, res = net.forward_src(inp["src_inputs"], only_enc=True)
+    img, mask = net.forward_tsf(inp["tsf_inputs"], enc, res, inp["Tst"])
+    torch.cuda.synchronize()
+    e_enc = np.abs(enc[2].cpu().numpy() - g["src_enc2"]).max()
+    e_res = np.abs(res[5].cpu().numpy() - g["src_res5"]).max()
+    e_img = np.abs(img.cpu().numpy() - g["tsf_img"]).max()
+    e_mask = np.abs(mask.cpu().numpy() - g["tsf_mask"]).max()
+    print("S=%d %s: max-abs err src_enc2 %.2e src_res5 %.2e tsf_img %.2e tsf_mask %.2e" % (S, precision, e_enc, e_res, e_img, e_mask))
+    assert e_img <= tol and e_mask <= tol, (e_img, e_mask)
+    assert e_enc <= 10 * tol and e_res <= 10 * tol
+
+
+def test_batched_frames_equal_single_frames(golden_dir):
+    """Frames are independent: a batch of B frames equals B single-frame calls bit for bit (deterministic kernels)."""
+    import make_golden
+    S = 128
+    inp = {k: torch.from_numpy(v).to("cuda:0") for k, v in make_golden.gen_inputs(S).items()}
+    net = _gen("fp16x2")
+    enc, res = net.forward_src(inp["src_inputs"], only_enc=True)
+    tsf = torch.cat([inp["tsf_inputs"], inp["tsf_inputs"].flip(-1), inp["tsf_inputs"] * 0.5], 0)
+    Tst = torch.cat([inp["Tst"], inp["Tst"].flip(2), inp["Tst"]], 0).contiguous()
+    bg = torch.rand(1, 3, S, S, device="cuda:0") * 2 - 1
+    img, mask, pred = net.forward_tsf(tsf, enc, res, Tst, bg_img=bg, return_pred=True)
+    for i in range(3):
+        im1, m1 = net.forward_tsf(tsf[i:i + 1].contiguous(), enc, res, Tst[i:i + 1].contiguous())
+        assert torch.equal(im1[0], img[i]) and torch.equal(m1[0], mask[i])
+    torch.testing.assert_close(pred, mask * bg + (1 - mask) * img, atol=1e-6, rtol=0)

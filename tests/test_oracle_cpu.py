@@ -1,0 +1,105 @@
+"""CPU tests: the oracle restatements against the golden fixtures produced by the REFERENCE's own code
+(tests/golden/make_golden.py), and internal consistency of the rasteriser restatement (parity unpinned)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import flow_ref, generator_ref, raster, synth, weights
+
+
+def test_raster_fast_equals_definition(template):
+    cams, verts = synth.pose_sweep(template, 2, total=7)
+    fv = flow_ref.vertices_to_faces(flow_ref.project(cams, verts), template["faces"])
+    fim_a, wim_a = raster.rasterize_fim_wim(fv, 48, fast=False)
+    fim_b, wim_b = raster.rasterize_fim_wim(fv, 48, fast=True)
+    assert (fim_a >= 0).sum() > 100
+    np.testing.assert_array_equal(fim_a, fim_b)
+    np.testing.assert_array_equal(wim_a, wim_b)
+
+
+def test_raster_known_answers():
+    """Hand-checkable cases of the upstream rules: winding, centre sampling, tie -> lowest index, near/far."""
+    S = 4
+    tri = lambda z, flip=False: np.array([[-1, -1, z], [-1, 3, z], [3, -1, z]] if not flip else
+                                         [[-1, -1, z], [3, -1, z], [-1, 3, z]], np.float32)
+    # CCW-in-NDC big triangle covers the whole image when front facing under the upstream backface rule
+    for flip in (False, True):
+        fim, wim = raster.rasterize_fim_wim(tri(1.0, flip)[None, None], S, fast=False)
+        if (fim >= 0).all():
+            front = flip
+    fim, wim = raster.rasterize_fim_wim(tri(1.0, front)[None, None], S, fast=False)
+    assert (fim == 0).all()
+    np.testing.assert_allclose(wim.sum(-1), 1.0, atol=1e-6)
+    back, _ = raster.rasterize_fim_wim(tri(1.0, not front)[None, None], S, fast=False)
+    assert (back == -1).all(), "back-facing triangle must be culled"
+    # two coincident faces: strict '<' keeps the lower index; a nearer face wins regardless of order
+    two = np.stack([tri(1.0, front), tri(1.0, front)])[None]
+    assert (raster.rasterize_fim_wim(two, S, fast=False)[0] == 0).all()
+    near_first = np.stack([tri(2.0, front), tri(1.0, front)])[None]
+    assert (raster.rasterize_fim_wim(near_first, S, fast=False)[0] == 1).all()
+    # near / far rejection (0.1, 100)
+    assert (raster.rasterize_fim_wim(tri(0.05, front)[None, None], S, fast=False)[0] == -1).all()
+    assert (raster.rasterize_fim_wim(tri(150.0, front)[None, None], S, fast=False)[0] == -1).all()
+    # vertical flip: a triangle in the upper NDC half (y>0) lands in the TOP image rows
+    up = np.array([[-1, 0.01, 1], [-1, 3, 1], [3, 0.01, 1]], np.float32)
+    up = up if not front else up[[0, 2, 1]]
+    f, _ = raster.rasterize_fim_wim(up[None, None], S, fast=False)
+    assert (f[0, :2] == 0).all() and (f[0, 2:] == -1).all()
+
+
+def test_raster_empty_and_ragged():
+    fim, wim = raster.rasterize_fim_wim(np.zeros((0, 5, 3, 3), np.float32), 8)
+    assert fim.shape == (0, 8, 8) and wim.shape == (0, 8, 8, 3)
+    # degenerate (zero-area) and NaN faces never win
+    deg = np.array([[[0, 0, 1], [0, 0, 1], [0, 0, 1]], [[np.nan, 0, 1], [0, 1, 1], [1, 0, 1]]], np.float32)[None]
+    fim, wim = raster.rasterize_fim_wim(deg, 8, fast=False)
+    fim2, _ = raster.rasterize_fim_wim(deg, 8, fast=True)
+    assert (fim == -1).all() and (fim2 == -1).all() and (wim == 0).all()
+
+
+@pytest.mark.parametrize("S", [64, 128])
+def test_flow_restatement_matches_reference(S, template, golden_dir):
+    g = np.load(os.path.join(golden_dir, "flow_S%d.npz" % S))
+    n = g["fim"].shape[0]
+    cams, verts = synth.pose_sweep(template, n, total=7)
+    scams, sverts = synth.source_views(template, 2)
+    uv_img = synth.smooth_image((1, 3, S, S), seed=11)
+    src_f2pts, _, _ = flow_ref.render_fim_wim(scams, sverts, template["faces"], S)
+    out = flow_ref.frame_inputs(cams, verts, template["faces"], template["map_fn"], template["f_uvs2img"], uv_img,
+                                src_f2pts, S)
+    np.testing.assert_array_equal(out["fim"], g["fim"])
+    np.testing.assert_array_equal(out["wim"], g["wim"])
+    np.testing.assert_array_equal(out["f2pts"], g["f2pts"])         # projection glue is bit-exact
+    np.testing.assert_array_equal(src_f2pts, g["src_f2pts"])
+    np.testing.assert_array_equal(out["cond"], g["cond"])
+    np.testing.assert_allclose(out["Tuv2t"], g["Tuv2t"], atol=1e-6, rtol=0)
+    np.testing.assert_allclose(out["Tst"], g["Tst"], atol=1e-6, rtol=0)
+    np.testing.assert_allclose(out["tsf_inputs"], g["tsf_inputs"], atol=1e-5, rtol=0)
+
+
+@pytest.mark.parametrize("S", [64, 256])
+def test_generator_restatement_matches_reference(S, golden_dir):
+    import make_golden
+    g = np.load(os.path.join(golden_dir, "gen_S%d.npz" % S))
+    inp = make_golden.gen_inputs(S)
+    sd = weights.synth_state_dict(0)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    with torch.no_grad():
+        se, sr = generator_ref.forward_src(sd, torch.from_numpy(inp["src_inputs"]))
+        img, mask = generator_ref.forward_tsf(sd, torch.from_numpy(inp["tsf_inputs"]), se, sr,
+                                              torch.from_numpy(inp["Tst"]))
+    np.testing.assert_allclose(se[2].numpy(), g["src_enc2"], atol=1e-5, rtol=0)
+    np.testing.assert_allclose(sr[5].numpy(), g["src_res5"], atol=1e-5, rtol=0)
+    np.testing.assert_allclose(img.numpy(), g["tsf_img"], atol=2e-5, rtol=0)
+    np.testing.assert_allclose(mask.numpy(), g["tsf_mask"], atol=2e-5, rtol=0)
+    if "bg_img" in g.files:
+        bg = generator_ref.forward_bg(sd, torch.from_numpy(inp["bg_inputs"]))
+        np.testing.assert_allclose(bg.numpy(), g["bg_img"], atol=2e-5, rtol=0)
+
+
+def test_state_dict_layout():
+    shapes = weights.generator_param_shapes()
+    assert len(shapes) == 221
+    assert sum(int(np.prod(s)) for _, s in shapes) == 36276992
