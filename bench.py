@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — 512x512 motion-imitation frames/sec (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the reference's algorithm on the host cores (oracle port), rank 0 only
+
+Workload (BASELINE.json configs[1]): one source set (ns=2) -> 300 synthetic target SMPL poses at
+512x512 per GPU; a "step" is one pass of the per-frame hot path (rows a1-a15) over those 300 frames in batches of B.
+`value`  : frames/s with the 300 frames' vertices/cameras already resident in HBM (whole job, all ranks; weak scaling:
+           every rank synthesizes its own 300-frame clip, no collective on the data path).
+`e2e`    : the same through the public host API FrameEngine.synthesize(): pinned host vertices in, uint8 frames out,
+           H2D/D2H inside the timed region.
+`roofline`: conv stack (tcgen05 implicit GEMM) — algorithmic 285.93 GFLOP/frame over the summed CUDA-event
+           duration of the conv launches of one batch, against the measured bf16 GEMM peak in MEASURED_PEAKS.json.
+`cpu_baseline`: oracle port of the reference path (CPU restatement, torch fp32 on all host cores), bounded sample.
+Weights are synthetic (oracle/weights.py; the real checkpoint is not available offline), data synthetic.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+CFG = dict(name="AttLWB-SPADE", BGNet=dict(cond_nc=4, n_res_block=6, num_filters=[64, 128, 128, 256]),
+           SIDNet=dict(cond_nc=6, n_res_block=6, num_filters=[64, 128, 256]),
+           TSFNet=dict(cond_nc=6, n_res_block=6, num_filters=[64, 128, 256]))
+FLOPS_PER_FRAME_512 = 285.93e9          # SURVEY.md §8a, 76 convs of forward_tsf, ns=2
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--frames", type=int, default=300)
+    ap.add_argument("--batch", type=int, default=20)
+    ap.add_argument("--ns", type=int, default=2)
+    ap.add_argument("--precision", default="fp16x2", choices=["fp16x2", "fp16"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=8)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# synthetic workload (oracle.synth only GENERATES inputs here)
+# ----------------------------------------------------------------------------------------------------------------------
+def make_workload(args, rank):
+    import numpy as np
+    from oracle import synth
+    tpl = synth.load_template()
+    S, ns = args.size, args.ns
+    cams, verts = synth.pose_sweep(tpl, args.frames, total=300, start=rank * args.frames)
+    scams, sverts = synth.source_views(tpl, ns)
+    return dict(tpl=tpl, cams=cams, verts=verts, scams=scams, sverts=sverts,
+                src_img=synth.smooth_image((ns, 3, S, S), seed=1), uv_img=synth.smooth_image((1, 3, S, S), seed=2),
+                bg_img=synth.smooth_image((1, 3, S, S), seed=3))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        time.sleep(0.05)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        if not sm:
+            return None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) > 2 + j and r[2 + j] == "Active" for r in self.rows)]
+        mx = max(int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit())
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference path on the host cores
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_frames_per_sec(args, wl, n_frames, repeats=1):
+    import numpy as np
+    import torch
+    from oracle import flow_ref, generator_ref, weights
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    S, tpl = args.size, wl["tpl"]
+    sd = weights.synth_state_dict(0)
+    src_f2pts, sfim, _ = flow_ref.render_fim_wim(wl["scams"], wl["sverts"], tpl["faces"], S)
+    scond = flow_ref.encode_fim(sfim, tpl["map_fn"])
+    src_inputs = torch.from_numpy(np.concatenate([wl["src_img"], scond], 1)[None])
+    bg = torch.from_numpy(wl["bg_img"])
+    with torch.no_grad():
+        se, sr = generator_ref.forward_src(sd, src_inputs)                 # one-time per source, untimed
+        times = []
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            for i in range(n_frames):
+                fi = flow_ref.frame_inputs(wl["cams"][i:i + 1], wl["verts"][i:i + 1], tpl["faces"], tpl["map_fn"],
+                                           tpl["f_uvs2img"], wl["uv_img"], src_f2pts, S)
+                img, mask = generator_ref.forward_tsf(sd, torch.from_numpy(fi["tsf_inputs"]), se, sr,
+                                                      torch.from_numpy(fi["Tst"]))
+                pred = generator_ref.composite(img, mask, bg)
+                _ = ((pred + 1) / 2.0 * 255).clamp(0, 255).to(torch.uint8)
+            times.append(time.perf_counter() - t0)
+    return n_frames / min(times), cores, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = make_workload(args, 0)
+    sample = 2 if args.size >= 512 else 4
+    for _ in range(max(args.warmup, 0) and 1):
+        cpu_frames_per_sec(args, wl, 1)
+    t0 = time.perf_counter()
+    _, cores, times = cpu_frames_per_sec(args, wl, sample, repeats=max(args.steps, 1))
+    fps = sample * len(times) / sum(times)
+    desc = "oracle port (CPU restatement of raster+flow+AttLWB-SPADE forward_tsf, torch fp32), %d frames of the " \
+           "300-pose clip per step" % sample
+    line = {"impl": "reference", "metric": "motion_imitation_frames_per_sec", "value": fps, "unit": "frames/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_block(args, 0),
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line))
+
+
+def config_block(args, launches):
+    return {"workload": "run_imitator %dx%d: 1 source set (ns=%d) -> %d synthetic target SMPL poses per GPU "
+                        "(BASELINE.json configs[1])" % (args.size, args.size, args.ns, args.frames),
+            "image_size": args.size, "num_source": args.ns, "frames_per_step_per_gpu": args.frames, "batch": args.batch,
+            "precision": args.precision, "cuda_graph": not args.no_graph,
+            "l2": "per-step working set (activations of %d-frame batches, several GB) exceeds the 126 MB L2" % args.batch,
+            "weights": "synthetic (oracle/weights.py), reference 221-tensor layout"}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ipercore_b200 import _lib, ops
+    from ipercore_b200.engine import FrameEngine
+    from ipercore_b200.generator import AttentionLWBGenerator
+    from ipercore_b200.renders import SMPLRenderer
+    from oracle import weights
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = make_workload(args, rank)
+    tpl, S, ns = wl["tpl"], args.size, args.ns
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    render = SMPLRenderer(image_size=S, tables=tpl, has_front=True, top_k=3).to(dev)
+    gen = AttentionLWBGenerator(CFG, precision=args.precision)
+    gen.load_state_dict(weights.synth_state_dict(0), strict=True)
+    gen = gen.to(dev).eval()
+    # one-time per source: geometry of the source views -> f2pts + cond; input_G_src = cat[src_img, cond]
+    src_f2pts, sfim, _ = render.render_fim_wim(t(wl["scams"]), t(wl["sverts"]))
+    scond, _ = render.encode_fim(fim=sfim)
+    src_inputs = torch.cat([t(wl["src_img"]), scond], 1)[None]
+    eng = FrameEngine(gen, render, batch=args.batch, use_graph=not args.no_graph, device=dev)
+    eng.set_source(src_inputs, t(wl["uv_img"]), t(wl["bg_img"]), src_f2pts)
+
+    T, B = args.frames, args.batch
+    cams_d, verts_d = t(wl["cams"]), t(wl["verts"])
+    cams_h = torch.from_numpy(wl["cams"]).pin_memory(); verts_h = torch.from_numpy(wl["verts"]).pin_memory()
+    out_h = torch.empty((T, S, S, 3), dtype=torch.uint8).pin_memory()
+    out_d = torch.empty((T, S, S, 3), dtype=torch.uint8, device=dev)
+    nb = (T + B - 1) // B
+    cur = torch.cuda.current_stream(dev)
+
+    def step_device():
+        for i in range(nb):
+            lo, hi = i * B, min((i + 1) * B, T)
+            u8 = eng.run_batch_device(cams_d[lo:hi], verts_d[lo:hi])
+            with torch.cuda.stream(eng.compute):
+                out_d[lo:hi].copy_(u8[:hi - lo], non_blocking=True)
+        cur.wait_stream(eng.compute)
+
+    def step_e2e():
+        eng.synthesize(cams_h, verts_h, out=out_h)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, sampler=None):
+        barrier()
+        eng.compute.wait_stream(cur); eng.copy.wait_stream(cur)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.start()
+        w0 = time.perf_counter()
+        e0.record(cur)
+        eng.compute.wait_event(e0); eng.copy.wait_event(e0)
+        for _ in range(steps):
+            fn()
+        e1.record(cur)
+        barrier()
+        wall = time.perf_counter() - w0
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt)
+        return ms, wall
+
+    for _ in range(max(args.warmup, 1)):
+        step_device()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = _lib.launch_count()
+    ms, wall = timed(step_device, args.steps, sampler)
+    clocks = sampler.stop() if sampler else None
+    fps = world * T * args.steps / (ms * 1e-3)
+    for _ in range(1):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    fps_e2e = world * T * args.steps / (ms_e2e * 1e-3)
+    launches = eng.launches_per_batch * nb * args.steps if eng.graph else _lib.launch_count() - launches0
+
+    # ---- roofline of the conv stack: CUDA events around every conv_gemm launch of one (un-graphed) batch ----
+    roof = None
+    if rank == 0:
+        recs = []
+        orig = ops.conv_gemm
+
+        def timed_conv(a, wpack, mode, ksize, rows, block_n, epi, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); orig(a, wpack, mode, ksize, rows, block_n, epi, **kw); e1.record()
+            phases = 4 if mode == ops.IPER_CONVT_4S2 else 1
+            opix = a.N * (a.H // 2) * (a.W // 2) if mode == ops.IPER_CONV_S2 else a.N * a.H * a.W
+            macs = opix * phases * rows * wpack.shape[2]
+            recs.append((e0, e1, macs * (3 if wpack.shape[0] == 2 else 1)))
+
+        with torch.cuda.stream(eng.compute):
+            eng._step()
+            ops.conv_gemm = timed_conv
+            try:
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record(); eng._step(); s1.record()
+            finally:
+                ops.conv_gemm = orig
+            torch.cuda.synchronize(dev)
+        conv_ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+        step_ms = s0.elapsed_time(s1)
+        exec_flops = 2.0 * sum(m for _, _, m in recs)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        alg = FLOPS_PER_FRAME_512 * (S / 512.0) ** 2 * (1 + (ns - 2) * 9.66 / 285.93) * B
+        ach = alg / (conv_ms * 1e-3) / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json"))).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
+        roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, %d launches per %d-frame batch)" % (len(recs), B),
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PFLOP/s sustained",
+                "algorithmic_flops_per_batch": alg, "executed_tflops": exec_flops / (conv_ms * 1e-3) / 1e12,
+                "executed_flops_note": "split-fp16 issues 3 MMAs per K step; fk/fv 1x1 convs are hoisted to once-per-source",
+                "conv_ms_per_batch": conv_ms, "batch_ms_ungraphed": step_ms, "conv_share_of_step": conv_ms / step_ms,
+                "traffic": traffic}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, cores, _ = cpu_frames_per_sec(args, wl, args.cpu_frames)
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+               "sample": "first %d frames of the 300-pose clip through the oracle port (CPU restatement of raster + "
+                         "flow + forward_tsf + composite, torch fp32, all host threads); source setup untimed" % args.cpu_frames}
+
+    if rank == 0:
+        line = {"metric": "motion_imitation_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16x2 (split fp16 operands, fp32 accumulate)" if args.precision == "fp16x2" else "f16 (fp32 accumulate)",
+                "data": "synthetic", "config": config_block(args, launches),
+                "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(cams_h.numel() * 4 + verts_h.numel() * 4),
+                        "d2h_bytes_per_step": int(out_h.numel()), "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "wall_s_timed_region": wall}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

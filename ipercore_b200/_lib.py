@@ -76,7 +76,17 @@ def _load():
 lib = _load()
 
 
+_LAUNCHES = 0
+
+
+def launch_count():
+    """Number of libiper_b200 kernel launches issued so far by this process (every C-ABI op is exactly one launch)."""
+    return _LAUNCHES
+
+
 def check(status, what=""):
+    global _LAUNCHES
+    _LAUNCHES += 1
     if status != 0:
         msg = lib.iper_last_error()
         raise RuntimeError("iper_b200 %s failed (status %d): %s" % (what, status, msg.decode() if msg else "?"))

@@ -401,9 +401,9 @@ using namespace iper;
 
 extern "C" int iper_rasterize_faces(const float* faces, int B, int nf, int S, float near_, float far_, int32_t* fim,
                                     float* wim, iper_stream_t stream) {
-    IPER_REQUIRE(faces && fim && wim, "iper_rasterize_faces: null pointer");
     IPER_REQUIRE(B >= 0 && nf > 0 && S > 0, "iper_rasterize_faces: bad sizes B=%d nf=%d S=%d", B, nf, S);
-    if (B == 0) return 0;
+    if (B == 0) return 0;   // empty batch: nothing to do (pointers may be null)
+    IPER_REQUIRE(faces && fim && wim, "iper_rasterize_faces: null pointer");
     RasterArgs a = {};
     a.face_verts = faces; a.B = B; a.nf = nf; a.S = S; a.near_ = near_; a.far_ = far_;
     a.fim = fim; a.wim = wim;
@@ -415,8 +415,9 @@ extern "C" int iper_raster_frames(const float* verts, const float* cams, const i
                                   const float* map_fn, const float* f_uvs2img, const float* uv_img,
                                   const float* src_f2pts, int ns, float* tsf_inputs, float* Tst,
                                   iper_stream_t stream) {
-    IPER_REQUIRE(verts && cams && faces, "iper_raster_frames: null geometry pointer");
     IPER_REQUIRE(B >= 0 && nv > 0 && nf > 0 && S > 0, "iper_raster_frames: bad sizes");
+    if (B == 0) return 0;
+    IPER_REQUIRE(verts && cams && faces, "iper_raster_frames: null geometry pointer");
     if (tsf_inputs || Tst) {
         IPER_REQUIRE(tsf_inputs && Tst && map_fn && f_uvs2img && uv_img && src_f2pts && ns > 0,
                      "iper_raster_frames: the fused frame-input outputs need map_fn, f_uvs2img, uv_img, src_f2pts, ns");

@@ -55,13 +55,16 @@ def test_conv_gemm_planes(N, H, W, Cin, Cout, mode, k, P):
     ops.conv_gemm(a, wp, mode, k, rows, 256 if rows >= 256 else rows, ops.IPER_EPI_PLANES, bias=bias.to(DEV), relu=True,
                   out=out)
     chk = Planes.empty(P, N, oH, oW, Cout, DEV)
-    ops.conv_direct(a, w.to(DEV), mode, k, Cout, ops.IPER_EPI_PLANES, bias=bias.to(DEV), relu=True, out=chk)
+    ops.conv_direct(a, wq.to(DEV), mode, k, Cout, ops.IPER_EPI_PLANES, bias=bias.to(DEV), relu=True, out=chk)
     torch.cuda.synchronize()
+    # expectation: plain PyTorch fp32 convolution of the SAME (rounded) operands; the remaining difference is fp32
+    # accumulation order (K up to 3456 terms) plus, for P=2, the dropped lo*lo term (~2^-22 relative)
     exp = F.relu(_ref_conv(xq, wq, mode, k) + bias.view(1, -1, 1, 1))
     got = _planes_value(out)
-    tol = 2e-5 if P == 2 else 2e-3     # P=2: fp32-grade; P=1: only the lo*x cross terms of the weights are dropped... no: both rounded
-    np.testing.assert_allclose(_planes_value(chk).numpy(), exp.numpy(), atol=2e-4 if P == 1 else 2e-5, rtol=0)
-    np.testing.assert_allclose(got.numpy(), exp.numpy(), atol=tol if P == 2 else 2e-4, rtol=0)
+    tol = 1e-4 if P == 2 else 1.5e-3   # P=1: the fp16 OUTPUT plane alone carries 11 significand bits
+    np.testing.assert_allclose(_planes_value(chk).numpy(), exp.numpy(), atol=tol, rtol=0)
+    np.testing.assert_allclose(got.numpy(), exp.numpy(), atol=tol, rtol=0)
+    np.testing.assert_allclose(got.numpy(), _planes_value(chk).numpy(), atol=tol, rtol=0)
 
 
 def test_conv_gemm_fp32_out_residual_and_windows():
@@ -110,11 +113,11 @@ def test_conv_gemm_spade_epilogue(C, P):
     mean = xq.mean((2, 3)); var = xq.var((2, 3), unbiased=False)
     np.testing.assert_allclose(stats[..., 0].cpu().numpy(), mean.numpy(), atol=1e-6, rtol=0)
     np.testing.assert_allclose(stats[..., 1].cpu().numpy(), (1 / torch.sqrt(var + 1e-5)).numpy(), rtol=2e-6, atol=0)
-    np.testing.assert_allclose(_planes_value(out).numpy(), exp.numpy(), atol=5e-5 if P == 2 else 1e-3, rtol=0)
+    np.testing.assert_allclose(_planes_value(out).numpy(), exp.numpy(), atol=1e-4 if P == 2 else 3e-3, rtol=0)
     chk = Planes.empty(P, N, H, W, C, DEV)
-    ops.conv_direct(a, torch.cat([wg, wb], 0).to(DEV), 0, 3, 2 * C, ops.IPER_EPI_SPADE, bias=torch.cat([bg, bb]).to(DEV),
+    ops.conv_direct(a, torch.cat([q(wg), q(wb)], 0).to(DEV), 0, 3, 2 * C, ops.IPER_EPI_SPADE, bias=torch.cat([bg, bb]).to(DEV),
                     out=chk, x=xp, mean_rstd=stats, spade_C=C)
-    np.testing.assert_allclose(_planes_value(chk).numpy(), exp.numpy(), atol=5e-5 if P == 2 else 1e-3, rtol=0)
+    np.testing.assert_allclose(_planes_value(chk).numpy(), exp.numpy(), atol=1e-4 if P == 2 else 3e-3, rtol=0)
 
 
 def test_conv_gemm_heads_epilogue():

@@ -54,6 +54,7 @@ def test_raster_edge_cases():
                       np.stack([tri * [1, 1, 2], tri]),                       # nearer face second
                       np.stack([tri[[0, 2, 1]], tri * [1, 1, 200]]),          # back-facing + beyond far
                       np.stack([np.zeros((3, 3), np.float32), np.full((3, 3), np.nan, np.float32)])])  # degenerate / NaN
+    cases = cases.astype(np.float32)
     fim_o, wim_o = raster.rasterize_fim_wim(cases, S, fast=False)
     fim, wim = ops.rasterize_faces(_t(cases), S)
     np.testing.assert_array_equal(fim.cpu().numpy(), fim_o)
