@@ -108,11 +108,24 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle port of the reference path on the host cores
 # ----------------------------------------------------------------------------------------------------------------------
+def host_cores():
+    """Host threads this process may really use: scheduler affinity capped by the cgroup CPU quota (a container that
+    sees 128 CPUs but is throttled to a few would otherwise oversubscribe and run far slower)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def cpu_frames_per_sec(args, wl, n_frames, repeats=1):
     import numpy as np
     import torch
     from oracle import flow_ref, generator_ref, weights
-    cores = os.cpu_count() or 1
+    cores = int(os.environ.get("IPER_CPU_THREADS", "0")) or host_cores()
     torch.set_num_threads(cores)
     S, tpl = args.size, wl["tpl"]
     sd = weights.synth_state_dict(0)

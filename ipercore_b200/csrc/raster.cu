@@ -8,9 +8,10 @@
 //   * FlowComposition.make_tsf_inputs / make_trans_flow (flowcomposition.py:206-248, 514-582)
 //
 // Design (B200): one CTA per 64x32 pixel tile per frame.  The frame's projected vertices are staged in shared
-// memory once per CTA (82 KB), every thread walks a strided slice of the 13 776 faces and BINS them against
-// the tile by bounding box; faces that overlap are scan-converted over (bbox ∩ tile) straight into a shared
-// memory z-buffer with a 64-bit atomicMin on (depth bits << 32 | face index) — which is exactly the upstream
+// memory once per CTA (82 KB); in chunks of 4096 faces every thread BINS a strided slice of the faces against the
+// tile by bounding box into a compact shared list, then each WARP takes binned faces and scan-converts them with
+// its lanes spread over the pixels of (bbox ∩ tile) — no per-face divergence — straight into a shared memory
+// z-buffer with a 64-bit atomicMin on (depth bits << 32 | face index) — which is exactly the upstream
 // rule "strictly smaller depth wins, lowest face index wins a tie".  A resolve pass then recomputes the winner's
 // barycentric weights (same float sequence, hence identical bits) and writes fim / wim / cond / flow / sampled
 // UV image with fully coalesced stores.  Work is proportional to covered area, not faces x pixels
@@ -28,6 +29,9 @@ constexpr int TILE_W = 64;
 constexpr int TILE_H = 32;
 constexpr int RASTER_THREADS = 256;
 constexpr unsigned long long ZBUF_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+constexpr int BIN_CHUNK = 4096;            // faces binned per pass (compact list of 16-bit offsets)
+constexpr int RASTER_ZBUF_BYTES = TILE_W * TILE_H * 8;
+constexpr int RASTER_FIXED_SMEM = RASTER_ZBUF_BYTES + BIN_CHUNK * 2 + (TILE_W + TILE_H) * 4 + 16;
 
 struct FaceGeom {
     float v[9];  // x0 y0 z0 x1 y1 z1 x2 y2 z2 (NDC, +y up after the reference's flip)
@@ -104,8 +108,9 @@ IPER_DEVINL bool weights_depth(const float* f, const float* inv, int xi, int yi,
     s = __fadd_rn(s, __fdiv_rn(w[1], f[5]));
     s = __fadd_rn(s, __fdiv_rn(w[2], f[8]));
     zp = __double2float_rn(__ddiv_rn(1.0, (double)s));
-    if (zp <= near_ || far_ <= zp) return false;
-    return true;
+    // upstream: reject zp <= near or far <= zp, then keep only if zp < depth_min (initially far): a NaN depth
+    // passes the first test but never the second, so eligibility is exactly near < zp < far
+    return (zp > near_) && (zp < far_);
 }
 
 // F.grid_sample(img, grid) for one location, bilinear / zeros / align_corners=False, C planes of an (C,S,S) image
@@ -159,7 +164,11 @@ template <bool FROM_VERTS>
 __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(const RasterArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* zbuf = reinterpret_cast<unsigned long long*>(smem_raw);
-    float* sv = reinterpret_cast<float*>(smem_raw + (size_t)TILE_W * TILE_H * sizeof(unsigned long long));
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(smem_raw + RASTER_ZBUF_BYTES);
+    float* s_xp = reinterpret_cast<float*>(smem_raw + RASTER_ZBUF_BYTES + BIN_CHUNK * sizeof(unsigned short));
+    float* s_yp = s_xp + TILE_W;
+    int* s_count = reinterpret_cast<int*>(s_yp + TILE_H);
+    float* sv = reinterpret_cast<float*>(smem_raw + RASTER_FIXED_SMEM);
 
     const int S = a.S, nf = a.nf;
     const int b = blockIdx.y;
@@ -200,10 +209,11 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(const RasterArgs
     const int xi_lo = tx0, xi_hi = min(tx0 + TILE_W, S) - 1;
     const int yi_hi = S - 1 - r0, yi_lo = S - 1 - (min(r0 + TILE_H, S) - 1);
     const float fS = (float)S;
+    // pixel-centre tables of the tile (the double-precision divisions happen once per CTA, not per test)
+    if (tid < TILE_W) s_xp[tid] = pixel_centre(tx0 + tid, S);
+    else if (tid < TILE_W + TILE_H) s_yp[tid - TILE_W] = pixel_centre(S - 1 - (r0 + tid - TILE_W), S);
 
-    // ---- binning + scan conversion into the shared z-buffer ----
-    for (int f = tid; f < nf; f += RASTER_THREADS) {
-        FaceGeom g;
+    auto load_face = [&](int f, FaceGeom& g) {
         if (FROM_VERTS) {
 #pragma unroll
             for (int k = 0; k < 3; k++) {
@@ -217,11 +227,12 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(const RasterArgs
 #pragma unroll
             for (int k = 0; k < 9; k++) g.v[k] = __ldg(src + k);
         }
-        if (is_backface(g.v)) continue;
-        // conservative pixel range of the face's bounding box, grown by one pixel on every side
+    };
+    // conservative pixel range of a face's bounding box (grown by one pixel) clipped to the tile
+    auto face_range = [&](const FaceGeom& g, int& x0, int& x1, int& y0, int& y1) {
         const float xmin = fminf(g.v[0], fminf(g.v[3], g.v[6])), xmax = fmaxf(g.v[0], fmaxf(g.v[3], g.v[6]));
         const float ymin = fminf(g.v[1], fminf(g.v[4], g.v[7])), ymax = fmaxf(g.v[1], fmaxf(g.v[4], g.v[7]));
-        int x0 = xi_lo, x1 = xi_hi, y0 = yi_lo, y1 = yi_hi;
+        x0 = xi_lo; x1 = xi_hi; y0 = yi_lo; y1 = yi_hi;
         const bool finite = (xmin == xmin) && (xmax == xmax) && (ymin == ymin) && (ymax == ymax) &&
                             fabsf(xmin) < 1e6f && fabsf(xmax) < 1e6f && fabsf(ymin) < 1e6f && fabsf(ymax) < 1e6f;
         if (finite) {
@@ -230,13 +241,38 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(const RasterArgs
             y0 = max(y0, (int)floorf((ymin * fS + fS - 1.f) * 0.5f) - 1);
             y1 = min(y1, (int)ceilf((ymax * fS + fS - 1.f) * 0.5f) + 1);
         }
-        if (x0 > x1 || y0 > y1) continue;  // face not binned to this tile
-        float inv[9];
-        face_inverse(g.v, S, inv);
-        for (int yi = y0; yi <= y1; yi++) {
-            const float yp = pixel_centre(yi, S);
-            for (int xi = x0; xi <= x1; xi++) {
-                const float xp = pixel_centre(xi, S);
+    };
+
+    // ---- per chunk of faces: (1) BIN front faces whose bbox touches the tile into a compact shared list,
+    //      (2) scan-convert the list one WARP per face, lanes over the pixels of (bbox ∩ tile) ----
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int base = 0; base < nf; base += BIN_CHUNK) {
+        if (tid == 0) *s_count = 0;
+        __syncthreads();
+        const int end = min(base + BIN_CHUNK, nf);
+        for (int f = base + tid; f < end; f += RASTER_THREADS) {
+            FaceGeom g;
+            load_face(f, g);
+            if (is_backface(g.v)) continue;
+            int x0, x1, y0, y1;
+            face_range(g, x0, x1, y0, y1);
+            if (x0 > x1 || y0 > y1) continue;
+            s_list[atomicAdd(s_count, 1)] = (unsigned short)(f - base);
+        }
+        __syncthreads();
+        const int count = *s_count;
+        for (int c = warp; c < count; c += RASTER_THREADS / 32) {
+            const int f = base + s_list[c];
+            FaceGeom g;
+            load_face(f, g);
+            int x0, x1, y0, y1;
+            face_range(g, x0, x1, y0, y1);
+            float inv[9];
+            face_inverse(g.v, S, inv);
+            const int bw = x1 - x0 + 1, npx = bw * (y1 - y0 + 1);
+            for (int i = lane; i < npx; i += 32) {
+                const int xi = x0 + i % bw, yi = y0 + i / bw;
+                const float xp = s_xp[xi - tx0], yp = s_yp[(S - 1 - yi) - r0];
                 if (!inside_face(g.v, xp, yp)) continue;
                 float w[3], zp;
                 if (!weights_depth(g.v, inv, xi, yi, a.near_, a.far_, w, zp)) continue;
@@ -258,19 +294,7 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(const RasterArgs
         float w[3] = {0.f, 0.f, 0.f};
         if (fn >= 0) {
             FaceGeom g;
-            if (FROM_VERTS) {
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    const int vi = __ldg(a.faces + 3 * fn + k);
-                    g.v[3 * k + 0] = sv[3 * vi + 0];
-                    g.v[3 * k + 1] = sv[3 * vi + 1];
-                    g.v[3 * k + 2] = sv[3 * vi + 2];
-                }
-            } else {
-                const float* src = a.face_verts + ((size_t)b * nf + fn) * 9;
-#pragma unroll
-                for (int k = 0; k < 9; k++) g.v[k] = __ldg(src + k);
-            }
+            load_face(fn, g);
             float inv[9], zp;
             face_inverse(g.v, S, inv);
             weights_depth(g.v, inv, xi, S - 1 - row, a.near_, a.far_, w, zp);
@@ -375,7 +399,7 @@ __global__ void flow_resize_kernel(const float* __restrict__ T, int n, int S, in
 }
 
 static size_t raster_smem_bytes(bool from_verts, int nv) {
-    return (size_t)TILE_W * TILE_H * sizeof(unsigned long long) + (from_verts ? (size_t)nv * 3 * sizeof(float) : 0);
+    return (size_t)RASTER_FIXED_SMEM + (from_verts ? (size_t)nv * 3 * sizeof(float) : 0);
 }
 
 static int launch_raster(const RasterArgs& a, bool from_verts, cudaStream_t stream) {

@@ -61,10 +61,11 @@ def test_conv_gemm_planes(N, H, W, Cin, Cout, mode, k, P):
     # accumulation order (K up to 3456 terms) plus, for P=2, the dropped lo*lo term (~2^-22 relative)
     exp = F.relu(_ref_conv(xq, wq, mode, k) + bias.view(1, -1, 1, 1))
     got = _planes_value(out)
-    tol = 1e-4 if P == 2 else 1.5e-3   # P=1: the fp16 OUTPUT plane alone carries 11 significand bits
-    np.testing.assert_allclose(_planes_value(chk).numpy(), exp.numpy(), atol=tol, rtol=0)
-    np.testing.assert_allclose(got.numpy(), exp.numpy(), atol=tol, rtol=0)
-    np.testing.assert_allclose(got.numpy(), _planes_value(chk).numpy(), atol=tol, rtol=0)
+    # P=1: the single fp16 OUTPUT plane carries 11 significand bits -> one fp16 ulp (2^-10 relative) of slack
+    atol, rtol = (1e-4, 0) if P == 2 else (5e-4, 1.1e-3)
+    np.testing.assert_allclose(_planes_value(chk).numpy(), exp.numpy(), atol=atol, rtol=rtol)
+    np.testing.assert_allclose(got.numpy(), exp.numpy(), atol=atol, rtol=rtol)
+    np.testing.assert_allclose(got.numpy(), _planes_value(chk).numpy(), atol=atol, rtol=rtol)
 
 
 def test_conv_gemm_fp32_out_residual_and_windows():

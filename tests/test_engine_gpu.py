@@ -80,8 +80,12 @@ def test_engine_frames_match_oracle(use_graph, template):
         se, sr = generator_ref.forward_src(sd, torch.from_numpy(src_inputs))
         fi = flow_ref.frame_inputs(cams, verts, template["faces"], template["map_fn"], template["f_uvs2img"], uv_img,
                                    src_f2pts, S)
-        img, mask = generator_ref.forward_tsf(sd, torch.from_numpy(fi["tsf_inputs"]), se, sr, torch.from_numpy(fi["Tst"]))
-        pred = generator_ref.composite(img, mask, torch.from_numpy(bg))
+        preds = []
+        for i in range(T):     # the reference's forward_tsf pairs src features (bs*ns) with Tst (bs,ns): one frame at a time
+            img, mask = generator_ref.forward_tsf(sd, torch.from_numpy(fi["tsf_inputs"][i:i + 1]), se, sr,
+                                                  torch.from_numpy(fi["Tst"][i:i + 1]))
+            preds.append(generator_ref.composite(img, mask, torch.from_numpy(bg)))
+        pred = torch.cat(preds, 0)
     exp = ((pred + 1) / 2.0 * 255).clamp(0, 255).numpy().astype(np.uint8)[:, ::-1].transpose(0, 2, 3, 1)   # BGR, HWC
     diff = np.abs(out.numpy().astype(np.int32) - exp.astype(np.int32))
     assert diff.max() <= 1, "uint8 frames differ from the oracle by more than one code value"
