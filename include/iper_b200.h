@@ -67,12 +67,13 @@ int iper_flow_resize(const float* T, int n, int S, int h, int w, float* out, ipe
  * ---------------------------------------------------------------------------------------------------------- */
 enum { IPER_CONV_S1 = 0,    /* k x k, stride 1, pad k/2 (k = 1, 3, 5)                                     */
        IPER_CONV_S2 = 1,    /* 3x3, stride 2, pad 1                                                        */
-       IPER_CONVT_4S2 = 2 };/* ConvTranspose2d(k=4, s=2, p=1) as four 2x2 phase convolutions               */
+       IPER_CONVT_4S2 = 2,  /* ConvTranspose2d(k=4, s=2, p=1) as four 2x2 phase convolutions               */
+       IPER_CONV_ROW5 = 3 };/* 5x5 s1 p2 heads: K = (dy, cin), rows = (dx, out) pairs, epilogue shift-add     */
 
 enum { IPER_EPI_PLANES = 0, /* out = [relu](acc + bias [+ residual x]) -> NHWC fp16 planes                 */
        IPER_EPI_F32 = 1,    /* out = acc + bias -> NHWC fp32                                               */
        IPER_EPI_SPADE = 2,  /* rows = [gamma block | beta block]; out = IN(x)*(1+gamma)+beta -> planes     */
-       IPER_EPI_HEADS = 3 };/* rows 0..2 tanh image, row 3 sigmoid mask, + composite with background       */
+       IPER_EPI_HEADS = 3 };/* (IPER_CONV_ROW5) out 0..2 tanh image, out 3 sigmoid mask, + composite with bg  */
 
 typedef struct {
     /* A operand: input activations, NHWC fp16 planes */
@@ -83,7 +84,7 @@ typedef struct {
     /* B operand: packed weights fp16 [plane][phase][rows][taps*Cin], K ordered (tap, cin), K-major          */
     const void* w; int w_planes; long long w_plane_stride;
     int rows;                                                /* GEMM N per phase (multiple of block_n)      */
-    int block_n;                                             /* 16, 64, 128 or 256                          */
+    int block_n;                                             /* 64, 128 or 256 (32 for the heads)           */
     /* epilogue */
     int epi; const float* bias; int relu;
     void* out; int out_planes; long long out_plane_stride; int out_pitch, out_coff;
@@ -110,9 +111,10 @@ int iper_conv_stem(const float* in_nchw, int N, int Cin, int H, int W, const flo
                    iper_stream_t stream);
 
 /* nn.InstanceNorm2d(affine=False) statistics (attlwb_spade_resunet.py:62, eps 1e-5, biased variance):
- * mean_rstd (N,C,2) = (mean, 1/sqrt(var+eps)) of an NHWC planes tensor. Deterministic (no atomics). */
+ * mean_rstd (N,C,2) = (mean, 1/sqrt(var+eps)) of an NHWC planes tensor.  workspace: N*C*2 doubles (fp64 sums,
+ * cleared and filled by the call; two launches + one memset on the stream). */
 int iper_instnorm_stats(const void* x, int x_planes, long long x_plane_stride, int N, int HW, int C, int x_pitch,
-                        int x_coff, float eps, float* mean_rstd, iper_stream_t stream);
+                        int x_coff, float eps, double* workspace, float* mean_rstd, iper_stream_t stream);
 
 /* Flow-guided warp + per-pixel source attention (LWB.transform :184-191, SelfAttentionBlock :102-139), using
  * fk(warp(x)) = warp(Wk x) + bk:  kv (ns,h,w,2C) fp32 holds [Wk x | Wv x] per source (no bias);

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libiper_b200.so")
 
 c_void_p, c_int, c_float, c_ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
 
-IPER_CONV_S1, IPER_CONV_S2, IPER_CONVT_4S2 = 0, 1, 2
+IPER_CONV_S1, IPER_CONV_S2, IPER_CONVT_4S2, IPER_CONV_ROW5 = 0, 1, 2, 3
 IPER_EPI_PLANES, IPER_EPI_F32, IPER_EPI_SPADE, IPER_EPI_HEADS = 0, 1, 2, 3
 
 
@@ -47,7 +47,8 @@ SIGNATURES = {
     "iper_conv_direct": [ctypes.POINTER(ConvGemmDesc), c_void_p, c_int, c_void_p],
     "iper_conv_stem": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_ll, c_int,
                        c_int, c_void_p],
-    "iper_instnorm_stats": [c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p],
+    "iper_instnorm_stats": [c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                            c_void_p],
     "iper_warp_attention": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                             c_void_p, c_int, c_ll, c_int, c_int, c_void_p],
     "iper_warp_nhwc": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],

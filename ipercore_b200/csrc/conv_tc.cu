@@ -9,6 +9,11 @@
 // (2*pitch, W/2, 2, H/2, N) of the same tensor so that each tap is again a dense box; the transposed 4x4/s2
 // convolution is four 2x2 phase convolutions with interleaved stores.
 //
+// The two 5x5 heads (64 -> 3 tanh, 64 -> 1 sigmoid) would be smem-bandwidth bound as a 25-tap N=16 GEMM, so they run
+// as IPER_CONV_ROW5: K walks only the 5 vertical taps (5 TMA loads per tile), N = 32 holds (dx, out) pairs
+// (D[p,(dx,o)] = sum_dy,c X[y+dy-2, p, c] W[o,c,dy,dx]) and the epilogue finishes the horizontal taps with a shift-add
+// out[x,o] = sum_dx D[x+dx-2,(dx,o)] through shared memory; tiles are 128-pixel row segments overlapping by 4.
+//
 // One persistent CTA per SM, warp-specialised:
 //   warp 0   : TMA producer (one lane)            smem ring of STAGES x {A planes, B planes}
 //   warp 1   : TMEM allocator + MMA issuer (one lane issues tcgen05.mma, tcgen05.commit frees ring slots)
@@ -70,7 +75,7 @@ IPER_DEVINL TileCoord decode_tile(const GemmArgs& a, int tile) {
     int r = tile / a.n_tiles;
     const int m = r % a.m_tiles;
     t.phase = r / a.m_tiles;
-    t.px0 = (m % a.tiles_x) * a.tw;
+    t.px0 = (a.mode == IPER_CONV_ROW5) ? (m % a.tiles_x) * (BLOCK_M - 4) - 2 : (m % a.tiles_x) * a.tw;
     const int r2 = m / a.tiles_x;
     t.py0 = (r2 % a.tiles_y) * a.th;
     t.pn0 = (r2 / a.tiles_y) * a.tn;
@@ -193,7 +198,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                             tma_load_5d(sA(stage, p), &a.mapA[p], &full_bar[stage], c0, t.px0 + sx, py, t.py0 + sy, t.pn0);
                     } else {
                         int oy, ox;
-                        if (a.mode == IPER_CONV_S1) {
+                        if (a.mode == IPER_CONV_ROW5) {
+                            oy = tap - 2; ox = 0;
+                        } else if (a.mode == IPER_CONV_S1) {
                             const int dy = tap / a.ksize, dx = tap - dy * a.ksize;
                             oy = dy - a.ksize / 2; ox = dx - a.ksize / 2;
                         } else {  // transposed 4x4 s2 p1, phase (py,px), tap (ta,tb): see pack order in generator.py
@@ -266,22 +273,38 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 
             if (a.epi == IPER_EPI_HEADS) {
-                uint32_t r[32];
-                tmem_ld16(taddr, r);
-                tmem_ld_wait();
-                if (valid) {
-                    const size_t hw = (size_t)a.oH * a.oW, p = (size_t)oy * a.oW + ox;
-                    const float m = 1.f / (1.f + expf(-__uint_as_float(r[3])));
-                    if (a.mask) a.mask[(size_t)n * hw + p] = m;
+                if constexpr (BN == 32) {
+                    __shared__ float s_ex[BLOCK_M * 21];          // D[row][dx*4+o], 20 used columns (+1 pad)
+                    uint32_t r[32];
+                    tmem_ld32(taddr, r);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        const float v = tanhf(__uint_as_float(r[c]));
-                        if (a.img) a.img[((size_t)n * 3 + c) * hw + p] = v;
-                        if (a.pred) {
-                            const float b = a.bg[(size_t)n * a.bg_batch_stride + c * hw + p];
-                            a.pred[((size_t)n * 3 + c) * hw + p] = m * b + (1.f - m) * v;   // imitator.py:393
+                    for (int i = 0; i < 20; i++) s_ex[row * 21 + i] = __uint_as_float(r[i]);
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    const int xo = t.px0 + row;
+                    if (row >= 2 && row < BLOCK_M - 2 && xo >= 0 && xo < a.Wo && n < a.N && y < a.Ho) {
+                        float o4[4];
+#pragma unroll
+                        for (int o = 0; o < 4; o++) {
+                            float acc4 = 0.f;
+#pragma unroll
+                            for (int dx = 0; dx < 5; dx++) acc4 += s_ex[(row + dx - 2) * 21 + dx * 4 + o];
+                            o4[o] = acc4;
+                        }
+                        const size_t hw = (size_t)a.oH * a.oW, p = (size_t)y * a.oW + xo;
+                        const float m = 1.f / (1.f + expf(-o4[3]));
+                        if (a.mask) a.mask[(size_t)n * hw + p] = m;
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            const float v = tanhf(o4[c]);
+                            if (a.img) a.img[((size_t)n * 3 + c) * hw + p] = v;
+                            if (a.pred) {
+                                const float bgv = a.bg[(size_t)n * a.bg_batch_stride + c * hw + p];
+                                a.pred[((size_t)n * 3 + c) * hw + p] = m * bgv + (1.f - m) * v;   // imitator.py:393
+                            }
                         }
                     }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");   // s_ex is reused by the next tile
                 }
             } else if (a.epi == IPER_EPI_SPADE) {
                 constexpr int CB = BN / 2;      // channels per tile: columns [0,CB) gamma, [CB,2CB) beta
@@ -419,8 +442,8 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
     IPER_REQUIRE(d->a_pitch % 8 == 0 && d->a_coff % 8 == 0 && d->a_coff + d->Cin <= d->a_pitch,
                  "iper_conv_gemm: bad channel window (pitch %d, offset %d, Cin %d)", d->a_pitch, d->a_coff, d->Cin);
     IPER_REQUIRE(((uintptr_t)d->a & 15) == 0 && ((uintptr_t)d->w & 15) == 0, "iper_conv_gemm: operands must be 16-byte aligned");
-    IPER_REQUIRE(d->block_n == 16 || d->block_n == 64 || d->block_n == 128 || d->block_n == 256,
-                 "iper_conv_gemm: block_n=%d not in {16,64,128,256}", d->block_n);
+    IPER_REQUIRE(d->block_n == 32 || d->block_n == 64 || d->block_n == 128 || d->block_n == 256,
+                 "iper_conv_gemm: block_n=%d not in {32,64,128,256}", d->block_n);
     IPER_REQUIRE(d->rows > 0 && d->rows % d->block_n == 0, "iper_conv_gemm: rows=%d not a multiple of block_n=%d", d->rows,
                  d->block_n);
     IPER_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0, "iper_conv_gemm: empty input");
@@ -436,6 +459,8 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
         taps = 9; g.ksize = 3; g.Ho = d->H / 2; g.Wo = d->W / 2; g.oH = g.Ho; g.oW = g.Wo; g.phases = 1;
     } else if (d->mode == IPER_CONVT_4S2) {
         taps = 4; g.Ho = d->H; g.Wo = d->W; g.oH = 2 * d->H; g.oW = 2 * d->W; g.phases = 4;
+    } else if (d->mode == IPER_CONV_ROW5) {
+        taps = 5; g.ksize = 5; g.Ho = d->H; g.Wo = d->W; g.oH = d->H; g.oW = d->W; g.phases = 1;
     } else {
         IPER_REQUIRE(false, "iper_conv_gemm: unknown mode %d", d->mode);
     }
@@ -444,6 +469,10 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
     g.th = floor_pow2(g.Ho < BLOCK_M / g.tw ? g.Ho : BLOCK_M / g.tw);
     g.tn = BLOCK_M / (g.tw * g.th);
     g.tiles_x = (g.Wo + g.tw - 1) / g.tw;
+    if (d->mode == IPER_CONV_ROW5) {       // 128-pixel row segments, 124 outputs each (2-pixel halo either side)
+        g.tw = BLOCK_M; g.th = 1; g.tn = 1;
+        g.tiles_x = (g.Wo + (BLOCK_M - 4) - 1) / (BLOCK_M - 4);
+    }
     g.tiles_y = (g.Ho + g.th - 1) / g.th;
     g.tiles_nb = (g.N + g.tn - 1) / g.tn;
     g.m_tiles = g.tiles_x * g.tiles_y * g.tiles_nb;
@@ -463,11 +492,12 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
 
     // ---- epilogue-specific validation ----
     if (d->epi == IPER_EPI_HEADS) {
-        IPER_REQUIRE(d->block_n == 16 && d->rows == 16, "iper_conv_gemm: heads epilogue needs rows = block_n = 16");
+        IPER_REQUIRE(d->mode == IPER_CONV_ROW5 && d->block_n == 32 && d->rows == 32,
+                     "iper_conv_gemm: heads epilogue needs mode IPER_CONV_ROW5 and rows = block_n = 32");
         IPER_REQUIRE(d->mask || d->img || d->pred, "iper_conv_gemm: heads epilogue without outputs");
         IPER_REQUIRE(!d->pred || d->bg, "iper_conv_gemm: pred needs bg");
     } else {
-        IPER_REQUIRE(d->block_n >= 64, "iper_conv_gemm: block_n=16 is reserved for the heads epilogue");
+        IPER_REQUIRE(d->block_n >= 64 && d->mode != IPER_CONV_ROW5, "iper_conv_gemm: block_n=32 / ROW5 are reserved for the heads epilogue");
         IPER_REQUIRE(d->out != nullptr, "iper_conv_gemm: null output");
         IPER_REQUIRE(d->out_pitch % 8 == 0 && d->out_coff % 8 == 0, "iper_conv_gemm: output channel window must be 8-aligned");
         if (d->epi == IPER_EPI_SPADE) {
@@ -508,7 +538,7 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
 #define IPER_DISPATCH(BNV)                                                     \
     return ns == 2 ? launch_gemm<BNV, 2>(g, d->max_ctas, s) : launch_gemm<BNV, 1>(g, d->max_ctas, s)
     switch (d->block_n) {
-        case 16: IPER_DISPATCH(16);
+        case 32: IPER_DISPATCH(32);
         case 64: IPER_DISPATCH(64);
         case 128: IPER_DISPATCH(128);
         default: IPER_DISPATCH(256);

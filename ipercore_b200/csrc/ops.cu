@@ -170,35 +170,69 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Instance-norm statistics over an NHWC planes tensor: grid (C/32, N); block 256 = 8 pixel-lanes x 32 channels.
-// Each warp-row walks pixels with a stride, fp32 partial sums are combined in a fixed order (deterministic).
+// Instance-norm statistics over an NHWC planes tensor, two launches:
+//   partial: grid (splits, N), block 256; a thread owns 8 consecutive channels (one 128-bit load per plane),
+//            C/8 lanes cover a pixel, the rest of the block strides over the CTA's pixel chunk; fp32 partial sums
+//            per thread are folded into fp64 shared accumulators and then into a global fp64 workspace (N,C,2);
+//   final  : mean / rstd as fp32 (biased variance, eps inside the sqrt) — F.instance_norm semantics.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) instnorm_stats_kernel(const __half* __restrict__ x, int x_planes,
-                                                             long long x_plane_stride, int HW, int C, int x_pitch,
-                                                             int x_coff, float eps, float* __restrict__ mean_rstd) {
-    const int n = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), lane_p = threadIdx.x >> 5;
-    __shared__ double s_sum[8][33], s_sq[8][33];
-    double sum = 0.0, sq = 0.0;
-    if (c < C) {
-        const size_t base = (size_t)n * HW * x_pitch + x_coff + c;
-        for (int p = lane_p; p < HW; p += 8) {
-            const float v = load_plane_val(x, x_planes, x_plane_stride, base + (size_t)p * x_pitch);
-            sum += (double)v;
-            sq += (double)v * (double)v;
+__global__ void __launch_bounds__(256) instnorm_partial_kernel(const __half* __restrict__ x, int x_planes,
+                                                               long long x_plane_stride, int HW, int C, int x_pitch,
+                                                               int x_coff, int chunk, double* __restrict__ ws) {
+    __shared__ double s_acc[2 * 256];
+    const int n = blockIdx.y, tid = threadIdx.x;
+    const int lpp = C >> 3;                       // lanes per pixel
+    const int cg = tid % lpp, pl = tid / lpp;     // channel group, pixel lane
+    const int ppl = 256 / lpp;                    // pixel lanes per block
+    for (int i = tid; i < 2 * C; i += 256) s_acc[i] = 0.0;
+    __syncthreads();
+    float sum[8], sq[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { sum[j] = 0.f; sq[j] = 0.f; }
+    const int p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, HW);
+    const size_t base = (size_t)n * HW * x_pitch + x_coff + cg * 8;
+    if (pl < ppl) {
+        for (int p = p0 + pl; p < p1; p += ppl) {
+            const size_t off = base + (size_t)p * x_pitch;
+            uint4 u = __ldg(reinterpret_cast<const uint4*>(x + off));
+            float v[8];
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+                v[2 * j] = f.x; v[2 * j + 1] = f.y;
+            }
+            if (x_planes > 1) {
+                u = __ldg(reinterpret_cast<const uint4*>(x + x_plane_stride + off));
+                const uint32_t w2[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w2[j]));
+                    v[2 * j] += f.x; v[2 * j + 1] += f.y;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) { sum[j] += v[j]; sq[j] += v[j] * v[j]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            atomicAdd(&s_acc[2 * (cg * 8 + j)], (double)sum[j]);
+            atomicAdd(&s_acc[2 * (cg * 8 + j) + 1], (double)sq[j]);
         }
     }
-    s_sum[lane_p][threadIdx.x & 31] = sum;
-    s_sq[lane_p][threadIdx.x & 31] = sq;
     __syncthreads();
-    if (lane_p == 0 && c < C) {
-        double ts = 0.0, tq = 0.0;
-        for (int i = 0; i < 8; i++) { ts += s_sum[i][threadIdx.x & 31]; tq += s_sq[i][threadIdx.x & 31]; }
-        const double mean = ts / HW;
-        double var = tq / HW - mean * mean;   // biased variance (F.instance_norm)
-        if (var < 0.0) var = 0.0;
-        mean_rstd[((size_t)n * C + c) * 2 + 0] = (float)mean;
-        mean_rstd[((size_t)n * C + c) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
-    }
+    for (int i = tid; i < 2 * C; i += 256) atomicAdd(&ws[(size_t)n * 2 * C + i], s_acc[i]);
+}
+
+__global__ void instnorm_final_kernel(const double* __restrict__ ws, int total, int HW, float eps,
+                                      float* __restrict__ mean_rstd) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const double mean = ws[2 * i] / HW;
+    double var = ws[2 * i + 1] / HW - mean * mean;   // biased variance (F.instance_norm)
+    if (var < 0.0) var = 0.0;
+    mean_rstd[2 * i] = (float)mean;
+    mean_rstd[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -227,82 +261,91 @@ IPER_DEVINL Taps bilinear_taps(float gx, float gy, int h, int w) {
     return t;
 }
 
+template <int C, int NSMAX>
 __global__ void __launch_bounds__(256) warp_attention_kernel(const float* __restrict__ q, const float* __restrict__ kv,
                                                              const float* __restrict__ bias_k,
                                                              const float* __restrict__ bias_v,
                                                              const float* __restrict__ T, int B, int ns, int h, int w,
-                                                             int C, __half* __restrict__ out, int out_planes,
+                                                             __half* __restrict__ out, int out_planes,
                                                              long long out_plane_stride, int out_pitch, int out_coff) {
-    const int lane = threadIdx.x & 31;
-    const size_t hw = (size_t)h * w;
-    const size_t total = (size_t)B * hw;
+    // a thread owns 8 consecutive channels (two 128-bit loads per map); LPP lanes cover one pixel
+    constexpr int LPP = C / 8, PPW = 32 / LPP;
+    const int lane = threadIdx.x & 31, cg = lane % LPP, sub = lane / LPP;
+    const size_t hw = (size_t)h * w, total = (size_t)B * hw;
     const float inv_sqrt = 1.f / sqrtf((float)C);
-    const int nvec = C / 4;                     // float4 per pixel per map
-    for (size_t pix = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5); pix < total; pix += (size_t)gridDim.x * 8) {
-        const size_t b = pix / hw, p = pix % hw;
-        const float4* qp = reinterpret_cast<const float4*>(q + pix * C);
-        float4 qv[2];
+    float bk[8], bv[8];
 #pragma unroll
-        for (int j = 0; j < 2; j++) qv[j] = (lane + 32 * j < nvec) ? __ldg(qp + lane + 32 * j) : make_float4(0, 0, 0, 0);
-        float logit[ATT_MAX_NS];
-        float4 vacc[ATT_MAX_NS][2];
+    for (int j = 0; j < 8; j++) { bk[j] = __ldg(bias_k + cg * 8 + j); bv[j] = __ldg(bias_v + cg * 8 + j); }
+    const size_t warps = (size_t)gridDim.x * 8;
+    for (size_t wi = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5); wi * PPW < total; wi += warps) {
+        const size_t pix = wi * PPW + sub;
+        const bool live = pix < total;
+        const size_t pc = live ? pix : total - 1;           // keep the whole warp in the shuffles
+        const size_t b = pc / hw, p = pc % hw;
+        float qv[8];
+        {
+            const float4* qp = reinterpret_cast<const float4*>(q + pc * C + cg * 8);
+            const float4 q0 = __ldg(qp), q1 = __ldg(qp + 1);
+            qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w; qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
+        }
+        float logit[NSMAX];
+        float vacc[NSMAX][8];
 #pragma unroll
-        for (int s = 0; s < ATT_MAX_NS; s++) {
+        for (int s = 0; s < NSMAX; s++) {
             if (s >= ns) break;
-            const float2 g = reinterpret_cast<const float2*>(T)[(b * ns + s) * hw + p];
+            const float2 g = __ldg(reinterpret_cast<const float2*>(T) + (b * ns + s) * hw + p);
             const Taps t = bilinear_taps(g.x, g.y, h, w);
-            const float4* src = reinterpret_cast<const float4*>(kv + (size_t)s * hw * 2 * C);
+            const float* src = kv + (size_t)s * hw * 2 * C + cg * 8;
+            float kk[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) { kk[j] = 0.f; vacc[s][j] = 0.f; }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (t.off[i] < 0) continue;
+                const float4* px = reinterpret_cast<const float4*>(src + (size_t)t.off[i] * 2 * C);
+                const float4 k0 = __ldg(px), k1 = __ldg(px + 1), v0 = __ldg(px + C / 4), v1 = __ldg(px + C / 4 + 1);
+                const float wt = t.wt[i];
+                kk[0] += k0.x * wt; kk[1] += k0.y * wt; kk[2] += k0.z * wt; kk[3] += k0.w * wt;
+                kk[4] += k1.x * wt; kk[5] += k1.y * wt; kk[6] += k1.z * wt; kk[7] += k1.w * wt;
+                vacc[s][0] += v0.x * wt; vacc[s][1] += v0.y * wt; vacc[s][2] += v0.z * wt; vacc[s][3] += v0.w * wt;
+                vacc[s][4] += v1.x * wt; vacc[s][5] += v1.y * wt; vacc[s][6] += v1.z * wt; vacc[s][7] += v1.w * wt;
+            }
             float dot = 0.f;
 #pragma unroll
-            for (int j = 0; j < 2; j++) {
-                const int cv = lane + 32 * j;
-                float4 kk = make_float4(0, 0, 0, 0), vv = make_float4(0, 0, 0, 0);
-                if (cv < nvec) {
+            for (int j = 0; j < 8; j++) { dot += (kk[j] + bk[j]) * qv[j]; vacc[s][j] += bv[j]; }
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        if (t.off[i] < 0) continue;
-                        const float4* px = src + (size_t)t.off[i] * (2 * nvec);
-                        const float4 a = __ldg(px + cv), c4 = __ldg(px + nvec + cv);
-                        const float wt = t.wt[i];
-                        kk.x += a.x * wt; kk.y += a.y * wt; kk.z += a.z * wt; kk.w += a.w * wt;
-                        vv.x += c4.x * wt; vv.y += c4.y * wt; vv.z += c4.z * wt; vv.w += c4.w * wt;
-                    }
-                    const float4 bk = __ldg(reinterpret_cast<const float4*>(bias_k) + cv);
-                    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias_v) + cv);
-                    kk.x += bk.x; kk.y += bk.y; kk.z += bk.z; kk.w += bk.w;
-                    vv.x += bv.x; vv.y += bv.y; vv.z += bv.z; vv.w += bv.w;
-                    dot += kk.x * qv[j].x + kk.y * qv[j].y + kk.z * qv[j].z + kk.w * qv[j].w;
-                }
-                vacc[s][j] = vv;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+            for (int o = LPP / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
             logit[s] = dot * inv_sqrt;
         }
         float mx = -INFINITY;
 #pragma unroll
-        for (int s = 0; s < ATT_MAX_NS; s++) if (s < ns) mx = fmaxf(mx, logit[s]);
+        for (int s = 0; s < NSMAX; s++) if (s < ns) mx = fmaxf(mx, logit[s]);
         float den = 0.f;
 #pragma unroll
-        for (int s = 0; s < ATT_MAX_NS; s++) if (s < ns) { logit[s] = expf(logit[s] - mx); den += logit[s]; }
+        for (int s = 0; s < NSMAX; s++) if (s < ns) { logit[s] = expf(logit[s] - mx); den += logit[s]; }
         const float rden = 1.f / den;
+        float o8[8];
 #pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const int cv = lane + 32 * j;
-            if (cv >= nvec) continue;
-            float4 o = make_float4(0, 0, 0, 0);
+        for (int j = 0; j < 8; j++) o8[j] = 0.f;
 #pragma unroll
-            for (int s = 0; s < ATT_MAX_NS; s++) {
-                if (s >= ns) break;
-                const float al = logit[s] * rden;
-                o.x += al * vacc[s][j].x; o.y += al * vacc[s][j].y; o.z += al * vacc[s][j].z; o.w += al * vacc[s][j].w;
+        for (int s = 0; s < NSMAX; s++) {
+            if (s >= ns) break;
+            const float al = logit[s] * rden;
+#pragma unroll
+            for (int j = 0; j < 8; j++) o8[j] += al * vacc[s][j];
+        }
+        if (live) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                __half h0, l0, h1, l1;
+                split_half(o8[2 * j], h0, l0); split_half(o8[2 * j + 1], h1, l1);
+                hi[j] = pack_half2(h0, h1); lo[j] = pack_half2(l0, l1);
             }
-            __half h0, l0, h1, l1, h2, l2, h3, l3;
-            split_half(o.x, h0, l0); split_half(o.y, h1, l1); split_half(o.z, h2, l2); split_half(o.w, h3, l3);
-            const size_t off = pix * out_pitch + out_coff + 4 * cv;
-            *reinterpret_cast<uint2*>(out + off) = make_uint2(pack_half2(h0, h1), pack_half2(h2, h3));
+            const size_t off = pix * out_pitch + out_coff + cg * 8;
+            *reinterpret_cast<uint4*>(out + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
             if (out_planes > 1)
-                *reinterpret_cast<uint2*>(out + out_plane_stride + off) = make_uint2(pack_half2(l0, l1), pack_half2(l2, l3));
+                *reinterpret_cast<uint4*>(out + out_plane_stride + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
     }
 }
@@ -441,12 +484,26 @@ extern "C" int iper_conv_stem(const float* in_nchw, int N, int Cin, int H, int W
 }
 
 extern "C" int iper_instnorm_stats(const void* x, int x_planes, long long x_plane_stride, int N, int HW, int C,
-                                   int x_pitch, int x_coff, float eps, float* mean_rstd, iper_stream_t stream) {
-    IPER_REQUIRE(x && mean_rstd, "iper_instnorm_stats: null pointer");
+                                   int x_pitch, int x_coff, float eps, double* workspace, float* mean_rstd,
+                                   iper_stream_t stream) {
+    IPER_REQUIRE(x && mean_rstd && workspace, "iper_instnorm_stats: null pointer");
+    IPER_REQUIRE(C % 8 == 0 && C >= 8 && C <= 256 && 256 % (C / 8) == 0,
+                 "iper_instnorm_stats: C=%d must be 8..256 with C/8 a power of two", C);
+    IPER_REQUIRE(x_pitch % 8 == 0 && x_coff % 8 == 0, "iper_instnorm_stats: channel window must be 8-aligned");
     if (N == 0) return 0;
-    dim3 grid((C + 31) / 32, N);
-    instnorm_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __half*>(x), x_planes,
-                                                                  x_plane_stride, HW, C, x_pitch, x_coff, eps, mean_rstd);
+    cudaStream_t s = (cudaStream_t)stream;
+    IPER_CHECK_CUDA(cudaMemsetAsync(workspace, 0, sizeof(double) * 2 * (size_t)N * C, s));
+    // enough CTAs to fill the machine (~4 per SM), at least 256 pixels per CTA
+    int splits = (148 * 4 + N - 1) / N;
+    const int max_splits = (HW + 255) / 256;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    const int chunk = (HW + splits - 1) / splits;
+    dim3 grid((HW + chunk - 1) / chunk, N);
+    instnorm_partial_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(x), x_planes, x_plane_stride, HW, C,
+                                                 x_pitch, x_coff, chunk, workspace);
+    IPER_CHECK_CUDA(cudaGetLastError());
+    instnorm_final_kernel<<<(N * C + 255) / 256, 256, 0, s>>>(workspace, N * C, HW, eps, mean_rstd);
     IPER_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -456,14 +513,25 @@ extern "C" int iper_warp_attention(const float* q, const float* kv, const float*
                                    long long out_plane_stride, int out_pitch, int out_coff, iper_stream_t stream) {
     IPER_REQUIRE(q && kv && bias_k && bias_v && T && out, "iper_warp_attention: null pointer");
     IPER_REQUIRE(ns >= 1 && ns <= ATT_MAX_NS, "iper_warp_attention: ns=%d not in [1,%d]", ns, ATT_MAX_NS);
-    IPER_REQUIRE(C % 4 == 0 && C <= 256, "iper_warp_attention: C=%d must be a multiple of 4, <= 256", C);
-    IPER_REQUIRE(out_pitch % 4 == 0 && out_coff % 4 == 0, "iper_warp_attention: output window must be 4-aligned");
+    IPER_REQUIRE(C == 64 || C == 128 || C == 256, "iper_warp_attention: C=%d not in {64,128,256}", C);
+    IPER_REQUIRE(out_pitch % 8 == 0 && out_coff % 8 == 0, "iper_warp_attention: output window must be 8-aligned");
     const size_t total = (size_t)B * h * w;
     if (total == 0) return 0;
-    const int blocks = (int)min((size_t)148 * 8, (total + 7) / 8);
-    warp_attention_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(q, kv, bias_k, bias_v, T, B, ns, h, w, C,
-                                                                   reinterpret_cast<__half*>(out), out_planes,
-                                                                   out_plane_stride, out_pitch, out_coff);
+    const int ppw = 32 / (C / 8);
+    const size_t nwarps = (total + ppw - 1) / ppw;
+    const int blocks = (int)min((size_t)148 * 16, (nwarps + 7) / 8);
+    __half* o = reinterpret_cast<__half*>(out);
+    cudaStream_t st = (cudaStream_t)stream;
+#define IPER_ATT(CV, NV)                                                                                             \
+    warp_attention_kernel<CV, NV><<<blocks, 256, 0, st>>>(q, kv, bias_k, bias_v, T, B, ns, h, w, o, out_planes,         \
+                                                          out_plane_stride, out_pitch, out_coff)
+#define IPER_ATT_C(CV)                                                                                               \
+    do {                                                                                                             \
+        if (ns <= 2) IPER_ATT(CV, 2); else if (ns <= 4) IPER_ATT(CV, 4); else IPER_ATT(CV, 8);                       \
+    } while (0)
+    if (C == 64) IPER_ATT_C(64); else if (C == 128) IPER_ATT_C(128); else IPER_ATT_C(256);
+#undef IPER_ATT_C
+#undef IPER_ATT
     IPER_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -211,8 +211,7 @@ class AttentionLWBGenerator(nn.Module):
             convT("tsf_net_dec.upconvs.%d.0" % i)
         for i in range(2):
             conv("tsf_net_dec.skippers.%d.0" % i)
-        heads = torch.cat([sd["tsf_img_reg.0.weight"], sd["tsf_att_reg.0.weight"]], 0)     # (4, 64, 5, 5)
-        pk["tsf_heads"] = (ops.pack_conv_weight(heads, P, pad_rows_to=16), None)
+        pk["tsf_heads"] = (ops.pack_heads_weight(sd["tsf_img_reg.0.weight"], sd["tsf_att_reg.0.weight"], P), None)
         self._packed, self._packed_key = pk, key
         return pk
 
@@ -354,7 +353,7 @@ class AttentionLWBGenerator(nn.Module):
             pred = torch.empty((B, 3, S, S), dtype=torch.float32, device=dev)
             heads.update(bg=bg_img, pred=pred)
         wh, _ = pk["tsf_heads"]
-        ops.conv_gemm(d2, wh, IPER_CONV_S1, 5, 16, 16, IPER_EPI_HEADS, heads=heads)
+        ops.conv_gemm(d2, wh, ops.IPER_CONV_ROW5, 5, 32, 32, IPER_EPI_HEADS, heads=heads)
         return (img, mask, pred) if return_pred else (img, mask)
 
     # -------------------------------------------------------------------------------------------------------------

@@ -6,7 +6,7 @@ import math
 import torch
 
 from . import _lib
-from ._lib import (ConvGemmDesc, IPER_CONV_S1, IPER_CONV_S2, IPER_CONVT_4S2, IPER_EPI_F32, IPER_EPI_HEADS,
+from ._lib import (ConvGemmDesc, IPER_CONV_ROW5, IPER_CONV_S1, IPER_CONV_S2, IPER_CONVT_4S2, IPER_EPI_F32, IPER_EPI_HEADS,
                    IPER_EPI_PLANES, IPER_EPI_SPADE, check, lib)
 
 # nmr.py:225 eye z, converted to float32 inside nr.look_at
@@ -195,8 +195,9 @@ def conv_stem(x_nchw, w_f32, bias, out):
 def instnorm_stats(x, eps=1e-5, out=None):
     if out is None:
         out = torch.empty((x.N, x.C, 2), dtype=torch.float32, device=x.data.device)
+    ws = torch.empty((x.N, x.C, 2), dtype=torch.float64, device=x.data.device)
     check(lib.iper_instnorm_stats(x.ptr(), x.P, x.plane_stride, x.N, x.H * x.W, x.C, x.pitch, x.coff, eps,
-                                  out.data_ptr(), _stream()), "instnorm_stats")
+                                  ws.data_ptr(), out.data_ptr(), _stream()), "instnorm_stats")
     return out
 
 
@@ -248,6 +249,16 @@ def pack_conv_weight(w, P, pad_rows_to=None):
     m = w.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).float()
     if pad_rows_to is not None and pad_rows_to > Cout:
         m = torch.cat([m, m.new_zeros(pad_rows_to - Cout, m.shape[1])], 0)
+    return split_planes(m, P)
+
+
+def pack_heads_weight(w_img, w_mask, P):
+    """tsf_img_reg (3,64,5,5) + tsf_att_reg (1,64,5,5) -> (P, 32, 5*64) for IPER_CONV_ROW5:
+    row n = dx*4 + o (o = r,g,b,mask; rows 20..31 zero), K = (dy, cin)."""
+    w = torch.cat([w_img, w_mask], 0).float()                  # (4, C, 5, 5) [o, c, dy, dx]
+    C = w.shape[1]
+    m = w.permute(3, 0, 2, 1).reshape(5 * 4, 5 * C)            # (dx, o) x (dy, c)
+    m = torch.cat([m, m.new_zeros(32 - 20, 5 * C)], 0)
     return split_planes(m, P)
 
 

@@ -121,17 +121,18 @@ def test_conv_gemm_spade_epilogue(C, P):
     np.testing.assert_allclose(_planes_value(chk).numpy(), exp.numpy(), atol=1e-4 if P == 2 else 3e-3, rtol=0)
 
 
-def test_conv_gemm_heads_epilogue():
+@pytest.mark.parametrize("S", [32, 300])
+def test_conv_gemm_heads_epilogue(S):
     """5x5 heads (64->3 tanh, 64->1 sigmoid) + composite (imitator.py:393)."""
     from ipercore_b200 import ops
     from ipercore_b200.ops import Planes
-    P, N, S = 2, 2, 32
+    P, N = 2, 2
     x = F.relu(_rand((N, 64, S, S), 31)); wi = _rand((3, 64, 5, 5), 32, 0.03); wm = _rand((1, 64, 5, 5), 33, 0.03)
     bgimg = _rand((1, 3, S, S), 34)
     a = Planes.from_nchw(x.to(DEV), P); xq = _planes_value(a)
-    wp = ops.pack_conv_weight(torch.cat([wi, wm], 0), P, pad_rows_to=16).to(DEV)
+    wp = ops.pack_heads_weight(wi, wm, P).to(DEV)
     img = torch.empty((N, 3, S, S), device=DEV); mask = torch.empty((N, 1, S, S), device=DEV); pred = torch.empty((N, 3, S, S), device=DEV)
-    ops.conv_gemm(a, wp, 0, 5, 16, 16, ops.IPER_EPI_HEADS, heads=dict(img=img, mask=mask, pred=pred, bg=bgimg.to(DEV)))
+    ops.conv_gemm(a, wp, ops.IPER_CONV_ROW5, 5, 32, 32, ops.IPER_EPI_HEADS, heads=dict(img=img, mask=mask, pred=pred, bg=bgimg.to(DEV)))
     q = lambda t: ops.split_planes(t, P).float().sum(0)
     ei = torch.tanh(F.conv2d(xq, q(wi), padding=2)); em = torch.sigmoid(F.conv2d(xq, q(wm), padding=2))
     np.testing.assert_allclose(img.cpu().numpy(), ei.numpy(), atol=2e-5, rtol=0)
