@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--ns", type=int, default=2)
     ap.add_argument("--precision", default="fp16x2", choices=["fp16x2", "fp16"])
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--streams", type=int, default=1, help="engines replaying alternate batches on separate streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=8)
     return ap.parse_args()
@@ -176,7 +177,7 @@ def config_block(args, launches):
     return {"workload": "run_imitator %dx%d: 1 source set (ns=%d) -> %d synthetic target SMPL poses per GPU "
                         "(BASELINE.json configs[1])" % (args.size, args.size, args.ns, args.frames),
             "image_size": args.size, "num_source": args.ns, "frames_per_step_per_gpu": args.frames, "batch": args.batch,
-            "precision": args.precision, "cuda_graph": not args.no_graph,
+            "precision": args.precision, "cuda_graph": not args.no_graph, "streams": args.streams,
             "l2": "per-step working set (activations of %d-frame batches, several GB) exceeds the 126 MB L2" % args.batch,
             "weights": "synthetic (oracle/weights.py), reference 221-tensor layout"}
 
@@ -213,8 +214,12 @@ def main():
     src_f2pts, sfim, _ = render.render_fim_wim(t(wl["scams"]), t(wl["sverts"]))
     scond, _ = render.encode_fim(fim=sfim)
     src_inputs = torch.cat([t(wl["src_img"]), scond], 1)[None]
-    eng = FrameEngine(gen, render, batch=args.batch, use_graph=not args.no_graph, device=dev)
-    eng.set_source(src_inputs, t(wl["uv_img"]), t(wl["bg_img"]), src_f2pts)
+    engines = []
+    for _ in range(max(args.streams, 1)):
+        e = FrameEngine(gen, render, batch=args.batch, use_graph=not args.no_graph, device=dev)
+        e.set_source(src_inputs, t(wl["uv_img"]), t(wl["bg_img"]), src_f2pts)
+        engines.append(e)
+    eng = engines[0]
 
     T, B = args.frames, args.batch
     cams_d, verts_d = t(wl["cams"]), t(wl["verts"])
@@ -227,10 +232,12 @@ def main():
     def step_device():
         for i in range(nb):
             lo, hi = i * B, min((i + 1) * B, T)
-            u8 = eng.run_batch_device(cams_d[lo:hi], verts_d[lo:hi])
-            with torch.cuda.stream(eng.compute):
+            e = engines[i % len(engines)]
+            u8 = e.run_batch_device(cams_d[lo:hi], verts_d[lo:hi])
+            with torch.cuda.stream(e.compute):
                 out_d[lo:hi].copy_(u8[:hi - lo], non_blocking=True)
-        cur.wait_stream(eng.compute)
+        for e in engines:
+            cur.wait_stream(e.compute)
 
     def step_e2e():
         eng.synthesize(cams_h, verts_h, out=out_h)
@@ -243,13 +250,15 @@ def main():
 
     def timed(fn, steps, sampler=None):
         barrier()
-        eng.compute.wait_stream(cur); eng.copy.wait_stream(cur)
+        for e in engines:
+            e.compute.wait_stream(cur); e.copy.wait_stream(cur)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if sampler:
             sampler.start()
         w0 = time.perf_counter()
         e0.record(cur)
-        eng.compute.wait_event(e0); eng.copy.wait_event(e0)
+        for e in engines:
+            e.compute.wait_event(e0); e.copy.wait_event(e0)
         for _ in range(steps):
             fn()
         e1.record(cur)

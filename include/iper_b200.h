@@ -116,6 +116,16 @@ int iper_conv_stem(const float* in_nchw, int N, int Cin, int H, int W, const flo
 int iper_instnorm_stats(const void* x, int x_planes, long long x_plane_stride, int N, int HW, int C, int x_pitch,
                         int x_coff, float eps, double* workspace, float* mean_rstd, iper_stream_t stream);
 
+/* InstanceNorm2d(affine=False) apply [+ReLU] [+ residual] on NHWC planes — the BGNet blocks (bg_inpaintor.py:13-21,
+ * 33-52): out = [res +] [relu]((x - mean) * rstd). */
+int iper_instnorm_apply(const void* x, int x_planes, long long x_plane_stride, int x_pitch, int x_coff,
+                        const float* mean_rstd, int N, int HW, int C, int relu, const void* res, int res_planes,
+                        long long res_plane_stride, int res_pitch, int res_coff, void* out, int out_planes,
+                        long long out_plane_stride, int out_pitch, int out_coff, iper_stream_t stream);
+
+/* tanh + NHWC fp32 (pitch channels per pixel, first C used) -> NCHW fp32: last layer of BGNet (bg_inpaintor.py:54-55). */
+int iper_tanh_nhwc_to_nchw(const float* in, int N, int HW, int C, int pitch, float* out, iper_stream_t stream);
+
 /* Flow-guided warp + per-pixel source attention (LWB.transform :184-191, SelfAttentionBlock :102-139), using
  * fk(warp(x)) = warp(Wk x) + bk:  kv (ns,h,w,2C) fp32 holds [Wk x | Wv x] per source (no bias);
  * q (B,h,w,C) fp32 (bias included); T (B,ns,h,w,2) flow at this resolution.

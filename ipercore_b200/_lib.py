@@ -49,6 +49,9 @@ SIGNATURES = {
                        c_int, c_void_p],
     "iper_instnorm_stats": [c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                             c_void_p],
+    "iper_instnorm_apply": [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                            c_ll, c_int, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p],
+    "iper_tanh_nhwc_to_nchw": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "iper_warp_attention": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                             c_void_p, c_int, c_ll, c_int, c_int, c_void_p],
     "iper_warp_nhwc": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],

@@ -235,6 +235,36 @@ __global__ void instnorm_final_kernel(const double* __restrict__ ws, int total, 
     mean_rstd[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// InstanceNorm2d apply (+ReLU) (+residual) on NHWC planes — BGNet blocks (bg_inpaintor.py:13-21, 33-52)
+__global__ void __launch_bounds__(256) instnorm_apply_kernel(const __half* __restrict__ x, int x_planes,
+                                                             long long x_plane_stride, int x_pitch, int x_coff,
+                                                             const float* __restrict__ mean_rstd, int N, int HW, int C,
+                                                             int relu, const __half* __restrict__ res, int res_planes,
+                                                             long long res_plane_stride, int res_pitch, int res_coff,
+                                                             __half* __restrict__ out, int out_planes,
+                                                             long long out_plane_stride, int out_pitch, int out_coff) {
+    const size_t total = (size_t)N * HW * C;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const size_t pix = i / C;
+        const int n = (int)(pix / HW);
+        const float* mr = mean_rstd + ((size_t)n * C + c) * 2;
+        float v = (load_plane_val(x, x_planes, x_plane_stride, pix * x_pitch + x_coff + c) - mr[0]) * mr[1];
+        if (relu) v = fmaxf(v, 0.f);
+        if (res) v = load_plane_val(res, res_planes, res_plane_stride, pix * res_pitch + res_coff + c) + v;
+        store_plane_val(out, out_planes, out_plane_stride, pix * out_pitch + out_coff + c, v);
+    }
+}
+
+__global__ void tanh_nhwc_to_nchw_kernel(const float* __restrict__ in, int N, int HW, int C, int pitch,
+                                         float* __restrict__ out) {
+    const size_t total = (size_t)N * C * HW;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = i % HW, c = (i / HW) % C, n = i / ((size_t)HW * C);
+        out[i] = tanhf(in[(n * HW + p) * pitch + c]);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Flow-guided warp + per-pixel source attention.  One warp per target pixel; lanes stride the channel dimension
 // with 128-bit (4 x fp32) gathers from the precomputed [Wk x | Wv x] source maps.  Bilinear taps / zero padding
@@ -586,6 +616,33 @@ extern "C" int iper_pred_to_u8(const float* pred, int B, int S, uint8_t* out, ip
     if (total == 0) return 0;
     const int blocks = (int)min((size_t)148 * 16, (total + 255) / 256);
     pred_to_u8_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pred, B, (size_t)S * S, out);
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int iper_instnorm_apply(const void* x, int x_planes, long long x_plane_stride, int x_pitch, int x_coff,
+                                   const float* mean_rstd, int N, int HW, int C, int relu, const void* res,
+                                   int res_planes, long long res_plane_stride, int res_pitch, int res_coff, void* out,
+                                   int out_planes, long long out_plane_stride, int out_pitch, int out_coff,
+                                   iper_stream_t stream) {
+    IPER_REQUIRE(x && mean_rstd && out, "iper_instnorm_apply: null pointer");
+    const size_t total = (size_t)N * HW * C;
+    if (total == 0) return 0;
+    const int blocks = (int)min((size_t)148 * 16, (total + 255) / 256);
+    instnorm_apply_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const __half*>(x), x_planes, x_plane_stride, x_pitch, x_coff, mean_rstd, N, HW, C, relu,
+        reinterpret_cast<const __half*>(res), res_planes, res_plane_stride, res_pitch, res_coff,
+        reinterpret_cast<__half*>(out), out_planes, out_plane_stride, out_pitch, out_coff);
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int iper_tanh_nhwc_to_nchw(const float* in, int N, int HW, int C, int pitch, float* out, iper_stream_t stream) {
+    IPER_REQUIRE(in && out, "iper_tanh_nhwc_to_nchw: null pointer");
+    const size_t total = (size_t)N * HW * C;
+    if (total == 0) return 0;
+    const int blocks = (int)min((size_t)148 * 16, (total + 255) / 256);
+    tanh_nhwc_to_nchw_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, N, HW, C, pitch, out);
     IPER_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -211,6 +211,15 @@ class AttentionLWBGenerator(nn.Module):
             convT("tsf_net_dec.upconvs.%d.0" % i)
         for i in range(2):
             conv("tsf_net_dec.skippers.%d.0" % i)
+        # BGNet (one-time per source): tensor-core layers packed, the two 7x7 ends stay fp32 for the CUDA-core kernel
+        pk["bg.in"] = (sd["bg_net.main.0.weight"], sd["bg_net.main.0.bias"])
+        for idx in (3, 6, 9):
+            conv("bg_net.main.%d" % idx)
+        for idx in range(12, 12 + self.n_res):
+            conv("bg_net.main.%d.main.0" % idx); conv("bg_net.main.%d.main.3" % idx)
+        for idx in (18, 21, 24):
+            convT("bg_net.main.%d" % idx)
+        pk["bg.out"] = sd["bg_net.main.27.weight"]
         pk["tsf_heads"] = (ops.pack_heads_weight(sd["tsf_img_reg.0.weight"], sd["tsf_att_reg.0.weight"], P), None)
         self._packed, self._packed_key = pk, key
         return pk
@@ -357,9 +366,45 @@ class AttentionLWBGenerator(nn.Module):
         return (img, mask, pred) if return_pred else (img, mask)
 
     # -------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
     def forward_bg(self, bg_inputs):
-        raise NotImplementedError("forward_bg (BGNet, one-time per source — SURVEY.md §8(f) rank 2) is not ported yet; "
-                                  "pass a background image (Imitator.source_setup bg_img=...)")
+        """AttentionLWBGenerator.forward_bg (attlwb_spade_resunet.py:615-631) -> ResNetInpaintor (bg_inpaintor.py:24-60).
+        bg_inputs (bs, ns, 4, S, S) -> (bs, ns, 3, S, S).  One-time per source (imitator.py:226)."""
+        pk = self._pack()
+        bs, ns, _, S, _ = bg_inputs.shape
+        N, P, dev = bs * ns, self.P, bg_inputs.device
+        x_in = Planes.from_nchw(bg_inputs.reshape(N, -1, S, S).float().contiguous(), P, pitch=8)    # 4 -> pitch 8
+
+        def in_relu(x, relu=True, res=None):
+            return ops.instnorm_apply(x, ops.instnorm_stats(x), Planes.empty(P, x.N, x.H, x.W, x.C, dev), relu=relu, res=res)
+
+        w, b = pk["bg.in"]
+        x = Planes.empty(P, N, S, S, 64, dev)
+        ops.conv_direct(x_in, w, IPER_CONV_S1, 7, 64, IPER_EPI_PLANES, bias=b, out=x)          # conv7x7 4->64 (CUDA cores)
+        x = in_relu(x)
+        for idx, c in ((3, 128), (6, 128), (9, 256)):
+            y = Planes.empty(P, N, x.H // 2, x.W // 2, c, dev)
+            x = in_relu(self._conv(pk, "bg_net.main.%d" % idx, x, IPER_CONV_S2, 3, y))
+        for idx in range(12, 12 + self.n_res):
+            y = Planes.empty(P, N, x.H, x.W, 256, dev)
+            y = in_relu(self._conv(pk, "bg_net.main.%d.main.0" % idx, x, IPER_CONV_S1, 3, y))
+            z = Planes.empty(P, N, x.H, x.W, 256, dev)
+            x = in_relu(self._conv(pk, "bg_net.main.%d.main.3" % idx, y, IPER_CONV_S1, 3, z), relu=False, res=x)
+        for idx, c in ((18, 128), (21, 128), (24, 64)):
+            y = Planes.empty(P, N, 2 * x.H, 2 * x.W, c, dev)
+            x = in_relu(self._conv(pk, "bg_net.main.%d" % idx, x, IPER_CONVT_4S2, 4, y))
+        o = torch.empty((N, S, S, 3), dtype=torch.float32, device=dev)
+        ops.conv_direct(x, pk["bg.out"], IPER_CONV_S1, 7, 3, IPER_EPI_F32, out=o)              # conv7x7 64->3
+        return ops.tanh_nhwc_to_nchw(o, 3).view(bs, ns, 3, S, S)
 
     def forward(self, bg_inputs, src_inputs, tsf_inputs, Tst, Ttt=None, only_tsf=True):
-        raise NotImplementedError("the training-shape forward (BGNet + SIDNet decoder) is not on the B200 hot path yet")
+        """AttentionLWBGenerator.forward (attlwb_spade_resunet.py:633-699), inference shape (only_tsf=True, no grad)."""
+        if not only_tsf:
+            raise NotImplementedError("only_tsf=False (SIDNet decoder outputs, training only) is not on the B200 path")
+        bg_img = self.forward_bg(bg_inputs)
+        enc, res = self.forward_src(src_inputs, only_enc=True)
+        imgs, masks = [], []
+        for t in range(tsf_inputs.shape[1]):
+            i, m = self.forward_tsf(tsf_inputs[:, t].contiguous(), enc, res, Tst[:, t].contiguous())
+            imgs.append(i); masks.append(m)
+        return bg_img, torch.stack(imgs, dim=1), torch.stack(masks, dim=1)

@@ -201,6 +201,24 @@ def instnorm_stats(x, eps=1e-5, out=None):
     return out
 
 
+def instnorm_apply(x, stats, out, relu=False, res=None):
+    """out = [res +] [relu](IN(x)) on Planes (bg_inpaintor.py ResidualBlock / conv-IN-ReLU blocks)."""
+    r = res
+    check(lib.iper_instnorm_apply(x.ptr(), x.P, x.plane_stride, x.pitch, x.coff, stats.data_ptr(), x.N, x.H * x.W, x.C,
+                                  int(relu), 0 if r is None else r.ptr(), 0 if r is None else r.P,
+                                  0 if r is None else r.plane_stride, 0 if r is None else r.pitch,
+                                  0 if r is None else r.coff, out.ptr(), out.P, out.plane_stride, out.pitch, out.coff,
+                                  _stream()), "instnorm_apply")
+    return out
+
+
+def tanh_nhwc_to_nchw(x, C):
+    N, H, W, pitch = x.shape
+    out = torch.empty((N, C, H, W), dtype=torch.float32, device=x.device)
+    check(lib.iper_tanh_nhwc_to_nchw(x.data_ptr(), N, H * W, C, pitch, out.data_ptr(), _stream()), "tanh_nhwc_to_nchw")
+    return out
+
+
 def warp_attention(q, kv, bias_k, bias_v, T, out):
     """q (B,h,w,C) f32; kv (ns,h,w,2C) f32; T (B,ns,h,w,2) f32 -> out Planes (B,h,w,C)."""
     B, h, w, C = q.shape; ns = kv.shape[0]

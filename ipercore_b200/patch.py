@@ -1,0 +1,144 @@
+"""install() — swap the B200 kernels into an importable iPERCore so its services run unchanged (seam B4).
+
+    import ipercore_b200.patch as p; p.install()          # before `import iPERCore.models` / services
+    from iPERCore.services.run_imitator import run_imitator
+
+What is replaced, at the reference's own seams:
+  B1  ``sys.modules["neural_renderer"]``  -> ipercore_b200.neural_renderer  (nmr.py:8 imports it as ``nr``)
+  B2  ``BaseSMPLRenderer/SMPLRenderer.render_fim_wim``, ``cal_bc_transform``, ``encode_fim`` (nmr.py:319-342, 390-401,
+      713-757, and the bs==3 loop :892-918) -> fused CUDA kernels; every other method and all buffers stay the reference's
+  B3  ``NetworksFactory.get_by_name("AttLWB-SPADE", cfg=..., temporal=False)`` (networks/__init__.py:14-16)
+      -> ipercore_b200.generator.AttentionLWBGenerator (loads the same checkpoints)
+  B4  ``Imitator.inference`` (models/imitator.py:327-382) -> batched FrameEngine when ``temporal`` is false and the
+      generator is ours; same arguments, same ``pred_{:0>8}.png`` outputs / returned list.
+Nothing else of iPERCore is touched: options, preprocessing, personalisation, source_setup, video fusion stay upstream.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+_INSTALLED = False
+
+
+def install(precision="fp16x2", batch=16, patch_inference=True):
+    global _INSTALLED
+    if _INSTALLED:
+        return
+    from . import neural_renderer as nr
+    from . import ops
+    sys.modules["neural_renderer"] = nr                                   # B1
+    from iPERCore.tools.human_digitalizer.renders import nmr               # noqa: E402  (imports `nr` -> ours)
+
+    def render_fim_wim(self, cam, vertices, smpl_faces=True):             # B2 (any batch size, incl. 3)
+        faces = self.smpl_faces if smpl_faces else self.obj_faces
+        out = ops.raster_frames(vertices.float().contiguous(), cam.float().contiguous(), faces.int().contiguous(),
+                                self.image_size)
+        return out["f2pts"], out["fim"], out["wim"]
+
+    def cal_bc_transform(self, src_f2pts, dst_fims, dst_wims):
+        return ops.cal_bc_transform(src_f2pts.float(), dst_fims.int(), dst_wims.float())
+
+    def encode_fim(self, cam=None, vertices=None, fim=None, transpose=True, map_fn=None):
+        assert (cam is not None and vertices is not None) or fim is not None
+        return ops.encode_fim(fim.int(), (self.map_fn if map_fn is None else map_fn).float(), transpose), fim
+
+    for cls in (nmr.BaseSMPLRenderer, nmr.SMPLRenderer):
+        cls.render_fim_wim = render_fim_wim
+        cls.cal_bc_transform = cal_bc_transform
+        cls.encode_fim = encode_fim
+
+    from iPERCore.models.networks import NetworksFactory                   # B3
+    from .generator import AttentionLWBGenerator
+    upstream_get = NetworksFactory.get_by_name
+
+    def get_by_name(network_name, *args, **kwargs):
+        if network_name == "AttLWB-SPADE" and not kwargs.get("temporal", False):
+            net = AttentionLWBGenerator(*args, precision=precision, **kwargs)
+            print("Network %s was created (ipercore_b200, %s)" % (network_name, precision))
+            return net
+        return upstream_get(network_name, *args, **kwargs)
+
+    NetworksFactory.get_by_name = staticmethod(get_by_name)
+
+    if patch_inference:                                                    # B4
+        from iPERCore.models import imitator as imod
+        upstream_inference = imod.Imitator.inference
+
+        def inference(self, tgt_smpls, cam_strategy="smooth", output_dir="", prefix="pred_", use_selected_f2pts=False,
+                      visualizer=None, verbose=True):
+            ours = isinstance(self.generator, AttentionLWBGenerator)
+            if not ours or self._opt.temporal or visualizer is not None or use_selected_f2pts or self._opt.only_vis:
+                return upstream_inference(self, tgt_smpls, cam_strategy, output_dir, prefix, use_selected_f2pts,
+                                          visualizer, verbose)
+            return batched_inference(self, tgt_smpls, cam_strategy, output_dir, prefix, batch)
+
+        imod.Imitator.inference = inference
+    _INSTALLED = True
+
+
+@torch.no_grad()
+def batched_inference(imitator, tgt_smpls, cam_strategy="smooth", output_dir="", prefix="pred_", batch=16):
+    """Imitator.inference (models/imitator.py:327-382) with the bs=1 loop replaced by the batched engine.
+
+    Per-sequence host pre-pass exactly as upstream (:337-339, :298-305): stabilise, first_cam, cam swap; the SMPL body
+    model (upstream SMPLH.get_details) still produces the vertices — it is row (f) rank 1 of SURVEY.md §8, not yet a
+    CUDA kernel here — in chunks of `batch` frames; frames then go through FrameEngine and are written with the
+    reference's file names.  Returns the list of paths (or of CHW float arrays when output_dir is empty)."""
+    from .engine import FrameEngine
+    import cv2
+    dev, opt, src = imitator.device, imitator._opt, imitator.src_info
+    tgt = torch.tensor(tgt_smpls).float().to(dev)
+    if cam_strategy == "smooth":
+        tgt = imitator.weak_cam_swapper.stabilize(tgt)
+    imitator.first_cam = tgt[0:1, 0:3].clone() if cam_strategy == "smooth" else None
+    eng = getattr(imitator, "_iper_engine", None)
+    if eng is None or eng.B != batch:
+        eng = FrameEngine(imitator.generator, _EngineRenderer(imitator.flow_comp.render), batch=batch, device=dev)
+        imitator._iper_engine = eng
+    eng.gen = imitator.generator
+    enc, res = src["feats"]
+    eng.src = dict(enc=enc, res=res, uv_img=src["uv_img"].float().contiguous(),
+                   bg=src["bg"].float().reshape(1, 3, opt.image_size, opt.image_size).contiguous(),
+                   src_f2pts=src["f2pts"].float().contiguous())
+    eng.graph = None
+    T = tgt.shape[0]
+    cams, verts = [], []
+    for lo in range(0, T, batch):
+        t = tgt[lo:lo + batch]
+        n = t.shape[0]
+        cam = imitator.weak_cam_swapper.cam_swap(src["cam"][0:1].expand(n, -1), t[:, 0:3],
+                                                 imitator.first_cam.expand(n, -1) if imitator.first_cam is not None else None,
+                                                 cam_strategy)
+        ref_smpl = torch.cat([cam, t[:, 3:-10], src["shape"][0:1].expand(n, -1)], dim=1)
+        info = imitator.body_rec.get_details(ref_smpl, src["offsets"], links_ids=src["links_ids"])
+        cams.append(info["cam"]); verts.append(info["verts"])
+    frames = eng.synthesize(torch.cat(cams).float().cpu().pin_memory(), torch.cat(verts).float().cpu().pin_memory())
+    torch.cuda.synchronize(dev)
+    outputs = []
+    for t in range(T):
+        if output_dir:
+            path = os.path.join(output_dir, prefix + "{:0>8}.png".format(t))
+            cv2.imwrite(path, frames[t].numpy())           # already uint8 BGR HWC (cv_utils.save_cv2_img semantics)
+            outputs.append(path)
+        else:
+            f = frames[t].numpy()[:, :, ::-1].astype(np.float32) / 255.0 * 2.0 - 1.0
+            outputs.append(np.ascontiguousarray(f.transpose(2, 0, 1)))
+    return outputs
+
+
+class _EngineRenderer:
+    """Adapter giving FrameEngine the fused frame_inputs() on top of the REFERENCE's SMPLRenderer buffers."""
+
+    def __init__(self, render):
+        self.r = render
+        self.image_size = render.image_size
+
+    def frame_inputs(self, cam, vertices, uv_img, src_f2pts, want_fim=False):
+        from . import ops
+        r, S = self.r, self.image_size
+        fused = dict(map_fn=r.map_fn.float().contiguous(), f_uvs2img=r.f_uvs2img.float().contiguous(),
+                     uv_img=uv_img.reshape(-1, 3, S, S)[0].float().contiguous(), src_f2pts=src_f2pts.float().contiguous())
+        return ops.raster_frames(vertices.float().contiguous(), cam.float().contiguous(), r.smpl_faces.int().contiguous(),
+                                 S, want_fim=want_fim, want_f2pts=False, fused=fused)

@@ -72,3 +72,36 @@ def test_weight_packing_layouts():
     torch.testing.assert_close(pt[0, 2 * 5 + 3, (0 * 2 + 1) * 4 + 2].float(), wt[2, 3, 0, 3], atol=2e-3, rtol=2e-3)
     hi_lo = ops.split_planes(torch.tensor([1.0001234, -3.14159265]), 2).float()
     torch.testing.assert_close(hi_lo.sum(0), torch.tensor([1.0001234, -3.14159265]), atol=1e-6, rtol=0)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/iPERCore"), reason="reference tree only exists in the build container")
+def test_patch_install_against_reference():
+    """install() wires the seams into the REAL iPERCore package (import level; runs in a subprocess to keep sys.modules clean)."""
+    import subprocess
+    import sys
+    code = r"""
+import sys, types
+sys.path.insert(0, %r); sys.path.insert(0, "/root/reference")
+import numpy as np; np.int = int; np.float = float
+ed = types.ModuleType("easydict")
+class AD(dict):
+    def __getattr__(s, k):
+        v = s[k]; return AD(v) if isinstance(v, dict) else v
+ed.EasyDict = AD; sys.modules["easydict"] = ed
+import ipercore_b200.patch as p
+p.install()
+import toml
+from iPERCore.models.networks import NetworksFactory
+cfg = AD(toml.load("/root/reference/assets/configs/neural_renders/AttLWB-SPADE.toml")["Generator"])
+g = NetworksFactory.get_by_name("AttLWB-SPADE", cfg=cfg, temporal=False)
+assert type(g).__module__ == "ipercore_b200.generator" and len(g.state_dict()) == 221
+from iPERCore.models import imitator as imod
+from iPERCore.tools.human_digitalizer.renders import SMPLRenderer
+assert SMPLRenderer.cal_bc_transform.__module__ == "ipercore_b200.patch"
+assert imod.Imitator.inference.__module__ == "ipercore_b200.patch"
+import neural_renderer
+assert neural_renderer.__name__ == "ipercore_b200.neural_renderer"
+print("OK")
+""" % ROOT
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-2000:]

@@ -55,3 +55,17 @@ def test_batched_frames_equal_single_frames(golden_dir):
         im1, m1 = net.forward_tsf(tsf[i:i + 1].contiguous(), enc, res, Tst[i:i + 1].contiguous())
         assert torch.equal(im1[0], img[i]) and torch.equal(m1[0], mask[i])
     torch.testing.assert_close(pred, mask * bg + (1 - mask) * img, atol=1e-6, rtol=0)
+
+
+def test_forward_bg_matches_reference(golden_dir):
+    """BGNet (bg_inpaintor.py:24-60), one-time per source: conv7x7 / IN / ReLU / s2 convs / res blocks / convT / tanh."""
+    import make_golden
+    S = 64
+    g = np.load(os.path.join(golden_dir, "gen_S%d.npz" % S))
+    inp = make_golden.gen_inputs(S)
+    net = _gen("fp16x2")
+    bg = net.forward_bg(torch.from_numpy(inp["bg_inputs"]).to("cuda:0"))
+    torch.cuda.synchronize()
+    err = np.abs(bg.cpu().numpy() - g["bg_img"]).max()
+    print("forward_bg max-abs err %.2e" % err)
+    assert bg.shape == (1, 1, 3, S, S) and err <= 1e-3
