@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--batch", type=int, default=20)
     ap.add_argument("--ns", type=int, default=2)
-    ap.add_argument("--precision", default="fp16x2", choices=["fp16x2", "fp16"])
+    ap.add_argument("--precision", default="fp16x2", choices=["fp16x2", "fp16", "fp16f8"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--streams", type=int, default=1, help="engines replaying alternate batches on separate streams")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -295,8 +295,8 @@ def main():
             e0.record(); orig(a, wpack, mode, ksize, rows, block_n, epi, **kw); e1.record()
             phases = 4 if mode == ops.IPER_CONVT_4S2 else 1
             opix = a.N * (a.H // 2) * (a.W // 2) if mode == ops.IPER_CONV_S2 else a.N * a.H * a.W
-            macs = opix * phases * rows * wpack.shape[2]
-            recs.append((e0, e1, macs * (3 if wpack.shape[0] == 2 else 1)))
+            macs = opix * phases * rows * wpack.K
+            recs.append((e0, e1, macs * {1: 1, 2: 3, 3: 2}[wpack.fmt]))   # fp16-equivalent MMA work per mode
 
         with torch.cuda.stream(eng.compute):
             eng._step()
@@ -327,7 +327,7 @@ def main():
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PFLOP/s sustained",
                 "algorithmic_flops_per_batch": alg, "executed_tflops": exec_flops / (conv_ms * 1e-3) / 1e12,
-                "executed_flops_note": "split-fp16 issues 3 MMAs per K step; fk/fv 1x1 convs are hoisted to once-per-source",
+                "executed_flops_note": "fp16-equivalent MMA work: fp16x2 = 3 MMAs per K step, fp16f8 = 1 fp16 + 2 e4m3 (2x rate) = 2; fk/fv hoisted to once-per-source",
                 "conv_ms_per_batch": conv_ms, "batch_ms_ungraphed": step_ms, "conv_share_of_step": conv_ms / step_ms,
                 "traffic": traffic}
 
@@ -342,7 +342,8 @@ def main():
         line = {"metric": "motion_imitation_frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
-                "dtype": "f16x2 (split fp16 operands, fp32 accumulate)" if args.precision == "fp16x2" else "f16 (fp32 accumulate)",
+                "dtype": {"fp16x2": "f16x2 (split fp16 operands, fp32 accumulate)", "fp16": "f16 (fp32 accumulate)",
+                          "fp16f8": "f16 + e4m3 cross terms (fp32 accumulate)"}[args.precision],
                 "data": "synthetic", "config": config_block(args, launches),
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(cams_h.numel() * 4 + verts_h.numel() * 4),
                         "d2h_bytes_per_step": int(out_h.numel()), "ms_per_step": ms_e2e / args.steps},

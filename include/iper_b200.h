@@ -62,8 +62,11 @@ int iper_flow_resize(const float* T, int n, int S, int h, int w, float* out, ipe
 
 /* ------------------------------------------------------------------------------------------------------------
  * Seam B3 — building blocks of the AttLWB-SPADE generator (attlwb_spade_resunet.py).  Activations live in HBM
- * as NHWC fp16 "planes": plane 0 = fp16(x), optional plane 1 = fp16(x - plane0) (split-fp16, ~22 significand
- * bits).  With two planes a convolution is three tcgen05 MMAs per K step (hi*hi + lo*hi + hi*lo), fp32 accumulate.
+ * as NHWC "planes"; every *_planes argument is the FORMAT of the tensor:
+ *   1: fp16(x)                      2: fp16(x) + fp16(x - hi)  (split fp16, ~22 bits, 3 MMAs per K step)
+ *   3: fp16(x) + two e4m3 planes stored where the lo plane would be: a8 = e4m3(8x), l8 = e4m3(2^14 (x - hi));
+ *      the conv does hi*w_hi in kind::f16 and the two cross terms in kind::f8f6f4 (2 MMA-equivalents per K step).
+ * A plane holds *_plane_stride elements; 8-bit planes start 2 and 3 plane_strides (in bytes) after the base.
  * ---------------------------------------------------------------------------------------------------------- */
 enum { IPER_CONV_S1 = 0,    /* k x k, stride 1, pad k/2 (k = 1, 3, 5)                                     */
        IPER_CONV_S2 = 1,    /* 3x3, stride 2, pad 1                                                        */
@@ -94,6 +97,9 @@ typedef struct {
     /* IPER_EPI_HEADS: NCHW fp32 outputs (N,3,H,W), (N,1,H,W), (N,3,H,W); bg (.,3,H,W) with batch stride     */
     const float* bg; long long bg_batch_stride; float* img; float* mask; float* pred;
     int max_ctas;                                            /* 0 = one persistent CTA per SM               */
+    /* planes format 3 (fp16 + e4m3 cross terms): e4m3 weights [phase][rows][K]: w8 = e4m3(w*sW), wl8 =
+     * e4m3((w - fp16(w))*sW*2^11); cross_scale = 1 / (2^14 * sW) turns the fp8 accumulator into the fp32 sum        */
+    const void* w8; const void* wl8; float cross_scale;
 } iper_conv_gemm_desc;
 
 /* tcgen05/TMEM implicit-GEMM convolution with TMA im2col tile loads (conv_tc.cu). */

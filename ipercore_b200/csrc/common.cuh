@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <cstdio>
@@ -137,6 +138,15 @@ IPER_DEVINL void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uin
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, kind::f8f6f4 (e4m3 operands, K = 32 per instruction, fp32 accumulate)
+IPER_DEVINL void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 IPER_DEVINL void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -170,10 +180,118 @@ IPER_DEVINL uint64_t umma_desc_sw128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;             // SWIZZLE_128B
     return d;
 }
+// K-major operand tile stored as rows of 64 bytes with the 64-byte swizzle (8-bit operands, 64 elements per row):
+// 8-row groups every 512 bytes, layout type 4 = SWIZZLE_64B.
+IPER_DEVINL uint64_t umma_desc_sw64(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;
+    return d;
+}
+// Instruction descriptor, kind::f8f6f4 with e4m3 (format 0) A/B, fp32 D.
+IPER_DEVINL constexpr uint32_t umma_idesc_e4m3(int M, int N) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 // Instruction descriptor, kind::f16: fp16 A/B (format 0), fp32 D (format 1), both K-major, dense.
 // [4,6) D fmt, [7,10) A fmt, [10,13) B fmt, [15] A major, [16] B major, [17,23) N>>3, [24,29) M>>4.
 IPER_DEVINL constexpr uint32_t umma_idesc_f16(int M, int N) {
     return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// activation "planes" formats (value of the *_planes arguments of the C ABI)
+//   1  FMT_H   : one fp16 plane                                   x ~ hi                      (11 bits)
+//   2  FMT_HL  : fp16 hi + fp16 lo                                x ~ hi + lo                 (~22 bits)
+//   3  FMT_H8  : fp16 hi + two e4m3 planes in the space of the lo plane:
+//                a8 = e4m3(x * 2^3), l8 = e4m3((x - hi) * 2^14)   x ~ hi + l8 / 2^14         (~15 bits)
+//                (the 8-bit planes feed the fp8 cross-term MMAs: hi*w_lo and lo*w_hi need only ~4 bits each)
+// A plane holds `plane_stride` elements; the 8-bit planes start at byte offset 2*plane_stride (a8) and
+// 3*plane_stride (l8) from the tensor base.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int FMT_H = 1, FMT_HL = 2, FMT_H8 = 3;
+constexpr float ACT_S8 = 8.0f;          // 2^3
+constexpr float ACT_SL8 = 16384.0f;     // 2^14  ( = ACT_S8 * 2^11 )
+
+IPER_DEVINL uint8_t to_e4m3(float v) { return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3); }
+IPER_DEVINL float from_e4m3(uint8_t b) {
+    const __half_raw h = __nv_cvt_fp8_to_halfraw((__nv_fp8_storage_t)b, __NV_E4M3);
+    return __half2float(*reinterpret_cast<const __half*>(&h));
+}
+IPER_DEVINL const uint8_t* plane_a8(const __half* x, long long plane_stride) {
+    return reinterpret_cast<const uint8_t*>(x + plane_stride);
+}
+IPER_DEVINL const uint8_t* plane_l8(const __half* x, long long plane_stride) {
+    return reinterpret_cast<const uint8_t*>(x + plane_stride) + plane_stride;
+}
+IPER_DEVINL float load_plane_val(const __half* x, int fmt, long long plane_stride, size_t off) {
+    float v = __half2float(x[off]);
+    if (fmt == FMT_HL) v += __half2float(x[plane_stride + off]);
+    else if (fmt == FMT_H8) v += from_e4m3(plane_l8(x, plane_stride)[off]) * (1.0f / ACT_SL8);
+    return v;
+}
+IPER_DEVINL void store_plane_val(__half* o, int fmt, long long plane_stride, size_t off, float v) {
+    const __half hi = __float2half_rn(v);
+    const float lo = v - __half2float(hi);
+    o[off] = hi;
+    if (fmt == FMT_HL) o[plane_stride + off] = __float2half_rn(lo);
+    else if (fmt == FMT_H8) {
+        uint8_t* a8 = reinterpret_cast<uint8_t*>(o + plane_stride);
+        a8[off] = to_e4m3(v * ACT_S8);
+        a8[plane_stride + off] = to_e4m3(lo * ACT_SL8);
+    }
+}
+// 8 consecutive channels (16-byte aligned) of one pixel
+IPER_DEVINL void load_planes8(const __half* x, int fmt, long long plane_stride, size_t off, float (&v)[8]) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + off));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+        v[2 * j] = f.x; v[2 * j + 1] = f.y;
+    }
+    if (fmt == FMT_HL) {
+        const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(x + plane_stride + off));
+        const uint32_t w2[4] = {u2.x, u2.y, u2.z, u2.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w2[j]));
+            v[2 * j] += f.x; v[2 * j + 1] += f.y;
+        }
+    } else if (fmt == FMT_H8) {
+        const uint2 l = __ldg(reinterpret_cast<const uint2*>(plane_l8(x, plane_stride) + off));
+        const uint32_t w2[2] = {l.x, l.y};
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] += from_e4m3((uint8_t)(w2[j >> 2] >> (8 * (j & 3)))) * (1.0f / ACT_SL8);
+    }
+}
+IPER_DEVINL void store_planes8(__half* o, int fmt, long long plane_stride, size_t off, const float (&v)[8]) {
+    uint32_t hi[4], lo[4];
+    float lof[8];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const __half h0 = __float2half_rn(v[2 * j]), h1 = __float2half_rn(v[2 * j + 1]);
+        lof[2 * j] = v[2 * j] - __half2float(h0); lof[2 * j + 1] = v[2 * j + 1] - __half2float(h1);
+        hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        lo[j] = (uint32_t)__half_as_ushort(__float2half_rn(lof[2 * j])) |
+                ((uint32_t)__half_as_ushort(__float2half_rn(lof[2 * j + 1])) << 16);
+    }
+    *reinterpret_cast<uint4*>(o + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    if (fmt == FMT_HL) {
+        *reinterpret_cast<uint4*>(o + plane_stride + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    } else if (fmt == FMT_H8) {
+        uint32_t a[2] = {0, 0}, l[2] = {0, 0};
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            a[j >> 2] |= (uint32_t)to_e4m3(v[j] * ACT_S8) << (8 * (j & 3));
+            l[j >> 2] |= (uint32_t)to_e4m3(lof[j] * ACT_SL8) << (8 * (j & 3));
+        }
+        uint8_t* a8 = reinterpret_cast<uint8_t*>(o + plane_stride);
+        *reinterpret_cast<uint2*>(a8 + off) = make_uint2(a[0], a[1]);
+        *reinterpret_cast<uint2*>(a8 + plane_stride + off) = make_uint2(l[0], l[1]);
+    }
 }
 
 // split an fp32 value into fp16 hi + fp16 lo (hi + lo carries ~22 significand bits)

@@ -20,8 +20,12 @@
 //   warps 2-5: epilogue — tcgen05.ld the fp32 accumulator (thread = pixel row), fused bias / ReLU / residual /
 //              SPADE(instance-norm) / heads+composite, stores; double-buffered accumulators overlap tile i's
 //              epilogue with tile i+1's MMAs.
-// Split-fp16 mode (NS = 2): activations and weights carry hi and lo fp16 planes; each K step issues
-// lo*hi + hi*lo + hi*hi into the same fp32 accumulator (≈ 22-bit operands) to meet the 1e-3 fp32 parity target.
+// Operand modes (template NS = planes format of A and of the packed weights):
+//   1  fp16                : one MMA per K sub-step
+//   2  split fp16 (hi+lo)  : lo*hi + hi*lo + hi*hi into one fp32 accumulator (~22-bit operands, 3 MMAs)
+//   3  fp16 + fp8 cross    : hi*hi in kind::f16 into accumulator D1; the two small cross terms lo*hi and hi*lo need
+//                            only ~4 bits, so they run in kind::f8f6f4 (e4m3, 2x rate) into a second accumulator D2
+//                            with power-of-two pre-scaling; the epilogue forms D1 + D2 * cross_scale (2 MMA-equivalents).
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -38,8 +42,8 @@ constexpr int MAX_STAGES = 8;
 constexpr int SMEM_BUDGET = 196 * 1024;   // ring buffer budget; keeps one CTA per SM (TMEM is per-CTA 512 cols)
 
 struct alignas(64) GemmArgs {
-    CUtensorMap mapA[2];
-    CUtensorMap mapB[2];
+    CUtensorMap mapA[3];
+    CUtensorMap mapB[3];
     int mode, ksize;
     int N, Ho, Wo;           // grid the M tiles walk (conv: output grid; convT: input grid)
     int oH, oW;              // stored output spatial dims
@@ -54,16 +58,26 @@ struct alignas(64) GemmArgs {
     const __half* x; int x_planes; long long x_plane_stride; int x_pitch, x_coff;
     const float* mean_rstd; int spade_C;
     const float* bg; long long bg_batch_stride; float* img; float* mask; float* pred;
+    float cross_scale;
 };
 
 template <int BN, int NS>
 struct Cfg {
     static constexpr int B_TILE_BYTES = BN * 128;
-    static constexpr int STAGE_BYTES = NS * (A_TILE_BYTES + B_TILE_BYTES);
+    // bytes per stage are the same for NS = 2 and 3: the two e4m3 tiles occupy the space of the lo fp16 tile
+    static constexpr int STAGE_BYTES = (NS == 1 ? 1 : 2) * (A_TILE_BYTES + B_TILE_BYTES);
     static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) < MAX_STAGES ? (SMEM_BUDGET / STAGE_BYTES) : MAX_STAGES;
-    static constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
+    static constexpr int ACC_COLS = (NS == 3 ? 2 : 1) * BN;          // NS=3: [D1 | D2]
+    static constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;        // double-buffer the accumulator when TMEM allows
+    static constexpr int TMEM_COLS = (NACC * ACC_COLS) < 32 ? 32 : (NACC * ACC_COLS);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
     static_assert(STAGES >= 2, "need at least a double-buffered ring");
+    static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns must be a power of two <= 512");
+    // smem offsets inside a stage
+    static constexpr int A16 = 0;
+    static constexpr int A_X = A_TILE_BYTES;                                   // NS=2: lo fp16 | NS=3: a8 then l8
+    static constexpr int B16 = (NS == 1 ? 1 : 2) * A_TILE_BYTES;
+    static constexpr int B_X = B16 + B_TILE_BYTES;                             // NS=2: lo fp16 | NS=3: w8 then wl8
 };
 
 struct TileCoord {
@@ -92,55 +106,24 @@ IPER_DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 
-// store 32 consecutive channels of one pixel as fp16 planes (hi, optional lo); 64 B contiguous per plane
+// store / load 32 consecutive channels of one pixel in the planes format `fmt` (common.cuh)
 IPER_DEVINL void store_planes32(const GemmArgs& a, size_t elem_off, const float (&v)[32]) {
-    __half* base = reinterpret_cast<__half*>(a.out) + elem_off;
-    uint32_t hi[16], lo[16];
+    __half* base = reinterpret_cast<__half*>(a.out);
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        __half h0, l0, h1, l1;
-        split_half(v[2 * i], h0, l0);
-        split_half(v[2 * i + 1], h1, l1);
-        hi[i] = pack_half2(h0, h1);
-        lo[i] = pack_half2(l0, l1);
-    }
-    uint4* p0 = reinterpret_cast<uint4*>(base);
+    for (int g = 0; g < 4; g++) {
+        float t[8];
 #pragma unroll
-    for (int i = 0; i < 4; i++) p0[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-    if (a.out_planes > 1) {
-        uint4* p1 = reinterpret_cast<uint4*>(base + a.out_plane_stride);
-#pragma unroll
-        for (int i = 0; i < 4; i++) p1[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+        for (int j = 0; j < 8; j++) t[j] = v[8 * g + j];
+        store_planes8(base, a.out_planes, a.out_plane_stride, elem_off + 8 * g, t);
     }
 }
-
-// load 32 consecutive channels of one pixel from fp16 planes as fp32 (hi + lo)
-IPER_DEVINL void load_planes32(const __half* x, int planes, long long plane_stride, size_t elem_off, float (&v)[32]) {
-    const uint4* p0 = reinterpret_cast<const uint4*>(x + elem_off);
+IPER_DEVINL void load_planes32(const __half* x, int fmt, long long plane_stride, size_t elem_off, float (&v)[32]) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const uint4 u = __ldg(p0 + i);
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int g = 0; g < 4; g++) {
+        float t[8];
+        load_planes8(x, fmt, plane_stride, elem_off + 8 * g, t);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
-            v[8 * i + 2 * j] = f.x;
-            v[8 * i + 2 * j + 1] = f.y;
-        }
-    }
-    if (planes > 1) {
-        const uint4* p1 = reinterpret_cast<const uint4*>(x + plane_stride + elem_off);
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint4 u = __ldg(p1 + i);
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
-                v[8 * i + 2 * j] += f.x;
-                v[8 * i + 2 * j + 1] += f.y;
-            }
-        }
+        for (int j = 0; j < 8; j++) v[8 * g + j] = t[j];
     }
 }
 
@@ -158,14 +141,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     // 1024-byte aligned ring buffer (SWIZZLE_128B atoms are 1024 B)
     const uint32_t ring = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     uint8_t* ring_ptr = smem_dyn + (ring - smem_u32(smem_dyn));
-    auto sA = [&](int stage, int p) -> uint8_t* { return ring_ptr + stage * C::STAGE_BYTES + p * A_TILE_BYTES; };
+    // operand tile p of a stage: p=0 fp16 hi; NS=2: p=1 fp16 lo; NS=3: p=1 e4m3 "a8/w8", p=2 e4m3 "l8/wl8" (half-size tiles)
+    auto sA = [&](int stage, int p) -> uint8_t* {
+        const int off = p == 0 ? C::A16 : (NS == 3 ? C::A_X + (p - 1) * (A_TILE_BYTES / 2) : C::A_X);
+        return ring_ptr + stage * C::STAGE_BYTES + off;
+    };
     auto sB = [&](int stage, int p) -> uint8_t* {
-        return ring_ptr + stage * C::STAGE_BYTES + NS * A_TILE_BYTES + p * C::B_TILE_BYTES;
+        const int off = p == 0 ? C::B16 : (NS == 3 ? C::B_X + (p - 1) * (C::B_TILE_BYTES / 2) : C::B_X);
+        return ring_ptr + stage * C::STAGE_BYTES + off;
     };
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::STAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
+        for (int i = 0; i < C::NACC; i++) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4); }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) {
@@ -222,29 +210,48 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     } else if (warp == 1) {
         // =========================== MMA issuer ===========================
         constexpr uint32_t idesc = umma_idesc_f16(BLOCK_M, BN);
+        constexpr uint32_t idesc8 = umma_idesc_e4m3(BLOCK_M, BN);
         int stage = 0; uint32_t ph = 0; int it = 0;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, it++) {
-            const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
+            const int acc = it % C::NACC; const uint32_t acc_ph = (it / C::NACC) & 1;
             mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BN;
+            const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS;
             for (int kb = 0; kb < a.num_k; kb++) {
                 mbar_wait(&full_bar[stage], ph);
                 tc_fence_after();
                 if (elect_one()) {
-                    uint32_t first = (kb == 0) ? 0u : 1u;
-                    // (A plane, B plane): small cross terms first, hi*hi last
-                    constexpr int NPAIR = (NS == 2) ? 3 : 1;
-                    const int pa[3] = {NS == 2 ? 1 : 0, 0, 0};
-                    const int pb[3] = {0, NS == 2 ? 1 : 0, 0};
+                    const uint32_t fresh = (kb == 0) ? 0u : 1u;
+                    if constexpr (NS == 3) {
+                        // D1 += hi * w_hi (kind::f16);  D2 += l8 * w8 + a8 * wl8 (kind::f8f6f4, K = 32 per instruction)
+                        const uint32_t a16 = smem_u32(sA(stage, 0)), b16 = smem_u32(sB(stage, 0));
 #pragma unroll
-                    for (int q = 0; q < NPAIR; q++) {
-                        const uint32_t abase = smem_u32(sA(stage, pa[q])), bbase = smem_u32(sB(stage, pb[q]));
+                        for (int k = 0; k < BLOCK_K / 16; k++)
+                            umma_f16(d_tmem, umma_desc_sw128(a16 + k * 32), umma_desc_sw128(b16 + k * 32), idesc,
+                                     (k == 0) ? fresh : 1u);
+                        const uint32_t a8 = smem_u32(sA(stage, 1)), l8 = smem_u32(sA(stage, 2));
+                        const uint32_t w8 = smem_u32(sB(stage, 1)), wl8 = smem_u32(sB(stage, 2));
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / 16; k++) {
-                            umma_f16(d_tmem, umma_desc_sw128(abase + k * 32), umma_desc_sw128(bbase + k * 32), idesc,
-                                     first);
-                            first = 1u;
+                        for (int k = 0; k < BLOCK_K / 32; k++) {
+                            umma_f8(d_tmem + BN, umma_desc_sw64(l8 + k * 32), umma_desc_sw64(w8 + k * 32), idesc8,
+                                    (k == 0) ? fresh : 1u);
+                            umma_f8(d_tmem + BN, umma_desc_sw64(a8 + k * 32), umma_desc_sw64(wl8 + k * 32), idesc8, 1u);
+                        }
+                    } else {
+                        uint32_t first = fresh;
+                        // (A plane, B plane): small cross terms first, hi*hi last
+                        constexpr int NPAIR = (NS == 2) ? 3 : 1;
+                        const int pa[3] = {NS == 2 ? 1 : 0, 0, 0};
+                        const int pb[3] = {0, NS == 2 ? 1 : 0, 0};
+#pragma unroll
+                        for (int q = 0; q < NPAIR; q++) {
+                            const uint32_t abase = smem_u32(sA(stage, pa[q])), bbase = smem_u32(sB(stage, pb[q]));
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / 16; k++) {
+                                umma_f16(d_tmem, umma_desc_sw128(abase + k * 32), umma_desc_sw128(bbase + k * 32), idesc,
+                                         first);
+                                first = 1u;
+                            }
                         }
                     }
                     umma_commit(&empty_bar[stage]);                        // ring slot reusable once MMAs retire
@@ -260,8 +267,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         const int row = q * 32 + lane;          // accumulator row = pixel index inside the patch
         const int tx = row % a.tw, ty = (row / a.tw) % a.th, tni = row / (a.tw * a.th);
         int it = 0;
+        // accumulator chunk: 32 fp32 columns of D1 (+ the matching columns of the fp8 cross-term accumulator D2)
+        auto ld_acc = [&](uint32_t taddr_col, uint32_t (&r)[32]) {
+            tmem_ld32(taddr_col, r);
+            if constexpr (NS == 3) {
+                uint32_t r2[32];
+                tmem_ld32(taddr_col + BN, r2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; i++)
+                    r[i] = __float_as_uint(fmaf(__uint_as_float(r2[i]), a.cross_scale, __uint_as_float(r[i])));
+            } else {
+                tmem_ld_wait();
+            }
+        };
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, it++) {
-            const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
+            const int acc = it % C::NACC; const uint32_t acc_ph = (it / C::NACC) & 1;
             const TileCoord t = decode_tile(a, tile);
             mbar_wait(&tmem_full_bar[acc], acc_ph);
             tc_fence_after();
@@ -270,14 +291,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             int oy = y, ox = xx;
             if (a.mode == IPER_CONVT_4S2) { oy = 2 * y + (t.phase >> 1); ox = 2 * xx + (t.phase & 1); }
             const size_t opix = ((size_t)n * a.oH + oy) * a.oW + ox;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS;
 
             if (a.epi == IPER_EPI_HEADS) {
                 if constexpr (BN == 32) {
                     __shared__ float s_ex[BLOCK_M * 21];          // D[row][dx*4+o], 20 used columns (+1 pad)
                     uint32_t r[32];
-                    tmem_ld32(taddr, r);
-                    tmem_ld_wait();
+                    ld_acc(taddr, r);
 #pragma unroll
                     for (int i = 0; i < 20; i++) s_ex[row * 21 + i] = __uint_as_float(r[i]);
                     asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -311,9 +331,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
 #pragma unroll 1
                 for (int j = 0; j < CB / 32; j++) {
                     uint32_t rg[32], rb[32];
-                    tmem_ld32(taddr + j * 32, rg);
-                    tmem_ld32(taddr + CB + j * 32, rb);
-                    tmem_ld_wait();
+                    ld_acc(taddr + j * 32, rg);
+                    ld_acc(taddr + CB + j * 32, rb);
                     if (valid) {
                         const int c0 = t.n_tile * CB + j * 32;
                         float xv[32], o[32];
@@ -334,8 +353,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
 #pragma unroll 1
                 for (int j = 0; j < BN / 32; j++) {
                     uint32_t r[32];
-                    tmem_ld32(taddr + j * 32, r);
-                    tmem_ld_wait();
+                    ld_acc(taddr + j * 32, r);
                     if (valid) {
                         const int c0 = t.n_tile * BN + j * 32;
                         float o[32];
@@ -394,14 +412,16 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                      const cuuint32_t* box) {
+                      const cuuint32_t* box, bool u8 = false) {
     PFN_cuTensorMapEncodeTiled_v12000 fn = get_encode_fn();
     IPER_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
-                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    // fp16 tiles: 128-byte rows / SWIZZLE_128B; e4m3 tiles: 64-byte rows / SWIZZLE_64B (64 K-elements per row either way)
+    CUresult r = fn(map, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
+                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    u8 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    IPER_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank);
+    IPER_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, u8 %d)", (int)r, rank, (int)u8);
     return 0;
 }
 
@@ -436,8 +456,10 @@ using namespace iper;
 extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream) {
     IPER_REQUIRE(d != nullptr, "iper_conv_gemm: null descriptor");
     IPER_REQUIRE(d->a && d->w, "iper_conv_gemm: null operand");
-    IPER_REQUIRE(d->a_planes == d->w_planes && (d->a_planes == 1 || d->a_planes == 2),
-                 "iper_conv_gemm: a_planes (%d) and w_planes (%d) must both be 1 or both be 2", d->a_planes, d->w_planes);
+    IPER_REQUIRE(d->a_planes == d->w_planes && d->a_planes >= 1 && d->a_planes <= 3,
+                 "iper_conv_gemm: a_planes (%d) and w_planes (%d) must be the same format 1, 2 or 3", d->a_planes, d->w_planes);
+    IPER_REQUIRE(d->a_planes != 3 || (d->w8 && d->wl8 && d->cross_scale > 0.f && d->a_pitch % 16 == 0 && d->a_coff % 16 == 0),
+                 "iper_conv_gemm: format 3 needs w8, wl8, cross_scale and a 16-aligned channel window");
     IPER_REQUIRE(d->Cin > 0 && d->Cin % BLOCK_K == 0, "iper_conv_gemm: Cin=%d must be a multiple of 64", d->Cin);
     IPER_REQUIRE(d->a_pitch % 8 == 0 && d->a_coff % 8 == 0 && d->a_coff + d->Cin <= d->a_pitch,
                  "iper_conv_gemm: bad channel window (pitch %d, offset %d, Cin %d)", d->a_pitch, d->a_coff, d->Cin);
@@ -489,6 +511,7 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
     g.x_pitch = d->x_pitch; g.x_coff = d->x_coff;
     g.mean_rstd = d->mean_rstd; g.spade_C = d->spade_C;
     g.bg = d->bg; g.bg_batch_stride = d->bg_batch_stride; g.img = d->img; g.mask = d->mask; g.pred = d->pred;
+    g.cross_scale = d->cross_scale;
 
     // ---- epilogue-specific validation ----
     if (d->epi == IPER_EPI_HEADS) {
@@ -508,35 +531,43 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
     }
 
     // ---- tensor maps ----
-    const size_t esz = 2;
-    for (int p = 0; p < d->a_planes; p++) {
-        const __half* base = reinterpret_cast<const __half*>(d->a) + (size_t)p * d->a_plane_stride;
+    const int fmt = d->a_planes;
+    const int nmaps = fmt;                       // 1: hi | 2: hi, lo | 3: hi, a8, l8
+    const cuuint64_t ktot = (cuuint64_t)taps * d->Cin;
+    for (int p = 0; p < nmaps; p++) {
+        const bool u8 = (fmt == 3 && p > 0);
+        const size_t esz = u8 ? 1 : 2;
+        const uint8_t* abase8 = reinterpret_cast<const uint8_t*>(d->a);
+        const void* base;
+        if (!u8) base = abase8 + (size_t)p * d->a_plane_stride * 2;                       // fp16 plane p
+        else base = abase8 + (size_t)d->a_plane_stride * 2 + (size_t)(p - 1) * d->a_plane_stride;   // a8 / l8
         if (d->mode == IPER_CONV_S2) {
             cuuint64_t dims[5] = {(cuuint64_t)2 * d->a_pitch, (cuuint64_t)d->W / 2, 2, (cuuint64_t)d->H / 2, (cuuint64_t)d->N};
             cuuint64_t str[4] = {(cuuint64_t)2 * d->a_pitch * esz, (cuuint64_t)d->W * d->a_pitch * esz,
                                  (cuuint64_t)2 * d->W * d->a_pitch * esz, (cuuint64_t)d->H * d->W * d->a_pitch * esz};
             cuuint32_t box[5] = {BLOCK_K, (cuuint32_t)g.tw, 1, (cuuint32_t)g.th, (cuuint32_t)g.tn};
-            if (int rc = encode_map(&g.mapA[p], base, 5, dims, str, box)) return rc;
+            if (int rc = encode_map(&g.mapA[p], base, 5, dims, str, box, u8)) return rc;
         } else {
             cuuint64_t dims[4] = {(cuuint64_t)d->a_pitch, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
             cuuint64_t str[3] = {(cuuint64_t)d->a_pitch * esz, (cuuint64_t)d->W * d->a_pitch * esz,
                                  (cuuint64_t)d->H * d->W * d->a_pitch * esz};
             cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)g.tw, (cuuint32_t)g.th, (cuuint32_t)g.tn};
-            if (int rc = encode_map(&g.mapA[p], base, 4, dims, str, box)) return rc;
+            if (int rc = encode_map(&g.mapA[p], base, 4, dims, str, box, u8)) return rc;
         }
-        const __half* wb = reinterpret_cast<const __half*>(d->w) + (size_t)p * d->w_plane_stride;
-        const cuuint64_t ktot = (cuuint64_t)taps * d->Cin;
+        const void* wb;
+        if (!u8) wb = reinterpret_cast<const __half*>(d->w) + (size_t)p * d->w_plane_stride;
+        else wb = (p == 1) ? d->w8 : d->wl8;
         cuuint64_t wdims[2] = {ktot, (cuuint64_t)d->rows * g.phases};
         cuuint64_t wstr[1] = {ktot * esz};
         cuuint32_t wbox[2] = {BLOCK_K, (cuuint32_t)d->block_n};
-        if (int rc = encode_map(&g.mapB[p], wb, 2, wdims, wstr, wbox)) return rc;
+        if (int rc = encode_map(&g.mapB[p], wb, 2, wdims, wstr, wbox, u8)) return rc;
     }
-    if (d->a_planes == 1) { g.mapA[1] = g.mapA[0]; g.mapB[1] = g.mapB[0]; }
+    for (int p = nmaps; p < 3; p++) { g.mapA[p] = g.mapA[0]; g.mapB[p] = g.mapB[0]; }
 
     cudaStream_t s = (cudaStream_t)stream;
-    const int ns = d->a_planes;
-#define IPER_DISPATCH(BNV)                                                     \
-    return ns == 2 ? launch_gemm<BNV, 2>(g, d->max_ctas, s) : launch_gemm<BNV, 1>(g, d->max_ctas, s)
+#define IPER_DISPATCH(BNV)                                                                                           \
+    return fmt == 3 ? launch_gemm<BNV, 3>(g, d->max_ctas, s)                                                         \
+                    : (fmt == 2 ? launch_gemm<BNV, 2>(g, d->max_ctas, s) : launch_gemm<BNV, 1>(g, d->max_ctas, s))
     switch (d->block_n) {
         case 32: IPER_DISPATCH(32);
         case 64: IPER_DISPATCH(64);

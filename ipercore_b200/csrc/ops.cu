@@ -6,18 +6,6 @@
 
 namespace iper {
 
-IPER_DEVINL float load_plane_val(const __half* x, int planes, long long plane_stride, size_t off) {
-    float v = __half2float(x[off]);
-    if (planes > 1) v += __half2float(x[plane_stride + off]);
-    return v;
-}
-IPER_DEVINL void store_plane_val(__half* o, int planes, long long plane_stride, size_t off, float v) {
-    __half hi, lo;
-    split_half(v, hi, lo);
-    o[off] = hi;
-    if (planes > 1) o[plane_stride + off] = lo;
-}
-
 // ------------------------------------------------------------------------------------------------------------
 // CUDA-core direct convolution on NHWC planes; one thread per (pixel, output channel), fp32 accumulate in the
 // reference's own weight layout.  Slow by design: it is the checker for conv_tc.cu and the fallback for shapes
@@ -153,19 +141,10 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(const float* __restrict_
             acc[0] += pv * w0.x; acc[1] += pv * w0.y; acc[2] += pv * w0.z; acc[3] += pv * w0.w;
             acc[4] += pv * w1.x; acc[5] += pv * w1.y; acc[6] += pv * w1.z; acc[7] += pv * w1.w;
         }
-        uint32_t hi[4], lo[4];
+        float o8[8];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            float v0 = acc[2 * j] + (bias ? bias[co0 + 2 * j] : 0.f);
-            float v1 = acc[2 * j + 1] + (bias ? bias[co0 + 2 * j + 1] : 0.f);
-            v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f);
-            __half h0, l0, h1, l1;
-            split_half(v0, h0, l0); split_half(v1, h1, l1);
-            hi[j] = pack_half2(h0, h1); lo[j] = pack_half2(l0, l1);
-        }
-        *reinterpret_cast<uint4*>(out + obase + co0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        if (out_planes > 1)
-            *reinterpret_cast<uint4*>(out + out_plane_stride + obase + co0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        for (int j = 0; j < 8; j++) o8[j] = fmaxf(acc[j] + (bias ? bias[co0 + j] : 0.f), 0.f);
+        store_planes8(out, out_planes, out_plane_stride, obase + co0, o8);
     }
 }
 
@@ -193,24 +172,8 @@ __global__ void __launch_bounds__(256) instnorm_partial_kernel(const __half* __r
     const size_t base = (size_t)n * HW * x_pitch + x_coff + cg * 8;
     if (pl < ppl) {
         for (int p = p0 + pl; p < p1; p += ppl) {
-            const size_t off = base + (size_t)p * x_pitch;
-            uint4 u = __ldg(reinterpret_cast<const uint4*>(x + off));
             float v[8];
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
-                v[2 * j] = f.x; v[2 * j + 1] = f.y;
-            }
-            if (x_planes > 1) {
-                u = __ldg(reinterpret_cast<const uint4*>(x + x_plane_stride + off));
-                const uint32_t w2[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w2[j]));
-                    v[2 * j] += f.x; v[2 * j + 1] += f.y;
-                }
-            }
+            load_planes8(x, x_planes, x_plane_stride, base + (size_t)p * x_pitch, v);
 #pragma unroll
             for (int j = 0; j < 8; j++) { sum[j] += v[j]; sq[j] += v[j] * v[j]; }
         }
@@ -364,19 +327,7 @@ __global__ void __launch_bounds__(256) warp_attention_kernel(const float* __rest
 #pragma unroll
             for (int j = 0; j < 8; j++) o8[j] += al * vacc[s][j];
         }
-        if (live) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                __half h0, l0, h1, l1;
-                split_half(o8[2 * j], h0, l0); split_half(o8[2 * j + 1], h1, l1);
-                hi[j] = pack_half2(h0, h1); lo[j] = pack_half2(l0, l1);
-            }
-            const size_t off = pix * out_pitch + out_coff + cg * 8;
-            *reinterpret_cast<uint4*>(out + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            if (out_planes > 1)
-                *reinterpret_cast<uint4*>(out + out_plane_stride + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        }
+        if (live) store_planes8(out, out_planes, out_plane_stride, pix * out_pitch + out_coff + cg * 8, o8);
     }
 }
 

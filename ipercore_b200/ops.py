@@ -29,24 +29,32 @@ def _req(t, dtype, name):
     return t
 
 
-class Planes:
-    """NHWC fp16 activation tensor with P planes: data (P, N, H, W, pitch); value = plane0 (+ plane1).
+FMT_H, FMT_HL, FMT_H8 = 1, 2, 3      # planes formats (include/iper_b200.h, common.cuh)
 
+
+class Planes:
+    """NHWC activation tensor in one of the planes formats; `P` is the FORMAT passed to the C ABI:
+      1: data (1,N,H,W,pitch) fp16            value = hi
+      2: data (2,N,H,W,pitch) fp16            value = hi + lo
+      3: data (2,...) fp16 storage; plane 1 holds two e4m3 planes (a8 = e4m3(8x), l8 = e4m3(2^14 (x-hi)))
     A `Planes` may be a channel window [coff, coff+C) of a wider buffer (used for the decoder's concatenations)."""
 
-    def __init__(self, data, C=None, coff=0):
+    def __init__(self, data, C=None, coff=0, fmt=None):
         assert data.dim() == 5 and data.dtype == torch.float16 and data.is_contiguous()
         self.data = data
-        self.P, self.N, self.H, self.W, self.pitch = data.shape
+        _, self.N, self.H, self.W, self.pitch = data.shape
+        self.P = data.shape[0] if fmt is None else fmt
+        assert data.shape[0] == (1 if self.P == 1 else 2)
         self.C = self.pitch if C is None else C
         self.coff = coff
 
     @staticmethod
-    def empty(P, N, H, W, C, device, pitch=None):
-        return Planes(torch.empty((P, N, H, W, pitch or C), dtype=torch.float16, device=device), C=C)
+    def empty(fmt, N, H, W, C, device, pitch=None):
+        return Planes(torch.empty((1 if fmt == 1 else 2, N, H, W, pitch or C), dtype=torch.float16, device=device),
+                      C=C, fmt=fmt)
 
     def window(self, coff, C):
-        return Planes(self.data, C=C, coff=self.coff + coff)
+        return Planes(self.data, C=C, coff=self.coff + coff, fmt=self.P)
 
     @property
     def plane_stride(self):
@@ -171,10 +179,11 @@ def _fill_desc(a, mode, ksize, rows, block_n, epi, bias=None, relu=False, out=No
 
 
 def conv_gemm(a, wpack, mode, ksize, rows, block_n, epi, **kw):
-    """tcgen05 implicit-GEMM convolution (conv_tc.cu). `wpack` = fp16 (P, phases*rows, taps*Cin) packed weights."""
+    """tcgen05 implicit-GEMM convolution (conv_tc.cu). `wpack` = PackedW from the pack_* helpers below."""
     d = _fill_desc(a, mode, ksize, rows, block_n, epi, **kw)
-    assert wpack.dtype == torch.float16 and wpack.is_contiguous() and wpack.dim() == 3
-    d.w = wpack.data_ptr(); d.w_planes = wpack.shape[0]; d.w_plane_stride = wpack[0].numel()
+    d.w = wpack.w.data_ptr(); d.w_planes = wpack.fmt; d.w_plane_stride = wpack.w[0].numel()
+    if wpack.fmt == FMT_H8:
+        d.w8 = wpack.w8.data_ptr(); d.wl8 = wpack.wl8.data_ptr(); d.cross_scale = wpack.cross_scale
     check(lib.iper_conv_gemm(d, _stream()), "conv_gemm")
 
 
@@ -252,13 +261,60 @@ def pred_to_u8(pred, out=None):
 # ------------------------------------------------------------------------------------------------------------------
 # weight packing (one-time, at load): reference layouts -> K-major fp16 planes for the tcgen05 kernel
 # ------------------------------------------------------------------------------------------------------------------
+ACT_S8, ACT_SL8 = 8.0, 16384.0       # activation e4m3 scales (common.cuh)
+
+
 def split_planes(w, P):
-    """fp32 -> (P, ...) fp16: plane0 = fp16(w), plane1 = fp16(w - plane0)."""
+    """fp32 -> (P, ...) fp16: plane0 = fp16(w), plane1 = fp16(w - plane0).  (P=3 keeps only the fp16 plane here.)"""
     hi = w.to(torch.float16)
-    if P == 1:
+    if P != 2:
         return hi[None].contiguous()
     lo = (w - hi.float()).to(torch.float16)
     return torch.stack([hi, lo], 0).contiguous()
+
+
+def _to_e4m3(t):
+    return t.clamp(-448.0, 448.0).to(torch.float8_e4m3fn)
+
+
+def e4m3_roundtrip(t, scale):
+    """value the kernels see for an e4m3 plane: e4m3(t*scale)/scale (test helper)."""
+    return _to_e4m3(t.float() * scale).float() / scale
+
+
+class PackedW:
+    """K-major packed weight matrix (rows_total, K) in planes format `fmt` (1, 2 or 3)."""
+
+    def __init__(self, m, fmt):
+        m = m.float().contiguous()
+        self.fmt, self.rows_total, self.K = fmt, m.shape[0], m.shape[1]
+        self.w = split_planes(m, fmt)
+        self.w8 = self.wl8 = None
+        self.cross_scale = 0.0
+        self.sW = 1.0
+        if fmt == FMT_H8:
+            hi = self.w[0].float()
+            mx = float(hi.abs().max())
+            self.sW = 2.0 ** math.floor(math.log2(240.0 / mx)) if mx > 0 else 1.0
+            self.w8 = _to_e4m3(hi * self.sW).view(torch.uint8).contiguous()
+            self.wl8 = _to_e4m3((m - hi) * (self.sW * 2048.0)).view(torch.uint8).contiguous()
+            self.cross_scale = 1.0 / (ACT_SL8 * self.sW)
+
+    def to(self, device):
+        self.w = self.w.to(device)
+        if self.w8 is not None:
+            self.w8, self.wl8 = self.w8.to(device), self.wl8.to(device)
+        return self
+
+    def effective(self):
+        """(w_main, w_for_lo_term, wlo_term) fp32 matrices the three MMA groups multiply with (test helper)."""
+        hi = self.w[0].float().cpu()
+        if self.fmt == 1:
+            return hi, None, None
+        if self.fmt == 2:
+            return hi, hi, self.w[1].float().cpu()
+        return hi, self.w8.cpu().view(torch.float8_e4m3fn).float() / self.sW, \
+            self.wl8.cpu().view(torch.float8_e4m3fn).float() / (self.sW * 2048.0)
 
 
 def pack_conv_weight(w, P, pad_rows_to=None):
@@ -267,7 +323,7 @@ def pack_conv_weight(w, P, pad_rows_to=None):
     m = w.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).float()
     if pad_rows_to is not None and pad_rows_to > Cout:
         m = torch.cat([m, m.new_zeros(pad_rows_to - Cout, m.shape[1])], 0)
-    return split_planes(m, P)
+    return PackedW(m, P)
 
 
 def pack_heads_weight(w_img, w_mask, P):
@@ -277,7 +333,7 @@ def pack_heads_weight(w_img, w_mask, P):
     C = w.shape[1]
     m = w.permute(3, 0, 2, 1).reshape(5 * 4, 5 * C)            # (dx, o) x (dy, c)
     m = torch.cat([m, m.new_zeros(32 - 20, 5 * C)], 0)
-    return split_planes(m, P)
+    return PackedW(m, P)
 
 
 def pack_convT_weight(w, P):
@@ -293,7 +349,7 @@ def pack_convT_weight(w, P):
                 for tb in range(2):
                     taps.append(w[:, :, kidx[py][ta], kidx[px][tb]].t())     # (Cout, Cin)
             phases.append(torch.cat(taps, 1))                               # (Cout, 4*Cin)
-    return split_planes(torch.cat(phases, 0).float(), P)                     # (4*Cout, 4*Cin)
+    return PackedW(torch.cat(phases, 0), P)                                  # (4*Cout, 4*Cin)
 
 
 def pack_spade_weight(wg, bg_, wb, bb, P, block_n):
@@ -304,4 +360,4 @@ def pack_spade_weight(wg, bg_, wb, bb, P, block_n):
     for t in range(C // cb):
         rows += [mg[t * cb:(t + 1) * cb], mb[t * cb:(t + 1) * cb]]
         bias += [bg_[t * cb:(t + 1) * cb], bb[t * cb:(t + 1) * cb]]
-    return split_planes(torch.cat(rows, 0), P), torch.cat(bias, 0).float().contiguous()
+    return PackedW(torch.cat(rows, 0), P), torch.cat(bias, 0).float().contiguous()

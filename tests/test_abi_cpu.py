@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_descriptor_struct_matches_header():
     from ipercore_b200._lib import ConvGemmDesc
-    assert ctypes.sizeof(ConvGemmDesc) == 240 and ConvGemmDesc.max_ctas.offset == 232
+    assert ctypes.sizeof(ConvGemmDesc) == 264 and ConvGemmDesc.max_ctas.offset == 232 and ConvGemmDesc.cross_scale.offset == 256
 
 
 def test_argument_validation_reports_errors():
@@ -62,16 +62,26 @@ def test_weight_packing_layouts():
     from ipercore_b200 import ops
     w = torch.arange(2 * 3 * 3 * 3, dtype=torch.float32).reshape(2, 3, 3, 3)
     p = ops.pack_conv_weight(w, 2)
-    assert p.shape == (2, 2, 27)
+    assert p.w.shape == (2, 2, 27) and p.fmt == 2 and p.rows_total == 2 and p.K == 27
     # K order is (tap, cin): element (co=1, tap=4 (ky=1,kx=1), ci=2)
-    assert float(p[0, 1, 4 * 3 + 2]) + float(p[1, 1, 4 * 3 + 2]) == float(w[1, 2, 1, 1])
+    assert float(p.w[0, 1, 4 * 3 + 2]) + float(p.w[1, 1, 4 * 3 + 2]) == float(w[1, 2, 1, 1])
     wt = torch.randn(4, 5, 4, 4)
     pt = ops.pack_convT_weight(wt, 1)
-    assert pt.shape == (1, 4 * 5, 4 * 4)
+    assert pt.w.shape == (1, 4 * 5, 4 * 4)
     # phase (py=1,px=0), tap (ta=0,tb=1): ky=0, kx=3
-    torch.testing.assert_close(pt[0, 2 * 5 + 3, (0 * 2 + 1) * 4 + 2].float(), wt[2, 3, 0, 3], atol=2e-3, rtol=2e-3)
+    torch.testing.assert_close(pt.w[0, 2 * 5 + 3, (0 * 2 + 1) * 4 + 2].float(), wt[2, 3, 0, 3], atol=2e-3, rtol=2e-3)
     hi_lo = ops.split_planes(torch.tensor([1.0001234, -3.14159265]), 2).float()
     torch.testing.assert_close(hi_lo.sum(0), torch.tensor([1.0001234, -3.14159265]), atol=1e-6, rtol=0)
+    # format 3: e4m3 planes reproduce w and (w - fp16(w)) to ~2^-4 relative, with a power-of-two scale
+    wr = (torch.rand(8, 64) - 0.5) * 0.2
+    p3 = ops.PackedW(wr, 3)
+    main, w_for_lo, wlo = p3.effective()
+    assert p3.w8.dtype == torch.uint8 and p3.w8.shape == (8, 64) and abs(p3.cross_scale * 16384.0 * p3.sW - 1.0) < 1e-12
+    assert float((w_for_lo - main).abs().max()) <= float(main.abs().max()) * 2 ** -4
+    lo = wr - wr.half().float()
+    assert float((wlo - lo).abs().max()) <= float(lo.abs().max()) * 2 ** -4 + 1e-12
+    heads = ops.pack_heads_weight(torch.randn(3, 64, 5, 5), torch.randn(1, 64, 5, 5), 2)
+    assert heads.w.shape == (2, 32, 320) and float(heads.w[:, 20:].abs().max()) == 0.0
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/iPERCore"), reason="reference tree only exists in the build container")

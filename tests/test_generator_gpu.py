@@ -22,7 +22,8 @@ def _gen(precision):
     return g.to("cuda:0").eval()
 
 
-@pytest.mark.parametrize("S,precision,tol", [(256, "fp16x2", 1e-3), (64, "fp16x2", 1e-3), (256, "fp16", 1e-2)])
+@pytest.mark.parametrize("S,precision,tol", [(256, "fp16x2", 1e-3), (64, "fp16x2", 1e-3), (256, "fp16f8", 1e-3),
+                                             (64, "fp16f8", 1e-3), (256, "fp16", 1e-2)])
 def test_forward_src_tsf_matches_reference(S, precision, tol, golden_dir):
     import make_golden
     g = np.load(os.path.join(golden_dir, "gen_S%d.npz" % S))
