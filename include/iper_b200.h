@@ -100,6 +100,7 @@ typedef struct {
     /* planes format 3 (fp16 + e4m3 cross terms): e4m3 weights [phase][rows][K]: w8 = e4m3(w*sW), wl8 =
      * e4m3((w - fp16(w))*sW*2^11); cross_scale = 1 / (2^14 * sW) turns the fp8 accumulator into the fp32 sum        */
     const void* w8; const void* wl8; float cross_scale;
+    int tiles_m;                                             /* 128-pixel M tiles per CTA: 0 = auto, 1 or 2   */
 } iper_conv_gemm_desc;
 
 /* tcgen05/TMEM implicit-GEMM convolution with TMA im2col tile loads (conv_tc.cu). */

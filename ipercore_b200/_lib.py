@@ -30,7 +30,7 @@ class ConvGemmDesc(ctypes.Structure):
         ("mean_rstd", c_void_p), ("spade_C", c_int),
         ("bg", c_void_p), ("bg_batch_stride", c_ll), ("img", c_void_p), ("mask", c_void_p), ("pred", c_void_p),
         ("max_ctas", c_int),
-        ("w8", c_void_p), ("wl8", c_void_p), ("cross_scale", c_float),
+        ("w8", c_void_p), ("wl8", c_void_p), ("cross_scale", c_float), ("tiles_m", c_int),
     ]
 
 

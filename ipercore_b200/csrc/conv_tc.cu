@@ -23,9 +23,10 @@
 // Operand modes (template NS = planes format of A and of the packed weights):
 //   1  fp16                : one MMA per K sub-step
 //   2  split fp16 (hi+lo)  : lo*hi + hi*lo + hi*hi into one fp32 accumulator (~22-bit operands, 3 MMAs)
-//   3  fp16 + fp8 cross    : hi*hi in kind::f16 into accumulator D1; the two small cross terms lo*hi and hi*lo need
+//   3  fp16 + fp8 cross    : hi*hi in kind::f16 into accumulator D1 (pass 0 over K); the two small cross terms lo*hi and hi*lo need
 //                            only ~4 bits, so they run in kind::f8f6f4 (e4m3, 2x rate) into a second accumulator D2
-//                            with power-of-two pre-scaling; the epilogue forms D1 + D2 * cross_scale (2 MMA-equivalents).
+//                            with power-of-two pre-scaling (pass 1 over K — the MMA kinds are never interleaved);
+//                            the epilogue forms D1 + D2 * cross_scale (2 MMA-equivalents).
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -36,8 +37,6 @@ namespace iper {
 
 constexpr int GEMM_THREADS = 192;
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;               // fp16 elements = 128 bytes = one swizzle row
-constexpr int A_TILE_BYTES = BLOCK_M * 128;
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_BUDGET = 196 * 1024;   // ring buffer budget; keeps one CTA per SM (TMEM is per-CTA 512 cols)
 
@@ -48,7 +47,7 @@ struct alignas(64) GemmArgs {
     int N, Ho, Wo;           // grid the M tiles walk (conv: output grid; convT: input grid)
     int oH, oW;              // stored output spatial dims
     int tw, th, tn;          // patch = tw x th x tn pixels = 128
-    int tiles_x, tiles_y, tiles_nb, m_tiles, n_tiles, phases, total_tiles;
+    int tiles_x, tiles_y, tiles_nb, m_tiles, m_groups, n_tiles, phases, total_tiles;
     int cin_chunks, num_k;
     int a_coff, a_pitch;
     int rows;
@@ -61,49 +60,50 @@ struct alignas(64) GemmArgs {
     float cross_scale;
 };
 
-template <int BN, int NS>
+// BN = GEMM-N tile (output channels), NS = operand format (1, 2, 3), TM = 128-pixel M tiles per CTA that share one
+// weight tile.  The kernel is bound by operand delivery (L2 -> smem, ~42 B/clk/SM chip-wide), so bytes per MMA are
+// what matters: TM = 2 halves the weight traffic per output.  TM = 2 stages hold 32 K-elements (64-byte rows,
+// SWIZZLE_64B) so that three stages still fit; TM = 1 stages hold 64 (128-byte rows, SWIZZLE_128B).
+template <int BN, int NS, int TM>
 struct Cfg {
-    static constexpr int B_TILE_BYTES = BN * 128;
-    // bytes per stage are the same for NS = 2 and 3: the two e4m3 tiles occupy the space of the lo fp16 tile
-    static constexpr int STAGE_BYTES = (NS == 1 ? 1 : 2) * (A_TILE_BYTES + B_TILE_BYTES);
+    static_assert(NS != 3 || TM == 1, "the fp16+fp8 mode keeps one M tile per CTA (TMEM holds D1 and D2)");
+    static constexpr int BK = (TM == 2) ? 32 : 64;
+    static constexpr int ROW16 = BK * 2;                              // bytes per fp16 operand row
+    static constexpr int A_TILE = BLOCK_M * ROW16;                    // one fp16 A tile
+    static constexpr int B_TILE = BN * ROW16;
+    static constexpr int PL = (NS == 2) ? 2 : 1;                      // fp16 planes resident per stage
+    // NS=3 walks K twice per tile (pass 0: fp16 tiles -> D1, pass 1: the four e4m3 tiles -> D2) so that the two MMA
+    // kinds are never interleaved; either pass fills a stage with A_TILE + B_TILE bytes
+    static constexpr int STAGE_BYTES = PL * (TM * A_TILE + B_TILE);
     static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) < MAX_STAGES ? (SMEM_BUDGET / STAGE_BYTES) : MAX_STAGES;
-    static constexpr int ACC_COLS = (NS == 3 ? 2 : 1) * BN;          // NS=3: [D1 | D2]
-    static constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;        // double-buffer the accumulator when TMEM allows
+    static constexpr int ACC_COLS = (NS == 3 ? 2 : 1) * TM * BN;      // TM accumulators (NS=3: [D1 | D2])
+    static constexpr int NACC = (2 * ACC_COLS <= 512) ? 2 : 1;        // double-buffer the accumulators when TMEM allows
     static constexpr int TMEM_COLS = (NACC * ACC_COLS) < 32 ? 32 : (NACC * ACC_COLS);
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;    // + alignment slack
+    static constexpr int B_BASE = PL * TM * A_TILE;
     static_assert(STAGES >= 2, "need at least a double-buffered ring");
     static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns must be a power of two <= 512");
-    // smem offsets inside a stage
-    static constexpr int A16 = 0;
-    static constexpr int A_X = A_TILE_BYTES;                                   // NS=2: lo fp16 | NS=3: a8 then l8
-    static constexpr int B16 = (NS == 1 ? 1 : 2) * A_TILE_BYTES;
-    static constexpr int B_X = B16 + B_TILE_BYTES;                             // NS=2: lo fp16 | NS=3: w8 then wl8
+    static_assert(SMEM_BYTES >= 116 * 1024, "ring must be large enough that only one CTA fits per SM (TMEM allocation)");
 };
 
 struct TileCoord {
     int phase, n_tile, pn0, py0, px0;
 };
-IPER_DEVINL TileCoord decode_tile(const GemmArgs& a, int tile) {
-    TileCoord t;
-    t.n_tile = tile % a.n_tiles;
+// tile -> (phase, M group, N tile); M tile `t` of the group.  A group index past the last M tile yields pn0 = N:
+// its loads are fully out of bounds (zero fill) and its epilogue rows are all invalid.
+template <int TM>
+IPER_DEVINL TileCoord decode_tile(const GemmArgs& a, int tile, int t) {
+    TileCoord c;
+    c.n_tile = tile % a.n_tiles;
     int r = tile / a.n_tiles;
-    const int m = r % a.m_tiles;
-    t.phase = r / a.m_tiles;
-    t.px0 = (a.mode == IPER_CONV_ROW5) ? (m % a.tiles_x) * (BLOCK_M - 4) - 2 : (m % a.tiles_x) * a.tw;
+    const int m = (r % a.m_groups) * TM + t;
+    c.phase = r / a.m_groups;
+    if (m >= a.m_tiles) { c.px0 = 0; c.py0 = 0; c.pn0 = a.N; return c; }
+    c.px0 = (a.mode == IPER_CONV_ROW5) ? (m % a.tiles_x) * (BLOCK_M - 4) - 2 : (m % a.tiles_x) * a.tw;
     const int r2 = m / a.tiles_x;
-    t.py0 = (r2 % a.tiles_y) * a.th;
-    t.pn0 = (r2 / a.tiles_y) * a.tn;
-    return t;
-}
-
-IPER_DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr)
-        : "memory");
+    c.py0 = (r2 % a.tiles_y) * a.th;
+    c.pn0 = (r2 / a.tiles_y) * a.tn;
+    return c;
 }
 
 // store / load 32 consecutive channels of one pixel in the planes format `fmt` (common.cuh)
@@ -127,9 +127,10 @@ IPER_DEVINL void load_planes32(const __half* x, int fmt, long long plane_stride,
     }
 }
 
-template <int BN, int NS>
+template <int BN, int NS, int TM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmArgs a) {
-    using C = Cfg<BN, NS>;
+    using C = Cfg<BN, NS, TM>;
+    constexpr int BK = C::BK;
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
     __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
@@ -138,18 +139,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // 1024-byte aligned ring buffer (SWIZZLE_128B atoms are 1024 B)
+    // 1024-byte aligned ring buffer (swizzle atoms are 1024 B / 512 B)
     const uint32_t ring = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     uint8_t* ring_ptr = smem_dyn + (ring - smem_u32(smem_dyn));
-    // operand tile p of a stage: p=0 fp16 hi; NS=2: p=1 fp16 lo; NS=3: p=1 e4m3 "a8/w8", p=2 e4m3 "l8/wl8" (half-size tiles)
-    auto sA = [&](int stage, int p) -> uint8_t* {
-        const int off = p == 0 ? C::A16 : (NS == 3 ? C::A_X + (p - 1) * (A_TILE_BYTES / 2) : C::A_X);
+    // operand tiles of a stage.  p = 0: fp16 hi; NS=2: p = 1 fp16 lo; NS=3 (pass 1, TM = 1): p = 1 / 2 = e4m3 a8 / l8
+    // (w8 / wl8), half-size tiles reusing the space of the pass-0 fp16 tile.
+    auto sA = [&](int stage, int t, int p) -> uint8_t* {
+        const int off = (NS == 3) ? (p == 2 ? C::A_TILE / 2 : 0) : (p * TM + t) * C::A_TILE;
         return ring_ptr + stage * C::STAGE_BYTES + off;
     };
     auto sB = [&](int stage, int p) -> uint8_t* {
-        const int off = p == 0 ? C::B16 : (NS == 3 ? C::B_X + (p - 1) * (C::B_TILE_BYTES / 2) : C::B_X);
-        return ring_ptr + stage * C::STAGE_BYTES + off;
+        const int off = (NS == 3) ? (p == 2 ? C::B_TILE / 2 : 0) : p * C::B_TILE;
+        return ring_ptr + stage * C::STAGE_BYTES + C::B_BASE + off;
     };
+    auto desc16 = [](uint32_t saddr) -> uint64_t { return BK == 64 ? umma_desc_sw128(saddr) : umma_desc_sw64(saddr); };
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < C::STAGES; i++) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -164,45 +167,57 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    constexpr int NPASS = (NS == 3) ? 2 : 1;
 
     if (warp == 0) {
         // =========================== TMA producer ===========================
         if (lane == 0) {
             int stage = 0; uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-                const TileCoord t = decode_tile(a, tile);
-                const int brow = t.phase * a.rows + t.n_tile * BN;
+                TileCoord tc[TM];
+#pragma unroll
+                for (int t = 0; t < TM; t++) tc[t] = decode_tile<TM>(a, tile, t);
+                const int brow = tc[0].phase * a.rows + tc[0].n_tile * BN;
+                for (int pass = 0; pass < NPASS; pass++)
                 for (int kb = 0; kb < a.num_k; kb++) {
+                    // operand planes loaded into this stage: NS=1: [0,1)  NS=2: [0,2)  NS=3: pass 0 -> [0,1), pass 1 -> [1,3)
+                    const int p_lo = (NS == 3 && pass == 1) ? 1 : 0;
+                    const int p_hi = (NS == 3) ? (pass == 0 ? 1 : 3) : NS;
                     const int tap = kb / a.cin_chunks, cc = kb - tap * a.cin_chunks;
                     mbar_wait(&empty_bar[stage], ph ^ 1);
                     mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-                    if (a.mode == IPER_CONV_S2) {
-                        // input pixel = 2*o - 1 + d : d=0 -> (parity 1, o-1), d=1 -> (parity 0, o), d=2 -> (parity 1, o)
-                        const int dy = tap / 3, dx = tap - 3 * dy;
-                        const int py = (dy != 1), sy = (dy == 0) ? -1 : 0;
-                        const int px = (dx != 1), sx = (dx == 0) ? -1 : 0;
-                        const int c0 = px * a.a_pitch + a.a_coff + cc * BLOCK_K;
-                        for (int p = 0; p < NS; p++)
-                            tma_load_5d(sA(stage, p), &a.mapA[p], &full_bar[stage], c0, t.px0 + sx, py, t.py0 + sy, t.pn0);
-                    } else {
-                        int oy, ox;
-                        if (a.mode == IPER_CONV_ROW5) {
-                            oy = tap - 2; ox = 0;
-                        } else if (a.mode == IPER_CONV_S1) {
-                            const int dy = tap / a.ksize, dx = tap - dy * a.ksize;
-                            oy = dy - a.ksize / 2; ox = dx - a.ksize / 2;
-                        } else {  // transposed 4x4 s2 p1, phase (py,px), tap (ta,tb): see pack order in generator.py
-                            const int py = t.phase >> 1, px = t.phase & 1;
-                            const int ta = tap >> 1, tb = tap & 1;
-                            oy = py == 0 ? (ta == 0 ? 0 : -1) : (ta == 0 ? 1 : 0);
-                            ox = px == 0 ? (tb == 0 ? 0 : -1) : (tb == 0 ? 1 : 0);
+#pragma unroll
+                    for (int t = 0; t < TM; t++) {
+                        if (a.mode == IPER_CONV_S2) {
+                            // input pixel = 2*o - 1 + d : d=0 -> (parity 1, o-1), d=1 -> (parity 0, o), d=2 -> (parity 1, o)
+                            const int dy = tap / 3, dx = tap - 3 * dy;
+                            const int py = (dy != 1), sy = (dy == 0) ? -1 : 0;
+                            const int px = (dx != 1), sx = (dx == 0) ? -1 : 0;
+                            const int c0 = px * a.a_pitch + a.a_coff + cc * BK;
+                            for (int p = p_lo; p < p_hi; p++)
+                                tma_load_5d(sA(stage, t, p), &a.mapA[p], &full_bar[stage], c0, tc[t].px0 + sx, py,
+                                            tc[t].py0 + sy, tc[t].pn0);
+                        } else {
+                            int oy, ox;
+                            if (a.mode == IPER_CONV_ROW5) {
+                                oy = tap - 2; ox = 0;
+                            } else if (a.mode == IPER_CONV_S1) {
+                                const int dy = tap / a.ksize, dx = tap - dy * a.ksize;
+                                oy = dy - a.ksize / 2; ox = dx - a.ksize / 2;
+                            } else {  // transposed 4x4 s2 p1, phase (py,px), tap (ta,tb): see pack_convT_weight (ops.py)
+                                const int py = tc[t].phase >> 1, px = tc[t].phase & 1;
+                                const int ta = tap >> 1, tb = tap & 1;
+                                oy = py == 0 ? (ta == 0 ? 0 : -1) : (ta == 0 ? 1 : 0);
+                                ox = px == 0 ? (tb == 0 ? 0 : -1) : (tb == 0 ? 1 : 0);
+                            }
+                            const int c0 = a.a_coff + cc * BK;
+                            for (int p = p_lo; p < p_hi; p++)
+                                tma_load_4d(sA(stage, t, p), &a.mapA[p], &full_bar[stage], c0, tc[t].px0 + ox,
+                                            tc[t].py0 + oy, tc[t].pn0);
                         }
-                        const int c0 = a.a_coff + cc * BLOCK_K;
-                        for (int p = 0; p < NS; p++)
-                            tma_load_4d(sA(stage, p), &a.mapA[p], &full_bar[stage], c0, t.px0 + ox, t.py0 + oy, t.pn0);
                     }
-                    for (int p = 0; p < NS; p++)
-                        tma_load_2d(sB(stage, p), &a.mapB[p], &full_bar[stage], kb * BLOCK_K, brow);
+                    for (int p = p_lo; p < p_hi; p++)
+                        tma_load_2d(sB(stage, p), &a.mapB[p], &full_bar[stage], kb * BK, brow);
                     if (++stage == C::STAGES) { stage = 0; ph ^= 1; }
                 }
             }
@@ -217,45 +232,49 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS;
+            for (int pass = 0; pass < NPASS; pass++)
             for (int kb = 0; kb < a.num_k; kb++) {
                 mbar_wait(&full_bar[stage], ph);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t fresh = (kb == 0) ? 0u : 1u;
                     if constexpr (NS == 3) {
-                        // D1 += hi * w_hi (kind::f16);  D2 += l8 * w8 + a8 * wl8 (kind::f8f6f4, K = 32 per instruction)
-                        const uint32_t a16 = smem_u32(sA(stage, 0)), b16 = smem_u32(sB(stage, 0));
+                        if (pass == 0) {            // D1 += hi * w_hi (kind::f16)
+                            const uint32_t a16 = smem_u32(sA(stage, 0, 0)), b16 = smem_u32(sB(stage, 0));
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / 16; k++)
-                            umma_f16(d_tmem, umma_desc_sw128(a16 + k * 32), umma_desc_sw128(b16 + k * 32), idesc,
-                                     (k == 0) ? fresh : 1u);
-                        const uint32_t a8 = smem_u32(sA(stage, 1)), l8 = smem_u32(sA(stage, 2));
-                        const uint32_t w8 = smem_u32(sB(stage, 1)), wl8 = smem_u32(sB(stage, 2));
+                            for (int k = 0; k < BK / 16; k++)
+                                umma_f16(d_tmem, desc16(a16 + k * 32), desc16(b16 + k * 32), idesc, (k == 0) ? fresh : 1u);
+                        } else {                    // D2 += l8 * w8 + a8 * wl8 (kind::f8f6f4, K = 32 per instruction)
+                            const uint32_t a8 = smem_u32(sA(stage, 0, 1)), l8 = smem_u32(sA(stage, 0, 2));
+                            const uint32_t w8 = smem_u32(sB(stage, 1)), wl8 = smem_u32(sB(stage, 2));
 #pragma unroll
-                        for (int k = 0; k < BLOCK_K / 32; k++) {
-                            umma_f8(d_tmem + BN, umma_desc_sw64(l8 + k * 32), umma_desc_sw64(w8 + k * 32), idesc8,
-                                    (k == 0) ? fresh : 1u);
-                            umma_f8(d_tmem + BN, umma_desc_sw64(a8 + k * 32), umma_desc_sw64(wl8 + k * 32), idesc8, 1u);
+                            for (int k = 0; k < BK / 32; k++) {
+                                umma_f8(d_tmem + BN, umma_desc_sw64(l8 + k * 32), umma_desc_sw64(w8 + k * 32), idesc8,
+                                        (k == 0) ? fresh : 1u);
+                                umma_f8(d_tmem + BN, umma_desc_sw64(a8 + k * 32), umma_desc_sw64(wl8 + k * 32), idesc8, 1u);
+                            }
                         }
                     } else {
-                        uint32_t first = fresh;
                         // (A plane, B plane): small cross terms first, hi*hi last
                         constexpr int NPAIR = (NS == 2) ? 3 : 1;
                         const int pa[3] = {NS == 2 ? 1 : 0, 0, 0};
                         const int pb[3] = {0, NS == 2 ? 1 : 0, 0};
 #pragma unroll
-                        for (int q = 0; q < NPAIR; q++) {
-                            const uint32_t abase = smem_u32(sA(stage, pa[q])), bbase = smem_u32(sB(stage, pb[q]));
+                        for (int t = 0; t < TM; t++) {
+                            uint32_t first = fresh;
 #pragma unroll
-                            for (int k = 0; k < BLOCK_K / 16; k++) {
-                                umma_f16(d_tmem, umma_desc_sw128(abase + k * 32), umma_desc_sw128(bbase + k * 32), idesc,
-                                         first);
-                                first = 1u;
+                            for (int q = 0; q < NPAIR; q++) {
+                                const uint32_t abase = smem_u32(sA(stage, t, pa[q])), bbase = smem_u32(sB(stage, pb[q]));
+#pragma unroll
+                                for (int k = 0; k < BK / 16; k++) {
+                                    umma_f16(d_tmem + t * BN, desc16(abase + k * 32), desc16(bbase + k * 32), idesc, first);
+                                    first = 1u;
+                                }
                             }
                         }
                     }
                     umma_commit(&empty_bar[stage]);                        // ring slot reusable once MMAs retire
-                    if (kb == a.num_k - 1) umma_commit(&tmem_full_bar[acc]);  // accumulator ready for the epilogue
+                    if (pass == NPASS - 1 && kb == a.num_k - 1) umma_commit(&tmem_full_bar[acc]);  // accumulators ready
                 }
                 __syncwarp();
                 if (++stage == C::STAGES) { stage = 0; ph ^= 1; }
@@ -283,15 +302,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         };
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, it++) {
             const int acc = it % C::NACC; const uint32_t acc_ph = (it / C::NACC) & 1;
-            const TileCoord t = decode_tile(a, tile);
             mbar_wait(&tmem_full_bar[acc], acc_ph);
             tc_fence_after();
+#pragma unroll 1
+            for (int tm = 0; tm < TM; tm++) {
+            const TileCoord t = decode_tile<TM>(a, tile, tm);
             const int n = t.pn0 + tni, y = t.py0 + ty, xx = t.px0 + tx;
             const bool valid = (n < a.N) && (y < a.Ho) && (xx < a.Wo);
             int oy = y, ox = xx;
             if (a.mode == IPER_CONVT_4S2) { oy = 2 * y + (t.phase >> 1); ox = 2 * xx + (t.phase & 1); }
             const size_t opix = ((size_t)n * a.oH + oy) * a.oW + ox;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS + tm * BN;
 
             if (a.epi == IPER_EPI_HEADS) {
                 if constexpr (BN == 32) {
@@ -384,7 +405,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                     }
                 }
             }
-            // accumulator drained: hand the TMEM buffer back to the MMA warp
+            }  // tm
+            // accumulators drained: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -411,28 +433,28 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
     return fn;
 }
 
+// swizzle = bytes of the inner box row: fp16 BK=64 -> 128, fp16 BK=32 -> 64, e4m3 BK=64 -> 64
 static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                      const cuuint32_t* box, bool u8 = false) {
+                      const cuuint32_t* box, bool u8, int row_bytes) {
     PFN_cuTensorMapEncodeTiled_v12000 fn = get_encode_fn();
     IPER_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    // fp16 tiles: 128-byte rows / SWIZZLE_128B; e4m3 tiles: 64-byte rows / SWIZZLE_64B (64 K-elements per row either way)
     CUresult r = fn(map, u8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    u8 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     IPER_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, u8 %d)", (int)r, rank, (int)u8);
     return 0;
 }
 
 static int floor_pow2(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 
-template <int BN, int NS>
+template <int BN, int NS, int TM>
 static int launch_gemm(const GemmArgs& g, int max_ctas, cudaStream_t stream) {
-    using C = Cfg<BN, NS>;
+    using C = Cfg<BN, NS, TM>;
     static bool attr_set = false;
     if (!attr_set) {
-        IPER_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        IPER_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, NS, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              C::SMEM_BYTES));
         attr_set = true;
     }
@@ -444,7 +466,7 @@ static int launch_gemm(const GemmArgs& g, int max_ctas, cudaStream_t stream) {
     }
     int grid = g.total_tiles < num_sms ? g.total_tiles : num_sms;
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-    conv_gemm_kernel<BN, NS><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(g);
+    conv_gemm_kernel<BN, NS, TM><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(g);
     IPER_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -460,7 +482,13 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
                  "iper_conv_gemm: a_planes (%d) and w_planes (%d) must be the same format 1, 2 or 3", d->a_planes, d->w_planes);
     IPER_REQUIRE(d->a_planes != 3 || (d->w8 && d->wl8 && d->cross_scale > 0.f && d->a_pitch % 16 == 0 && d->a_coff % 16 == 0),
                  "iper_conv_gemm: format 3 needs w8, wl8, cross_scale and a 16-aligned channel window");
-    IPER_REQUIRE(d->Cin > 0 && d->Cin % BLOCK_K == 0, "iper_conv_gemm: Cin=%d must be a multiple of 64", d->Cin);
+    IPER_REQUIRE(d->Cin > 0 && d->Cin % 64 == 0, "iper_conv_gemm: Cin=%d must be a multiple of 64", d->Cin);
+    // two M tiles per CTA (weight tile reused) whenever the weight tile is the larger operand; the fp16+fp8 mode and the
+    // narrow tiles keep one
+    const int fmt = d->a_planes;
+    const int TMv = (d->tiles_m == 1 || d->tiles_m == 2) ? d->tiles_m : ((fmt != 3 && d->block_n >= 128) ? 2 : 1);
+    IPER_REQUIRE(!(fmt == 3 && TMv == 2), "iper_conv_gemm: format 3 supports tiles_m = 1 only");
+    const int BKv = TMv == 2 ? 32 : 64;
     IPER_REQUIRE(d->a_pitch % 8 == 0 && d->a_coff % 8 == 0 && d->a_coff + d->Cin <= d->a_pitch,
                  "iper_conv_gemm: bad channel window (pitch %d, offset %d, Cin %d)", d->a_pitch, d->a_coff, d->Cin);
     IPER_REQUIRE(((uintptr_t)d->a & 15) == 0 && ((uintptr_t)d->w & 15) == 0, "iper_conv_gemm: operands must be 16-byte aligned");
@@ -498,9 +526,10 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
     g.tiles_y = (g.Ho + g.th - 1) / g.th;
     g.tiles_nb = (g.N + g.tn - 1) / g.tn;
     g.m_tiles = g.tiles_x * g.tiles_y * g.tiles_nb;
+    g.m_groups = (g.m_tiles + TMv - 1) / TMv;
     g.n_tiles = d->rows / d->block_n;
-    g.total_tiles = g.m_tiles * g.n_tiles * g.phases;
-    g.cin_chunks = d->Cin / BLOCK_K;
+    g.total_tiles = g.m_groups * g.n_tiles * g.phases;
+    g.cin_chunks = d->Cin / BKv;
     g.num_k = taps * g.cin_chunks;
     g.a_coff = d->a_coff; g.a_pitch = d->a_pitch;
     g.rows = d->rows;
@@ -531,12 +560,12 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
     }
 
     // ---- tensor maps ----
-    const int fmt = d->a_planes;
     const int nmaps = fmt;                       // 1: hi | 2: hi, lo | 3: hi, a8, l8
     const cuuint64_t ktot = (cuuint64_t)taps * d->Cin;
     for (int p = 0; p < nmaps; p++) {
         const bool u8 = (fmt == 3 && p > 0);
         const size_t esz = u8 ? 1 : 2;
+        const int row_bytes = (int)(BKv * esz);
         const uint8_t* abase8 = reinterpret_cast<const uint8_t*>(d->a);
         const void* base;
         if (!u8) base = abase8 + (size_t)p * d->a_plane_stride * 2;                       // fp16 plane p
@@ -545,29 +574,32 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
             cuuint64_t dims[5] = {(cuuint64_t)2 * d->a_pitch, (cuuint64_t)d->W / 2, 2, (cuuint64_t)d->H / 2, (cuuint64_t)d->N};
             cuuint64_t str[4] = {(cuuint64_t)2 * d->a_pitch * esz, (cuuint64_t)d->W * d->a_pitch * esz,
                                  (cuuint64_t)2 * d->W * d->a_pitch * esz, (cuuint64_t)d->H * d->W * d->a_pitch * esz};
-            cuuint32_t box[5] = {BLOCK_K, (cuuint32_t)g.tw, 1, (cuuint32_t)g.th, (cuuint32_t)g.tn};
-            if (int rc = encode_map(&g.mapA[p], base, 5, dims, str, box, u8)) return rc;
+            cuuint32_t box[5] = {(cuuint32_t)BKv, (cuuint32_t)g.tw, 1, (cuuint32_t)g.th, (cuuint32_t)g.tn};
+            if (int rc = encode_map(&g.mapA[p], base, 5, dims, str, box, u8, row_bytes)) return rc;
         } else {
             cuuint64_t dims[4] = {(cuuint64_t)d->a_pitch, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
             cuuint64_t str[3] = {(cuuint64_t)d->a_pitch * esz, (cuuint64_t)d->W * d->a_pitch * esz,
                                  (cuuint64_t)d->H * d->W * d->a_pitch * esz};
-            cuuint32_t box[4] = {BLOCK_K, (cuuint32_t)g.tw, (cuuint32_t)g.th, (cuuint32_t)g.tn};
-            if (int rc = encode_map(&g.mapA[p], base, 4, dims, str, box, u8)) return rc;
+            cuuint32_t box[4] = {(cuuint32_t)BKv, (cuuint32_t)g.tw, (cuuint32_t)g.th, (cuuint32_t)g.tn};
+            if (int rc = encode_map(&g.mapA[p], base, 4, dims, str, box, u8, row_bytes)) return rc;
         }
         const void* wb;
         if (!u8) wb = reinterpret_cast<const __half*>(d->w) + (size_t)p * d->w_plane_stride;
         else wb = (p == 1) ? d->w8 : d->wl8;
         cuuint64_t wdims[2] = {ktot, (cuuint64_t)d->rows * g.phases};
         cuuint64_t wstr[1] = {ktot * esz};
-        cuuint32_t wbox[2] = {BLOCK_K, (cuuint32_t)d->block_n};
-        if (int rc = encode_map(&g.mapB[p], wb, 2, wdims, wstr, wbox, u8)) return rc;
+        cuuint32_t wbox[2] = {(cuuint32_t)BKv, (cuuint32_t)d->block_n};
+        if (int rc = encode_map(&g.mapB[p], wb, 2, wdims, wstr, wbox, u8, row_bytes)) return rc;
     }
     for (int p = nmaps; p < 3; p++) { g.mapA[p] = g.mapA[0]; g.mapB[p] = g.mapB[0]; }
 
     cudaStream_t s = (cudaStream_t)stream;
 #define IPER_DISPATCH(BNV)                                                                                           \
-    return fmt == 3 ? launch_gemm<BNV, 3>(g, d->max_ctas, s)                                                         \
-                    : (fmt == 2 ? launch_gemm<BNV, 2>(g, d->max_ctas, s) : launch_gemm<BNV, 1>(g, d->max_ctas, s))
+    do {                                                                                                             \
+        if (fmt == 3) return launch_gemm<BNV, 3, 1>(g, d->max_ctas, s);                                              \
+        if (fmt == 2) return TMv == 2 ? launch_gemm<BNV, 2, 2>(g, d->max_ctas, s) : launch_gemm<BNV, 2, 1>(g, d->max_ctas, s); \
+        return TMv == 2 ? launch_gemm<BNV, 1, 2>(g, d->max_ctas, s) : launch_gemm<BNV, 1, 1>(g, d->max_ctas, s);       \
+    } while (0)
     switch (d->block_n) {
         case 32: IPER_DISPATCH(32);
         case 64: IPER_DISPATCH(64);

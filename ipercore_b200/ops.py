@@ -153,7 +153,7 @@ def flow_resize(T, h, w):
 # generator building blocks
 # ------------------------------------------------------------------------------------------------------------------
 def _fill_desc(a, mode, ksize, rows, block_n, epi, bias=None, relu=False, out=None, x=None, mean_rstd=None,
-               spade_C=0, heads=None, max_ctas=0):
+               spade_C=0, heads=None, max_ctas=0, tiles_m=0):
     d = ConvGemmDesc()
     d.a = a.ptr(); d.a_planes = a.P; d.a_plane_stride = a.plane_stride
     d.N, d.H, d.W = a.N, a.H, a.W
@@ -175,6 +175,7 @@ def _fill_desc(a, mode, ksize, rows, block_n, epi, bias=None, relu=False, out=No
         d.bg = _ptr(bg); d.bg_batch_stride = 0 if bg is None or bg.shape[0] == 1 else bg[0].numel()
         d.img = _ptr(heads.get("img")); d.mask = _ptr(heads.get("mask")); d.pred = _ptr(heads.get("pred"))
     d.max_ctas = max_ctas
+    d.tiles_m = tiles_m
     return d
 
 

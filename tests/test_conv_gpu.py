@@ -97,10 +97,17 @@ def test_conv_gemm_planes(N, H, W, Cin, Cout, mode, k, P):
     # precision of the OUTPUT planes themselves (P=1: 11 bits; P=3: ~15 bits; P=2: ~22 bits)
     atol, rtol = {2: (1e-4, 0), 3: (1.5e-4, 1e-4), 1: (5e-4, 1.1e-3)}[P]
     np.testing.assert_allclose(got.numpy(), exp.numpy(), atol=atol, rtol=rtol)
+    if P != 3:      # both CTA shapes: one or two 128-pixel M tiles per weight tile (K stages of 64 / 32 channels)
+        for tm in (1, 2):
+            alt = Planes.empty(P, N, oH, oW, Cout, DEV)
+            ops.conv_gemm(a, wp, mode, k, rows, 256 if rows >= 256 else rows, ops.IPER_EPI_PLANES, bias=bias.to(DEV),
+                          relu=True, out=alt, tiles_m=tm)
+            np.testing.assert_allclose(_planes_value(alt).numpy(), exp.numpy(), atol=atol, rtol=rtol)
     # on-device cross-check (CUDA-core direct convolution of the stored activation values with the fp16-rounded weights)
     chk = Planes.empty(P, N, oH, oW, Cout, DEV)
-    ops.conv_direct(a, unpack(wp.effective()[0]).to(DEV), mode, k, Cout, ops.IPER_EPI_PLANES, bias=bias.to(DEV), relu=True,
-                    out=chk)
+    wm, _, wlo = wp.effective()
+    w_total = wm if wlo is None else wm + wlo            # the weight value the MMA groups add up to
+    ops.conv_direct(a, unpack(w_total).to(DEV), mode, k, Cout, ops.IPER_EPI_PLANES, bias=bias.to(DEV), relu=True, out=chk)
     np.testing.assert_allclose(got.numpy(), _planes_value(chk).numpy(), atol={2: 2e-4, 3: 4e-4, 1: 5e-4}[P],
                                rtol={2: 0, 3: 1e-4, 1: 1.1e-3}[P])
 
