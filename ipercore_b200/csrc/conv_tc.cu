@@ -483,10 +483,10 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
     IPER_REQUIRE(d->a_planes != 3 || (d->w8 && d->wl8 && d->cross_scale > 0.f && d->a_pitch % 16 == 0 && d->a_coff % 16 == 0),
                  "iper_conv_gemm: format 3 needs w8, wl8, cross_scale and a 16-aligned channel window");
     IPER_REQUIRE(d->Cin > 0 && d->Cin % 64 == 0, "iper_conv_gemm: Cin=%d must be a multiple of 64", d->Cin);
-    // two M tiles per CTA (weight tile reused) whenever the weight tile is the larger operand; the fp16+fp8 mode and the
-    // narrow tiles keep one
+    // tiles_m = 2: two M tiles per CTA share one weight tile (32-channel K stages).  Measured SLOWER on B200 than one
+    // tile with 64-channel stages (64-byte TMA rows deliver fewer bytes per request), so auto = 1; kept selectable.
     const int fmt = d->a_planes;
-    const int TMv = (d->tiles_m == 1 || d->tiles_m == 2) ? d->tiles_m : ((fmt != 3 && d->block_n >= 128) ? 2 : 1);
+    const int TMv = (d->tiles_m == 2 && fmt != 3) ? 2 : 1;
     IPER_REQUIRE(!(fmt == 3 && TMv == 2), "iper_conv_gemm: format 3 supports tiles_m = 1 only");
     const int BKv = TMv == 2 ? 32 : 64;
     IPER_REQUIRE(d->a_pitch % 8 == 0 && d->a_coff % 8 == 0 && d->a_coff + d->Cin <= d->a_pitch,
