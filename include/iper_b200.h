@@ -101,6 +101,9 @@ typedef struct {
      * e4m3((w - fp16(w))*sW*2^11); cross_scale = 1 / (2^14 * sW) turns the fp8 accumulator into the fp32 sum        */
     const void* w8; const void* wl8; float cross_scale;
     int tiles_m;                                             /* 128-pixel M tiles per CTA: 0 = auto, 1 or 2   */
+    /* IPER_EPI_PLANES only: fused instance-norm statistics of the stored output — (N, rows, 2) fp64 workspace of
+     * (sum, sum of squares), cleared by the call; finish with iper_instnorm_finalize                              */
+    double* stats_ws;
 } iper_conv_gemm_desc;
 
 /* tcgen05/TMEM implicit-GEMM convolution with TMA im2col tile loads (conv_tc.cu). */
@@ -115,13 +118,16 @@ int iper_conv_direct(const iper_conv_gemm_desc* d, const float* w_f32, int Cout,
  * (tsf_net_enc.layers.0 / src_net.encoders.layers.0, attlwb_spade_resunet.py:268-271). */
 int iper_conv_stem(const float* in_nchw, int N, int Cin, int H, int W, const float* w_f32, const float* bias, int Cout,
                    void* out, int out_planes, long long out_plane_stride, int out_pitch, int out_coff,
-                   iper_stream_t stream);
+                   double* stats_ws /* optional (N,Cout,2) fp64 sums, cleared by the call */, iper_stream_t stream);
 
 /* nn.InstanceNorm2d(affine=False) statistics (attlwb_spade_resunet.py:62, eps 1e-5, biased variance):
  * mean_rstd (N,C,2) = (mean, 1/sqrt(var+eps)) of an NHWC planes tensor.  workspace: N*C*2 doubles (fp64 sums,
  * cleared and filled by the call; two launches + one memset on the stream). */
 int iper_instnorm_stats(const void* x, int x_planes, long long x_plane_stride, int N, int HW, int C, int x_pitch,
                         int x_coff, float eps, double* workspace, float* mean_rstd, iper_stream_t stream);
+
+/* (sum, sum of squares) fp64 workspace (N*C*2) -> mean_rstd (N,C,2) fp32: mean, 1/sqrt(var_biased + eps). */
+int iper_instnorm_finalize(const double* workspace, int N, int C, int HW, float eps, float* mean_rstd, iper_stream_t stream);
 
 /* InstanceNorm2d(affine=False) apply [+ReLU] [+ residual] on NHWC planes — the BGNet blocks (bg_inpaintor.py:13-21,
  * 33-52): out = [res +] [relu]((x - mean) * rstd). */
@@ -133,13 +139,15 @@ int iper_instnorm_apply(const void* x, int x_planes, long long x_plane_stride, i
 /* tanh + NHWC fp32 (pitch channels per pixel, first C used) -> NCHW fp32: last layer of BGNet (bg_inpaintor.py:54-55). */
 int iper_tanh_nhwc_to_nchw(const float* in, int N, int HW, int C, int pitch, float* out, iper_stream_t stream);
 
-/* Flow-guided warp + per-pixel source attention (LWB.transform :184-191, SelfAttentionBlock :102-139), using
- * fk(warp(x)) = warp(Wk x) + bk:  kv (ns,h,w,2C) fp32 holds [Wk x | Wv x] per source (no bias);
- * q (B,h,w,C) fp32 (bias included); T (B,ns,h,w,2) flow at this resolution.
- * out x (B,h,w,C) planes = sum_s softmax_s(K_s.q / sqrt(C)) V_s. */
-int iper_warp_attention(const float* q, const float* kv, const float* bias_k, const float* bias_v, const float* T,
-                        int B, int ns, int h, int w, int C, void* out, int out_planes, long long out_plane_stride,
-                        int out_pitch, int out_coff, iper_stream_t stream);
+/* Flow-guided warp + per-pixel source attention (LWB.transform :184-191, SelfAttentionBlock :102-139) with the 1x1
+ * projections hoisted to the source side.  With q = Wq x_t + bq and K_s = warp(Wk x_s) + bk,
+ *   K_s . q = warp((Wq^T Wk) x_s) . x_t + warp((Wk^T bq) . x_s) + bk . q,   and bk . q cancels in softmax over s.
+ * kv (ns,h,w,2C+64) fp32 per source pixel: [ (Wq^T Wk) x_s | Wv x_s | (Wk^T bq) . x_s | pad ];  xt = target features
+ * (B,h,w,C) planes;  T (B,ns,h,w,2) flow at this resolution;  out (B,h,w,C) planes = sum_s softmax_s(.) (warp(Wv x_s) + bv). */
+int iper_warp_attention(const void* xt, int xt_planes, long long xt_plane_stride, int xt_pitch, int xt_coff,
+                        const float* kv, const float* bias_v, const float* T, int B, int ns, int h, int w, int C,
+                        void* out, int out_planes, long long out_plane_stride, int out_pitch, int out_coff,
+                        iper_stream_t stream);
 
 /* LWB.transform alone: grid_sample(src (ns,h,w,C) fp32 NHWC, T (B,ns,h,w,2)) -> (B,ns,h,w,C) fp32 (seam/debug). */
 int iper_warp_nhwc(const float* src, const float* T, int B, int ns, int h, int w, int C, float* out,

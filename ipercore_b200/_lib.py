@@ -31,6 +31,7 @@ class ConvGemmDesc(ctypes.Structure):
         ("bg", c_void_p), ("bg_batch_stride", c_ll), ("img", c_void_p), ("mask", c_void_p), ("pred", c_void_p),
         ("max_ctas", c_int),
         ("w8", c_void_p), ("wl8", c_void_p), ("cross_scale", c_float), ("tiles_m", c_int),
+        ("stats_ws", c_void_p),
     ]
 
 
@@ -47,14 +48,15 @@ SIGNATURES = {
     "iper_conv_gemm": [ctypes.POINTER(ConvGemmDesc), c_void_p],
     "iper_conv_direct": [ctypes.POINTER(ConvGemmDesc), c_void_p, c_int, c_void_p],
     "iper_conv_stem": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_ll, c_int,
-                       c_int, c_void_p],
+                       c_int, c_void_p, c_void_p],
+    "iper_instnorm_finalize": [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p],
     "iper_instnorm_stats": [c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                             c_void_p],
     "iper_instnorm_apply": [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                             c_ll, c_int, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p],
     "iper_tanh_nhwc_to_nchw": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
-    "iper_warp_attention": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
-                            c_void_p, c_int, c_ll, c_int, c_int, c_void_p],
+    "iper_warp_attention": [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                            c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p],
     "iper_warp_nhwc": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "iper_nchw_to_planes": [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p],
     "iper_planes_to_nchw": [c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],

@@ -294,6 +294,22 @@ IPER_DEVINL void store_planes8(__half* o, int fmt, long long plane_stride, size_
     }
 }
 
+// Warp transpose-reduce: every lane holds v[0..31] (32 channels of ITS pixel); afterwards lane c holds, in v[0], the sum
+// over the 32 lanes (pixels) of channel c.  31 shuffles instead of 32 x 5.
+IPER_DEVINL float warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int j = 0; j < half; j++) {
+            const float keep = up ? v[j + half] : v[j];
+            const float send = up ? v[j] : v[j + half];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+
 // split an fp32 value into fp16 hi + fp16 lo (hi + lo carries ~22 significand bits)
 IPER_DEVINL void split_half(float v, __half& hi, __half& lo) {
     hi = __float2half_rn(v);

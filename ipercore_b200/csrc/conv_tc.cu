@@ -58,6 +58,7 @@ struct alignas(64) GemmArgs {
     const float* mean_rstd; int spade_C;
     const float* bg; long long bg_batch_stride; float* img; float* mask; float* pred;
     float cross_scale;
+    double* stats_ws;        // optional (N, Cout, 2) fp64 sums of the stored output (instance-norm statistics)
 };
 
 // BN = GEMM-N tile (output channels), NS = operand format (1, 2, 3), TM = 128-pixel M tiles per CTA that share one
@@ -371,15 +372,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                     }
                 }
             } else {
+                const bool warp_uniform_n = (a.tw * a.th) % 32 == 0;      // all 32 rows of a warp lie in one image
 #pragma unroll 1
                 for (int j = 0; j < BN / 32; j++) {
                     uint32_t r[32];
                     ld_acc(taddr + j * 32, r);
-                    if (valid) {
-                        const int c0 = t.n_tile * BN + j * 32;
-                        float o[32];
+                    const int c0 = t.n_tile * BN + j * 32;
+                    float o[32];
 #pragma unroll
-                        for (int i = 0; i < 32; i++) o[i] = __uint_as_float(r[i]);
+                    for (int i = 0; i < 32; i++) o[i] = __uint_as_float(r[i]);
+                    if (valid) {
                         if (a.bias) {
 #pragma unroll
                             for (int i = 0; i < 32; i++) o[i] += __ldg(a.bias + c0 + i);
@@ -401,6 +403,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
                             for (int i = 0; i < 8; i++) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
                         } else {
                             store_planes32(a, opix * a.out_pitch + a.out_coff + c0, o);
+                        }
+                    }
+                    if (a.stats_ws != nullptr) {
+                        // fused instance-norm statistics of the value just stored (invalid rows contribute 0)
+                        if (warp_uniform_n) {
+                            // transpose-reduce over the warp's 32 pixels, then one fp64 atomic per channel (lane = channel)
+                            float sq[32];
+#pragma unroll
+                            for (int i = 0; i < 32; i++) { o[i] = valid ? o[i] : 0.f; sq[i] = o[i] * o[i]; }
+                            const float s1 = warp_transpose_sum32(o, lane), s2 = warp_transpose_sum32(sq, lane);
+                            const int nw = __shfl_sync(0xffffffffu, n, 0);
+                            if (nw < a.N) {
+                                atomicAdd(a.stats_ws + ((size_t)nw * a.rows + c0 + lane) * 2, (double)s1);
+                                atomicAdd(a.stats_ws + ((size_t)nw * a.rows + c0 + lane) * 2 + 1, (double)s2);
+                            }
+                        } else if (valid) {     // tiny maps (a warp spans several images): plain per-value atomics
+                            for (int i = 0; i < 32; i++) {
+                                atomicAdd(a.stats_ws + ((size_t)n * a.rows + c0 + i) * 2, (double)o[i]);
+                                atomicAdd(a.stats_ws + ((size_t)n * a.rows + c0 + i) * 2 + 1, (double)o[i] * (double)o[i]);
+                            }
                         }
                     }
                 }
@@ -541,6 +563,7 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
     g.mean_rstd = d->mean_rstd; g.spade_C = d->spade_C;
     g.bg = d->bg; g.bg_batch_stride = d->bg_batch_stride; g.img = d->img; g.mask = d->mask; g.pred = d->pred;
     g.cross_scale = d->cross_scale;
+    g.stats_ws = d->stats_ws;
 
     // ---- epilogue-specific validation ----
     if (d->epi == IPER_EPI_HEADS) {
@@ -594,6 +617,10 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
     for (int p = nmaps; p < 3; p++) { g.mapA[p] = g.mapA[0]; g.mapB[p] = g.mapB[0]; }
 
     cudaStream_t s = (cudaStream_t)stream;
+    if (d->stats_ws) {
+        IPER_REQUIRE(d->epi == IPER_EPI_PLANES && d->mode != IPER_CONVT_4S2, "iper_conv_gemm: fused statistics need the planes epilogue of a (strided) conv");
+        IPER_CHECK_CUDA(cudaMemsetAsync(d->stats_ws, 0, sizeof(double) * 2 * (size_t)d->N * d->rows, s));
+    }
 #define IPER_DISPATCH(BNV)                                                                                           \
     do {                                                                                                             \
         if (fmt == 3) return launch_gemm<BNV, 3, 1>(g, d->max_ctas, s);                                              \

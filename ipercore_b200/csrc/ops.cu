@@ -98,8 +98,10 @@ template <int CIN>
 __global__ void __launch_bounds__(256) conv_stem_kernel(const float* __restrict__ in, int N, int H, int W,
                                                         const float* __restrict__ wgt, const float* __restrict__ bias,
                                                         int Cout, __half* __restrict__ out, int out_planes,
-                                                        long long out_plane_stride, int out_pitch, int out_coff) {
+                                                        long long out_plane_stride, int out_pitch, int out_coff,
+                                                        double* __restrict__ stats_ws) {
     extern __shared__ __align__(16) float sm[];
+    __shared__ float s_stat[2 * 128];
     constexpr int HALO_W = 2 * STEM_TW + 1, HALO_H = 2 * STEM_TH + 1;
     float* s_in = sm;                                  // [CIN][HALO_H][HALO_W]
     float* s_w = sm + stem_halo_floats(CIN);           // [9*CIN][Cout]  (ci,ky,kx major, cout fastest)
@@ -127,7 +129,13 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(const float* __restrict_
 #pragma unroll
         for (int t = 0; t < 9; t++)
             patch[c * 9 + t] = s_in[(c * HALO_H + 2 * ly + t / 3) * HALO_W + 2 * lx + t % 3];
-    if (oy >= Ho || ox >= Wo) return;
+    const bool inside = (oy < Ho) && (ox < Wo);
+    if (stats_ws) {
+        for (int i = tid; i < 2 * Cout; i += 256) s_stat[i] = 0.f;
+        __syncthreads();
+    } else if (!inside) {
+        return;
+    }
     const size_t obase = (((size_t)n * Ho + oy) * Wo + ox) * out_pitch + out_coff;
     for (int co0 = 0; co0 < Cout; co0 += 8) {
         float acc[8];
@@ -144,7 +152,20 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(const float* __restrict_
         float o8[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) o8[j] = fmaxf(acc[j] + (bias ? bias[co0 + j] : 0.f), 0.f);
-        store_planes8(out, out_planes, out_plane_stride, obase + co0, o8);
+        if (inside) store_planes8(out, out_planes, out_plane_stride, obase + co0, o8);
+        if (stats_ws) {     // fused instance-norm statistics: warp shuffle -> shared fp32 -> global fp64 (below)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                float s1 = inside ? o8[j] : 0.f, s2 = s1 * s1;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+                if ((tid & 31) == 0) { atomicAdd(&s_stat[2 * (co0 + j)], s1); atomicAdd(&s_stat[2 * (co0 + j) + 1], s2); }
+            }
+        }
+    }
+    if (stats_ws) {
+        __syncthreads();
+        for (int i = tid; i < 2 * Cout; i += 256) atomicAdd(&stats_ws[(size_t)n * 2 * Cout + i], (double)s_stat[i]);
     }
 }
 
@@ -254,33 +275,33 @@ IPER_DEVINL Taps bilinear_taps(float gx, float gy, int h, int w) {
     return t;
 }
 
+// Source-side maps per source pixel (fp32, pitch 2C+64): [ K'' = (Wq^T Wk) x_s | V' = Wv x_s | k0 = (Wk^T bq) . x_s | pad ].
+// With q = Wq x_t + bq and K_s = warp(Wk x_s) + bk:  K_s . q = warp(K'')_s . x_t + warp(k0)_s + (bk . q), and the last
+// term is the same for every source s, so it cancels in softmax_s — the per-frame q projection disappears.
 template <int C, int NSMAX>
-__global__ void __launch_bounds__(256) warp_attention_kernel(const float* __restrict__ q, const float* __restrict__ kv,
-                                                             const float* __restrict__ bias_k,
+__global__ void __launch_bounds__(256) warp_attention_kernel(const __half* __restrict__ xt, int xt_planes,
+                                                             long long xt_plane_stride, int xt_pitch, int xt_coff,
+                                                             const float* __restrict__ kv,
                                                              const float* __restrict__ bias_v,
                                                              const float* __restrict__ T, int B, int ns, int h, int w,
                                                              __half* __restrict__ out, int out_planes,
                                                              long long out_plane_stride, int out_pitch, int out_coff) {
     // a thread owns 8 consecutive channels (two 128-bit loads per map); LPP lanes cover one pixel
-    constexpr int LPP = C / 8, PPW = 32 / LPP;
+    constexpr int LPP = C / 8, PPW = 32 / LPP, KVP = 2 * C + 64;
     const int lane = threadIdx.x & 31, cg = lane % LPP, sub = lane / LPP;
     const size_t hw = (size_t)h * w, total = (size_t)B * hw;
     const float inv_sqrt = 1.f / sqrtf((float)C);
-    float bk[8], bv[8];
+    float bv[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) { bk[j] = __ldg(bias_k + cg * 8 + j); bv[j] = __ldg(bias_v + cg * 8 + j); }
+    for (int j = 0; j < 8; j++) bv[j] = __ldg(bias_v + cg * 8 + j);
     const size_t warps = (size_t)gridDim.x * 8;
     for (size_t wi = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5); wi * PPW < total; wi += warps) {
         const size_t pix = wi * PPW + sub;
         const bool live = pix < total;
         const size_t pc = live ? pix : total - 1;           // keep the whole warp in the shuffles
         const size_t b = pc / hw, p = pc % hw;
-        float qv[8];
-        {
-            const float4* qp = reinterpret_cast<const float4*>(q + pc * C + cg * 8);
-            const float4 q0 = __ldg(qp), q1 = __ldg(qp + 1);
-            qv[0] = q0.x; qv[1] = q0.y; qv[2] = q0.z; qv[3] = q0.w; qv[4] = q1.x; qv[5] = q1.y; qv[6] = q1.z; qv[7] = q1.w;
-        }
+        float xv[8];
+        load_planes8(xt, xt_planes, xt_plane_stride, pc * xt_pitch + xt_coff + cg * 8, xv);
         float logit[NSMAX];
         float vacc[NSMAX][8];
 #pragma unroll
@@ -288,24 +309,26 @@ __global__ void __launch_bounds__(256) warp_attention_kernel(const float* __rest
             if (s >= ns) break;
             const float2 g = __ldg(reinterpret_cast<const float2*>(T) + (b * ns + s) * hw + p);
             const Taps t = bilinear_taps(g.x, g.y, h, w);
-            const float* src = kv + (size_t)s * hw * 2 * C + cg * 8;
-            float kk[8];
+            const float* src = kv + (size_t)s * hw * KVP;
+            float kk[8], k0 = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; j++) { kk[j] = 0.f; vacc[s][j] = 0.f; }
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 if (t.off[i] < 0) continue;
-                const float4* px = reinterpret_cast<const float4*>(src + (size_t)t.off[i] * 2 * C);
-                const float4 k0 = __ldg(px), k1 = __ldg(px + 1), v0 = __ldg(px + C / 4), v1 = __ldg(px + C / 4 + 1);
+                const float* pxf = src + (size_t)t.off[i] * KVP;
+                const float4* px = reinterpret_cast<const float4*>(pxf + cg * 8);
+                const float4 k0v = __ldg(px), k1 = __ldg(px + 1), v0 = __ldg(px + C / 4), v1 = __ldg(px + C / 4 + 1);
                 const float wt = t.wt[i];
-                kk[0] += k0.x * wt; kk[1] += k0.y * wt; kk[2] += k0.z * wt; kk[3] += k0.w * wt;
+                if (cg == 0) k0 += __ldg(pxf + 2 * C) * wt;
+                kk[0] += k0v.x * wt; kk[1] += k0v.y * wt; kk[2] += k0v.z * wt; kk[3] += k0v.w * wt;
                 kk[4] += k1.x * wt; kk[5] += k1.y * wt; kk[6] += k1.z * wt; kk[7] += k1.w * wt;
                 vacc[s][0] += v0.x * wt; vacc[s][1] += v0.y * wt; vacc[s][2] += v0.z * wt; vacc[s][3] += v0.w * wt;
                 vacc[s][4] += v1.x * wt; vacc[s][5] += v1.y * wt; vacc[s][6] += v1.z * wt; vacc[s][7] += v1.w * wt;
             }
-            float dot = 0.f;
+            float dot = k0;                                  // only the cg == 0 lane carries warp(k0)
 #pragma unroll
-            for (int j = 0; j < 8; j++) { dot += (kk[j] + bk[j]) * qv[j]; vacc[s][j] += bv[j]; }
+            for (int j = 0; j < 8; j++) { dot += kk[j] * xv[j]; vacc[s][j] += bv[j]; }
 #pragma unroll
             for (int o = LPP / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
             logit[s] = dot * inv_sqrt;
@@ -440,12 +463,13 @@ extern "C" int iper_conv_direct(const iper_conv_gemm_desc* g, const float* w_f32
 
 extern "C" int iper_conv_stem(const float* in_nchw, int N, int Cin, int H, int W, const float* w_f32, const float* bias,
                               int Cout, void* out, int out_planes, long long out_plane_stride, int out_pitch,
-                              int out_coff, iper_stream_t stream) {
+                              int out_coff, double* stats_ws, iper_stream_t stream) {
     IPER_REQUIRE(in_nchw && w_f32 && out, "iper_conv_stem: null pointer");
     IPER_REQUIRE(Cin >= 1 && Cin <= STEM_MAXC, "iper_conv_stem: Cin=%d not in [1,8]", Cin);
     IPER_REQUIRE(Cout % 8 == 0 && Cout <= 128, "iper_conv_stem: Cout=%d must be a multiple of 8, <= 128", Cout);
     IPER_REQUIRE(H % 2 == 0 && W % 2 == 0, "iper_conv_stem: H, W must be even");
     IPER_REQUIRE(out_pitch % 8 == 0 && out_coff % 8 == 0, "iper_conv_stem: output window must be 8-aligned");
+    if (stats_ws) IPER_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * (size_t)N * Cout, (cudaStream_t)stream));
     const size_t smem = sizeof(float) * ((size_t)stem_halo_floats(Cin) + (size_t)9 * Cin * Cout);
     dim3 grid((W / 2 + STEM_TW - 1) / STEM_TW, (H / 2 + STEM_TH - 1) / STEM_TH, N);
 #define IPER_STEM_CASE(CI)                                                                                              \
@@ -453,13 +477,22 @@ extern "C" int iper_conv_stem(const float* in_nchw, int N, int Cin, int H, int W
         IPER_CHECK_CUDA(cudaFuncSetAttribute(conv_stem_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         conv_stem_kernel<CI><<<grid, 256, smem, (cudaStream_t)stream>>>(in_nchw, N, H, W, w_f32, bias, Cout,              \
                                                                        reinterpret_cast<__half*>(out), out_planes,     \
-                                                                       out_plane_stride, out_pitch, out_coff);         \
+                                                                       out_plane_stride, out_pitch, out_coff, stats_ws); \
         break;
     switch (Cin) {
         IPER_STEM_CASE(1) IPER_STEM_CASE(2) IPER_STEM_CASE(3) IPER_STEM_CASE(4)
         IPER_STEM_CASE(5) IPER_STEM_CASE(6) IPER_STEM_CASE(7) IPER_STEM_CASE(8)
     }
 #undef IPER_STEM_CASE
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int iper_instnorm_finalize(const double* workspace, int N, int C, int HW, float eps, float* mean_rstd,
+                                      iper_stream_t stream) {
+    IPER_REQUIRE(workspace && mean_rstd, "iper_instnorm_finalize: null pointer");
+    if (N * C == 0) return 0;
+    instnorm_final_kernel<<<(N * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(workspace, N * C, HW, eps, mean_rstd);
     IPER_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -489,23 +522,27 @@ extern "C" int iper_instnorm_stats(const void* x, int x_planes, long long x_plan
     return 0;
 }
 
-extern "C" int iper_warp_attention(const float* q, const float* kv, const float* bias_k, const float* bias_v,
-                                   const float* T, int B, int ns, int h, int w, int C, void* out, int out_planes,
-                                   long long out_plane_stride, int out_pitch, int out_coff, iper_stream_t stream) {
-    IPER_REQUIRE(q && kv && bias_k && bias_v && T && out, "iper_warp_attention: null pointer");
+extern "C" int iper_warp_attention(const void* xt, int xt_planes, long long xt_plane_stride, int xt_pitch, int xt_coff,
+                                   const float* kv, const float* bias_v, const float* T, int B, int ns, int h, int w,
+                                   int C, void* out, int out_planes, long long out_plane_stride, int out_pitch,
+                                   int out_coff, iper_stream_t stream) {
+    IPER_REQUIRE(xt && kv && bias_v && T && out, "iper_warp_attention: null pointer");
     IPER_REQUIRE(ns >= 1 && ns <= ATT_MAX_NS, "iper_warp_attention: ns=%d not in [1,%d]", ns, ATT_MAX_NS);
     IPER_REQUIRE(C == 64 || C == 128 || C == 256, "iper_warp_attention: C=%d not in {64,128,256}", C);
-    IPER_REQUIRE(out_pitch % 8 == 0 && out_coff % 8 == 0, "iper_warp_attention: output window must be 8-aligned");
+    IPER_REQUIRE(out_pitch % 8 == 0 && out_coff % 8 == 0 && xt_pitch % 8 == 0 && xt_coff % 8 == 0,
+                 "iper_warp_attention: channel windows must be 8-aligned");
     const size_t total = (size_t)B * h * w;
     if (total == 0) return 0;
     const int ppw = 32 / (C / 8);
     const size_t nwarps = (total + ppw - 1) / ppw;
     const int blocks = (int)min((size_t)148 * 16, (nwarps + 7) / 8);
     __half* o = reinterpret_cast<__half*>(out);
+    const __half* x = reinterpret_cast<const __half*>(xt);
     cudaStream_t st = (cudaStream_t)stream;
 #define IPER_ATT(CV, NV)                                                                                             \
-    warp_attention_kernel<CV, NV><<<blocks, 256, 0, st>>>(q, kv, bias_k, bias_v, T, B, ns, h, w, o, out_planes,         \
-                                                          out_plane_stride, out_pitch, out_coff)
+    warp_attention_kernel<CV, NV><<<blocks, 256, 0, st>>>(x, xt_planes, xt_plane_stride, xt_pitch, xt_coff, kv, bias_v, \
+                                                          T, B, ns, h, w, o, out_planes, out_plane_stride, out_pitch,   \
+                                                          out_coff)
 #define IPER_ATT_C(CV)                                                                                               \
     do {                                                                                                             \
         if (ns <= 2) IPER_ATT(CV, 2); else if (ns <= 4) IPER_ATT(CV, 4); else IPER_ATT(CV, 8);                       \

@@ -17,8 +17,10 @@ Precision modes (``precision=``):
   "fp16"              single fp16 plane, 1 MMA per K step (≈ TF32-grade operands; ~3e-3 max-abs on the golden case).
 
 Algebraic restructuring used (SURVEY.md §8a note): fk/fv are 1x1 convs of a bilinear warp of constant source features,
-and warp is linear, so  fk(warp(x)) = warp(Wk x) + bk.  ``forward_src`` therefore projects the source features once
-(``[Wk x | Wv x]`` per stage) and ``forward_tsf`` gathers those with the flow inside the attention kernel.
+and warp is linear, so  fk(warp(x)) = warp(Wk x) + bk; moreover  K_s.q = warp(Wq^T Wk x_s).x_t + warp(Wk^T bq . x_s) + bk.q
+where the last term is the same for every source and cancels in the softmax.  ``forward_src`` therefore projects the
+source features once (``[Wq^T Wk x | Wv x | Wk^T bq . x]`` per stage) and ``forward_tsf`` needs no q/k/v convolution at
+all: the attention kernel gathers those maps with the flow and dots them with the target features directly.
 """
 import torch
 import torch.nn as nn
@@ -191,10 +193,11 @@ class AttentionLWBGenerator(nn.Module):
             pk[name] = (ops.pack_convT_weight(sd[name + ".weight"], P), sd.get(name + ".bias"))
 
         def att(prefix, c):
-            wkv = torch.cat([sd[prefix + ".fk.weight"], sd[prefix + ".fv.weight"]], 0)      # (2C, C, 1, 1)
+            # source-side projection with fq folded in: [Wq^T Wk | Wv | Wk^T bq | pad] (ops.attention_source_weight)
+            wkv = ops.attention_source_weight(sd[prefix + ".fq.weight"], sd[prefix + ".fq.bias"], sd[prefix + ".fk.weight"],
+                                              sd[prefix + ".fv.weight"])
             pk[prefix + ".kv"] = (ops.pack_conv_weight(wkv, P), None)
-            pk[prefix + ".bk"] = sd[prefix + ".fk.bias"]; pk[prefix + ".bv"] = sd[prefix + ".fv.bias"]
-            conv(prefix + ".fq")
+            pk[prefix + ".bv"] = sd[prefix + ".fv.bias"]
             conv(prefix + ".spade.mlp_shared.0")
             pk[prefix + ".spade.gb"] = ops.pack_spade_weight(
                 sd[prefix + ".spade.mlp_gamma.weight"], sd[prefix + ".spade.mlp_gamma.bias"],
@@ -228,17 +231,18 @@ class AttentionLWBGenerator(nn.Module):
         return pk
 
     # -------------------------------------------------------------------------------------------------------------
-    def _conv(self, pk, name, a, mode, ksize, out, relu=False, x=None):
+    def _conv(self, pk, name, a, mode, ksize, out, relu=False, x=None, stats_ws=None):
         w, b = pk[name]
         rows = w.rows_total // (4 if mode == IPER_CONVT_4S2 else 1)
-        ops.conv_gemm(a, w, mode, ksize, rows, _bn_for(rows), IPER_EPI_PLANES, bias=b, relu=relu, out=out, x=x)
+        ops.conv_gemm(a, w, mode, ksize, rows, _bn_for(rows), IPER_EPI_PLANES, bias=b, relu=relu, out=out, x=x,
+                      stats_ws=stats_ws)
         return out
 
     def _project_kv(self, pk, prefix, feat):
-        """[Wk x | Wv x] (no bias) of source features: Planes (ns,h,w,C) -> fp32 (ns,h,w,2C)."""
+        """source maps [(Wq^T Wk) x | Wv x | (Wk^T bq).x | pad] of source features: Planes (ns,h,w,C) -> fp32 (ns,h,w,2C+64)."""
         w, _ = pk[prefix + ".kv"]
         kv = torch.empty((feat.N, feat.H, feat.W, w.rows_total), dtype=torch.float32, device=feat.data.device)
-        ops.conv_gemm(feat, w, IPER_CONV_S1, 1, w.rows_total, _bn_for(w.rows_total), IPER_EPI_F32, out=kv)
+        ops.conv_gemm(feat, w, IPER_CONV_S1, 1, w.rows_total, 64, IPER_EPI_F32, out=kv)
         return kv
 
     def _stage_prefixes(self):
@@ -310,15 +314,12 @@ class AttentionLWBGenerator(nn.Module):
                 flows[h] = ops.flow_resize(Tst, h, h) if h != S else Tst
             return flows[h]
 
-        def att_block(prefix, x, src_x, out):
-            """SelfAttentionLWB.forward (attlwb_spade_resunet.py:208-252)."""
+        def att_block(prefix, x, src_x, out, ws):
+            """SelfAttentionLWB.forward (attlwb_spade_resunet.py:208-252); `ws` = fp64 sums of x from its producer."""
             C, h = x.C, x.H
-            stats = ops.instnorm_stats(x)
-            wq, bq = pk[prefix + ".fq"]
-            q = torch.empty((B, h, h, C), dtype=torch.float32, device=dev)
-            ops.conv_gemm(x, wq, IPER_CONV_S1, 1, C, _bn_for(C), IPER_EPI_F32, bias=bq, out=q)
+            stats = ops.instnorm_finalize(ws, h * h)
             a = Planes.empty(P, B, h, h, C, dev)
-            ops.warp_attention(q, self._kv_for(pk, prefix, src_x), pk[prefix + ".bk"], pk[prefix + ".bv"], flow_at(h), a)
+            ops.warp_attention(x, self._kv_for(pk, prefix, src_x), pk[prefix + ".bv"], flow_at(h), a)
             actv = Planes.empty(P, B, h, h, 128, dev)
             self._conv(pk, prefix + ".spade.mlp_shared.0", a, IPER_CONV_S1, 3, actv, relu=True)
             wgb, bgb = pk[prefix + ".spade.gb"]
@@ -331,19 +332,22 @@ class AttentionLWBGenerator(nn.Module):
         # 1. encoder (:507-519)
         w, b = pk["tsf_net_enc.stem"]
         x = Planes.empty(P, B, S // 2, S // 2, nf[0], dev)
-        ops.conv_stem(tsf_inputs, w, b, x)
+        ws = ops.stats_workspace(B, nf[0], dev)
+        ops.conv_stem(tsf_inputs, w, b, x, stats_ws=ws)          # instance-norm statistics fused into every producer
         for i in range(3):
             if i > 0:
                 y = Planes.empty(P, B, x.H // 2, x.W // 2, nf[i], dev)
-                x = self._conv(pk, "tsf_net_enc.layers.%d.0" % i, x, IPER_CONV_S2, 3, y, relu=True)
-            x = att_block("enc_attlwbs.%d" % i, x, src_enc_outs[i], enc_dst[i])
+                ws = ops.stats_workspace(B, nf[i], dev)
+                x = self._conv(pk, "tsf_net_enc.layers.%d.0" % i, x, IPER_CONV_S2, 3, y, relu=True, stats_ws=ws)
+            x = att_block("enc_attlwbs.%d" % i, x, src_enc_outs[i], enc_dst[i], ws)
         # 2. residual blocks (:522-529)
         for i in range(self.n_res):
             y = Planes.empty(P, B, x.H, x.W, 256, dev)
             self._conv(pk, "res_blocks.%d.main.0" % i, x, IPER_CONV_S1, 3, y, relu=True)
             z = Planes.empty(P, B, x.H, x.W, 256, dev)
-            x = self._conv(pk, "res_blocks.%d.main.2" % i, y, IPER_CONV_S1, 3, z, x=x)
-            x = att_block("res_attlwbs.%d" % i, x, src_res_outs[i], None)
+            ws = ops.stats_workspace(B, 256, dev)
+            x = self._conv(pk, "res_blocks.%d.main.2" % i, y, IPER_CONV_S1, 3, z, x=x, stats_ws=ws)
+            x = att_block("res_attlwbs.%d" % i, x, src_res_outs[i], None, ws)
         # 3. SkipDecoder (:348-357)
         self._conv(pk, "tsf_net_dec.upconvs.0.0", x, IPER_CONVT_4S2, 4, cat1.window(nf[1], nf[2]), relu=True)
         s0 = Planes.empty(P, B, S // 4, S // 4, nf[2], dev)

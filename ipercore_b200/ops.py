@@ -153,7 +153,7 @@ def flow_resize(T, h, w):
 # generator building blocks
 # ------------------------------------------------------------------------------------------------------------------
 def _fill_desc(a, mode, ksize, rows, block_n, epi, bias=None, relu=False, out=None, x=None, mean_rstd=None,
-               spade_C=0, heads=None, max_ctas=0, tiles_m=0):
+               spade_C=0, heads=None, max_ctas=0, tiles_m=0, stats_ws=None):
     d = ConvGemmDesc()
     d.a = a.ptr(); d.a_planes = a.P; d.a_plane_stride = a.plane_stride
     d.N, d.H, d.W = a.N, a.H, a.W
@@ -176,6 +176,7 @@ def _fill_desc(a, mode, ksize, rows, block_n, epi, bias=None, relu=False, out=No
         d.img = _ptr(heads.get("img")); d.mask = _ptr(heads.get("mask")); d.pred = _ptr(heads.get("pred"))
     d.max_ctas = max_ctas
     d.tiles_m = tiles_m
+    d.stats_ws = _ptr(stats_ws)
     return d
 
 
@@ -195,11 +196,23 @@ def conv_direct(a, w_f32, mode, ksize, Cout, epi, **kw):
     check(lib.iper_conv_direct(d, w_f32.data_ptr(), Cout, _stream()), "conv_direct")
 
 
-def conv_stem(x_nchw, w_f32, bias, out):
+def conv_stem(x_nchw, w_f32, bias, out, stats_ws=None):
     x_nchw = _req(x_nchw, torch.float32, "x"); w_f32 = _req(w_f32, torch.float32, "w")
     N, Cin, H, W = x_nchw.shape
     check(lib.iper_conv_stem(x_nchw.data_ptr(), N, Cin, H, W, w_f32.data_ptr(), _ptr(bias), w_f32.shape[0], out.ptr(),
-                             out.P, out.plane_stride, out.pitch, out.coff, _stream()), "conv_stem")
+                             out.P, out.plane_stride, out.pitch, out.coff, _ptr(stats_ws), _stream()), "conv_stem")
+
+
+def stats_workspace(N, C, device):
+    return torch.empty((N, C, 2), dtype=torch.float64, device=device)
+
+
+def instnorm_finalize(ws, HW, eps=1e-5):
+    """fp64 (sum, sumsq) workspace filled by a producer's fused statistics -> mean_rstd (N,C,2) fp32."""
+    N, C = ws.shape[:2]
+    out = torch.empty((N, C, 2), dtype=torch.float32, device=ws.device)
+    check(lib.iper_instnorm_finalize(ws.data_ptr(), N, C, HW, eps, out.data_ptr(), _stream()), "instnorm_finalize")
+    return out
 
 
 def instnorm_stats(x, eps=1e-5, out=None):
@@ -229,12 +242,25 @@ def tanh_nhwc_to_nchw(x, C):
     return out
 
 
-def warp_attention(q, kv, bias_k, bias_v, T, out):
-    """q (B,h,w,C) f32; kv (ns,h,w,2C) f32; T (B,ns,h,w,2) f32 -> out Planes (B,h,w,C)."""
-    B, h, w, C = q.shape; ns = kv.shape[0]
-    check(lib.iper_warp_attention(q.data_ptr(), kv.data_ptr(), bias_k.data_ptr(), bias_v.data_ptr(), T.data_ptr(), B, ns,
-                                  h, w, C, out.ptr(), out.P, out.plane_stride, out.pitch, out.coff, _stream()),
-          "warp_attention")
+def warp_attention(xt, kv, bias_v, T, out):
+    """xt Planes (B,h,w,C) target features; kv (ns,h,w,2C+64) f32 source maps [(Wq^T Wk)x | Wv x | (Wk^T bq).x | pad];
+    T (B,ns,h,w,2) f32 -> out Planes (B,h,w,C) (include/iper_b200.h: iper_warp_attention)."""
+    B, h, w, C = xt.N, xt.H, xt.W, xt.C
+    ns = kv.shape[0]
+    assert kv.shape[-1] == 2 * C + 64 and kv.dtype == torch.float32 and kv.is_contiguous()
+    check(lib.iper_warp_attention(xt.ptr(), xt.P, xt.plane_stride, xt.pitch, xt.coff, kv.data_ptr(), bias_v.data_ptr(),
+                                  T.data_ptr(), B, ns, h, w, C, out.ptr(), out.P, out.plane_stride, out.pitch, out.coff,
+                                  _stream()), "warp_attention")
+
+
+def attention_source_weight(wq, bq, wk, wv):
+    """Conv2d-shaped (2C+64, C, 1, 1) weight of the source-side projection [Wq^T Wk | Wv | Wk^T bq | 0...] (see
+    iper_warp_attention); wq/wk/wv (C,C,1,1), bq (C,)."""
+    C = wq.shape[0]
+    Wq, Wk = wq.reshape(C, C).double(), wk.reshape(C, C).double()
+    rows = torch.cat([Wq.t() @ Wk, wv.reshape(C, C).double(), (Wk.t() @ bq.double())[None],
+                      torch.zeros(63, C, dtype=torch.float64, device=wq.device)], 0)
+    return rows.float().reshape(2 * C + 64, C, 1, 1)
 
 
 def warp_nhwc(src, T):

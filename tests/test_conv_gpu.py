@@ -195,18 +195,48 @@ def test_stem_and_attention_kernels():
     ops.conv_stem(x.to(DEV), w.to(DEV), b.to(DEV), out)
     exp = F.relu(F.conv2d(x, w, b, stride=2, padding=1))
     np.testing.assert_allclose(_planes_value(out).numpy(), exp.numpy(), atol=1e-5, rtol=0)
-    # attention: K = warp(Wk x)+bk etc. against the reference formulation (warp first, then 1x1 convs)
-    B, ns, h, C = 2, 2, 16, 64
-    src = _rand((ns, C, h, h), 44); q = _rand((B, C, h, h), 45)
-    wk = _rand((C, C, 1, 1), 46, 0.2); wv = _rand((C, C, 1, 1), 47, 0.2); bk = _rand((C,), 48, 0.1); bv = _rand((C,), 49, 0.1)
-    T = _rand((B, ns, h, h, 2), 50, 1.3)                      # some samples fall outside [-1,1] -> zero padding
-    kv = torch.cat([F.conv2d(src, wk), F.conv2d(src, wv)], 1).permute(0, 2, 3, 1).contiguous()
-    att = Planes.empty(P, B, h, h, C, DEV)
-    ops.warp_attention(q.permute(0, 2, 3, 1).contiguous().to(DEV), kv.to(DEV), bk.to(DEV), bv.to(DEV), T.to(DEV), att)
-    exp = []
-    for bi in range(B):
-        warp = F.grid_sample(src, T[bi], mode="bilinear", padding_mode="zeros", align_corners=False)
-        K = F.conv2d(warp, wk, bk); V = F.conv2d(warp, wv, bv)
-        logit = (K * q[bi:bi + 1]).sum(1, keepdim=True) / math.sqrt(C)
-        exp.append((torch.softmax(logit, 0) * V).sum(0))
-    np.testing.assert_allclose(_planes_value(att).numpy(), torch.stack(exp).numpy(), atol=2e-5, rtol=0)
+    # attention with the projections hoisted to the source side, against the reference formulation
+    # (warp first, then fk/fv/fq 1x1 convs, softmax over sources — attlwb_spade_resunet.py:208-252)
+    for (B, ns, h, C) in ((2, 2, 16, 64), (1, 3, 8, 256)):
+        src = _rand((ns, C, h, h), 44); xt = _rand((B, C, h, h), 45)
+        wq = _rand((C, C, 1, 1), 51, 0.1); bq = _rand((C,), 52, 0.3)
+        wk = _rand((C, C, 1, 1), 46, 0.2); wv = _rand((C, C, 1, 1), 47, 0.2); bk = _rand((C,), 48, 0.3); bv = _rand((C,), 49, 0.1)
+        T = _rand((B, ns, h, h, 2), 50, 1.3)                      # some samples fall outside [-1,1] -> zero padding
+        kv = F.conv2d(src, ops.attention_source_weight(wq, bq, wk, wv)).permute(0, 2, 3, 1).contiguous()
+        xp = Planes.from_nchw(xt.to(DEV), P); xq = _planes_value(xp)
+        att = Planes.empty(P, B, h, h, C, DEV)
+        ops.warp_attention(xp, kv.to(DEV), bv.to(DEV), T.to(DEV), att)
+        exp = []
+        for bi in range(B):
+            warp = F.grid_sample(src, T[bi], mode="bilinear", padding_mode="zeros", align_corners=False)
+            K = F.conv2d(warp, wk, bk); V = F.conv2d(warp, wv, bv)
+            q = F.conv2d(xq[bi:bi + 1], wq, bq)
+            logit = (K * q).sum(1, keepdim=True) / math.sqrt(C)
+            exp.append((torch.softmax(logit, 0) * V).sum(0))
+        np.testing.assert_allclose(_planes_value(att).numpy(), torch.stack(exp).numpy(), atol=3e-5, rtol=0)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,mode", [(3, 16, 16, 64, 128, 0), (2, 32, 32, 64, 128, 1), (5, 4, 4, 128, 256, 0)])
+def test_fused_instnorm_statistics(N, H, W, Cin, Cout, mode):
+    """statistics fused into the producing conv (+residual/ReLU) == statistics of the stored tensor (stand-alone kernel)."""
+    from ipercore_b200 import ops
+    from ipercore_b200.ops import Planes
+    P = 2
+    x = _rand((N, Cin, H, W), 61); w = _rand((Cout, Cin, 3, 3), 62, 0.05); b = _rand((Cout,), 63, 0.2)
+    a = Planes.from_nchw(x.to(DEV), P)
+    oH, oW = (H // 2, W // 2) if mode == 1 else (H, W)
+    out = Planes.empty(P, N, oH, oW, Cout, DEV)
+    ws = ops.stats_workspace(N, Cout, DEV)
+    ops.conv_gemm(a, ops.pack_conv_weight(w, P).to(DEV), mode, 3, Cout, 256 if Cout >= 256 else Cout, ops.IPER_EPI_PLANES,
+                  bias=b.to(DEV), relu=True, out=out, stats_ws=ws)
+    fused = ops.instnorm_finalize(ws, oH * oW)
+    alone = ops.instnorm_stats(out)
+    torch.testing.assert_close(fused[..., 0], alone[..., 0], atol=2e-6, rtol=0)
+    torch.testing.assert_close(fused[..., 1], alone[..., 1], atol=0, rtol=2e-5)
+    # stem
+    xi = _rand((N, 6, 2 * H, 2 * W), 64); ws2 = ops.stats_workspace(N, 64, DEV)
+    so = Planes.empty(P, N, H, W, 64, DEV)
+    ops.conv_stem(xi.to(DEV), _rand((64, 6, 3, 3), 65, 0.2).to(DEV), None, so, stats_ws=ws2)
+    f2 = ops.instnorm_finalize(ws2, H * W); a2 = ops.instnorm_stats(so)
+    torch.testing.assert_close(f2[..., 0], a2[..., 0], atol=2e-6, rtol=0)
+    torch.testing.assert_close(f2[..., 1], a2[..., 1], atol=0, rtol=2e-5)
