@@ -153,14 +153,30 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(const float* __restrict_
 #pragma unroll
         for (int j = 0; j < 8; j++) o8[j] = fmaxf(acc[j] + (bias ? bias[co0 + j] : 0.f), 0.f);
         if (inside) store_planes8(out, out_planes, out_plane_stride, obase + co0, o8);
-        if (stats_ws) {     // fused instance-norm statistics: warp shuffle -> shared fp32 -> global fp64 (below)
+        if (stats_ws) {
+            // fused instance-norm statistics: 8 channels x 32 pixels per warp -> exchange-and-halve (8 -> 4 -> 2 -> 1
+            // values, 7 shuffles) then two plain xor steps; lane l < 8 ends with the warp's sum of channel co0 + l
+            float s1[8], s2[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                float s1 = inside ? o8[j] : 0.f, s2 = s1 * s1;
+            for (int j = 0; j < 8; j++) { s1[j] = inside ? o8[j] : 0.f; s2[j] = s1[j] * s1[j]; }
+            const int lane = tid & 31;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
-                if ((tid & 31) == 0) { atomicAdd(&s_stat[2 * (co0 + j)], s1); atomicAdd(&s_stat[2 * (co0 + j) + 1], s2); }
+            for (int half = 4; half >= 1; half >>= 1) {
+                const bool up = (lane & half) != 0;
+#pragma unroll
+                for (int j = 0; j < half; j++) {
+                    const float k1 = up ? s1[j + half] : s1[j], d1 = up ? s1[j] : s1[j + half];
+                    const float k2 = up ? s2[j + half] : s2[j], d2 = up ? s2[j] : s2[j + half];
+                    s1[j] = k1 + __shfl_xor_sync(0xffffffffu, d1, half);
+                    s2[j] = k2 + __shfl_xor_sync(0xffffffffu, d2, half);
+                }
             }
+#pragma unroll
+            for (int o = 8; o <= 16; o <<= 1) {
+                s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], o);
+                s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], o);
+            }
+            if (lane < 8) { atomicAdd(&s_stat[2 * (co0 + lane)], s1[0]); atomicAdd(&s_stat[2 * (co0 + lane) + 1], s2[0]); }
         }
     }
     if (stats_ws) {
@@ -279,7 +295,7 @@ IPER_DEVINL Taps bilinear_taps(float gx, float gy, int h, int w) {
 // With q = Wq x_t + bq and K_s = warp(Wk x_s) + bk:  K_s . q = warp(K'')_s . x_t + warp(k0)_s + (bk . q), and the last
 // term is the same for every source s, so it cancels in softmax_s — the per-frame q projection disappears.
 template <int C, int NSMAX>
-__global__ void __launch_bounds__(256) warp_attention_kernel(const __half* __restrict__ xt, int xt_planes,
+__global__ void __launch_bounds__(256, 3) warp_attention_kernel(const __half* __restrict__ xt, int xt_planes,
                                                              long long xt_plane_stride, int xt_pitch, int xt_coff,
                                                              const float* __restrict__ kv,
                                                              const float* __restrict__ bias_v,
@@ -302,17 +318,18 @@ __global__ void __launch_bounds__(256) warp_attention_kernel(const __half* __res
         const size_t b = pc / hw, p = pc % hw;
         float xv[8];
         load_planes8(xt, xt_planes, xt_plane_stride, pc * xt_pitch + xt_coff + cg * 8, xv);
-        float logit[NSMAX];
-        float vacc[NSMAX][8];
+        // online softmax over the sources: running max m, denominator den and weighted value sum o8
+        float m = -INFINITY, den = 0.f, o8[8];
 #pragma unroll
-        for (int s = 0; s < NSMAX; s++) {
-            if (s >= ns) break;
+        for (int j = 0; j < 8; j++) o8[j] = 0.f;
+#pragma unroll 1
+        for (int s = 0; s < ns; s++) {
             const float2 g = __ldg(reinterpret_cast<const float2*>(T) + (b * ns + s) * hw + p);
             const Taps t = bilinear_taps(g.x, g.y, h, w);
             const float* src = kv + (size_t)s * hw * KVP;
-            float kk[8], k0 = 0.f;
+            float kk[8], vv[8], k0 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 8; j++) { kk[j] = 0.f; vacc[s][j] = 0.f; }
+            for (int j = 0; j < 8; j++) { kk[j] = 0.f; vv[j] = bv[j]; }
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 if (t.off[i] < 0) continue;
@@ -323,33 +340,25 @@ __global__ void __launch_bounds__(256) warp_attention_kernel(const __half* __res
                 if (cg == 0) k0 += __ldg(pxf + 2 * C) * wt;
                 kk[0] += k0v.x * wt; kk[1] += k0v.y * wt; kk[2] += k0v.z * wt; kk[3] += k0v.w * wt;
                 kk[4] += k1.x * wt; kk[5] += k1.y * wt; kk[6] += k1.z * wt; kk[7] += k1.w * wt;
-                vacc[s][0] += v0.x * wt; vacc[s][1] += v0.y * wt; vacc[s][2] += v0.z * wt; vacc[s][3] += v0.w * wt;
-                vacc[s][4] += v1.x * wt; vacc[s][5] += v1.y * wt; vacc[s][6] += v1.z * wt; vacc[s][7] += v1.w * wt;
+                vv[0] += v0.x * wt; vv[1] += v0.y * wt; vv[2] += v0.z * wt; vv[3] += v0.w * wt;
+                vv[4] += v1.x * wt; vv[5] += v1.y * wt; vv[6] += v1.z * wt; vv[7] += v1.w * wt;
             }
             float dot = k0;                                  // only the cg == 0 lane carries warp(k0)
 #pragma unroll
-            for (int j = 0; j < 8; j++) { dot += kk[j] * xv[j]; vacc[s][j] += bv[j]; }
+            for (int j = 0; j < 8; j++) dot += kk[j] * xv[j];
 #pragma unroll
             for (int o = LPP / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-            logit[s] = dot * inv_sqrt;
+            const float logit = dot * inv_sqrt;
+            const float m_new = fmaxf(m, logit);
+            const float scale = expf(m - m_new), e = expf(logit - m_new);      // first source: exp(-inf) = 0
+            den = den * scale + e;
+#pragma unroll
+            for (int j = 0; j < 8; j++) o8[j] = o8[j] * scale + e * vv[j];
+            m = m_new;
         }
-        float mx = -INFINITY;
-#pragma unroll
-        for (int s = 0; s < NSMAX; s++) if (s < ns) mx = fmaxf(mx, logit[s]);
-        float den = 0.f;
-#pragma unroll
-        for (int s = 0; s < NSMAX; s++) if (s < ns) { logit[s] = expf(logit[s] - mx); den += logit[s]; }
         const float rden = 1.f / den;
-        float o8[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) o8[j] = 0.f;
-#pragma unroll
-        for (int s = 0; s < NSMAX; s++) {
-            if (s >= ns) break;
-            const float al = logit[s] * rden;
-#pragma unroll
-            for (int j = 0; j < 8; j++) o8[j] += al * vacc[s][j];
-        }
+        for (int j = 0; j < 8; j++) o8[j] *= rden;
         if (live) store_planes8(out, out_planes, out_plane_stride, pix * out_pitch + out_coff + cg * 8, o8);
     }
 }
