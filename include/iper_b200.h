@@ -153,6 +153,21 @@ int iper_warp_attention(const void* xt, int xt_planes, long long xt_plane_stride
 int iper_warp_nhwc(const float* src, const float* T, int B, int ns, int h, int w, int C, float* out,
                    iper_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * SMPL / SMPLH linear blend skinning — iPERCore/tools/human_digitalizer/smplx/lbs.py:137-227,
+ * bodynets/batch_smplh.py:137-180, base_smpl.py:28-50 (link).
+ * iper_lbs_shape (once per shape): v_shaped (nv,3) = v_template (+offsets) + shapedirs(nv,3,nb) . betas ;
+ *                                  J_rest (nj,3) = J_regressor (nj,nv) @ v_shaped
+ * iper_lbs_frames (per batch)    : pose (B,nj*3) axis-angle -> verts (B,nv,3) [+ posed joints (B,nj,3)];
+ *     posedirs ((nj-1)*9, nv*3), weights_t (nj,nv) = lbs_weights^T, src_of (nv) or NULL = cloth-link source vertex of
+ *     every output vertex; pose_feature (B,(nj-1)*9) and A (B,nj,12) are caller-provided scratch.
+ * ---------------------------------------------------------------------------------------------------------- */
+int iper_lbs_shape(const float* v_template, const float* offsets, const float* shapedirs, const float* betas,
+                   const float* J_regressor, int nv, int nb, int nj, float* v_shaped, float* J_rest, iper_stream_t stream);
+int iper_lbs_frames(const float* pose, int B, int nj, const float* v_shaped, const float* J_rest, const int32_t* parents,
+                    const float* posedirs, const float* weights_t, const int32_t* src_of, int nv, float* pose_feature,
+                    float* A, float* joints, float* verts, iper_stream_t stream);
+
 /* layout converters between the reference's NCHW fp32 tensors and NHWC planes */
 int iper_nchw_to_planes(const float* in, int N, int C, int HW, void* out, int out_planes, long long out_plane_stride,
                         int out_pitch, int out_coff, iper_stream_t stream);

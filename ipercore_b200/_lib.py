@@ -55,6 +55,9 @@ SIGNATURES = {
     "iper_instnorm_apply": [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                             c_ll, c_int, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p],
     "iper_tanh_nhwc_to_nchw": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "iper_lbs_shape": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "iper_lbs_frames": [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                        c_void_p, c_void_p, c_void_p, c_void_p],
     "iper_warp_attention": [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                             c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p],
     "iper_warp_nhwc": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],

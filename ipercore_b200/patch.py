@@ -20,10 +20,14 @@ import numpy as np
 import torch
 
 _INSTALLED = False
+_DEVICE_LBS = True
 
 
-def install(precision="fp16x2", batch=16, patch_inference=True):
-    global _INSTALLED
+def install(precision="fp16x2", batch=16, patch_inference=True, device_lbs=True):
+    """device_lbs: run SMPLH linear blend skinning of the target frames on the LBS kernels (ipercore_b200.smpl) built
+    from the reference body model's own buffers, instead of the reference's per-frame torch implementation."""
+    global _INSTALLED, _DEVICE_LBS
+    _DEVICE_LBS = device_lbs
     if _INSTALLED:
         return
     from . import neural_renderer as nr
@@ -83,9 +87,9 @@ def batched_inference(imitator, tgt_smpls, cam_strategy="smooth", output_dir="",
     """Imitator.inference (models/imitator.py:327-382) with the bs=1 loop replaced by the batched engine.
 
     Per-sequence host pre-pass exactly as upstream (:337-339, :298-305): stabilise, first_cam, cam swap; the SMPL body
-    model (upstream SMPLH.get_details) still produces the vertices — it is row (f) rank 1 of SURVEY.md §8, not yet a
-    CUDA kernel here — in chunks of `batch` frames; frames then go through FrameEngine and are written with the
-    reference's file names.  Returns the list of paths (or of CHW float arrays when output_dir is empty)."""
+    model produces the vertices in chunks of `batch` frames — on the device LBS kernels (ipercore_b200.smpl, built from
+    the reference body model's buffers) unless install(device_lbs=False) or the model uses hand PCA; frames then go through
+    FrameEngine and are written with the reference's file names.  Returns the list of paths (or of CHW float arrays when output_dir is empty)."""
     from .engine import FrameEngine
     import cv2
     dev, opt, src = imitator.device, imitator._opt, imitator.src_info
@@ -103,8 +107,15 @@ def batched_inference(imitator, tgt_smpls, cam_strategy="smooth", output_dir="",
                    bg=src["bg"].float().reshape(1, 3, opt.image_size, opt.image_size).contiguous(),
                    src_f2pts=src["f2pts"].float().contiguous())
     eng.graph = None
-    T = tgt.shape[0]
-    cams, verts = [], []
+    body = imitator.body_rec
+    if _DEVICE_LBS and not getattr(body, "use_pca", False) and not (hasattr(src["links_ids"], "ndim") and src["links_ids"].ndim == 3):
+        if getattr(imitator, "_iper_smpl", None) is None:
+            from .smpl import SMPLHDevice
+            imitator._iper_smpl = SMPLHDevice.from_reference(body).to(dev)
+        body = imitator._iper_smpl
+    T, S = tgt.shape[0], opt.image_size
+    frames = torch.empty((T, S, S, 3), dtype=torch.uint8).pin_memory()
+    cur = torch.cuda.current_stream(dev)
     for lo in range(0, T, batch):
         t = tgt[lo:lo + batch]
         n = t.shape[0]
@@ -112,17 +123,22 @@ def batched_inference(imitator, tgt_smpls, cam_strategy="smooth", output_dir="",
                                                  imitator.first_cam.expand(n, -1) if imitator.first_cam is not None else None,
                                                  cam_strategy)
         ref_smpl = torch.cat([cam, t[:, 3:-10], src["shape"][0:1].expand(n, -1)], dim=1)
-        info = imitator.body_rec.get_details(ref_smpl, src["offsets"], links_ids=src["links_ids"])
-        cams.append(info["cam"]); verts.append(info["verts"])
-    frames = eng.synthesize(torch.cat(cams).float().cpu().pin_memory(), torch.cat(verts).float().cpu().pin_memory())
-    torch.cuda.synchronize(dev)
+        info = body.get_details(ref_smpl, src["offsets"], links_ids=src["links_ids"])
+        eng.compute.wait_stream(cur)                       # vertices stay on the device: LBS -> raster -> generator
+        u8 = eng.run_batch_device(info["cam"].float().contiguous(), info["verts"].float().contiguous())
+        with torch.cuda.stream(eng.compute):
+            frames[lo:lo + n].copy_(u8[:n], non_blocking=True)
+    eng.compute.synchronize()
     outputs = []
-    for t in range(T):
-        if output_dir:
-            path = os.path.join(output_dir, prefix + "{:0>8}.png".format(t))
-            cv2.imwrite(path, frames[t].numpy())           # already uint8 BGR HWC (cv_utils.save_cv2_img semantics)
-            outputs.append(path)
-        else:
+    if output_dir:
+        # PNG encode off the GPU's critical path: a small thread pool (cv2.imwrite releases the GIL)
+        from concurrent.futures import ThreadPoolExecutor
+        paths = [os.path.join(output_dir, prefix + "{:0>8}.png".format(t)) for t in range(T)]
+        with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 4)) as pool:
+            list(pool.map(lambda a: cv2.imwrite(a[0], a[1]), ((paths[t], frames[t].numpy()) for t in range(T))))
+        outputs = paths                                      # frames are uint8 BGR HWC (cv_utils.save_cv2_img semantics)
+    else:
+        for t in range(T):
             f = frames[t].numpy()[:, :, ::-1].astype(np.float32) / 255.0 * 2.0 - 1.0
             outputs.append(np.ascontiguousarray(f.transpose(2, 0, 1)))
     return outputs

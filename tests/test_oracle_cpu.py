@@ -103,3 +103,19 @@ def test_state_dict_layout():
     shapes = weights.generator_param_shapes()
     assert len(shapes) == 221
     assert sum(int(np.prod(s)) for _, s in shapes) == 36276992
+
+
+def test_lbs_restatement_matches_reference(template, golden_dir):
+    """oracle/lbs_ref.py against verts/joints produced by the reference's own lbs() + link() (tests/golden/lbs.npz)."""
+    import make_golden
+    from oracle import lbs_ref
+    g = np.load(os.path.join(golden_dir, "lbs.npz"))
+    m = lbs_ref.synthetic_smplh(template=template["verts"])
+    betas, pose, links, offsets = make_golden.lbs_inputs()
+    v, j = lbs_ref.lbs(m, betas, pose, offsets=offsets, links=links)
+    np.testing.assert_allclose(v, g["verts"], atol=2e-6, rtol=0)
+    np.testing.assert_allclose(j, g["joints"], atol=2e-6, rtol=0)
+    # 72-dim body pose path pads the hands mean (batch_smplh.py:158-160)
+    v72, _ = lbs_ref.smplh_forward(m, betas, pose[:, :72])
+    full = np.concatenate([pose[:, :66], np.repeat(m["hands_mean"][None], 3, 0)], 1)
+    np.testing.assert_array_equal(v72, lbs_ref.lbs(m, betas, full)[0])
