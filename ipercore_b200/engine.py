@@ -86,7 +86,9 @@ class FrameEngine:
                     self.graph = False
 
     def run_batch_device(self, cams_d, verts_d):
-        """Synthesize B frames whose inputs are already on the device; returns the static uint8 (B,S,S,3) BGR buffer."""
+        """Synthesize B frames whose inputs are already on the device; returns the static uint8 (B,S,S,3) BGR buffer.
+        Work is issued on `self.compute`: the inputs must be safe to read there (long-lived tensors, or produced on that
+        stream) and the caller orders its own stream against `self.compute`."""
         self._ensure_ready(verts_d.shape[1])
         with torch.cuda.stream(self.compute):
             n = cams_d.shape[0]

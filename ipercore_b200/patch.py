@@ -107,10 +107,11 @@ def batched_inference(imitator, tgt_smpls, cam_strategy="smooth", output_dir="",
                    bg=src["bg"].float().reshape(1, 3, opt.image_size, opt.image_size).contiguous(),
                    src_f2pts=src["f2pts"].float().contiguous())
     eng.graph = None
+    from .smpl import SMPLHDevice
     body = imitator.body_rec
-    if _DEVICE_LBS and not getattr(body, "use_pca", False) and not (hasattr(src["links_ids"], "ndim") and src["links_ids"].ndim == 3):
+    if (_DEVICE_LBS and not isinstance(body, SMPLHDevice) and not getattr(body, "use_pca", False)
+            and not (hasattr(src["links_ids"], "ndim") and src["links_ids"].ndim == 3)):
         if getattr(imitator, "_iper_smpl", None) is None:
-            from .smpl import SMPLHDevice
             imitator._iper_smpl = SMPLHDevice.from_reference(body).to(dev)
         body = imitator._iper_smpl
     T, S = tgt.shape[0], opt.image_size
@@ -123,10 +124,12 @@ def batched_inference(imitator, tgt_smpls, cam_strategy="smooth", output_dir="",
                                                  imitator.first_cam.expand(n, -1) if imitator.first_cam is not None else None,
                                                  cam_strategy)
         ref_smpl = torch.cat([cam, t[:, 3:-10], src["shape"][0:1].expand(n, -1)], dim=1)
-        info = body.get_details(ref_smpl, src["offsets"], links_ids=src["links_ids"])
-        eng.compute.wait_stream(cur)                       # vertices stay on the device: LBS -> raster -> generator
-        u8 = eng.run_batch_device(info["cam"].float().contiguous(), info["verts"].float().contiguous())
+        eng.compute.wait_stream(cur)
         with torch.cuda.stream(eng.compute):
+            # everything of a batch is issued on the engine's stream (LBS -> raster -> generator -> u8 -> D2H), so the
+            # vertices never leave the device and no tensor crosses streams
+            info = body.get_details(ref_smpl, src["offsets"], links_ids=src["links_ids"])
+            u8 = eng.run_batch_device(info["cam"].float().contiguous(), info["verts"].float().contiguous())
             frames[lo:lo + n].copy_(u8[:n], non_blocking=True)
     eng.compute.synchronize()
     outputs = []
