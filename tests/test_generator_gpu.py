@@ -73,3 +73,36 @@ def test_forward_bg_matches_reference(golden_dir):
     err = np.abs(bg.cpu().numpy() - g["bg_img"]).max()
     print("forward_bg max-abs err %.2e" % err)
     assert bg.shape == (1, 1, 3, S, S) and err <= 1e-3
+
+
+@pytest.mark.parametrize("S,ns,B", [(192, 3, 2), (320, 1, 1)])
+def test_generic_sizes_and_source_counts(S, ns, B, template):
+    """Sizes that are not powers of two (partial tiles at every level) and ns != 2, whole path vs the CPU oracle."""
+    from ipercore_b200.renders import SMPLRenderer
+    from oracle import flow_ref, generator_ref, synth, weights
+    dev = "cuda:0"
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    sd = weights.synth_state_dict(0)
+    net = _gen("fp16x2")
+    r = SMPLRenderer(image_size=S, tables=template).to(dev)
+    cams, verts = synth.pose_sweep(template, B, total=9, start=1)
+    scams, sverts = synth.source_views(template, ns)
+    uv_img = synth.smooth_image((1, 3, S, S), seed=21); src_img = synth.smooth_image((ns, 3, S, S), seed=22)
+    src_f2pts, sfim, _ = flow_ref.render_fim_wim(scams, sverts, template["faces"], S)
+    src_inputs = np.concatenate([src_img, flow_ref.encode_fim(sfim, template["map_fn"])], 1)[None]
+    want = flow_ref.frame_inputs(cams, verts, template["faces"], template["map_fn"], template["f_uvs2img"], uv_img,
+                                 src_f2pts, S)
+    got = r.frame_inputs(t(cams), t(verts), t(uv_img), t(src_f2pts), want_fim=True)
+    np.testing.assert_array_equal(got["fim"].cpu().numpy(), want["fim"])
+    np.testing.assert_allclose(got["Tst"].cpu().numpy(), want["Tst"], atol=1e-6, rtol=0)
+    enc, res = net.forward_src(t(src_inputs))
+    img, mask = net.forward_tsf(got["tsf_inputs"], enc, res, got["Tst"])
+    err = 0.0
+    with torch.no_grad():
+        se, sr = generator_ref.forward_src(sd, torch.from_numpy(src_inputs))
+        for i in range(B):
+            ei, em = generator_ref.forward_tsf(sd, torch.from_numpy(want["tsf_inputs"][i:i + 1]), se, sr,
+                                               torch.from_numpy(want["Tst"][i:i + 1]))
+            err = max(err, float((img[i:i + 1].cpu() - ei).abs().max()), float((mask[i:i + 1].cpu() - em).abs().max()))
+    print("S=%d ns=%d: max-abs err %.2e" % (S, ns, err))
+    assert err <= 1e-3
