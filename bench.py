@@ -290,7 +290,7 @@ def main():
         recs = []
         orig = ops.conv_gemm
 
-        def timed_conv(a, wpack, mode, ksize, rows, block_n, epi, **kw):
+        def timed_conv(a, wpack, mode, ksize, rows, block_n, epi, **kw):  # noqa: E306
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(); orig(a, wpack, mode, ksize, rows, block_n, epi, **kw); e1.record()
             phases = 4 if mode == ops.IPER_CONVT_4S2 else 1

@@ -104,6 +104,7 @@ typedef struct {
     /* IPER_EPI_PLANES only: fused instance-norm statistics of the stored output — (N, rows, 2) fp64 workspace of
      * (sum, sum of squares), cleared by the call; finish with iper_instnorm_finalize                              */
     double* stats_ws;
+    int cta_pair;                                            /* 1: 2-CTA clusters (cta_group::2), weight tile split across the pair */
 } iper_conv_gemm_desc;
 
 /* tcgen05/TMEM implicit-GEMM convolution with TMA im2col tile loads (conv_tc.cu). */

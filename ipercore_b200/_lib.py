@@ -31,7 +31,7 @@ class ConvGemmDesc(ctypes.Structure):
         ("bg", c_void_p), ("bg_batch_stride", c_ll), ("img", c_void_p), ("mask", c_void_p), ("pred", c_void_p),
         ("max_ctas", c_int),
         ("w8", c_void_p), ("wl8", c_void_p), ("cross_scale", c_float), ("tiles_m", c_int),
-        ("stats_ws", c_void_p),
+        ("stats_ws", c_void_p), ("cta_pair", c_int),
     ]
 
 

@@ -147,6 +147,68 @@ IPER_DEVINL void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint
         ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms: the leader CTA of a 2-CTA cluster issues MMAs that read A/B from BOTH CTAs' smem ----
+IPER_DEVINL uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+IPER_DEVINL void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+IPER_DEVINL void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {   // arrive on the same-offset barrier of CTA `cta`
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(cta)
+        : "memory");
+}
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit: the barrier of CTA 0 of the pair
+IPER_DEVINL void tma_load_2d_2sm(void* smem, const void* desc, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+IPER_DEVINL void tma_load_4d_2sm(void* smem, const void* desc, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3)
+        : "memory");
+}
+IPER_DEVINL void tma_load_5d_2sm(void* smem, const void* desc, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1),
+        "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+IPER_DEVINL void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {   // same warp id in both CTAs, same dst offset
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+IPER_DEVINL void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 from each CTA] * B[N rows: N/2 from each CTA]
+IPER_DEVINL void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on the same-offset mbarrier of every CTA in `mask` once the MMAs issued so far have completed
+IPER_DEVINL void umma_commit_2sm(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+
 // arrive on an mbarrier once all previously issued MMAs of this thread have completed
 IPER_DEVINL void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

@@ -128,6 +128,145 @@ IPER_DEVINL void load_planes32(const __half* x, int fmt, long long plane_stride,
     }
 }
 
+// Epilogue of one 128-pixel tile: thread = accumulator row (pixel); `taddr` = TMEM address of the tile's D1 columns
+// for this warp's lane quarter.  Shared by the single-CTA and the CTA-pair kernels.
+template <int BN, int NS>
+IPER_DEVINL void epilogue_tile(const GemmArgs& a, const TileCoord& t, uint32_t taddr, int row, int lane, int tx, int ty,
+                               int tni) {
+    // accumulator chunk: 32 fp32 columns of D1 (+ the matching columns of the fp8 cross-term accumulator D2)
+    auto ld_acc = [&](uint32_t taddr_col, uint32_t (&r)[32]) {
+        tmem_ld32(taddr_col, r);
+        if constexpr (NS == 3) {
+            uint32_t r2[32];
+            tmem_ld32(taddr_col + BN, r2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; i++)
+                r[i] = __float_as_uint(fmaf(__uint_as_float(r2[i]), a.cross_scale, __uint_as_float(r[i])));
+        } else {
+            tmem_ld_wait();
+        }
+    };
+            const int n = t.pn0 + tni, y = t.py0 + ty, xx = t.px0 + tx;
+            const bool valid = (n < a.N) && (y < a.Ho) && (xx < a.Wo);
+            int oy = y, ox = xx;
+            if (a.mode == IPER_CONVT_4S2) { oy = 2 * y + (t.phase >> 1); ox = 2 * xx + (t.phase & 1); }
+            const size_t opix = ((size_t)n * a.oH + oy) * a.oW + ox;
+
+            if (a.epi == IPER_EPI_HEADS) {
+                if constexpr (BN == 32) {
+                    __shared__ float s_ex[BLOCK_M * 21];          // D[row][dx*4+o], 20 used columns (+1 pad)
+                    uint32_t r[32];
+                    ld_acc(taddr, r);
+#pragma unroll
+                    for (int i = 0; i < 20; i++) s_ex[row * 21 + i] = __uint_as_float(r[i]);
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    const int xo = t.px0 + row;
+                    if (row >= 2 && row < BLOCK_M - 2 && xo >= 0 && xo < a.Wo && n < a.N && y < a.Ho) {
+                        float o4[4];
+#pragma unroll
+                        for (int o = 0; o < 4; o++) {
+                            float acc4 = 0.f;
+#pragma unroll
+                            for (int dx = 0; dx < 5; dx++) acc4 += s_ex[(row + dx - 2) * 21 + dx * 4 + o];
+                            o4[o] = acc4;
+                        }
+                        const size_t hw = (size_t)a.oH * a.oW, p = (size_t)y * a.oW + xo;
+                        const float m = 1.f / (1.f + expf(-o4[3]));
+                        if (a.mask) a.mask[(size_t)n * hw + p] = m;
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            const float v = tanhf(o4[c]);
+                            if (a.img) a.img[((size_t)n * 3 + c) * hw + p] = v;
+                            if (a.pred) {
+                                const float bgv = a.bg[(size_t)n * a.bg_batch_stride + c * hw + p];
+                                a.pred[((size_t)n * 3 + c) * hw + p] = m * bgv + (1.f - m) * v;   // imitator.py:393
+                            }
+                        }
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");   // s_ex is reused by the next tile
+                }
+            } else if (a.epi == IPER_EPI_SPADE) {
+                constexpr int CB = BN / 2;      // channels per tile: columns [0,CB) gamma, [CB,2CB) beta
+#pragma unroll 1
+                for (int j = 0; j < CB / 32; j++) {
+                    uint32_t rg[32], rb[32];
+                    ld_acc(taddr + j * 32, rg);
+                    ld_acc(taddr + CB + j * 32, rb);
+                    if (valid) {
+                        const int c0 = t.n_tile * CB + j * 32;
+                        float xv[32], o[32];
+                        load_planes32(a.x, a.x_planes, a.x_plane_stride, opix * a.x_pitch + a.x_coff + c0, xv);
+                        const float* mr = a.mean_rstd + ((size_t)n * a.spade_C + c0) * 2;
+                        const float* bgm = a.bias + t.n_tile * BN + j * 32;
+#pragma unroll
+                        for (int i = 0; i < 32; i++) {
+                            const float gamma = __uint_as_float(rg[i]) + __ldg(bgm + i);
+                            const float beta = __uint_as_float(rb[i]) + __ldg(bgm + CB + i);
+                            const float nrm = (xv[i] - __ldg(mr + 2 * i)) * __ldg(mr + 2 * i + 1);
+                            o[i] = nrm * (1.f + gamma) + beta;                // attlwb_spade_resunet.py:92
+                        }
+                        store_planes32(a, opix * a.out_pitch + a.out_coff + c0, o);
+                    }
+                }
+            } else {
+                const bool warp_uniform_n = (a.tw * a.th) % 32 == 0;      // all 32 rows of a warp lie in one image
+#pragma unroll 1
+                for (int j = 0; j < BN / 32; j++) {
+                    uint32_t r[32];
+                    ld_acc(taddr + j * 32, r);
+                    const int c0 = t.n_tile * BN + j * 32;
+                    float o[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i++) o[i] = __uint_as_float(r[i]);
+                    if (valid) {
+                        if (a.bias) {
+#pragma unroll
+                            for (int i = 0; i < 32; i++) o[i] += __ldg(a.bias + c0 + i);
+                        }
+                        if (a.x) {   // residual (ResidualBlock: x + main(x), attlwb_spade_resunet.py:25)
+                            float xv[32];
+                            load_planes32(a.x, a.x_planes, a.x_plane_stride, opix * a.x_pitch + a.x_coff + c0, xv);
+#pragma unroll
+                            for (int i = 0; i < 32; i++) o[i] = xv[i] + o[i];
+                        }
+                        if (a.relu) {
+#pragma unroll
+                            for (int i = 0; i < 32; i++) o[i] = fmaxf(o[i], 0.f);
+                        }
+                        if (a.epi == IPER_EPI_F32) {
+                            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) +
+                                                                    opix * a.out_pitch + a.out_coff + c0);
+#pragma unroll
+                            for (int i = 0; i < 8; i++) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                        } else {
+                            store_planes32(a, opix * a.out_pitch + a.out_coff + c0, o);
+                        }
+                    }
+                    if (a.stats_ws != nullptr) {
+                        // fused instance-norm statistics of the value just stored (invalid rows contribute 0)
+                        if (warp_uniform_n) {
+                            // transpose-reduce over the warp's 32 pixels, then one fp64 atomic per channel (lane = channel)
+                            float sq[32];
+#pragma unroll
+                            for (int i = 0; i < 32; i++) { o[i] = valid ? o[i] : 0.f; sq[i] = o[i] * o[i]; }
+                            const float s1 = warp_transpose_sum32(o, lane), s2 = warp_transpose_sum32(sq, lane);
+                            const int nw = __shfl_sync(0xffffffffu, n, 0);
+                            if (nw < a.N) {
+                                atomicAdd(a.stats_ws + ((size_t)nw * a.rows + c0 + lane) * 2, (double)s1);
+                                atomicAdd(a.stats_ws + ((size_t)nw * a.rows + c0 + lane) * 2 + 1, (double)s2);
+                            }
+                        } else if (valid) {     // tiny maps (a warp spans several images): plain per-value atomics
+                            for (int i = 0; i < 32; i++) {
+                                atomicAdd(a.stats_ws + ((size_t)n * a.rows + c0 + i) * 2, (double)o[i]);
+                                atomicAdd(a.stats_ws + ((size_t)n * a.rows + c0 + i) * 2 + 1, (double)o[i] * (double)o[i]);
+                            }
+                        }
+                    }
+                }
+            }
+}
+
 template <int BN, int NS, int TM>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ GemmArgs a) {
     using C = Cfg<BN, NS, TM>;
@@ -287,20 +426,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         const int row = q * 32 + lane;          // accumulator row = pixel index inside the patch
         const int tx = row % a.tw, ty = (row / a.tw) % a.th, tni = row / (a.tw * a.th);
         int it = 0;
-        // accumulator chunk: 32 fp32 columns of D1 (+ the matching columns of the fp8 cross-term accumulator D2)
-        auto ld_acc = [&](uint32_t taddr_col, uint32_t (&r)[32]) {
-            tmem_ld32(taddr_col, r);
-            if constexpr (NS == 3) {
-                uint32_t r2[32];
-                tmem_ld32(taddr_col + BN, r2);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; i++)
-                    r[i] = __float_as_uint(fmaf(__uint_as_float(r2[i]), a.cross_scale, __uint_as_float(r[i])));
-            } else {
-                tmem_ld_wait();
-            }
-        };
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, it++) {
             const int acc = it % C::NACC; const uint32_t acc_ph = (it / C::NACC) & 1;
             mbar_wait(&tmem_full_bar[acc], acc_ph);
@@ -308,125 +433,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
 #pragma unroll 1
             for (int tm = 0; tm < TM; tm++) {
             const TileCoord t = decode_tile<TM>(a, tile, tm);
-            const int n = t.pn0 + tni, y = t.py0 + ty, xx = t.px0 + tx;
-            const bool valid = (n < a.N) && (y < a.Ho) && (xx < a.Wo);
-            int oy = y, ox = xx;
-            if (a.mode == IPER_CONVT_4S2) { oy = 2 * y + (t.phase >> 1); ox = 2 * xx + (t.phase & 1); }
-            const size_t opix = ((size_t)n * a.oH + oy) * a.oW + ox;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS + tm * BN;
-
-            if (a.epi == IPER_EPI_HEADS) {
-                if constexpr (BN == 32) {
-                    __shared__ float s_ex[BLOCK_M * 21];          // D[row][dx*4+o], 20 used columns (+1 pad)
-                    uint32_t r[32];
-                    ld_acc(taddr, r);
-#pragma unroll
-                    for (int i = 0; i < 20; i++) s_ex[row * 21 + i] = __uint_as_float(r[i]);
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    const int xo = t.px0 + row;
-                    if (row >= 2 && row < BLOCK_M - 2 && xo >= 0 && xo < a.Wo && n < a.N && y < a.Ho) {
-                        float o4[4];
-#pragma unroll
-                        for (int o = 0; o < 4; o++) {
-                            float acc4 = 0.f;
-#pragma unroll
-                            for (int dx = 0; dx < 5; dx++) acc4 += s_ex[(row + dx - 2) * 21 + dx * 4 + o];
-                            o4[o] = acc4;
-                        }
-                        const size_t hw = (size_t)a.oH * a.oW, p = (size_t)y * a.oW + xo;
-                        const float m = 1.f / (1.f + expf(-o4[3]));
-                        if (a.mask) a.mask[(size_t)n * hw + p] = m;
-#pragma unroll
-                        for (int c = 0; c < 3; c++) {
-                            const float v = tanhf(o4[c]);
-                            if (a.img) a.img[((size_t)n * 3 + c) * hw + p] = v;
-                            if (a.pred) {
-                                const float bgv = a.bg[(size_t)n * a.bg_batch_stride + c * hw + p];
-                                a.pred[((size_t)n * 3 + c) * hw + p] = m * bgv + (1.f - m) * v;   // imitator.py:393
-                            }
-                        }
-                    }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");   // s_ex is reused by the next tile
-                }
-            } else if (a.epi == IPER_EPI_SPADE) {
-                constexpr int CB = BN / 2;      // channels per tile: columns [0,CB) gamma, [CB,2CB) beta
-#pragma unroll 1
-                for (int j = 0; j < CB / 32; j++) {
-                    uint32_t rg[32], rb[32];
-                    ld_acc(taddr + j * 32, rg);
-                    ld_acc(taddr + CB + j * 32, rb);
-                    if (valid) {
-                        const int c0 = t.n_tile * CB + j * 32;
-                        float xv[32], o[32];
-                        load_planes32(a.x, a.x_planes, a.x_plane_stride, opix * a.x_pitch + a.x_coff + c0, xv);
-                        const float* mr = a.mean_rstd + ((size_t)n * a.spade_C + c0) * 2;
-                        const float* bgm = a.bias + t.n_tile * BN + j * 32;
-#pragma unroll
-                        for (int i = 0; i < 32; i++) {
-                            const float gamma = __uint_as_float(rg[i]) + __ldg(bgm + i);
-                            const float beta = __uint_as_float(rb[i]) + __ldg(bgm + CB + i);
-                            const float nrm = (xv[i] - __ldg(mr + 2 * i)) * __ldg(mr + 2 * i + 1);
-                            o[i] = nrm * (1.f + gamma) + beta;                // attlwb_spade_resunet.py:92
-                        }
-                        store_planes32(a, opix * a.out_pitch + a.out_coff + c0, o);
-                    }
-                }
-            } else {
-                const bool warp_uniform_n = (a.tw * a.th) % 32 == 0;      // all 32 rows of a warp lie in one image
-#pragma unroll 1
-                for (int j = 0; j < BN / 32; j++) {
-                    uint32_t r[32];
-                    ld_acc(taddr + j * 32, r);
-                    const int c0 = t.n_tile * BN + j * 32;
-                    float o[32];
-#pragma unroll
-                    for (int i = 0; i < 32; i++) o[i] = __uint_as_float(r[i]);
-                    if (valid) {
-                        if (a.bias) {
-#pragma unroll
-                            for (int i = 0; i < 32; i++) o[i] += __ldg(a.bias + c0 + i);
-                        }
-                        if (a.x) {   // residual (ResidualBlock: x + main(x), attlwb_spade_resunet.py:25)
-                            float xv[32];
-                            load_planes32(a.x, a.x_planes, a.x_plane_stride, opix * a.x_pitch + a.x_coff + c0, xv);
-#pragma unroll
-                            for (int i = 0; i < 32; i++) o[i] = xv[i] + o[i];
-                        }
-                        if (a.relu) {
-#pragma unroll
-                            for (int i = 0; i < 32; i++) o[i] = fmaxf(o[i], 0.f);
-                        }
-                        if (a.epi == IPER_EPI_F32) {
-                            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(a.out) +
-                                                                    opix * a.out_pitch + a.out_coff + c0);
-#pragma unroll
-                            for (int i = 0; i < 8; i++) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-                        } else {
-                            store_planes32(a, opix * a.out_pitch + a.out_coff + c0, o);
-                        }
-                    }
-                    if (a.stats_ws != nullptr) {
-                        // fused instance-norm statistics of the value just stored (invalid rows contribute 0)
-                        if (warp_uniform_n) {
-                            // transpose-reduce over the warp's 32 pixels, then one fp64 atomic per channel (lane = channel)
-                            float sq[32];
-#pragma unroll
-                            for (int i = 0; i < 32; i++) { o[i] = valid ? o[i] : 0.f; sq[i] = o[i] * o[i]; }
-                            const float s1 = warp_transpose_sum32(o, lane), s2 = warp_transpose_sum32(sq, lane);
-                            const int nw = __shfl_sync(0xffffffffu, n, 0);
-                            if (nw < a.N) {
-                                atomicAdd(a.stats_ws + ((size_t)nw * a.rows + c0 + lane) * 2, (double)s1);
-                                atomicAdd(a.stats_ws + ((size_t)nw * a.rows + c0 + lane) * 2 + 1, (double)s2);
-                            }
-                        } else if (valid) {     // tiny maps (a warp spans several images): plain per-value atomics
-                            for (int i = 0; i < 32; i++) {
-                                atomicAdd(a.stats_ws + ((size_t)n * a.rows + c0 + i) * 2, (double)o[i]);
-                                atomicAdd(a.stats_ws + ((size_t)n * a.rows + c0 + i) * 2 + 1, (double)o[i] * (double)o[i]);
-                            }
-                        }
-                    }
-                }
-            }
+            epilogue_tile<BN, NS>(a, t, taddr, row, lane, tx, ty, tni);
             }  // tm
             // accumulators drained: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
@@ -438,6 +446,181 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2).  A 2-CTA cluster computes two 128-pixel M tiles against one N tile: every CTA
+// stages its own A tile and HALF of the weight tile (N/2 rows); the leader CTA issues tcgen05.mma.cta_group::2
+// (M = 256, N = BN) that reads A and B from both CTAs' shared memory and writes each CTA's own TMEM.  Per CTA a K step
+// is A + B/2 bytes (64 KB instead of 96 KB for BN = 256, split fp16), so the ring is 3 deep instead of 2 and every SM
+// ingests 1.5x fewer operand bytes per MMA.  Barriers: TMA of both CTAs completes on the LEADER's full barrier; the
+// leader's tcgen05.commit multicasts to both CTAs' empty / tmem_full barriers; both epilogues arrive on the leader's
+// tmem_empty barrier.  NS in {1, 2}.
+// ------------------------------------------------------------------------------------------------------------
+template <int BN, int NS>
+struct Cfg2 {
+    static_assert(NS == 1 || NS == 2, "CTA pairs support fp16 and split fp16");
+    static constexpr int BK = 64;
+    static constexpr int A_TILE = BLOCK_M * 128;
+    static constexpr int B_HALF = (BN / 2) * 128;
+    static constexpr int STAGE_BYTES = NS * (A_TILE + B_HALF);          // per CTA
+    static constexpr int STAGES = (SMEM_BUDGET / STAGE_BYTES) < MAX_STAGES ? (SMEM_BUDGET / STAGE_BYTES) : MAX_STAGES;
+    static constexpr int ACC_COLS = BN;
+    static constexpr int NACC = 2;
+    static constexpr int TMEM_COLS = (NACC * ACC_COLS) < 32 ? 32 : (NACC * ACC_COLS);
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;
+    static_assert(SMEM_BYTES >= 116 * 1024, "one CTA per SM");
+};
+
+template <int BN, int NS>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_pair_kernel(const __grid_constant__ GemmArgs a) {
+    using C = Cfg2<BN, NS>;
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];     // used in the leader CTA (count 2 + tx bytes of both CTAs)
+    __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];    // per CTA, signalled by the leader's multicast commit
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];         // per CTA, multicast commit
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];        // used in the leader CTA (8 epilogue warps of the pair)
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();                   // 0 = leader
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const uint32_t ring = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    uint8_t* ring_ptr = smem_dyn + (ring - smem_u32(smem_dyn));
+    auto sA = [&](int stage, int p) -> uint8_t* { return ring_ptr + stage * C::STAGE_BYTES + p * C::A_TILE; };
+    auto sB = [&](int stage, int p) -> uint8_t* { return ring_ptr + stage * C::STAGE_BYTES + NS * C::A_TILE + p * C::B_HALF; };
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < C::STAGES; i++) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 8); }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        for (int p = 0; p < NS; p++) { tma_prefetch_desc(&a.mapA[p]); tma_prefetch_desc(&a.mapB[p]); }
+    }
+    if (warp == 1) tmem_alloc_2sm(&tmem_base_slot, C::TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();            // barriers of BOTH CTAs are initialised before any remote arrive / TMA completion
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    // work unit = (phase, n tile, pair of consecutive M tiles); this CTA owns M tile 2*pair + rank
+    const int m_pairs = (a.m_tiles + 1) >> 1;
+    const int units = m_pairs * a.n_tiles * a.phases;
+    auto unit_coord = [&](int u) -> TileCoord {
+        TileCoord c;
+        c.n_tile = u % a.n_tiles;
+        const int r = u / a.n_tiles;
+        const int m = (r % m_pairs) * 2 + (int)rank;
+        c.phase = r / m_pairs;
+        if (m >= a.m_tiles) { c.px0 = 0; c.py0 = 0; c.pn0 = a.N; return c; }
+        c.px0 = (m % a.tiles_x) * a.tw;
+        const int r2 = m / a.tiles_x;
+        c.py0 = (r2 % a.tiles_y) * a.th;
+        c.pn0 = (r2 / a.tiles_y) * a.tn;
+        return c;
+    };
+
+    if (warp == 0) {
+        // =========================== TMA producer (both CTAs) ===========================
+        if (lane == 0) {
+            int stage = 0; uint32_t ph = 0;
+            for (int u = cluster_id; u < units; u += num_clusters) {
+                const TileCoord t = unit_coord(u);
+                const int brow = t.phase * a.rows + t.n_tile * BN + (int)rank * (BN / 2);     // this CTA's half of the N tile
+                for (int kb = 0; kb < a.num_k; kb++) {
+                    const int tap = kb / a.cin_chunks, cc = kb - tap * a.cin_chunks;
+                    mbar_wait(&empty_bar[stage], ph ^ 1);
+                    if (a.mode == IPER_CONV_S2) {
+                        const int dy = tap / 3, dx = tap - 3 * dy;
+                        const int py = (dy != 1), sy = (dy == 0) ? -1 : 0;
+                        const int px = (dx != 1), sx = (dx == 0) ? -1 : 0;
+                        const int c0 = px * a.a_pitch + a.a_coff + cc * C::BK;
+                        for (int p = 0; p < NS; p++)
+                            tma_load_5d_2sm(sA(stage, p), &a.mapA[p], &full_bar[stage], c0, t.px0 + sx, py, t.py0 + sy, t.pn0);
+                    } else {
+                        int oy, ox;
+                        if (a.mode == IPER_CONV_S1) {
+                            const int dy = tap / a.ksize, dx = tap - dy * a.ksize;
+                            oy = dy - a.ksize / 2; ox = dx - a.ksize / 2;
+                        } else {
+                            const int py = t.phase >> 1, px = t.phase & 1;
+                            const int ta = tap >> 1, tb = tap & 1;
+                            oy = py == 0 ? (ta == 0 ? 0 : -1) : (ta == 0 ? 1 : 0);
+                            ox = px == 0 ? (tb == 0 ? 0 : -1) : (tb == 0 ? 1 : 0);
+                        }
+                        const int c0 = a.a_coff + cc * C::BK;
+                        for (int p = 0; p < NS; p++)
+                            tma_load_4d_2sm(sA(stage, p), &a.mapA[p], &full_bar[stage], c0, t.px0 + ox, t.py0 + oy, t.pn0);
+                    }
+                    for (int p = 0; p < NS; p++)
+                        tma_load_2d_2sm(sB(stage, p), &a.mapB[p], &full_bar[stage], kb * C::BK, brow);
+                    // the leader's full barrier collects the bytes of both CTAs and one arrival from each producer
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+                    else mbar_arrive_remote(&full_bar[stage], 0);
+                    if (++stage == C::STAGES) { stage = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer (leader CTA only) ===========================
+        if (rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(2 * BLOCK_M, BN);
+            int stage = 0; uint32_t ph = 0; int it = 0;
+            for (int u = cluster_id; u < units; u += num_clusters, it++) {
+                const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS;
+                for (int kb = 0; kb < a.num_k; kb++) {
+                    mbar_wait(&full_bar[stage], ph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        uint32_t first = (kb == 0) ? 0u : 1u;
+                        constexpr int NPAIR = (NS == 2) ? 3 : 1;
+                        const int pa[3] = {NS == 2 ? 1 : 0, 0, 0};
+                        const int pb[3] = {0, NS == 2 ? 1 : 0, 0};
+#pragma unroll
+                        for (int q = 0; q < NPAIR; q++) {
+                            const uint32_t abase = smem_u32(sA(stage, pa[q])), bbase = smem_u32(sB(stage, pb[q]));
+#pragma unroll
+                            for (int k = 0; k < C::BK / 16; k++) {
+                                umma_f16_2sm(d_tmem, umma_desc_sw128(abase + k * 32), umma_desc_sw128(bbase + k * 32), idesc, first);
+                                first = 1u;
+                            }
+                        }
+                        umma_commit_2sm(&empty_bar[stage], 0x3);                       // free the slot in both CTAs
+                        if (kb == a.num_k - 1) umma_commit_2sm(&tmem_full_bar[acc], 0x3);   // wake both epilogues
+                    }
+                    __syncwarp();
+                    if (++stage == C::STAGES) { stage = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else {
+        // =========================== epilogue (warps 2..5, both CTAs) ===========================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int tx = row % a.tw, ty = (row / a.tw) % a.th, tni = row / (a.tw * a.th);
+        int it = 0;
+        for (int u = cluster_id; u < units; u += num_clusters, it++) {
+            const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
+            mbar_wait(&tmem_full_bar[acc], acc_ph);
+            tc_fence_after();
+            const TileCoord t = unit_coord(u);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS;
+            epilogue_tile<BN, NS>(a, t, taddr, row, lane, tx, ty, tni);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                else mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();            // neither CTA may exit (or free TMEM) while the pair still has work in flight
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, C::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -493,6 +676,35 @@ static int launch_gemm(const GemmArgs& g, int max_ctas, cudaStream_t stream) {
     return 0;
 }
 
+template <int BN, int NS>
+static int launch_gemm_pair(const GemmArgs& g, int max_ctas, cudaStream_t stream) {
+    using C = Cfg2<BN, NS>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        IPER_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             C::SMEM_BYTES));
+        attr_set = true;
+    }
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        IPER_CHECK_CUDA(cudaGetDevice(&dev));
+        IPER_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int units = ((g.m_tiles + 1) / 2) * g.n_tiles * g.phases;
+    int clusters = num_sms / 2;
+    if (max_ctas > 0 && clusters > max_ctas / 2) clusters = max_ctas / 2 > 0 ? max_ctas / 2 : 1;
+    if (clusters > units) clusters = units;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = C::SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    IPER_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_pair_kernel<BN, NS>, g));
+    return 0;
+}
+
 }  // namespace iper
 
 using namespace iper;
@@ -509,6 +721,13 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
     // tile with 64-channel stages (64-byte TMA rows deliver fewer bytes per request), so auto = 1; kept selectable.
     const int fmt = d->a_planes;
     const int TMv = (d->tiles_m == 2 && fmt != 3) ? 2 : 1;
+    // cta_pair: 2-CTA clusters (cta_group::2) — each CTA stages its own A tile and half of the weight tile
+    const bool pair = d->cta_pair != 0;
+    if (pair) {
+        IPER_REQUIRE(fmt != 3 && TMv == 1 && (d->block_n == 128 || d->block_n == 256) && d->epi != IPER_EPI_HEADS &&
+                     d->mode != IPER_CONV_ROW5,
+                     "iper_conv_gemm: cta_pair supports formats 1/2, tiles_m = 1, block_n 128/256, no heads epilogue");
+    }
     IPER_REQUIRE(!(fmt == 3 && TMv == 2), "iper_conv_gemm: format 3 supports tiles_m = 1 only");
     const int BKv = TMv == 2 ? 32 : 64;
     IPER_REQUIRE(d->a_pitch % 8 == 0 && d->a_coff % 8 == 0 && d->a_coff + d->Cin <= d->a_pitch,
@@ -611,7 +830,7 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
         else wb = (p == 1) ? d->w8 : d->wl8;
         cuuint64_t wdims[2] = {ktot, (cuuint64_t)d->rows * g.phases};
         cuuint64_t wstr[1] = {ktot * esz};
-        cuuint32_t wbox[2] = {(cuuint32_t)BKv, (cuuint32_t)d->block_n};
+        cuuint32_t wbox[2] = {(cuuint32_t)BKv, (cuuint32_t)(pair ? d->block_n / 2 : d->block_n)};
         if (int rc = encode_map(&g.mapB[p], wb, 2, wdims, wstr, wbox, u8, row_bytes)) return rc;
     }
     for (int p = nmaps; p < 3; p++) { g.mapA[p] = g.mapA[0]; g.mapB[p] = g.mapB[0]; }
@@ -620,6 +839,10 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
     if (d->stats_ws) {
         IPER_REQUIRE(d->epi == IPER_EPI_PLANES && d->mode != IPER_CONVT_4S2, "iper_conv_gemm: fused statistics need the planes epilogue of a (strided) conv");
         IPER_CHECK_CUDA(cudaMemsetAsync(d->stats_ws, 0, sizeof(double) * 2 * (size_t)d->N * d->rows, s));
+    }
+    if (pair) {
+        if (d->block_n == 256) return fmt == 2 ? launch_gemm_pair<256, 2>(g, d->max_ctas, s) : launch_gemm_pair<256, 1>(g, d->max_ctas, s);
+        return fmt == 2 ? launch_gemm_pair<128, 2>(g, d->max_ctas, s) : launch_gemm_pair<128, 1>(g, d->max_ctas, s);
     }
 #define IPER_DISPATCH(BNV)                                                                                           \
     do {                                                                                                             \

@@ -134,8 +134,11 @@ def _attach(t, **attrs):
 class AttentionLWBGenerator(nn.Module):
     """B200 drop-in for attlwb_spade_resunet.AttentionLWBGenerator(cfg, temporal=False)."""
 
-    def __init__(self, cfg, temporal=False, precision="fp16x2"):
+    def __init__(self, cfg, temporal=False, precision="fp16x2", cta_pair=None):
         super().__init__()
+        import os
+        # CTA pairs (cta_group::2, weight tile split across two SMs) for every conv with >= 128 output rows
+        self.cta_pair = (os.environ.get("IPER_CTA_PAIR", "1") != "0") if cta_pair is None else bool(cta_pair)
         if temporal:
             raise NotImplementedError("temporal=True (TemporalFIFO recurrence, default false in deploy.toml:40) is not "
                                       "on the B200 hot path yet")
@@ -235,8 +238,11 @@ class AttentionLWBGenerator(nn.Module):
         w, b = pk[name]
         rows = w.rows_total // (4 if mode == IPER_CONVT_4S2 else 1)
         ops.conv_gemm(a, w, mode, ksize, rows, _bn_for(rows), IPER_EPI_PLANES, bias=b, relu=relu, out=out, x=x,
-                      stats_ws=stats_ws)
+                      stats_ws=stats_ws, cta_pair=self._pair(rows))
         return out
+
+    def _pair(self, rows):
+        return int(self.cta_pair and self.P != 3 and rows >= 128)
 
     def _project_kv(self, pk, prefix, feat):
         """source maps [(Wq^T Wk) x | Wv x | (Wk^T bq).x | pad] of source features: Planes (ns,h,w,C) -> fp32 (ns,h,w,2C+64)."""
@@ -326,7 +332,7 @@ class AttentionLWBGenerator(nn.Module):
             if out is None:
                 out = Planes.empty(P, B, h, h, C, dev)
             ops.conv_gemm(actv, wgb, IPER_CONV_S1, 3, 2 * C, _bn_for(2 * C), IPER_EPI_SPADE, bias=bgb, out=out, x=x,
-                          mean_rstd=stats, spade_C=C)
+                          mean_rstd=stats, spade_C=C, cta_pair=self._pair(2 * C))
             return out
 
         # 1. encoder (:507-519)

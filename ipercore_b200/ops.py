@@ -153,7 +153,7 @@ def flow_resize(T, h, w):
 # generator building blocks
 # ------------------------------------------------------------------------------------------------------------------
 def _fill_desc(a, mode, ksize, rows, block_n, epi, bias=None, relu=False, out=None, x=None, mean_rstd=None,
-               spade_C=0, heads=None, max_ctas=0, tiles_m=0, stats_ws=None):
+               spade_C=0, heads=None, max_ctas=0, tiles_m=0, stats_ws=None, cta_pair=0):
     d = ConvGemmDesc()
     d.a = a.ptr(); d.a_planes = a.P; d.a_plane_stride = a.plane_stride
     d.N, d.H, d.W = a.N, a.H, a.W
@@ -177,6 +177,7 @@ def _fill_desc(a, mode, ksize, rows, block_n, epi, bias=None, relu=False, out=No
     d.max_ctas = max_ctas
     d.tiles_m = tiles_m
     d.stats_ws = _ptr(stats_ws)
+    d.cta_pair = int(cta_pair)
     return d
 
 

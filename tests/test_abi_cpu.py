@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_descriptor_struct_matches_header():
     from ipercore_b200._lib import ConvGemmDesc
-    assert ctypes.sizeof(ConvGemmDesc) == 272 and ConvGemmDesc.tiles_m.offset == 260 and ConvGemmDesc.stats_ws.offset == 264 and ConvGemmDesc.max_ctas.offset == 232 and ConvGemmDesc.cross_scale.offset == 256
+    assert ctypes.sizeof(ConvGemmDesc) == 280 and ConvGemmDesc.cta_pair.offset == 272 and ConvGemmDesc.tiles_m.offset == 260 and ConvGemmDesc.stats_ws.offset == 264 and ConvGemmDesc.max_ctas.offset == 232 and ConvGemmDesc.cross_scale.offset == 256
 
 
 def test_argument_validation_reports_errors():

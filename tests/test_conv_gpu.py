@@ -103,6 +103,12 @@ def test_conv_gemm_planes(N, H, W, Cin, Cout, mode, k, P):
             ops.conv_gemm(a, wp, mode, k, rows, 256 if rows >= 256 else rows, ops.IPER_EPI_PLANES, bias=bias.to(DEV),
                           relu=True, out=alt, tiles_m=tm)
             np.testing.assert_allclose(_planes_value(alt).numpy(), exp.numpy(), atol=atol, rtol=rtol)
+        if rows >= 128:     # CTA pairs (cta_group::2): the weight tile is split across two SMs
+            alt = Planes.empty(P, N, oH, oW, Cout, DEV)
+            ops.conv_gemm(a, wp, mode, k, rows, 256 if rows >= 256 else rows, ops.IPER_EPI_PLANES, bias=bias.to(DEV),
+                          relu=True, out=alt, cta_pair=1)
+            torch.cuda.synchronize()
+            np.testing.assert_allclose(_planes_value(alt).numpy(), exp.numpy(), atol=atol, rtol=rtol)
     # on-device cross-check (CUDA-core direct convolution of the stored activation values with the fp16-rounded weights)
     chk = Planes.empty(P, N, oH, oW, Cout, DEV)
     wm, _, wlo = wp.effective()
