@@ -12,6 +12,7 @@
 #ifndef IPER_B200_H
 #define IPER_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -28,9 +29,13 @@ int iper_abi_version(void);
  * (third-party CUDA ext; call sites iPERCore/tools/human_digitalizer/renders/nmr.py:337 and :356).
  * faces (B,nf,3,3) f32 NDC  ->  fim (B,S,S) i32 (-1 = background), wim (B,S,S,3) f32 (0 on background).
  * Correct for any B (the reference loops around an upstream B==3 bug, nmr.py:892-918).
+ * workspace: device scratch of iper_raster_workspace_bytes(B, nf, from_verts) bytes (per-face tile bins, and the
+ * projected face corners when the library computes them: from_verts=0 here, 1 for iper_raster_frames); the caller
+ * owns it so the library never allocates — it may be reused by the next call on the same stream.
  * ---------------------------------------------------------------------------------------------------------- */
+size_t iper_raster_workspace_bytes(int B, int nf, int from_verts);
 int iper_rasterize_faces(const float* faces, int B, int nf, int S, float near_, float far_, int32_t* fim, float* wim,
-                         iper_stream_t stream);
+                         void* workspace, size_t workspace_bytes, iper_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Seam B2 / engine — replaces SMPLRenderer.render_fim_wim (nmr.py:319-342: orthographic projection :34-52, y flip,
@@ -45,7 +50,8 @@ int iper_rasterize_faces(const float* faces, int B, int nf, int S, float near_, 
 int iper_raster_frames(const float* verts, const float* cams, const int32_t* faces, int B, int nv, int nf, int S,
                        float eye_z, float near_, float far_, int32_t* fim, float* wim, float* f2pts,
                        const float* map_fn, const float* f_uvs2img, const float* uv_img, const float* src_f2pts,
-                       int ns, float* tsf_inputs, float* Tst, iper_stream_t stream);
+                       int ns, float* tsf_inputs, float* Tst, void* workspace, size_t workspace_bytes,
+                       iper_stream_t stream);
 
 /* SMPLRenderer.cal_bc_transform (nmr.py:713-757).  T (nb,nsrc,S,S,2): item (b,s) combines fim/wim[b] with
  * f2pts[s] (f2pts_per_item=0, shape (nsrc,nf,3,2)) or f2pts[b] (f2pts_per_item=1, nsrc must be 1). */

@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libiper_b200.so")
 
 c_void_p, c_int, c_float, c_ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
+c_size_t = ctypes.c_size_t
 
 IPER_CONV_S1, IPER_CONV_S2, IPER_CONVT_4S2, IPER_CONV_ROW5 = 0, 1, 2, 3
 IPER_EPI_PLANES, IPER_EPI_F32, IPER_EPI_SPADE, IPER_EPI_HEADS = 0, 1, 2, 3
@@ -38,10 +39,11 @@ class ConvGemmDesc(ctypes.Structure):
 # name -> argtypes; every function returns int status except iper_last_error
 SIGNATURES = {
     "iper_abi_version": [],
-    "iper_rasterize_faces": [c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p],
+    "iper_rasterize_faces": [c_void_p, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_size_t,
+                             c_void_p],
     "iper_raster_frames": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_float, c_float,
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
-                           c_void_p, c_void_p],
+                           c_void_p, c_void_p, c_size_t, c_void_p],
     "iper_flow_from_fim_wim": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "iper_encode_fim": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "iper_flow_resize": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
@@ -78,6 +80,8 @@ def _load():
         fn = getattr(lib, name)          # AttributeError here = ABI drift; fail loudly
         fn.argtypes = argtypes
         fn.restype = c_int
+    lib.iper_raster_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.iper_raster_workspace_bytes.restype = c_size_t
     lib.iper_last_error.argtypes = []
     lib.iper_last_error.restype = ctypes.c_char_p
     return lib
@@ -90,7 +94,7 @@ _LAUNCHES = 0
 
 
 def launch_count():
-    """Number of libiper_b200 kernel launches issued so far by this process (every C-ABI op is exactly one launch)."""
+    """Number of libiper_b200 kernel launches issued so far by this process (a lower bound: every C-ABI op is at least one launch)."""
     return _LAUNCHES
 
 

@@ -7,15 +7,18 @@
 //   * SMPLRenderer.cal_bc_transform                 (nmr.py:713-757)
 //   * FlowComposition.make_tsf_inputs / make_trans_flow (flowcomposition.py:206-248, 514-582)
 //
-// Design (B200): one CTA per 64x32 pixel tile per frame.  The frame's projected vertices are staged in shared
-// memory once per CTA (82 KB); in chunks of 4096 faces every thread BINS a strided slice of the faces against the
-// tile by bounding box into a compact shared list, then each WARP takes binned faces and scan-converts them with
-// its lanes spread over the pixels of (bbox ∩ tile) — no per-face divergence — straight into a shared memory
-// z-buffer with a 64-bit atomicMin on (depth bits << 32 | face index) — which is exactly the upstream
+// Design (B200), two launches per batch of frames:
+//   raster_setup_kernel  one thread per (frame, face): project the three vertices (a1), write the face's corners
+//                        (B,nf,3,3) and f2pts (a3), cull back faces, and BIN the face: its conservative pixel bounding box
+//                        (grown by one pixel) becomes a packed tile range (4 x 8 bits) — done once per face per frame.
+//   raster_kernel        one CTA per 64x32 pixel tile per frame: scans the 4-byte bins (coalesced, L2-resident) into a
+//                        compact shared list of the faces touching the tile, then each WARP takes binned faces and
+//                        scan-converts them with its lanes spread over the pixels of (bbox ∩ tile) — no per-face divergence —
+//                        straight into a shared memory z-buffer with a 64-bit atomicMin on (depth bits << 32 | face index) — which is exactly the upstream
 // rule "strictly smaller depth wins, lowest face index wins a tie".  A resolve pass then recomputes the winner's
 // barycentric weights (same float sequence, hence identical bits) and writes fim / wim / cond / flow / sampled
 // UV image with fully coalesced stores.  Work is proportional to covered area, not faces x pixels
-// (upstream: 262 144 px x 13 776 faces per 512^2 frame).
+// (upstream: 262 144 px x 13 776 faces per 512^2 frame); 25 KB of shared memory per CTA.
 //
 // Parity contract: every float operation below that feeds the inside test, the weights or the depth is an
 // explicitly rounded binary32 op (__fmul_rn/__fadd_rn/__fdiv_rn — never contracted into FMA) in the same order
@@ -143,7 +146,8 @@ struct RasterArgs {
     const float* cams;     // (B, 3)
     const int32_t* faces;  // (nf, 3)
     // geometry source B: pre-gathered, already projected faces (neural_renderer seam)
-    const float* face_verts;  // (B, nf, 3, 3) or null
+    const float* face_verts;  // (B, nf, 3, 3): given (seam B1) or written by the setup kernel into the workspace
+    const uint32_t* bins;     // (B, nf) packed tile ranges from the setup kernel (0xFFFFFFFF = culled)
     int B, nv, nf, S;
     float near_, far_, eye_z;
     // outputs (any may be null)
@@ -160,7 +164,65 @@ struct RasterArgs {
     float* Tst;         // (B, ns, S, S, 2)
 };
 
+constexpr uint32_t BIN_CULLED = 0xFFFFFFFFu;
+
+// one thread per (frame, face): projection (FROM_VERTS) / corners, f2pts, back-face cull, tile-range bin
 template <bool FROM_VERTS>
+__global__ void __launch_bounds__(256) raster_setup_kernel(const RasterArgs a, float* __restrict__ face_out,
+                                                           uint32_t* __restrict__ bins) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (f >= a.nf) return;
+    FaceGeom g;
+    if (FROM_VERTS) {
+        // a1: orthographic_proj_withz_idrot + y flip + look_at (identity rotation, z -> z - eye_z)
+        const float s = a.cams[3 * b + 0], tx = a.cams[3 * b + 1], ty = a.cams[3 * b + 2];
+        const float* v = a.verts + (size_t)b * a.nv * 3;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int vi = __ldg(a.faces + 3 * f + k);
+            const float x = v[3 * vi + 0], y = v[3 * vi + 1], z = v[3 * vi + 2];
+            g.v[3 * k + 0] = __fmul_rn(s, __fadd_rn(x, tx));
+            g.v[3 * k + 1] = -__fmul_rn(s, __fadd_rn(y, ty));
+            g.v[3 * k + 2] = __fsub_rn(z, a.eye_z);
+        }
+        float* o = face_out + ((size_t)b * a.nf + f) * 9;
+#pragma unroll
+        for (int k = 0; k < 9; k++) o[k] = g.v[k];
+        if (a.f2pts) {      // a3: image-space corners with y flipped back (nmr.py:339-340)
+            float* p = a.f2pts + ((size_t)b * a.nf + f) * 6;
+#pragma unroll
+            for (int k = 0; k < 3; k++) { p[2 * k] = g.v[3 * k]; p[2 * k + 1] = -g.v[3 * k + 1]; }
+        }
+    } else {
+        const float* src = a.face_verts + ((size_t)b * a.nf + f) * 9;
+#pragma unroll
+        for (int k = 0; k < 9; k++) g.v[k] = __ldg(src + k);
+    }
+    uint32_t bin = BIN_CULLED;
+    if (!is_backface(g.v)) {
+        const int S = a.S;
+        const float fS = (float)S;
+        const float xmin = fminf(g.v[0], fminf(g.v[3], g.v[6])), xmax = fmaxf(g.v[0], fmaxf(g.v[3], g.v[6]));
+        const float ymin = fminf(g.v[1], fminf(g.v[4], g.v[7])), ymax = fmaxf(g.v[1], fmaxf(g.v[4], g.v[7]));
+        int x0 = 0, x1 = S - 1, y0 = 0, y1 = S - 1;     // pixel-index range in the upstream (xi, yi) frame
+        const bool finite = (xmin == xmin) && (xmax == xmax) && (ymin == ymin) && (ymax == ymax) &&
+                            fabsf(xmin) < 1e6f && fabsf(xmax) < 1e6f && fabsf(ymin) < 1e6f && fabsf(ymax) < 1e6f;
+        if (finite) {       // NaN / huge corners: keep the whole image (such faces never win, like upstream)
+            x0 = max(x0, (int)floorf((xmin * fS + fS - 1.f) * 0.5f) - 1);
+            x1 = min(x1, (int)ceilf((xmax * fS + fS - 1.f) * 0.5f) + 1);
+            y0 = max(y0, (int)floorf((ymin * fS + fS - 1.f) * 0.5f) - 1);
+            y1 = min(y1, (int)ceilf((ymax * fS + fS - 1.f) * 0.5f) + 1);
+        }
+        if (x0 <= x1 && y0 <= y1) {
+            // image rows r = S-1-yi: rows [S-1-y1, S-1-y0]
+            const int r0 = S - 1 - y1, r1 = S - 1 - y0;
+            bin = (uint32_t)(x0 / TILE_W) | ((uint32_t)(x1 / TILE_W) << 8) | ((uint32_t)(r0 / TILE_H) << 16) |
+                  ((uint32_t)(r1 / TILE_H) << 24);
+        }
+    }
+    bins[(size_t)b * a.nf + f] = bin;
+}
+
 __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(const RasterArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long* zbuf = reinterpret_cast<unsigned long long*>(smem_raw);
@@ -168,42 +230,18 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(const RasterArgs
     float* s_xp = reinterpret_cast<float*>(smem_raw + RASTER_ZBUF_BYTES + BIN_CHUNK * sizeof(unsigned short));
     float* s_yp = s_xp + TILE_W;
     int* s_count = reinterpret_cast<int*>(s_yp + TILE_H);
-    float* sv = reinterpret_cast<float*>(smem_raw + RASTER_FIXED_SMEM);
 
     const int S = a.S, nf = a.nf;
     const int b = blockIdx.y;
     const int tiles_x = (S + TILE_W - 1) / TILE_W;
-    const int tx0 = (blockIdx.x % tiles_x) * TILE_W;
-    const int r0 = (blockIdx.x / tiles_x) * TILE_H;  // image rows r0 .. r0+TILE_H-1
+    const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    const int tx0 = tile_x * TILE_W;
+    const int r0 = tile_y * TILE_H;  // image rows r0 .. r0+TILE_H-1
     const int tid = threadIdx.x;
 
     for (int i = tid; i < TILE_W * TILE_H; i += RASTER_THREADS) zbuf[i] = ZBUF_EMPTY;
 
-    if (FROM_VERTS) {
-        // a1: orthographic_proj_withz_idrot + y flip + look_at (identity rotation, z -> z - eye_z)
-        const float s = a.cams[3 * b + 0], tx = a.cams[3 * b + 1], ty = a.cams[3 * b + 2];
-        const float* v = a.verts + (size_t)b * a.nv * 3;
-        for (int i = tid; i < a.nv; i += RASTER_THREADS) {
-            const float x = v[3 * i + 0], y = v[3 * i + 1], z = v[3 * i + 2];
-            sv[3 * i + 0] = __fmul_rn(s, __fadd_rn(x, tx));
-            sv[3 * i + 1] = -__fmul_rn(s, __fadd_rn(y, ty));
-            sv[3 * i + 2] = __fsub_rn(z, a.eye_z);
-        }
-    }
     __syncthreads();
-
-    // f2pts (a3) is per frame, not per tile: the x-tile 0 / row-tile 0 CTA of each frame writes it
-    if (FROM_VERTS && a.f2pts != nullptr && blockIdx.x == 0) {
-        float* o = a.f2pts + (size_t)b * nf * 6;
-        for (int f = tid; f < nf; f += RASTER_THREADS) {
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const int vi = a.faces[3 * f + k];
-                o[6 * f + 2 * k + 0] = sv[3 * vi + 0];
-                o[6 * f + 2 * k + 1] = -sv[3 * vi + 1];
-            }
-        }
-    }
 
     // pixel-index bounds of this tile in the upstream (xi, yi) frame: yi = S-1-row
     const int xi_lo = tx0, xi_hi = min(tx0 + TILE_W, S) - 1;
@@ -214,19 +252,9 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(const RasterArgs
     else if (tid < TILE_W + TILE_H) s_yp[tid - TILE_W] = pixel_centre(S - 1 - (r0 + tid - TILE_W), S);
 
     auto load_face = [&](int f, FaceGeom& g) {
-        if (FROM_VERTS) {
+        const float* src = a.face_verts + ((size_t)b * nf + f) * 9;
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                const int vi = __ldg(a.faces + 3 * f + k);
-                g.v[3 * k + 0] = sv[3 * vi + 0];
-                g.v[3 * k + 1] = sv[3 * vi + 1];
-                g.v[3 * k + 2] = sv[3 * vi + 2];
-            }
-        } else {
-            const float* src = a.face_verts + ((size_t)b * nf + f) * 9;
-#pragma unroll
-            for (int k = 0; k < 9; k++) g.v[k] = __ldg(src + k);
-        }
+        for (int k = 0; k < 9; k++) g.v[k] = __ldg(src + k);
     };
     // conservative pixel range of a face's bounding box (grown by one pixel) clipped to the tile
     auto face_range = [&](const FaceGeom& g, int& x0, int& x1, int& y0, int& y1) {
@@ -251,12 +279,10 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(const RasterArgs
         __syncthreads();
         const int end = min(base + BIN_CHUNK, nf);
         for (int f = base + tid; f < end; f += RASTER_THREADS) {
-            FaceGeom g;
-            load_face(f, g);
-            if (is_backface(g.v)) continue;
-            int x0, x1, y0, y1;
-            face_range(g, x0, x1, y0, y1);
-            if (x0 > x1 || y0 > y1) continue;
+            const uint32_t bin = __ldg(a.bins + (size_t)b * nf + f);
+            if (bin == BIN_CULLED) continue;
+            const int bx0 = bin & 0xFF, bx1 = (bin >> 8) & 0xFF, by0 = (bin >> 16) & 0xFF, by1 = bin >> 24;
+            if (tile_x < bx0 || tile_x > bx1 || tile_y < by0 || tile_y > by1) continue;
             s_list[atomicAdd(s_count, 1)] = (unsigned short)(f - base);
         }
         __syncthreads();
@@ -398,23 +424,32 @@ __global__ void flow_resize_kernel(const float* __restrict__ T, int n, int S, in
     }
 }
 
-static size_t raster_smem_bytes(bool from_verts, int nv) {
-    return (size_t)RASTER_FIXED_SMEM + (from_verts ? (size_t)nv * 3 * sizeof(float) : 0);
+static size_t raster_ws_bytes(int B, int nf, bool from_verts) {
+    // bins (B, nf) u32, then — when the corners are computed here — face corners (B, nf, 9) f32
+    return (size_t)B * nf * sizeof(uint32_t) + (from_verts ? (size_t)B * nf * 9 * sizeof(float) : 0);
 }
 
-static int launch_raster(const RasterArgs& a, bool from_verts, cudaStream_t stream) {
+static int launch_raster(RasterArgs a, bool from_verts, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     const int S = a.S;
-    const int tiles = ((S + TILE_W - 1) / TILE_W) * ((S + TILE_H - 1) / TILE_H);
-    const size_t smem = raster_smem_bytes(from_verts, a.nv);
-    IPER_REQUIRE(smem <= 227 * 1024, "rasteriser: %d vertices do not fit the shared-memory staging buffer", a.nv);
-    dim3 grid(tiles, a.B);
+    const int tiles_x = (S + TILE_W - 1) / TILE_W, tiles_y = (S + TILE_H - 1) / TILE_H;
+    IPER_REQUIRE(tiles_x <= 256 && tiles_y <= 256, "rasteriser: image size %d exceeds the 8-bit tile index range", S);
+    IPER_REQUIRE(a.nf <= (1 << 24), "rasteriser: too many faces (%d)", a.nf);
+    IPER_REQUIRE(workspace && workspace_bytes >= raster_ws_bytes(a.B, a.nf, from_verts),
+                 "rasteriser: workspace of %zu bytes needed (iper_raster_workspace_bytes), got %zu",
+                 raster_ws_bytes(a.B, a.nf, from_verts), workspace_bytes);
+    uint32_t* bins = reinterpret_cast<uint32_t*>(workspace);
+    float* corners = reinterpret_cast<float*>(bins + (size_t)a.B * a.nf);
+    dim3 sgrid((a.nf + 255) / 256, a.B);
     if (from_verts) {
-        IPER_CHECK_CUDA(cudaFuncSetAttribute(raster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        raster_kernel<true><<<grid, RASTER_THREADS, smem, stream>>>(a);
+        raster_setup_kernel<true><<<sgrid, 256, 0, stream>>>(a, corners, bins);
+        a.face_verts = corners;
     } else {
-        IPER_CHECK_CUDA(cudaFuncSetAttribute(raster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        raster_kernel<false><<<grid, RASTER_THREADS, smem, stream>>>(a);
+        raster_setup_kernel<false><<<sgrid, 256, 0, stream>>>(a, nullptr, bins);
     }
+    IPER_CHECK_CUDA(cudaGetLastError());
+    a.bins = bins;
+    dim3 grid(tiles_x * tiles_y, a.B);
+    raster_kernel<<<grid, RASTER_THREADS, RASTER_FIXED_SMEM, stream>>>(a);
     IPER_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -423,22 +458,27 @@ static int launch_raster(const RasterArgs& a, bool from_verts, cudaStream_t stre
 
 using namespace iper;
 
+extern "C" size_t iper_raster_workspace_bytes(int B, int nf, int from_verts) {
+    if (B <= 0 || nf <= 0) return 0;
+    return raster_ws_bytes(B, nf, from_verts != 0);
+}
+
 extern "C" int iper_rasterize_faces(const float* faces, int B, int nf, int S, float near_, float far_, int32_t* fim,
-                                    float* wim, iper_stream_t stream) {
+                                    float* wim, void* workspace, size_t workspace_bytes, iper_stream_t stream) {
     IPER_REQUIRE(B >= 0 && nf > 0 && S > 0, "iper_rasterize_faces: bad sizes B=%d nf=%d S=%d", B, nf, S);
     if (B == 0) return 0;   // empty batch: nothing to do (pointers may be null)
     IPER_REQUIRE(faces && fim && wim, "iper_rasterize_faces: null pointer");
     RasterArgs a = {};
     a.face_verts = faces; a.B = B; a.nf = nf; a.S = S; a.near_ = near_; a.far_ = far_;
     a.fim = fim; a.wim = wim;
-    return launch_raster(a, false, (cudaStream_t)stream);
+    return launch_raster(a, false, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int iper_raster_frames(const float* verts, const float* cams, const int32_t* faces, int B, int nv, int nf,
                                   int S, float eye_z, float near_, float far_, int32_t* fim, float* wim, float* f2pts,
                                   const float* map_fn, const float* f_uvs2img, const float* uv_img,
                                   const float* src_f2pts, int ns, float* tsf_inputs, float* Tst,
-                                  iper_stream_t stream) {
+                                  void* workspace, size_t workspace_bytes, iper_stream_t stream) {
     IPER_REQUIRE(B >= 0 && nv > 0 && nf > 0 && S > 0, "iper_raster_frames: bad sizes");
     if (B == 0) return 0;
     IPER_REQUIRE(verts && cams && faces, "iper_raster_frames: null geometry pointer");
@@ -446,14 +486,13 @@ extern "C" int iper_raster_frames(const float* verts, const float* cams, const i
         IPER_REQUIRE(tsf_inputs && Tst && map_fn && f_uvs2img && uv_img && src_f2pts && ns > 0,
                      "iper_raster_frames: the fused frame-input outputs need map_fn, f_uvs2img, uv_img, src_f2pts, ns");
     }
-    if (B == 0) return 0;
     RasterArgs a = {};
     a.verts = verts; a.cams = cams; a.faces = faces; a.B = B; a.nv = nv; a.nf = nf; a.S = S;
     a.near_ = near_; a.far_ = far_; a.eye_z = eye_z;
     a.fim = fim; a.wim = wim; a.f2pts = f2pts;
     a.map_fn = map_fn; a.f_uvs2img = f_uvs2img; a.uv_img = uv_img; a.src_f2pts = src_f2pts; a.ns = ns;
     a.tsf_inputs = tsf_inputs; a.Tst = Tst;
-    return launch_raster(a, true, (cudaStream_t)stream);
+    return launch_raster(a, true, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 extern "C" int iper_flow_from_fim_wim(const float* f2pts, int f2pts_per_item, const int32_t* fim, const float* wim,

@@ -83,14 +83,20 @@ class Planes:
 # ------------------------------------------------------------------------------------------------------------------
 # raster / flow
 # ------------------------------------------------------------------------------------------------------------------
+def _raster_workspace(B, nf, from_verts, device):
+    """Caller-owned rasteriser scratch (tile bins + projected corners), sized by the library."""
+    return torch.empty((max(int(lib.iper_raster_workspace_bytes(B, nf, from_verts)), 1),), dtype=torch.uint8, device=device)
+
+
 def rasterize_faces(faces, image_size, near=NEAR, far=FAR):
     """neural_renderer.rasterize_face_index_map_and_weight_map(faces, image_size, False) (nmr.py:337,356)."""
     faces = _req(faces, torch.float32, "faces")
     B, nf = faces.shape[:2]
     fim = torch.empty((B, image_size, image_size), dtype=torch.int32, device=faces.device)
     wim = torch.empty((B, image_size, image_size, 3), dtype=torch.float32, device=faces.device)
+    ws = _raster_workspace(B, nf, 0, faces.device)
     check(lib.iper_rasterize_faces(faces.data_ptr(), B, nf, image_size, near, far, fim.data_ptr(), wim.data_ptr(),
-                                   _stream()), "rasterize_faces")
+                                   _ptr(ws), ws.numel(), _stream()), "rasterize_faces")
     return fim, wim
 
 
@@ -112,9 +118,11 @@ def raster_frames(verts, cams, faces, image_size, want_fim=True, want_f2pts=True
         ns = src_f2pts.shape[0]
         tsf = torch.empty((B, 6, S, S), dtype=torch.float32, device=dev)
         Tst = torch.empty((B, ns, S, S, 2), dtype=torch.float32, device=dev)
+    ws = _raster_workspace(B, nf, 1, dev)
     check(lib.iper_raster_frames(verts.data_ptr(), cams.data_ptr(), faces.data_ptr(), B, nv, nf, S, EYE_Z, NEAR, FAR,
                                  _ptr(fim), _ptr(wim), _ptr(f2pts), _ptr(map_fn), _ptr(f_uv), _ptr(uv_img),
-                                 _ptr(src_f2pts), ns, _ptr(tsf), _ptr(Tst), _stream()), "raster_frames")
+                                 _ptr(src_f2pts), ns, _ptr(tsf), _ptr(Tst), _ptr(ws), ws.numel(), _stream()),
+          "raster_frames")
     return dict(fim=fim, wim=wim, f2pts=f2pts, tsf_inputs=tsf, Tst=Tst)
 
 

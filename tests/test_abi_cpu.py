@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     raw = ctypes.CDLL(_lib.LIB_PATH)
     for n in names:
         assert hasattr(raw, n), "libiper_b200.so does not export %s" % n
-    assert set(_lib.SIGNATURES) | {"iper_last_error"} == set(names), "ctypes table and header drifted apart"
+    assert set(_lib.SIGNATURES) | {"iper_last_error", "iper_raster_workspace_bytes"} == set(names), "ctypes table and header drifted apart"
     assert _lib.lib.iper_abi_version() == 1
 
 
@@ -39,7 +39,7 @@ def test_argument_validation_reports_errors():
     assert _lib.lib.iper_conv_gemm(ctypes.byref(d), None) != 0
     assert b"null" in _lib.lib.iper_last_error()
     with pytest.raises(RuntimeError, match="iper_b200"):
-        _lib.check(_lib.lib.iper_rasterize_faces(None, 1, 1, 8, 0.1, 100.0, None, None, None), "rasterize_faces")
+        _lib.check(_lib.lib.iper_rasterize_faces(None, 1, 1, 8, 0.1, 100.0, None, None, None, 0, None), "rasterize_faces")
 
 
 def test_generator_loads_reference_checkpoint_layout():

@@ -102,3 +102,16 @@ def test_flow_resize_and_warp_match_torch(template):
                                          align_corners=False) for b in range(2)])                  # (B,ns,C,h,w)
         w = ops.warp_nhwc(_t(feat).permute(0, 2, 3, 1).contiguous(), got)
         np.testing.assert_allclose(w.permute(0, 1, 4, 2, 3).cpu().numpy(), exp.numpy(), atol=2e-5, rtol=0)
+
+
+def test_raster_workspace_too_small_fails_loudly():
+    """The caller owns the rasteriser scratch; an undersized one is an error, never a silent overrun."""
+    from ipercore_b200 import _lib
+    faces = torch.zeros((1, 4, 3, 3), device="cuda")
+    fim = torch.empty((1, 32, 32), dtype=torch.int32, device="cuda")
+    wim = torch.empty((1, 32, 32, 3), device="cuda")
+    ws = torch.empty(8, dtype=torch.uint8, device="cuda")
+    assert _lib.lib.iper_raster_workspace_bytes(1, 4, 0) == 16 and _lib.lib.iper_raster_workspace_bytes(2, 4, 1) == 32 + 288
+    with pytest.raises(RuntimeError, match="workspace"):
+        _lib.check(_lib.lib.iper_rasterize_faces(faces.data_ptr(), 1, 4, 32, 0.1, 100.0, fim.data_ptr(), wim.data_ptr(),
+                                                 ws.data_ptr(), 8, None), "rasterize_faces")
