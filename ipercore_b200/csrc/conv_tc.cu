@@ -40,6 +40,19 @@ constexpr int BLOCK_M = 128;
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_BUDGET = 196 * 1024;   // ring buffer budget; keeps one CTA per SM (TMEM is per-CTA 512 cols)
 
+// Tap program of the halo kernel (conv_halo_pair_kernel).  An A LOAD fetches the tile's pixels plus `halo` extra image
+// rows for one horizontal tap offset; every ENTRY is one tap's MMA group: it reads the 128-pixel view of that box that
+// starts `a_row_off` smem rows down (a vertical tap = a 1024-byte-aligned offset into the same box), multiplies with the
+// weight tile at (K column b_k + chunk*64, row b_row + n_tile*BN) and accumulates into accumulator block `acc`.
+constexpr int HALO_MAX_LOADS = 3, HALO_MAX_ENTRIES = 16;
+struct HaloEntry { int a_row_off, b_row, b_k, acc; };
+struct HaloSched {
+    int n_loads, acc_blocks, box_rows;          // box_rows = (th + halo) * tw
+    int na, nb, a_plane_bytes, tmem_cols;       // ring depths, bytes of one A plane of a slot, TMEM columns to allocate
+    int ox[HALO_MAX_LOADS], oy[HALO_MAX_LOADS], first[HALO_MAX_LOADS], count[HALO_MAX_LOADS];
+    HaloEntry e[HALO_MAX_ENTRIES];
+};
+
 struct alignas(64) GemmArgs {
     CUtensorMap mapA[3];
     CUtensorMap mapB[3];
@@ -59,6 +72,7 @@ struct alignas(64) GemmArgs {
     const float* bg; long long bg_batch_stride; float* img; float* mask; float* pred;
     float cross_scale;
     double* stats_ws;        // optional (N, Cout, 2) fp64 sums of the stored output (instance-norm statistics)
+    HaloSched hs;            // conv_halo_pair_kernel only
 };
 
 // BN = GEMM-N tile (output channels), NS = operand format (1, 2, 3), TM = 128-pixel M tiles per CTA that share one
@@ -161,8 +175,10 @@ IPER_DEVINL void epilogue_tile(const GemmArgs& a, const TileCoord& t, uint32_t t
 #pragma unroll
                     for (int i = 0; i < 20; i++) s_ex[row * 21 + i] = __uint_as_float(r[i]);
                     asm volatile("bar.sync 1, 128;" ::: "memory");
-                    const int xo = t.px0 + row;
-                    if (row >= 2 && row < BLOCK_M - 2 && xo >= 0 && xo < a.Wo && n < a.N && y < a.Ho) {
+                    // horizontal taps: output x of a tw-pixel row segment needs D of x-2 .. x+2 (same image row = same
+                    // segment of s_ex rows), so the two outermost pixels either side are recomputed by the neighbour tile
+                    const int xo = t.px0 + tx;
+                    if (tx >= 2 && tx < a.tw - 2 && xo >= 0 && xo < a.Wo && n < a.N && y < a.Ho) {
                         float o4[4];
 #pragma unroll
                         for (int o = 0; o < 4; o++) {
@@ -624,6 +640,194 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_pair_kernel(const _
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Halo variant of the CTA-pair kernel: vertical taps share one operand load.
+// The chip delivers ~6300 B/clk from L2 to shared memory (42 B/clk/SM), and a split-fp16 MMA group of the plain
+// implicit GEMM needs exactly that (a 3x3 / 256-channel layer re-reads every activation tile 9 times), so the plain
+// kernels sit at the delivery cap.  Here a tile is tw x th = 16 x 8 (heads: 32 x 4) pixels and ONE TMA box per
+// horizontal tap brings th + halo image rows; the vertical taps are views into that box at offsets of tw smem rows
+// (tw * 128 B, a multiple of the 1024-byte swizzle atom, so the UMMA descriptor is just advanced).  Operand bytes per
+// MMA drop by 3*th/(th+2) on A (2.4x for 3x3; 2.5x for the 5-tap heads); the weights still stream through their own ring.
+// The transposed 4x4/s2 convolution runs all four output phases from the same three boxes into four accumulator blocks
+// (16 (phase, tap) MMA groups), 3.5x fewer activation bytes than four separate phase GEMMs.
+//   warp 0: A producer   warp 1: MMA issuer (leader CTA)   warps 2-5: epilogue   warp 6: weight producer
+// ------------------------------------------------------------------------------------------------------------
+constexpr int HALO_THREADS = 224;
+constexpr int HALO_MAX_NA = 4, HALO_MAX_NB = 8;
+constexpr int HALO_SMEM_BUDGET = 212 * 1024;
+
+template <int BN, int NS>
+__global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const __grid_constant__ GemmArgs a) {
+    static_assert(NS == 1 || NS == 2, "halo kernel supports fp16 and split fp16");
+    constexpr int B_PLANE = (BN / 2) * 128;                    // this CTA's half of a weight tile, one plane
+    constexpr int B_SLOT = NS * B_PLANE;
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t a_full[HALO_MAX_NA];      // leader: 2 arrivals + bytes of both CTAs
+    __shared__ __align__(8) uint64_t a_empty[HALO_MAX_NA];     // per CTA, multicast commit
+    __shared__ __align__(8) uint64_t b_full[HALO_MAX_NB];
+    __shared__ __align__(8) uint64_t b_empty[HALO_MAX_NB];
+    __shared__ __align__(8) uint64_t tmem_full_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const HaloSched& hs = a.hs;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+    const uint32_t ring = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    uint8_t* ring_ptr = smem_dyn + (ring - smem_u32(smem_dyn));
+    const int a_slot = NS * hs.a_plane_bytes;
+    uint8_t* b_ring = ring_ptr + hs.na * a_slot;
+    auto sA = [&](int slot, int p) -> uint8_t* { return ring_ptr + slot * a_slot + p * hs.a_plane_bytes; };
+    auto sB = [&](int slot, int p) -> uint8_t* { return b_ring + slot * B_SLOT + p * B_PLANE; };
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < hs.na; i++) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < hs.nb; i++) { mbar_init(&b_full[i], 2); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 8); }
+        fence_barrier_init();
+    }
+    if ((warp == 0 || warp == 6) && lane == 0) {
+        for (int p = 0; p < NS; p++) tma_prefetch_desc(warp == 0 ? &a.mapA[p] : &a.mapB[p]);
+    }
+    if (warp == 1) tmem_alloc_2sm(&tmem_base_slot, (uint32_t)hs.tmem_cols);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    const int acc_cols = hs.acc_blocks * BN;
+
+    // work unit = (n tile, pair of consecutive M tiles); this CTA owns M tile 2*pair + rank (all phases of it)
+    const int m_pairs = (a.m_tiles + 1) >> 1;
+    const int units = m_pairs * a.n_tiles;
+    auto unit_coord = [&](int u) -> TileCoord {
+        TileCoord c;
+        c.phase = 0;
+        c.n_tile = u % a.n_tiles;
+        const int m = (u / a.n_tiles) * 2 + (int)rank;
+        if (m >= a.m_tiles) { c.px0 = 0; c.py0 = 0; c.pn0 = a.N; return c; }
+        c.px0 = (a.mode == IPER_CONV_ROW5) ? (m % a.tiles_x) * (a.tw - 4) - 2 : (m % a.tiles_x) * a.tw;
+        const int r2 = m / a.tiles_x;
+        c.py0 = (r2 % a.tiles_y) * a.th;
+        c.pn0 = r2 / a.tiles_y;
+        return c;
+    };
+
+    if (warp == 0) {
+        // =========================== activation producer (both CTAs) ===========================
+        if (lane == 0) {
+            int slot = 0; uint32_t ph = 0;
+            for (int u = cluster_id; u < units; u += num_clusters) {
+                const TileCoord t = unit_coord(u);
+                for (int cc = 0; cc < a.cin_chunks; cc++)
+                    for (int l = 0; l < hs.n_loads; l++) {
+                        mbar_wait(&a_empty[slot], ph ^ 1);
+                        for (int p = 0; p < NS; p++)
+                            tma_load_4d_2sm(sA(slot, p), &a.mapA[p], &a_full[slot], a.a_coff + cc * 64, t.px0 + hs.ox[l],
+                                            t.py0 + hs.oy[l], t.pn0);
+                        if (rank == 0) mbar_arrive_expect_tx(&a_full[slot], 2u * (uint32_t)a_slot);
+                        else mbar_arrive_remote(&a_full[slot], 0);
+                        if (++slot == hs.na) { slot = 0; ph ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 6) {
+        // =========================== weight producer (both CTAs) ===========================
+        if (lane == 0) {
+            int slot = 0; uint32_t ph = 0;
+            for (int u = cluster_id; u < units; u += num_clusters) {
+                const int brow = (u % a.n_tiles) * BN + (int)rank * (BN / 2);
+                for (int cc = 0; cc < a.cin_chunks; cc++)
+                    for (int l = 0; l < hs.n_loads; l++)
+                        for (int i = hs.first[l]; i < hs.first[l] + hs.count[l]; i++) {
+                            mbar_wait(&b_empty[slot], ph ^ 1);
+                            for (int p = 0; p < NS; p++)
+                                tma_load_2d_2sm(sB(slot, p), &a.mapB[p], &b_full[slot], hs.e[i].b_k + cc * 64, hs.e[i].b_row + brow);
+                            if (rank == 0) mbar_arrive_expect_tx(&b_full[slot], 2u * B_SLOT);
+                            else mbar_arrive_remote(&b_full[slot], 0);
+                            if (++slot == hs.nb) { slot = 0; ph ^= 1; }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        // =========================== MMA issuer (leader CTA only) ===========================
+        if (rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(2 * BLOCK_M, BN);
+            int aslot = 0, bslot = 0; uint32_t aph = 0, bph = 0; int it = 0;
+            for (int u = cluster_id; u < units; u += num_clusters, it++) {
+                const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * acc_cols;
+                uint32_t touched = 0;            // accumulator blocks already written for this unit
+                for (int cc = 0; cc < a.cin_chunks; cc++)
+                    for (int l = 0; l < hs.n_loads; l++) {
+                        mbar_wait(&a_full[aslot], aph);
+                        tc_fence_after();
+                        const bool last_load = (cc == a.cin_chunks - 1) && (l == hs.n_loads - 1);
+                        for (int i = hs.first[l]; i < hs.first[l] + hs.count[l]; i++) {
+                            mbar_wait(&b_full[bslot], bph);
+                            tc_fence_after();
+                            const HaloEntry e = hs.e[i];
+                            const bool last_entry = (i == hs.first[l] + hs.count[l] - 1);
+                            if (elect_one()) {
+                                uint32_t first = (touched >> e.acc) & 1u;
+                                constexpr int NPAIR = (NS == 2) ? 3 : 1;
+                                const int pa[3] = {NS == 2 ? 1 : 0, 0, 0};
+                                const int pb[3] = {0, NS == 2 ? 1 : 0, 0};
+#pragma unroll
+                                for (int q = 0; q < NPAIR; q++) {
+                                    const uint32_t abase = smem_u32(sA(aslot, pa[q])) + (uint32_t)e.a_row_off * 128u;
+                                    const uint32_t bbase = smem_u32(sB(bslot, pb[q]));
+#pragma unroll
+                                    for (int k = 0; k < 4; k++) {
+                                        umma_f16_2sm(d_tmem + e.acc * BN, umma_desc_sw128(abase + k * 32),
+                                                     umma_desc_sw128(bbase + k * 32), idesc, first);
+                                        first = 1u;
+                                    }
+                                }
+                                umma_commit_2sm(&b_empty[bslot], 0x3);
+                                if (last_entry) umma_commit_2sm(&a_empty[aslot], 0x3);
+                                if (last_entry && last_load) umma_commit_2sm(&tmem_full_bar[acc], 0x3);
+                            }
+                            __syncwarp();
+                            touched |= 1u << e.acc;
+                            if (++bslot == hs.nb) { bslot = 0; bph ^= 1; }
+                        }
+                        if (++aslot == hs.na) { aslot = 0; aph ^= 1; }
+                    }
+            }
+        }
+    } else {
+        // =========================== epilogue (warps 2..5, both CTAs) ===========================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int tx = row % a.tw, ty = (row / a.tw) % a.th;
+        int it = 0;
+        for (int u = cluster_id; u < units; u += num_clusters, it++) {
+            const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
+            mbar_wait(&tmem_full_bar[acc], acc_ph);
+            tc_fence_after();
+            TileCoord t = unit_coord(u);
+            for (int blk = 0; blk < hs.acc_blocks; blk++) {
+                t.phase = blk;                  // transposed conv: accumulator block = output phase
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols + blk * BN;
+                epilogue_tile<BN, NS>(a, t, taddr, row, lane, tx, ty, 0);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                else mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, (uint32_t)hs.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
@@ -705,6 +909,67 @@ static int launch_gemm_pair(const GemmArgs& g, int max_ctas, cudaStream_t stream
     return 0;
 }
 
+template <int BN, int NS>
+static int launch_gemm_halo(const GemmArgs& g, int max_ctas, cudaStream_t stream) {
+    const int a_slot = NS * g.hs.a_plane_bytes, b_slot = NS * (BN / 2) * 128;
+    int smem = g.hs.na * a_slot + g.hs.nb * b_slot + 1024;
+    if (smem < 120 * 1024) smem = 120 * 1024;            // one CTA per SM (TMEM allocation)
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        IPER_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_pair_kernel<BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        IPER_CHECK_CUDA(cudaGetDevice(&dev));
+        IPER_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int units = ((g.m_tiles + 1) / 2) * g.n_tiles;
+    int clusters = num_sms / 2;
+    if (max_ctas > 0 && clusters > max_ctas / 2) clusters = max_ctas / 2 > 0 ? max_ctas / 2 : 1;
+    if (clusters > units) clusters = units;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters); cfg.blockDim = dim3(HALO_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    IPER_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_pair_kernel<BN, NS>, g));
+    return 0;
+}
+
+// tap program of the halo kernel for one layer (see HaloSched)
+static void build_halo_sched(HaloSched& hs, int mode, int Cin, int rows, int tw, int th) {
+    hs = HaloSched{};
+    int ne = 0;
+    if (mode == IPER_CONV_S1) {                 // 3x3: one box per horizontal tap, three vertical views
+        hs.n_loads = 3; hs.acc_blocks = 1; hs.box_rows = (th + 2) * tw;
+        for (int dx = 0; dx < 3; dx++) {
+            hs.ox[dx] = dx - 1; hs.oy[dx] = -1; hs.first[dx] = ne; hs.count[dx] = 3;
+            for (int dy = 0; dy < 3; dy++) hs.e[ne++] = HaloEntry{dy * tw, 0, (dy * 3 + dx) * Cin, 0};
+        }
+    } else if (mode == IPER_CONV_ROW5) {        // heads: one box, five vertical views
+        hs.n_loads = 1; hs.acc_blocks = 1; hs.box_rows = (th + 4) * tw;
+        hs.ox[0] = 0; hs.oy[0] = -2; hs.first[0] = 0; hs.count[0] = 5;
+        for (int dy = 0; dy < 5; dy++) hs.e[ne++] = HaloEntry{dy * tw, 0, dy * Cin, 0};
+    } else {                                    // transposed 4x4 s2: phase (py,px), tap (ta,tb) as in conv_gemm_kernel
+        hs.n_loads = 3; hs.acc_blocks = 4; hs.box_rows = (th + 2) * tw;
+        for (int l = 0; l < 3; l++) {
+            hs.ox[l] = l - 1; hs.oy[l] = -1; hs.first[l] = ne;
+            for (int phase = 0; phase < 4; phase++)
+                for (int tap = 0; tap < 4; tap++) {
+                    const int py = phase >> 1, px = phase & 1, ta = tap >> 1, tb = tap & 1;
+                    const int oy = py == 0 ? (ta == 0 ? 0 : -1) : (ta == 0 ? 1 : 0);
+                    const int ox = px == 0 ? (tb == 0 ? 0 : -1) : (tb == 0 ? 1 : 0);
+                    if (ox != l - 1) continue;
+                    hs.e[ne++] = HaloEntry{(oy + 1) * tw, phase * rows, tap * Cin, phase};
+                }
+            hs.count[l] = ne - hs.first[l];
+        }
+    }
+}
+
 }  // namespace iper
 
 using namespace iper;
@@ -722,8 +987,17 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
     const int fmt = d->a_planes;
     const int TMv = (d->tiles_m == 2 && fmt != 3) ? 2 : 1;
     // cta_pair: 2-CTA clusters (cta_group::2) — each CTA stages its own A tile and half of the weight tile
+    const bool halo = d->cta_pair == 2;
     const bool pair = d->cta_pair != 0;
-    if (pair) {
+    IPER_REQUIRE(d->cta_pair >= 0 && d->cta_pair <= 2, "iper_conv_gemm: cta_pair=%d not in {0,1,2}", d->cta_pair);
+    if (halo) {
+        const bool ok_mode = (d->mode == IPER_CONV_S1 && d->ksize == 3 && d->block_n >= 64) ||
+                             (d->mode == IPER_CONVT_4S2 && d->block_n == 64) ||
+                             (d->mode == IPER_CONV_ROW5 && d->block_n == 32);
+        IPER_REQUIRE(fmt != 3 && TMv == 1 && ok_mode,
+                     "iper_conv_gemm: cta_pair=2 (halo) supports formats 1/2 and 3x3 stride-1 (block_n >= 64), transposed "
+                     "(block_n 64) or ROW5 heads (block_n 32) layers");
+    } else if (pair) {
         IPER_REQUIRE(fmt != 3 && TMv == 1 && (d->block_n == 128 || d->block_n == 256) && d->epi != IPER_EPI_HEADS &&
                      d->mode != IPER_CONV_ROW5,
                      "iper_conv_gemm: cta_pair supports formats 1/2, tiles_m = 1, block_n 128/256, no heads epilogue");
@@ -764,12 +1038,30 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
         g.tw = BLOCK_M; g.th = 1; g.tn = 1;
         g.tiles_x = (g.Wo + (BLOCK_M - 4) - 1) / (BLOCK_M - 4);
     }
+    if (halo) {                            // 16 x 8 pixel tiles (heads: 32 x 4 with a 4-pixel horizontal overlap), one image each
+        g.tw = d->mode == IPER_CONV_ROW5 ? 32 : 16; g.th = BLOCK_M / g.tw; g.tn = 1;
+        IPER_REQUIRE(g.Wo >= g.tw && g.Ho >= g.th, "iper_conv_gemm: cta_pair=2 (halo) needs a map of at least %dx%d pixels", g.tw, g.th);
+        g.tiles_x = d->mode == IPER_CONV_ROW5 ? (g.Wo + (g.tw - 4) - 1) / (g.tw - 4) : (g.Wo + g.tw - 1) / g.tw;
+    }
     g.tiles_y = (g.Ho + g.th - 1) / g.th;
     g.tiles_nb = (g.N + g.tn - 1) / g.tn;
     g.m_tiles = g.tiles_x * g.tiles_y * g.tiles_nb;
     g.m_groups = (g.m_tiles + TMv - 1) / TMv;
     g.n_tiles = d->rows / d->block_n;
     g.total_tiles = g.m_groups * g.n_tiles * g.phases;
+    if (halo) {
+        build_halo_sched(g.hs, d->mode, d->Cin, d->rows, g.tw, g.th);
+        g.hs.a_plane_bytes = g.hs.box_rows * 128;
+        const int a_slot = fmt * g.hs.a_plane_bytes, b_slot = fmt * (d->block_n / 2) * 128;
+        g.hs.na = (3 * a_slot + 6 * b_slot <= HALO_SMEM_BUDGET) ? 3 : 2;
+        g.hs.nb = (HALO_SMEM_BUDGET - g.hs.na * a_slot) / b_slot;
+        if (g.hs.nb > HALO_MAX_NB) g.hs.nb = HALO_MAX_NB;
+        IPER_REQUIRE(g.hs.nb >= 3, "iper_conv_gemm: halo rings do not fit shared memory");
+        int cols = 32;
+        while (cols < 2 * g.hs.acc_blocks * d->block_n) cols *= 2;
+        IPER_REQUIRE(cols <= 512, "iper_conv_gemm: halo accumulators exceed TMEM");
+        g.hs.tmem_cols = cols;
+    }
     g.cin_chunks = d->Cin / BKv;
     g.num_k = taps * g.cin_chunks;
     g.a_coff = d->a_coff; g.a_pitch = d->a_pitch;
@@ -822,7 +1114,7 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
             cuuint64_t dims[4] = {(cuuint64_t)d->a_pitch, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
             cuuint64_t str[3] = {(cuuint64_t)d->a_pitch * esz, (cuuint64_t)d->W * d->a_pitch * esz,
                                  (cuuint64_t)d->H * d->W * d->a_pitch * esz};
-            cuuint32_t box[4] = {(cuuint32_t)BKv, (cuuint32_t)g.tw, (cuuint32_t)g.th, (cuuint32_t)g.tn};
+            cuuint32_t box[4] = {(cuuint32_t)BKv, (cuuint32_t)g.tw, (cuuint32_t)(halo ? g.hs.box_rows / g.tw : g.th), (cuuint32_t)g.tn};
             if (int rc = encode_map(&g.mapA[p], base, 4, dims, str, box, u8, row_bytes)) return rc;
         }
         const void* wb;
@@ -839,6 +1131,14 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
     if (d->stats_ws) {
         IPER_REQUIRE(d->epi == IPER_EPI_PLANES && d->mode != IPER_CONVT_4S2, "iper_conv_gemm: fused statistics need the planes epilogue of a (strided) conv");
         IPER_CHECK_CUDA(cudaMemsetAsync(d->stats_ws, 0, sizeof(double) * 2 * (size_t)d->N * d->rows, s));
+    }
+    if (halo) {
+        switch (d->block_n) {
+            case 32: return fmt == 2 ? launch_gemm_halo<32, 2>(g, d->max_ctas, s) : launch_gemm_halo<32, 1>(g, d->max_ctas, s);
+            case 64: return fmt == 2 ? launch_gemm_halo<64, 2>(g, d->max_ctas, s) : launch_gemm_halo<64, 1>(g, d->max_ctas, s);
+            case 128: return fmt == 2 ? launch_gemm_halo<128, 2>(g, d->max_ctas, s) : launch_gemm_halo<128, 1>(g, d->max_ctas, s);
+            default: return fmt == 2 ? launch_gemm_halo<256, 2>(g, d->max_ctas, s) : launch_gemm_halo<256, 1>(g, d->max_ctas, s);
+        }
     }
     if (pair) {
         if (d->block_n == 256) return fmt == 2 ? launch_gemm_pair<256, 2>(g, d->max_ctas, s) : launch_gemm_pair<256, 1>(g, d->max_ctas, s);
