@@ -110,7 +110,11 @@ typedef struct {
     /* IPER_EPI_PLANES only: fused instance-norm statistics of the stored output — (N, rows, 2) fp64 workspace of
      * (sum, sum of squares), cleared by the call; finish with iper_instnorm_finalize                              */
     double* stats_ws;
-    int cta_pair;                                            /* 1: 2-CTA clusters (cta_group::2), weight tile split across the pair */
+    /* 0: one CTA per 128-pixel tile.  1: 2-CTA clusters (cta_group::2), weight tile split across the pair (formats 1/2,
+     * block_n 128/256).  2: CTA pair + vertical halo — 16x8-pixel tiles whose vertical taps are views of ONE TMA box per
+     * horizontal tap (3x3 stride-1, block_n >= 64; 5x5 heads as IPER_CONV_ROW5 with 32x4 tiles), and the transposed
+     * conv runs its four phases fused from the same boxes (block_n 64); needs a map of >= 16x8 (heads 32x4) pixels.  */
+    int cta_pair;
 } iper_conv_gemm_desc;
 
 /* tcgen05/TMEM implicit-GEMM convolution with TMA im2col tile loads (conv_tc.cu). */

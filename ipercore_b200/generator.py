@@ -139,6 +139,9 @@ class AttentionLWBGenerator(nn.Module):
         import os
         # CTA pairs (cta_group::2, weight tile split across two SMs) for every conv with >= 128 output rows
         self.cta_pair = (os.environ.get("IPER_CTA_PAIR", "1") != "0") if cta_pair is None else bool(cta_pair)
+        # halo variant of the CTA-pair kernel (vertical taps share one TMA box; fused transposed-conv phases) wherever
+        # a layer qualifies: 3x3 stride-1 convs, the 128->64 transposed conv, the 5x5 heads
+        self.halo = self.cta_pair and os.environ.get("IPER_HALO", "1") != "0"
         if temporal:
             raise NotImplementedError("temporal=True (TemporalFIFO recurrence, default false in deploy.toml:40) is not "
                                       "on the B200 hot path yet")
@@ -238,11 +241,20 @@ class AttentionLWBGenerator(nn.Module):
         w, b = pk[name]
         rows = w.rows_total // (4 if mode == IPER_CONVT_4S2 else 1)
         ops.conv_gemm(a, w, mode, ksize, rows, _bn_for(rows), IPER_EPI_PLANES, bias=b, relu=relu, out=out, x=x,
-                      stats_ws=stats_ws, cta_pair=self._pair(rows))
+                      stats_ws=stats_ws, cta_pair=self._pair(rows, mode, ksize, a))
         return out
 
-    def _pair(self, rows):
-        return int(self.cta_pair and self.P != 3 and rows >= 128)
+    def _pair(self, rows, mode=None, ksize=0, a=None):
+        """iper_conv_gemm's cta_pair: 0 = one CTA per tile, 1 = CTA pair, 2 = CTA pair + vertical-halo operand reuse."""
+        if not self.cta_pair or self.P == 3:
+            return 0
+        if self.halo and a is not None and a.H >= 8 and a.W >= 16:
+            bn = _bn_for(rows)
+            if (mode == IPER_CONV_S1 and ksize == 3 and bn >= 64) or (mode == IPER_CONVT_4S2 and bn == 64):
+                return 2
+            if mode == ops.IPER_CONV_ROW5 and a.W >= 32:
+                return 2
+        return int(rows >= 128 and mode != ops.IPER_CONV_ROW5)
 
     def _project_kv(self, pk, prefix, feat):
         """source maps [(Wq^T Wk) x | Wv x | (Wk^T bq).x | pad] of source features: Planes (ns,h,w,C) -> fp32 (ns,h,w,2C+64)."""
@@ -332,7 +344,7 @@ class AttentionLWBGenerator(nn.Module):
             if out is None:
                 out = Planes.empty(P, B, h, h, C, dev)
             ops.conv_gemm(actv, wgb, IPER_CONV_S1, 3, 2 * C, _bn_for(2 * C), IPER_EPI_SPADE, bias=bgb, out=out, x=x,
-                          mean_rstd=stats, spade_C=C, cta_pair=self._pair(2 * C))
+                          mean_rstd=stats, spade_C=C, cta_pair=self._pair(2 * C, IPER_CONV_S1, 3, actv))
             return out
 
         # 1. encoder (:507-519)
@@ -375,7 +387,8 @@ class AttentionLWBGenerator(nn.Module):
             pred = torch.empty((B, 3, S, S), dtype=torch.float32, device=dev)
             heads.update(bg=bg_img, pred=pred)
         wh, _ = pk["tsf_heads"]
-        ops.conv_gemm(d2, wh, ops.IPER_CONV_ROW5, 5, 32, 32, IPER_EPI_HEADS, heads=heads)
+        ops.conv_gemm(d2, wh, ops.IPER_CONV_ROW5, 5, 32, 32, IPER_EPI_HEADS, heads=heads,
+                      cta_pair=self._pair(32, ops.IPER_CONV_ROW5, 5, d2))
         return (img, mask, pred) if return_pred else (img, mask)
 
     # -------------------------------------------------------------------------------------------------------------

@@ -32,7 +32,14 @@ CASES = [
     (2, 16, 16, 64, 64, 0, 3), (1, 32, 32, 128, 128, 0, 3), (2, 16, 16, 256, 256, 0, 3), (3, 8, 8, 64, 256, 0, 1),
     (1, 20, 12, 64, 64, 0, 3), (2, 32, 32, 64, 128, 1, 3), (2, 16, 16, 128, 256, 1, 3),
     (2, 8, 8, 256, 256, 2, 4), (1, 16, 16, 256, 128, 2, 4), (1, 16, 16, 128, 64, 2, 4), (1, 16, 16, 384, 256, 0, 3),
+    # halo kernel (cta_pair=2): partial 16x8 tiles, an odd tile count (the pair's second tile is empty), two n tiles
+    (1, 20, 24, 64, 128, 0, 3), (3, 8, 16, 128, 128, 0, 3), (1, 24, 40, 128, 512, 0, 3), (3, 8, 16, 128, 64, 2, 4),
 ]
+
+
+def _halo_ok(mode, k, bn, H, W):
+    """layers the vertical-halo CTA-pair kernel accepts (iper_conv_gemm, cta_pair = 2)"""
+    return H >= 8 and W >= 16 and ((mode == 0 and k == 3 and bn >= 64) or (mode == 2 and bn == 64))
 
 
 def _operand_terms(x, P):
@@ -109,6 +116,13 @@ def test_conv_gemm_planes(N, H, W, Cin, Cout, mode, k, P):
                           relu=True, out=alt, cta_pair=1)
             torch.cuda.synchronize()
             np.testing.assert_allclose(_planes_value(alt).numpy(), exp.numpy(), atol=atol, rtol=rtol)
+        if _halo_ok(mode, k, 256 if rows >= 256 else rows, H, W):     # vertical taps share one TMA box; fused convT phases
+            alt = Planes.empty(P, N, oH, oW, Cout, DEV)
+            alt.data.fill_(7.0)
+            ops.conv_gemm(a, wp, mode, k, rows, 256 if rows >= 256 else rows, ops.IPER_EPI_PLANES, bias=bias.to(DEV),
+                          relu=True, out=alt, cta_pair=2)
+            torch.cuda.synchronize()
+            np.testing.assert_allclose(_planes_value(alt).numpy(), exp.numpy(), atol=atol, rtol=rtol)
     # on-device cross-check (CUDA-core direct convolution of the stored activation values with the fp16-rounded weights)
     chk = Planes.empty(P, N, oH, oW, Cout, DEV)
     wm, _, wlo = wp.effective()
@@ -165,6 +179,12 @@ def test_conv_gemm_spade_epilogue(C, P):
     np.testing.assert_allclose(stats[..., 0].cpu().numpy(), mean.numpy(), atol=1e-6, rtol=0)
     np.testing.assert_allclose(stats[..., 1].cpu().numpy(), (1 / torch.sqrt(var + 1e-5)).numpy(), rtol=2e-6, atol=0)
     np.testing.assert_allclose(_planes_value(out).numpy(), exp.numpy(), atol={2: 1e-4, 3: 1.5e-3, 1: 3e-3}[P], rtol=0)
+    if P != 3:
+        for mode_pair in (1, 2) if bn >= 128 else (2,):      # CTA pair, CTA pair + halo
+            alt = Planes.empty(P, N, H, W, C, DEV)
+            ops.conv_gemm(a, wpk.to(DEV), 0, 3, 2 * C, bn, ops.IPER_EPI_SPADE, bias=bpk.to(DEV), out=alt, x=xp,
+                          mean_rstd=stats, spade_C=C, cta_pair=mode_pair)
+            np.testing.assert_allclose(_planes_value(alt).numpy(), exp.numpy(), atol={2: 1e-4, 1: 3e-3}[P], rtol=0)
     chk = Planes.empty(P, N, H, W, C, DEV)
     ops.conv_direct(a, torch.cat([q(wg), q(wb)], 0).to(DEV), 0, 3, 2 * C, ops.IPER_EPI_SPADE, bias=torch.cat([bg, bb]).to(DEV),
                     out=chk, x=xp, mean_rstd=stats, spade_C=C)
@@ -189,6 +209,13 @@ def test_conv_gemm_heads_epilogue(S, P):
     np.testing.assert_allclose(img.cpu().numpy(), ei.numpy(), atol=tol, rtol=0)
     np.testing.assert_allclose(mask.cpu().numpy(), em.numpy(), atol=tol, rtol=0)
     np.testing.assert_allclose(pred.cpu().numpy(), (em * bgimg + (1 - em) * ei).numpy(), atol=1.5 * tol, rtol=0)
+    if P != 3:      # halo kernel: 32x4 tiles, the five vertical taps are views of one 32x8 box
+        img2 = torch.full_like(img, 9.0); mask2 = torch.full_like(mask, 9.0); pred2 = torch.full_like(pred, 9.0)
+        ops.conv_gemm(a, wp, ops.IPER_CONV_ROW5, 5, 32, 32, ops.IPER_EPI_HEADS,
+                      heads=dict(img=img2, mask=mask2, pred=pred2, bg=bgimg.to(DEV)), cta_pair=2)
+        np.testing.assert_allclose(img2.cpu().numpy(), ei.numpy(), atol=tol, rtol=0)
+        np.testing.assert_allclose(mask2.cpu().numpy(), em.numpy(), atol=tol, rtol=0)
+        np.testing.assert_allclose(pred2.cpu().numpy(), (em * bgimg + (1 - em) * ei).numpy(), atol=1.5 * tol, rtol=0)
 
 
 def test_stem_and_attention_kernels():
@@ -239,6 +266,13 @@ def test_fused_instnorm_statistics(N, H, W, Cin, Cout, mode):
     alone = ops.instnorm_stats(out)
     torch.testing.assert_close(fused[..., 0], alone[..., 0], atol=2e-6, rtol=0)
     torch.testing.assert_close(fused[..., 1], alone[..., 1], atol=0, rtol=2e-5)
+    if mode == 0 and H >= 8 and W >= 16:       # the halo kernel shares the epilogue
+        ws3 = ops.stats_workspace(N, Cout, DEV)
+        ops.conv_gemm(a, ops.pack_conv_weight(w, P).to(DEV), mode, 3, Cout, 256 if Cout >= 256 else Cout, ops.IPER_EPI_PLANES,
+                      bias=b.to(DEV), relu=True, out=out, stats_ws=ws3, cta_pair=2)
+        f3 = ops.instnorm_finalize(ws3, oH * oW)
+        torch.testing.assert_close(f3[..., 0], alone[..., 0], atol=2e-6, rtol=0)
+        torch.testing.assert_close(f3[..., 1], alone[..., 1], atol=0, rtol=2e-5)
     # stem
     xi = _rand((N, 6, 2 * H, 2 * W), 64); ws2 = ops.stats_workspace(N, 64, DEV)
     so = Planes.empty(P, N, H, W, 64, DEV)
