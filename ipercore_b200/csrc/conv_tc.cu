@@ -48,7 +48,8 @@ constexpr int HALO_MAX_LOADS = 3, HALO_MAX_ENTRIES = 16;
 struct HaloEntry { int a_row_off, b_row, b_k, acc; };
 struct HaloSched {
     int n_loads, acc_blocks, box_rows;          // box_rows = (th + halo) * tw
-    int na, nb, a_plane_bytes, tmem_cols;       // ring depths, bytes of one A plane of a slot, TMEM columns to allocate
+    int na, nb, a_plane_bytes, tmem_cols;       // ring depths, bytes of one A box of a slot, TMEM columns to allocate
+    int k8;                                     // format 3: e4m3 channels per step (128: 128-byte rows, 64: 64-byte rows)
     int ox[HALO_MAX_LOADS], oy[HALO_MAX_LOADS], first[HALO_MAX_LOADS], count[HALO_MAX_LOADS];
     HaloEntry e[HALO_MAX_ENTRIES];
 };
@@ -655,18 +656,30 @@ constexpr int HALO_THREADS = 224;
 constexpr int HALO_MAX_NA = 4, HALO_MAX_NB = 8;
 constexpr int HALO_SMEM_BUDGET = 212 * 1024;
 
+// K walk of the halo kernel.  A ring slot always holds two operand boxes (A: box_rows x 128 B each; B: BN/2 rows each):
+//   NS = 2             one pass, 64 channels per step: boxes = fp16 hi, fp16 lo
+//   NS = 1, NS = 3 pass 0   128 channels per step (64 for an odd tail): boxes = hi[c0 .. +64), hi[c0+64 .. +128)  -> D1 (kind::f16)
+//   NS = 3, pass 1     k8 (128 or 64) channels per step: boxes = e4m3 a8, l8                                  -> D2 (kind::f8f6f4)
+// Every role walks the same (pass, step, load, entry) sequence.
+struct HaloWalk {
+    int npass, k8;
+    IPER_DEVINL int steps(int pass, int NS, int cin) const {
+        if (NS == 2) return cin / 64;
+        return pass == 0 ? (cin + 127) / 128 : cin / k8;
+    }
+};
+
 template <int BN, int NS>
 __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const __grid_constant__ GemmArgs a) {
-    static_assert(NS == 1 || NS == 2, "halo kernel supports fp16 and split fp16");
-    constexpr int B_PLANE = (BN / 2) * 128;                    // this CTA's half of a weight tile, one plane
-    constexpr int B_SLOT = NS * B_PLANE;
+    constexpr int B_PLANE = (BN / 2) * 128;                    // this CTA's half of a weight tile, one box
+    constexpr int B_SLOT = 2 * B_PLANE;
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t a_full[HALO_MAX_NA];      // leader: 2 arrivals + bytes of both CTAs
     __shared__ __align__(8) uint64_t a_empty[HALO_MAX_NA];     // per CTA, multicast commit
     __shared__ __align__(8) uint64_t b_full[HALO_MAX_NB];
     __shared__ __align__(8) uint64_t b_empty[HALO_MAX_NB];
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
-    __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+    __shared__ __align__(8) uint64_t tmem_empty_bar[2];        // NS=3: [0] = D1 drained, [1] = D2 drained
     __shared__ uint32_t tmem_base_slot;
 
     const HaloSched& hs = a.hs;
@@ -675,10 +688,13 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const _
     const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
     const uint32_t ring = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     uint8_t* ring_ptr = smem_dyn + (ring - smem_u32(smem_dyn));
-    const int a_slot = NS * hs.a_plane_bytes;
+    const int a_slot = 2 * hs.a_plane_bytes;
     uint8_t* b_ring = ring_ptr + hs.na * a_slot;
     auto sA = [&](int slot, int p) -> uint8_t* { return ring_ptr + slot * a_slot + p * hs.a_plane_bytes; };
     auto sB = [&](int slot, int p) -> uint8_t* { return b_ring + slot * B_SLOT + p * B_PLANE; };
+    const int cin = a.cin_chunks * 64;
+    HaloWalk walk;
+    walk.npass = (NS == 3) ? 2 : 1; walk.k8 = hs.k8;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < hs.na; i++) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); }
@@ -718,16 +734,32 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const _
             int slot = 0; uint32_t ph = 0;
             for (int u = cluster_id; u < units; u += num_clusters) {
                 const TileCoord t = unit_coord(u);
-                for (int cc = 0; cc < a.cin_chunks; cc++)
-                    for (int l = 0; l < hs.n_loads; l++) {
-                        mbar_wait(&a_empty[slot], ph ^ 1);
-                        for (int p = 0; p < NS; p++)
-                            tma_load_4d_2sm(sA(slot, p), &a.mapA[p], &a_full[slot], a.a_coff + cc * 64, t.px0 + hs.ox[l],
-                                            t.py0 + hs.oy[l], t.pn0);
-                        if (rank == 0) mbar_arrive_expect_tx(&a_full[slot], 2u * (uint32_t)a_slot);
-                        else mbar_arrive_remote(&a_full[slot], 0);
-                        if (++slot == hs.na) { slot = 0; ph ^= 1; }
-                    }
+                for (int pass = 0; pass < walk.npass; pass++) {
+                    const int nsteps = walk.steps(pass, NS, cin);
+                    for (int cc = 0; cc < nsteps; cc++)
+                        for (int l = 0; l < hs.n_loads; l++) {
+                            mbar_wait(&a_empty[slot], ph ^ 1);
+                            const int x = t.px0 + hs.ox[l], y = t.py0 + hs.oy[l];
+                            uint32_t bytes;
+                            if constexpr (NS == 2) {
+                                for (int p = 0; p < 2; p++)
+                                    tma_load_4d_2sm(sA(slot, p), &a.mapA[p], &a_full[slot], a.a_coff + cc * 64, x, y, t.pn0);
+                                bytes = 2 * hs.a_plane_bytes;
+                            } else if (pass == 0) {
+                                const int nbox = (cin - cc * 128 >= 128) ? 2 : 1;
+                                for (int h = 0; h < nbox; h++)
+                                    tma_load_4d_2sm(sA(slot, h), &a.mapA[0], &a_full[slot], a.a_coff + cc * 128 + h * 64, x, y, t.pn0);
+                                bytes = nbox * hs.a_plane_bytes;
+                            } else {
+                                for (int p = 0; p < 2; p++)
+                                    tma_load_4d_2sm(sA(slot, p), &a.mapA[1 + p], &a_full[slot], a.a_coff + cc * walk.k8, x, y, t.pn0);
+                                bytes = 2 * hs.box_rows * walk.k8;
+                            }
+                            if (rank == 0) mbar_arrive_expect_tx(&a_full[slot], 2u * bytes);
+                            else mbar_arrive_remote(&a_full[slot], 0);
+                            if (++slot == hs.na) { slot = 0; ph ^= 1; }
+                        }
+                }
             }
         }
     } else if (warp == 6) {
@@ -736,65 +768,120 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const _
             int slot = 0; uint32_t ph = 0;
             for (int u = cluster_id; u < units; u += num_clusters) {
                 const int brow = (u % a.n_tiles) * BN + (int)rank * (BN / 2);
-                for (int cc = 0; cc < a.cin_chunks; cc++)
-                    for (int l = 0; l < hs.n_loads; l++)
-                        for (int i = hs.first[l]; i < hs.first[l] + hs.count[l]; i++) {
-                            mbar_wait(&b_empty[slot], ph ^ 1);
-                            for (int p = 0; p < NS; p++)
-                                tma_load_2d_2sm(sB(slot, p), &a.mapB[p], &b_full[slot], hs.e[i].b_k + cc * 64, hs.e[i].b_row + brow);
-                            if (rank == 0) mbar_arrive_expect_tx(&b_full[slot], 2u * B_SLOT);
-                            else mbar_arrive_remote(&b_full[slot], 0);
-                            if (++slot == hs.nb) { slot = 0; ph ^= 1; }
-                        }
+                for (int pass = 0; pass < walk.npass; pass++) {
+                    const int nsteps = walk.steps(pass, NS, cin);
+                    for (int cc = 0; cc < nsteps; cc++)
+                        for (int l = 0; l < hs.n_loads; l++)
+                            for (int i = hs.first[l]; i < hs.first[l] + hs.count[l]; i++) {
+                                mbar_wait(&b_empty[slot], ph ^ 1);
+                                const int r = hs.e[i].b_row + brow;
+                                uint32_t bytes;
+                                if constexpr (NS == 2) {
+                                    for (int p = 0; p < 2; p++)
+                                        tma_load_2d_2sm(sB(slot, p), &a.mapB[p], &b_full[slot], hs.e[i].b_k + cc * 64, r);
+                                    bytes = 2 * B_PLANE;
+                                } else if (pass == 0) {
+                                    const int nbox = (cin - cc * 128 >= 128) ? 2 : 1;
+                                    for (int h = 0; h < nbox; h++)
+                                        tma_load_2d_2sm(sB(slot, h), &a.mapB[0], &b_full[slot], hs.e[i].b_k + cc * 128 + h * 64, r);
+                                    bytes = nbox * B_PLANE;
+                                } else {
+                                    for (int p = 0; p < 2; p++)
+                                        tma_load_2d_2sm(sB(slot, p), &a.mapB[1 + p], &b_full[slot], hs.e[i].b_k + cc * walk.k8, r);
+                                    bytes = 2 * (BN / 2) * walk.k8;
+                                }
+                                if (rank == 0) mbar_arrive_expect_tx(&b_full[slot], 2u * bytes);
+                                else mbar_arrive_remote(&b_full[slot], 0);
+                                if (++slot == hs.nb) { slot = 0; ph ^= 1; }
+                            }
+                }
             }
         }
     } else if (warp == 1) {
         // =========================== MMA issuer (leader CTA only) ===========================
         if (rank == 0) {
             constexpr uint32_t idesc = umma_idesc_f16(2 * BLOCK_M, BN);
+            constexpr uint32_t idesc8 = umma_idesc_e4m3(2 * BLOCK_M, BN);
             int aslot = 0, bslot = 0; uint32_t aph = 0, bph = 0; int it = 0;
             for (int u = cluster_id; u < units; u += num_clusters, it++) {
-                const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
-                mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
-                tc_fence_after();
+                // NS != 3: two accumulator sets, one per unit parity.  NS == 3: one set [D1 | D2], D1 is handed back early.
+                const int acc = (NS == 3) ? 0 : (it & 1);
+                const uint32_t acc_ph = (NS == 3) ? (it & 1) : ((it >> 1) & 1);
                 const uint32_t d_tmem = tmem_base + acc * acc_cols;
-                uint32_t touched = 0;            // accumulator blocks already written for this unit
-                for (int cc = 0; cc < a.cin_chunks; cc++)
-                    for (int l = 0; l < hs.n_loads; l++) {
-                        mbar_wait(&a_full[aslot], aph);
-                        tc_fence_after();
-                        const bool last_load = (cc == a.cin_chunks - 1) && (l == hs.n_loads - 1);
-                        for (int i = hs.first[l]; i < hs.first[l] + hs.count[l]; i++) {
-                            mbar_wait(&b_full[bslot], bph);
+                for (int pass = 0; pass < walk.npass; pass++) {
+                    mbar_wait(&tmem_empty_bar[NS == 3 ? pass : acc], acc_ph ^ 1);
+                    tc_fence_after();
+                    uint32_t touched = 0;            // accumulator blocks already written in this pass
+                    const uint32_t d_pass = d_tmem + pass * acc_cols;
+                    const int nsteps = walk.steps(pass, NS, cin);
+                    for (int cc = 0; cc < nsteps; cc++)
+                        for (int l = 0; l < hs.n_loads; l++) {
+                            mbar_wait(&a_full[aslot], aph);
                             tc_fence_after();
-                            const HaloEntry e = hs.e[i];
-                            const bool last_entry = (i == hs.first[l] + hs.count[l] - 1);
-                            if (elect_one()) {
-                                uint32_t first = (touched >> e.acc) & 1u;
-                                constexpr int NPAIR = (NS == 2) ? 3 : 1;
-                                const int pa[3] = {NS == 2 ? 1 : 0, 0, 0};
-                                const int pb[3] = {0, NS == 2 ? 1 : 0, 0};
+                            const bool last_load = (pass == walk.npass - 1) && (cc == nsteps - 1) && (l == hs.n_loads - 1);
+                            for (int i = hs.first[l]; i < hs.first[l] + hs.count[l]; i++) {
+                                mbar_wait(&b_full[bslot], bph);
+                                tc_fence_after();
+                                const HaloEntry e = hs.e[i];
+                                const bool last_entry = (i == hs.first[l] + hs.count[l] - 1);
+                                if (elect_one()) {
+                                    uint32_t first = (touched >> e.acc) & 1u;
+                                    const uint32_t d = d_pass + e.acc * BN;
+                                    if constexpr (NS == 2) {
+                                        const int pa[3] = {1, 0, 0};      // lo*hi, hi*lo, hi*hi
+                                        const int pb[3] = {0, 1, 0};
 #pragma unroll
-                                for (int q = 0; q < NPAIR; q++) {
-                                    const uint32_t abase = smem_u32(sA(aslot, pa[q])) + (uint32_t)e.a_row_off * 128u;
-                                    const uint32_t bbase = smem_u32(sB(bslot, pb[q]));
+                                        for (int q = 0; q < 3; q++) {
+                                            const uint32_t abase = smem_u32(sA(aslot, pa[q])) + (uint32_t)e.a_row_off * 128u;
+                                            const uint32_t bbase = smem_u32(sB(bslot, pb[q]));
 #pragma unroll
-                                    for (int k = 0; k < 4; k++) {
-                                        umma_f16_2sm(d_tmem + e.acc * BN, umma_desc_sw128(abase + k * 32),
-                                                     umma_desc_sw128(bbase + k * 32), idesc, first);
-                                        first = 1u;
+                                            for (int k = 0; k < 4; k++) {
+                                                umma_f16_2sm(d, umma_desc_sw128(abase + k * 32), umma_desc_sw128(bbase + k * 32), idesc, first);
+                                                first = 1u;
+                                            }
+                                        }
+                                    } else if (pass == 0) {          // D1 += hi * w_hi over one or two 64-channel boxes
+                                        const int nbox = (cin - cc * 128 >= 128) ? 2 : 1;
+                                        for (int h = 0; h < nbox; h++) {
+                                            const uint32_t abase = smem_u32(sA(aslot, h)) + (uint32_t)e.a_row_off * 128u;
+                                            const uint32_t bbase = smem_u32(sB(bslot, h));
+#pragma unroll
+                                            for (int k = 0; k < 4; k++) {
+                                                umma_f16_2sm(d, umma_desc_sw128(abase + k * 32), umma_desc_sw128(bbase + k * 32), idesc, first);
+                                                first = 1u;
+                                            }
+                                        }
+                                    } else {                         // D2 += l8 * w8 + a8 * wl8 (e4m3, K = 32 per instruction)
+                                        const uint32_t off = (uint32_t)(e.a_row_off * walk.k8);
+                                        const uint32_t a8 = smem_u32(sA(aslot, 0)) + off, l8 = smem_u32(sA(aslot, 1)) + off;
+                                        const uint32_t w8 = smem_u32(sB(bslot, 0)), wl8 = smem_u32(sB(bslot, 1));
+                                        if (walk.k8 == 128) {
+#pragma unroll
+                                            for (int k = 0; k < 4; k++) {
+                                                umma_f8_2sm(d, umma_desc_sw128(l8 + k * 32), umma_desc_sw128(w8 + k * 32), idesc8, first);
+                                                umma_f8_2sm(d, umma_desc_sw128(a8 + k * 32), umma_desc_sw128(wl8 + k * 32), idesc8, 1u);
+                                                first = 1u;
+                                            }
+                                        } else {
+#pragma unroll
+                                            for (int k = 0; k < 2; k++) {
+                                                umma_f8_2sm(d, umma_desc_sw64(l8 + k * 32), umma_desc_sw64(w8 + k * 32), idesc8, first);
+                                                umma_f8_2sm(d, umma_desc_sw64(a8 + k * 32), umma_desc_sw64(wl8 + k * 32), idesc8, 1u);
+                                                first = 1u;
+                                            }
+                                        }
                                     }
+                                    umma_commit_2sm(&b_empty[bslot], 0x3);
+                                    if (last_entry) umma_commit_2sm(&a_empty[aslot], 0x3);
+                                    if (last_entry && last_load) umma_commit_2sm(&tmem_full_bar[acc], 0x3);
                                 }
-                                umma_commit_2sm(&b_empty[bslot], 0x3);
-                                if (last_entry) umma_commit_2sm(&a_empty[aslot], 0x3);
-                                if (last_entry && last_load) umma_commit_2sm(&tmem_full_bar[acc], 0x3);
+                                __syncwarp();
+                                touched |= 1u << e.acc;
+                                if (++bslot == hs.nb) { bslot = 0; bph ^= 1; }
                             }
-                            __syncwarp();
-                            touched |= 1u << e.acc;
-                            if (++bslot == hs.nb) { bslot = 0; bph ^= 1; }
+                            if (++aslot == hs.na) { aslot = 0; aph ^= 1; }
                         }
-                        if (++aslot == hs.na) { aslot = 0; aph ^= 1; }
-                    }
+                }
             }
         }
     } else {
@@ -802,23 +889,45 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const _
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int tx = row % a.tw, ty = (row / a.tw) % a.th;
-        int it = 0;
-        for (int u = cluster_id; u < units; u += num_clusters, it++) {
-            const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
-            mbar_wait(&tmem_full_bar[acc], acc_ph);
-            tc_fence_after();
-            TileCoord t = unit_coord(u);
-            for (int blk = 0; blk < hs.acc_blocks; blk++) {
-                t.phase = blk;                  // transposed conv: accumulator block = output phase
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols + blk * BN;
-                epilogue_tile<BN, NS>(a, t, taddr, row, lane, tx, ty, 0);
-            }
+        auto release = [&](uint64_t* bar) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (rank == 0) mbar_arrive(&tmem_empty_bar[acc]);
-                else mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+                if (rank == 0) mbar_arrive(bar);
+                else mbar_arrive_remote(bar, 0);
             }
+        };
+        int it = 0;
+        for (int u = cluster_id; u < units; u += num_clusters, it++) {
+            const int acc = (NS == 3) ? 0 : (it & 1);
+            const uint32_t acc_ph = (NS == 3) ? (it & 1) : ((it >> 1) & 1);
+            mbar_wait(&tmem_full_bar[acc], acc_ph);
+            tc_fence_after();
+            TileCoord t = unit_coord(u);
+            const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + acc * acc_cols;
+            uint32_t src = lane_base;
+            if constexpr (NS == 3) {
+                // fold the fp16 accumulator into the e4m3 one (D2 <- D1 + D2 * cross_scale) so that D1 goes back to the
+                // MMA warp at once: the next unit's fp16 pass overlaps the stores below
+                for (int j = 0; j < acc_cols / 32; j++) {
+                    uint32_t r1[32], r2[32];
+                    tmem_ld32(lane_base + j * 32, r1);
+                    tmem_ld32(lane_base + acc_cols + j * 32, r2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; i++)
+                        r2[i] = __float_as_uint(fmaf(__uint_as_float(r2[i]), a.cross_scale, __uint_as_float(r1[i])));
+                    tmem_st32(lane_base + acc_cols + j * 32, r2);
+                }
+                tmem_st_wait();
+                release(&tmem_empty_bar[0]);
+                src = lane_base + acc_cols;
+            }
+            for (int blk = 0; blk < hs.acc_blocks; blk++) {
+                t.phase = blk;                  // transposed conv: accumulator block = output phase
+                epilogue_tile<BN, (NS == 3 ? 1 : NS)>(a, t, src + blk * BN, row, lane, tx, ty, 0);
+            }
+            release(&tmem_empty_bar[NS == 3 ? 1 : acc]);
         }
     }
 
@@ -911,7 +1020,7 @@ static int launch_gemm_pair(const GemmArgs& g, int max_ctas, cudaStream_t stream
 
 template <int BN, int NS>
 static int launch_gemm_halo(const GemmArgs& g, int max_ctas, cudaStream_t stream) {
-    const int a_slot = NS * g.hs.a_plane_bytes, b_slot = NS * (BN / 2) * 128;
+    const int a_slot = 2 * g.hs.a_plane_bytes, b_slot = 2 * (BN / 2) * 128;
     int smem = g.hs.na * a_slot + g.hs.nb * b_slot + 1024;
     if (smem < 120 * 1024) smem = 120 * 1024;            // one CTA per SM (TMEM allocation)
     static int attr_smem = 0;
@@ -994,9 +1103,9 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
         const bool ok_mode = (d->mode == IPER_CONV_S1 && d->ksize == 3 && d->block_n >= 64) ||
                              (d->mode == IPER_CONVT_4S2 && d->block_n == 64) ||
                              (d->mode == IPER_CONV_ROW5 && d->block_n == 32);
-        IPER_REQUIRE(fmt != 3 && TMv == 1 && ok_mode,
-                     "iper_conv_gemm: cta_pair=2 (halo) supports formats 1/2 and 3x3 stride-1 (block_n >= 64), transposed "
-                     "(block_n 64) or ROW5 heads (block_n 32) layers");
+        IPER_REQUIRE(TMv == 1 && ok_mode,
+                     "iper_conv_gemm: cta_pair=2 (halo) supports 3x3 stride-1 (block_n >= 64), transposed (block_n 64) or "
+                     "ROW5 heads (block_n 32) layers");
     } else if (pair) {
         IPER_REQUIRE(fmt != 3 && TMv == 1 && (d->block_n == 128 || d->block_n == 256) && d->epi != IPER_EPI_HEADS &&
                      d->mode != IPER_CONV_ROW5,
@@ -1052,7 +1161,8 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
     if (halo) {
         build_halo_sched(g.hs, d->mode, d->Cin, d->rows, g.tw, g.th);
         g.hs.a_plane_bytes = g.hs.box_rows * 128;
-        const int a_slot = fmt * g.hs.a_plane_bytes, b_slot = fmt * (d->block_n / 2) * 128;
+        g.hs.k8 = (d->Cin % 128 == 0) ? 128 : 64;
+        const int a_slot = 2 * g.hs.a_plane_bytes, b_slot = 2 * (d->block_n / 2) * 128;      // two boxes per slot
         g.hs.na = (3 * a_slot + 6 * b_slot <= HALO_SMEM_BUDGET) ? 3 : 2;
         g.hs.nb = (HALO_SMEM_BUDGET - g.hs.na * a_slot) / b_slot;
         if (g.hs.nb > HALO_MAX_NB) g.hs.nb = HALO_MAX_NB;
@@ -1099,7 +1209,8 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
     for (int p = 0; p < nmaps; p++) {
         const bool u8 = (fmt == 3 && p > 0);
         const size_t esz = u8 ? 1 : 2;
-        const int row_bytes = (int)(BKv * esz);
+        const int kbox = (u8 && halo) ? g.hs.k8 : BKv;          // K elements per box row
+        const int row_bytes = (int)(kbox * esz);
         const uint8_t* abase8 = reinterpret_cast<const uint8_t*>(d->a);
         const void* base;
         if (!u8) base = abase8 + (size_t)p * d->a_plane_stride * 2;                       // fp16 plane p
@@ -1114,7 +1225,7 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
             cuuint64_t dims[4] = {(cuuint64_t)d->a_pitch, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
             cuuint64_t str[3] = {(cuuint64_t)d->a_pitch * esz, (cuuint64_t)d->W * d->a_pitch * esz,
                                  (cuuint64_t)d->H * d->W * d->a_pitch * esz};
-            cuuint32_t box[4] = {(cuuint32_t)BKv, (cuuint32_t)g.tw, (cuuint32_t)(halo ? g.hs.box_rows / g.tw : g.th), (cuuint32_t)g.tn};
+            cuuint32_t box[4] = {(cuuint32_t)kbox, (cuuint32_t)g.tw, (cuuint32_t)(halo ? g.hs.box_rows / g.tw : g.th), (cuuint32_t)g.tn};
             if (int rc = encode_map(&g.mapA[p], base, 4, dims, str, box, u8, row_bytes)) return rc;
         }
         const void* wb;
@@ -1122,7 +1233,7 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
         else wb = (p == 1) ? d->w8 : d->wl8;
         cuuint64_t wdims[2] = {ktot, (cuuint64_t)d->rows * g.phases};
         cuuint64_t wstr[1] = {ktot * esz};
-        cuuint32_t wbox[2] = {(cuuint32_t)BKv, (cuuint32_t)(pair ? d->block_n / 2 : d->block_n)};
+        cuuint32_t wbox[2] = {(cuuint32_t)kbox, (cuuint32_t)(pair ? d->block_n / 2 : d->block_n)};
         if (int rc = encode_map(&g.mapB[p], wb, 2, wdims, wstr, wbox, u8, row_bytes)) return rc;
     }
     for (int p = nmaps; p < 3; p++) { g.mapA[p] = g.mapA[0]; g.mapB[p] = g.mapB[0]; }
@@ -1134,10 +1245,14 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
     }
     if (halo) {
         switch (d->block_n) {
-            case 32: return fmt == 2 ? launch_gemm_halo<32, 2>(g, d->max_ctas, s) : launch_gemm_halo<32, 1>(g, d->max_ctas, s);
-            case 64: return fmt == 2 ? launch_gemm_halo<64, 2>(g, d->max_ctas, s) : launch_gemm_halo<64, 1>(g, d->max_ctas, s);
-            case 128: return fmt == 2 ? launch_gemm_halo<128, 2>(g, d->max_ctas, s) : launch_gemm_halo<128, 1>(g, d->max_ctas, s);
-            default: return fmt == 2 ? launch_gemm_halo<256, 2>(g, d->max_ctas, s) : launch_gemm_halo<256, 1>(g, d->max_ctas, s);
+#define IPER_HALO_CASE(BNV)                                                                                           \
+    case BNV:                                                                                                        \
+        return fmt == 3 ? launch_gemm_halo<BNV, 3>(g, d->max_ctas, s)                                                \
+                        : (fmt == 2 ? launch_gemm_halo<BNV, 2>(g, d->max_ctas, s) : launch_gemm_halo<BNV, 1>(g, d->max_ctas, s));
+            IPER_HALO_CASE(32) IPER_HALO_CASE(64) IPER_HALO_CASE(128)
+            default: return fmt == 3 ? launch_gemm_halo<256, 3>(g, d->max_ctas, s)
+                                     : (fmt == 2 ? launch_gemm_halo<256, 2>(g, d->max_ctas, s) : launch_gemm_halo<256, 1>(g, d->max_ctas, s));
+#undef IPER_HALO_CASE
         }
     }
     if (pair) {

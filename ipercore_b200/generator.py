@@ -246,7 +246,7 @@ class AttentionLWBGenerator(nn.Module):
 
     def _pair(self, rows, mode=None, ksize=0, a=None):
         """iper_conv_gemm's cta_pair: 0 = one CTA per tile, 1 = CTA pair, 2 = CTA pair + vertical-halo operand reuse."""
-        if not self.cta_pair or self.P == 3:
+        if not self.cta_pair:
             return 0
         if self.halo and a is not None and a.H >= 8 and a.W >= 16:
             bn = _bn_for(rows)
@@ -254,7 +254,7 @@ class AttentionLWBGenerator(nn.Module):
                 return 2
             if mode == ops.IPER_CONV_ROW5 and a.W >= 32:
                 return 2
-        return int(rows >= 128 and mode != ops.IPER_CONV_ROW5)
+        return int(self.P != 3 and rows >= 128 and mode != ops.IPER_CONV_ROW5)     # plain CTA pairs: formats 1/2 only
 
     def _project_kv(self, pk, prefix, feat):
         """source maps [(Wq^T Wk) x | Wv x | (Wk^T bq).x | pad] of source features: Planes (ns,h,w,C) -> fp32 (ns,h,w,2C+64)."""

@@ -116,13 +116,13 @@ def test_conv_gemm_planes(N, H, W, Cin, Cout, mode, k, P):
                           relu=True, out=alt, cta_pair=1)
             torch.cuda.synchronize()
             np.testing.assert_allclose(_planes_value(alt).numpy(), exp.numpy(), atol=atol, rtol=rtol)
-        if _halo_ok(mode, k, 256 if rows >= 256 else rows, H, W):     # vertical taps share one TMA box; fused convT phases
-            alt = Planes.empty(P, N, oH, oW, Cout, DEV)
-            alt.data.fill_(7.0)
-            ops.conv_gemm(a, wp, mode, k, rows, 256 if rows >= 256 else rows, ops.IPER_EPI_PLANES, bias=bias.to(DEV),
-                          relu=True, out=alt, cta_pair=2)
-            torch.cuda.synchronize()
-            np.testing.assert_allclose(_planes_value(alt).numpy(), exp.numpy(), atol=atol, rtol=rtol)
+    if _halo_ok(mode, k, 256 if rows >= 256 else rows, H, W):     # vertical taps share one TMA box; fused convT phases
+        alt = Planes.empty(P, N, oH, oW, Cout, DEV)
+        alt.data.fill_(7.0)
+        ops.conv_gemm(a, wp, mode, k, rows, 256 if rows >= 256 else rows, ops.IPER_EPI_PLANES, bias=bias.to(DEV),
+                      relu=True, out=alt, cta_pair=2)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(_planes_value(alt).numpy(), exp.numpy(), atol=atol, rtol=rtol)
     # on-device cross-check (CUDA-core direct convolution of the stored activation values with the fp16-rounded weights)
     chk = Planes.empty(P, N, oH, oW, Cout, DEV)
     wm, _, wlo = wp.effective()
@@ -179,19 +179,18 @@ def test_conv_gemm_spade_epilogue(C, P):
     np.testing.assert_allclose(stats[..., 0].cpu().numpy(), mean.numpy(), atol=1e-6, rtol=0)
     np.testing.assert_allclose(stats[..., 1].cpu().numpy(), (1 / torch.sqrt(var + 1e-5)).numpy(), rtol=2e-6, atol=0)
     np.testing.assert_allclose(_planes_value(out).numpy(), exp.numpy(), atol={2: 1e-4, 3: 1.5e-3, 1: 3e-3}[P], rtol=0)
-    if P != 3:
-        for mode_pair in (1, 2) if bn >= 128 else (2,):      # CTA pair, CTA pair + halo
-            alt = Planes.empty(P, N, H, W, C, DEV)
-            ops.conv_gemm(a, wpk.to(DEV), 0, 3, 2 * C, bn, ops.IPER_EPI_SPADE, bias=bpk.to(DEV), out=alt, x=xp,
-                          mean_rstd=stats, spade_C=C, cta_pair=mode_pair)
-            np.testing.assert_allclose(_planes_value(alt).numpy(), exp.numpy(), atol={2: 1e-4, 1: 3e-3}[P], rtol=0)
+    for mode_pair in ((1, 2) if bn >= 128 else (2,)) if P != 3 else (2,):      # CTA pair, CTA pair + halo
+        alt = Planes.empty(P, N, H, W, C, DEV)
+        ops.conv_gemm(a, wpk.to(DEV), 0, 3, 2 * C, bn, ops.IPER_EPI_SPADE, bias=bpk.to(DEV), out=alt, x=xp,
+                      mean_rstd=stats, spade_C=C, cta_pair=mode_pair)
+        np.testing.assert_allclose(_planes_value(alt).numpy(), exp.numpy(), atol={2: 1e-4, 3: 1.5e-3, 1: 3e-3}[P], rtol=0)
     chk = Planes.empty(P, N, H, W, C, DEV)
     ops.conv_direct(a, torch.cat([q(wg), q(wb)], 0).to(DEV), 0, 3, 2 * C, ops.IPER_EPI_SPADE, bias=torch.cat([bg, bb]).to(DEV),
                     out=chk, x=xp, mean_rstd=stats, spade_C=C)
     np.testing.assert_allclose(_planes_value(chk).numpy(), exp.numpy(), atol={2: 1e-4, 3: 1.5e-3, 1: 3e-3}[P], rtol=0)
 
 
-@pytest.mark.parametrize("S,P", [(32, 2), (300, 2), (300, 3)])
+@pytest.mark.parametrize("S,P", [(32, 2), (300, 2), (300, 3), (64, 1)])
 def test_conv_gemm_heads_epilogue(S, P):
     """5x5 heads (64->3 tanh, 64->1 sigmoid) + composite (imitator.py:393)."""
     from ipercore_b200 import ops
@@ -205,11 +204,11 @@ def test_conv_gemm_heads_epilogue(S, P):
     ops.conv_gemm(a, wp, ops.IPER_CONV_ROW5, 5, 32, 32, ops.IPER_EPI_HEADS, heads=dict(img=img, mask=mask, pred=pred, bg=bgimg.to(DEV)))
     q = lambda t: ops.split_planes(t, P).float().sum(0)
     ei = torch.tanh(F.conv2d(xq, q(wi), padding=2)); em = torch.sigmoid(F.conv2d(xq, q(wm), padding=2))
-    tol = 3e-5 if P == 2 else 3e-4
+    tol = {2: 3e-5, 3: 3e-4, 1: 2e-3}[P]
     np.testing.assert_allclose(img.cpu().numpy(), ei.numpy(), atol=tol, rtol=0)
     np.testing.assert_allclose(mask.cpu().numpy(), em.numpy(), atol=tol, rtol=0)
     np.testing.assert_allclose(pred.cpu().numpy(), (em * bgimg + (1 - em) * ei).numpy(), atol=1.5 * tol, rtol=0)
-    if P != 3:      # halo kernel: 32x4 tiles, the five vertical taps are views of one 32x8 box
+    if True:        # halo kernel: 32x4 tiles, the five vertical taps are views of one 32x8 box
         img2 = torch.full_like(img, 9.0); mask2 = torch.full_like(mask, 9.0); pred2 = torch.full_like(pred, 9.0)
         ops.conv_gemm(a, wp, ops.IPER_CONV_ROW5, 5, 32, 32, ops.IPER_EPI_HEADS,
                       heads=dict(img=img2, mask=mask2, pred=pred2, bg=bgimg.to(DEV)), cta_pair=2)
