@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--precision", default="fp16x2", choices=["fp16x2", "fp16", "fp16f8"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--streams", type=int, default=1, help="engines replaying alternate batches on separate streams")
+    ap.add_argument("--dump-layers", default="", help="write the per-launch conv timing table (JSON) to this path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=8)
     return ap.parse_args()
@@ -296,7 +297,9 @@ def main():
             phases = 4 if mode == ops.IPER_CONVT_4S2 else 1
             opix = a.N * (a.H // 2) * (a.W // 2) if mode == ops.IPER_CONV_S2 else a.N * a.H * a.W
             macs = opix * phases * rows * wpack.K
-            recs.append((e0, e1, macs * {1: 1, 2: 3, 3: 2}[wpack.fmt]))   # fp16-equivalent MMA work per mode
+            recs.append((e0, e1, macs * {1: 1, 2: 3, 3: 2}[wpack.fmt],    # fp16-equivalent MMA work per mode
+                         dict(mode=mode, ksize=ksize, rows=rows, K=wpack.K, N=a.N, H=a.H, W=a.W, epi=epi,
+                              cta_pair=kw.get("cta_pair", 0))))
 
         with torch.cuda.stream(eng.compute):
             eng._step()
@@ -307,9 +310,14 @@ def main():
             finally:
                 ops.conv_gemm = orig
             torch.cuda.synchronize(dev)
-        conv_ms = sum(a.elapsed_time(b) for a, b, _ in recs)
+        conv_ms = sum(r[0].elapsed_time(r[1]) for r in recs)
         step_ms = s0.elapsed_time(s1)
-        exec_flops = 2.0 * sum(m for _, _, m in recs)
+        exec_flops = 2.0 * sum(r[2] for r in recs)
+        if args.dump_layers:     # per-launch table of the conv stack (ms, executed fp16-equivalent TFLOP/s)
+            rows_ = [dict(r[3], ms=r[0].elapsed_time(r[1]), exec_tflops=2.0 * r[2] / (r[0].elapsed_time(r[1]) * 1e-3) / 1e12)
+                     for r in recs]
+            with open(args.dump_layers, "w") as f:
+                json.dump(rows_, f, indent=0)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

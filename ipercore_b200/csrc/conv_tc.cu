@@ -145,9 +145,11 @@ IPER_DEVINL void load_planes32(const __half* x, int fmt, long long plane_stride,
 
 // Epilogue of one 128-pixel tile: thread = accumulator row (pixel); `taddr` = TMEM address of the tile's D1 columns
 // for this warp's lane quarter.  Shared by the single-CTA and the CTA-pair kernels.
+// `nsplit` warps share a TMEM lane quarter (1: the 4-warp epilogue of conv_gemm[_pair]_kernel, 2: the 8-warp epilogue of
+// the halo kernel); warp `hsel` of them takes the 32-column chunks j with j % nsplit == hsel.
 template <int BN, int NS>
 IPER_DEVINL void epilogue_tile(const GemmArgs& a, const TileCoord& t, uint32_t taddr, int row, int lane, int tx, int ty,
-                               int tni) {
+                               int tni, int hsel = 0, int nsplit = 1) {
     // accumulator chunk: 32 fp32 columns of D1 (+ the matching columns of the fp8 cross-term accumulator D2)
     auto ld_acc = [&](uint32_t taddr_col, uint32_t (&r)[32]) {
         tmem_ld32(taddr_col, r);
@@ -171,29 +173,31 @@ IPER_DEVINL void epilogue_tile(const GemmArgs& a, const TileCoord& t, uint32_t t
             if (a.epi == IPER_EPI_HEADS) {
                 if constexpr (BN == 32) {
                     __shared__ float s_ex[BLOCK_M * 21];          // D[row][dx*4+o], 20 used columns (+1 pad)
-                    uint32_t r[32];
-                    ld_acc(taddr, r);
+                    const int nthr = 128 * nsplit;
+                    if (hsel == 0) {
+                        uint32_t r[32];
+                        ld_acc(taddr, r);
 #pragma unroll
-                    for (int i = 0; i < 20; i++) s_ex[row * 21 + i] = __uint_as_float(r[i]);
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                        for (int i = 0; i < 20; i++) s_ex[row * 21 + i] = __uint_as_float(r[i]);
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
                     // horizontal taps: output x of a tw-pixel row segment needs D of x-2 .. x+2 (same image row = same
-                    // segment of s_ex rows), so the two outermost pixels either side are recomputed by the neighbour tile
+                    // segment of s_ex rows), so the two outermost pixels either side are recomputed by the neighbour tile.
+                    // With two warps per pixel quarter, warp 0 writes img/pred channels 0-1, warp 1 channel 2 and the mask.
                     const int xo = t.px0 + tx;
                     if (tx >= 2 && tx < a.tw - 2 && xo >= 0 && xo < a.Wo && n < a.N && y < a.Ho) {
-                        float o4[4];
-#pragma unroll
-                        for (int o = 0; o < 4; o++) {
+                        auto head = [&](int o) {
                             float acc4 = 0.f;
 #pragma unroll
                             for (int dx = 0; dx < 5; dx++) acc4 += s_ex[(row + dx - 2) * 21 + dx * 4 + o];
-                            o4[o] = acc4;
-                        }
+                            return acc4;
+                        };
                         const size_t hw = (size_t)a.oH * a.oW, p = (size_t)y * a.oW + xo;
-                        const float m = 1.f / (1.f + expf(-o4[3]));
-                        if (a.mask) a.mask[(size_t)n * hw + p] = m;
-#pragma unroll
-                        for (int c = 0; c < 3; c++) {
-                            const float v = tanhf(o4[c]);
+                        const float m = 1.f / (1.f + expf(-head(3)));
+                        if (a.mask && hsel == nsplit - 1) a.mask[(size_t)n * hw + p] = m;
+                        const int c_lo = (nsplit == 1) ? 0 : (hsel == 0 ? 0 : 2), c_hi = (nsplit == 1) ? 3 : (hsel == 0 ? 2 : 3);
+                        for (int c = c_lo; c < c_hi; c++) {
+                            const float v = tanhf(head(c));
                             if (a.img) a.img[((size_t)n * 3 + c) * hw + p] = v;
                             if (a.pred) {
                                 const float bgv = a.bg[(size_t)n * a.bg_batch_stride + c * hw + p];
@@ -201,12 +205,12 @@ IPER_DEVINL void epilogue_tile(const GemmArgs& a, const TileCoord& t, uint32_t t
                             }
                         }
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");   // s_ex is reused by the next tile
+                    asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");   // s_ex is reused by the next tile
                 }
             } else if (a.epi == IPER_EPI_SPADE) {
                 constexpr int CB = BN / 2;      // channels per tile: columns [0,CB) gamma, [CB,2CB) beta
 #pragma unroll 1
-                for (int j = 0; j < CB / 32; j++) {
+                for (int j = hsel; j < CB / 32; j += nsplit) {
                     uint32_t rg[32], rb[32];
                     ld_acc(taddr + j * 32, rg);
                     ld_acc(taddr + CB + j * 32, rb);
@@ -229,7 +233,7 @@ IPER_DEVINL void epilogue_tile(const GemmArgs& a, const TileCoord& t, uint32_t t
             } else {
                 const bool warp_uniform_n = (a.tw * a.th) % 32 == 0;      // all 32 rows of a warp lie in one image
 #pragma unroll 1
-                for (int j = 0; j < BN / 32; j++) {
+                for (int j = hsel; j < BN / 32; j += nsplit) {
                     uint32_t r[32];
                     ld_acc(taddr + j * 32, r);
                     const int c0 = t.n_tile * BN + j * 32;
@@ -650,9 +654,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_pair_kernel(const _
 // MMA drop by 3*th/(th+2) on A (2.4x for 3x3; 2.5x for the 5-tap heads); the weights still stream through their own ring.
 // The transposed 4x4/s2 convolution runs all four output phases from the same three boxes into four accumulator blocks
 // (16 (phase, tap) MMA groups), 3.5x fewer activation bytes than four separate phase GEMMs.
-//   warp 0: A producer   warp 1: MMA issuer (leader CTA)   warps 2-5: epilogue   warp 6: weight producer
+//   warp 0: A producer   warp 1: MMA issuer (leader CTA)   warp 2: weight producer   warps 3-10: epilogue — two warps
+//   per TMEM lane quarter, each taking every other 32-column chunk (the epilogue, not the MMA, paces the big layers)
 // ------------------------------------------------------------------------------------------------------------
-constexpr int HALO_THREADS = 224;
+constexpr int HALO_THREADS = 352;          // warps: 0 A producer, 1 MMA issuer, 2 weight producer, 3..10 epilogue
 constexpr int HALO_MAX_NA = 4, HALO_MAX_NB = 8;
 constexpr int HALO_SMEM_BUDGET = 212 * 1024;
 
@@ -699,10 +704,10 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const _
     if (threadIdx.x == 0) {
         for (int i = 0; i < hs.na; i++) { mbar_init(&a_full[i], 2); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < hs.nb; i++) { mbar_init(&b_full[i], 2); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 8); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 16); }
         fence_barrier_init();
     }
-    if ((warp == 0 || warp == 6) && lane == 0) {
+    if ((warp == 0 || warp == 2) && lane == 0) {
         for (int p = 0; p < NS; p++) tma_prefetch_desc(warp == 0 ? &a.mapA[p] : &a.mapB[p]);
     }
     if (warp == 1) tmem_alloc_2sm(&tmem_base_slot, (uint32_t)hs.tmem_cols);
@@ -762,7 +767,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const _
                 }
             }
         }
-    } else if (warp == 6) {
+    } else if (warp == 2) {
         // =========================== weight producer (both CTAs) ===========================
         if (lane == 0) {
             int slot = 0; uint32_t ph = 0;
@@ -885,8 +890,9 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const _
             }
         }
     } else {
-        // =========================== epilogue (warps 2..5, both CTAs) ===========================
-        const int q = warp & 3;
+        // =========================== epilogue (warps 3..10, both CTAs) ===========================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int hsel = (warp - 3) >> 2;       // which of the two warps of the quarter
         const int row = q * 32 + lane;
         const int tx = row % a.tw, ty = (row / a.tw) % a.th;
         auto release = [&](uint64_t* bar) {
@@ -909,7 +915,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const _
             if constexpr (NS == 3) {
                 // fold the fp16 accumulator into the e4m3 one (D2 <- D1 + D2 * cross_scale) so that D1 goes back to the
                 // MMA warp at once: the next unit's fp16 pass overlaps the stores below
-                for (int j = 0; j < acc_cols / 32; j++) {
+                for (int j = hsel; j < acc_cols / 32; j += 2) {
                     uint32_t r1[32], r2[32];
                     tmem_ld32(lane_base + j * 32, r1);
                     tmem_ld32(lane_base + acc_cols + j * 32, r2);
@@ -920,12 +926,13 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const _
                     tmem_st32(lane_base + acc_cols + j * 32, r2);
                 }
                 tmem_st_wait();
+                asm volatile("bar.sync 2, 256;" ::: "memory");      // every chunk of D2 holds the folded sum
                 release(&tmem_empty_bar[0]);
                 src = lane_base + acc_cols;
             }
             for (int blk = 0; blk < hs.acc_blocks; blk++) {
                 t.phase = blk;                  // transposed conv: accumulator block = output phase
-                epilogue_tile<BN, (NS == 3 ? 1 : NS)>(a, t, src + blk * BN, row, lane, tx, ty, 0);
+                epilogue_tile<BN, (NS == 3 ? 1 : NS)>(a, t, src + blk * BN, row, lane, tx, ty, 0, hsel, 2);
             }
             release(&tmem_empty_bar[NS == 3 ? 1 : acc]);
         }
