@@ -331,7 +331,7 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json"))).get("dram_bytes_per_launch")
         except (OSError, ValueError):
             pass
-        roof = {"bound": "tensor", "kernel": "conv_gemm_kernel (tcgen05 implicit GEMM, %d launches per %d-frame batch)" % (len(recs), B),
+        roof = {"bound": "tensor", "kernel": "conv_halo_pair_kernel / conv_gemm_pair_kernel (tcgen05 cta_group::2 implicit GEMM, %d launches per %d-frame batch)" % (len(recs), B),
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (measured)" if peaks else "fallback 1.4 PFLOP/s sustained",
                 "algorithmic_flops_per_batch": alg, "executed_tflops": exec_flops / (conv_ms * 1e-3) / 1e12,
