@@ -328,7 +328,10 @@ def main():
         ach = alg / (conv_ms * 1e-3) / 1e12
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json"))).get("dram_bytes_per_launch")
+            # DRAM bytes of the conv launches of one batch (ncu --set full capture, per frame x frames per batch); like
+            # `achieved` it covers the whole conv stack of a batch, the unit the roofline is stated for
+            per_frame = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json"))).get("dram_bytes_per_frame")
+            traffic = per_frame * B * (S / 512.0) ** 2 if per_frame else None
         except (OSError, ValueError):
             pass
         roof = {"bound": "tensor", "kernel": "conv_halo_pair_kernel / conv_gemm_pair_kernel (tcgen05 cta_group::2 implicit GEMM, %d launches per %d-frame batch)" % (len(recs), B),
@@ -337,7 +340,9 @@ def main():
                 "algorithmic_flops_per_batch": alg, "executed_tflops": exec_flops / (conv_ms * 1e-3) / 1e12,
                 "executed_flops_note": "fp16-equivalent MMA work: fp16x2 = 3 MMAs per K step, fp16f8 = 1 fp16 + 2 e4m3 (2x rate) = 2; fk/fv hoisted to once-per-source",
                 "conv_ms_per_batch": conv_ms, "batch_ms_ungraphed": step_ms, "conv_share_of_step": conv_ms / step_ms,
-                "traffic": traffic}
+                "traffic": traffic,
+                "traffic_note": "dram__bytes_read+write of the batch's conv launches (profiles/conv_traffic.json, ncu --set full); "
+                                "the stack is tensor-bound, DRAM runs at ~1.4 TB/s"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

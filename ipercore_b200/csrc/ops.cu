@@ -1,6 +1,8 @@
 // HBM-bound kernels of the generator path (sm_100a): stem conv, instance-norm statistics, flow-guided warp +
 // per-pixel source attention, layout converters, and a CUDA-core direct convolution used as the on-device
 // cross-check of the tcgen05 path.  Reference line citations are in include/iper_b200.h.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "iper_b200.h"
 
@@ -294,8 +296,10 @@ IPER_DEVINL Taps bilinear_taps(float gx, float gy, int h, int w) {
 // Source-side maps per source pixel (fp32, pitch 2C+64): [ K'' = (Wq^T Wk) x_s | V' = Wv x_s | k0 = (Wk^T bq) . x_s | pad ].
 // With q = Wq x_t + bq and K_s = warp(Wk x_s) + bk:  K_s . q = warp(K'')_s . x_t + warp(k0)_s + (bk . q), and the last
 // term is the same for every source s, so it cancels in softmax_s — the per-frame q projection disappears.
-template <int C, int NSMAX>
-__global__ void __launch_bounds__(256, 3) warp_attention_kernel(const __half* __restrict__ xt, int xt_planes,
+// WIDE = 1: the 16 128-bit gathers of a source (4 corners x {K'' lo, K'' hi, V' lo, V' hi}) are issued before any of them
+// is consumed (out-of-range corners read pixel 0 with weight 0), two CTAs per SM; WIDE = 0: corner by corner, three CTAs.
+template <int C, int NSMAX, int WIDE>
+__global__ void __launch_bounds__(256, WIDE ? 2 : 3) warp_attention_kernel(const __half* __restrict__ xt, int xt_planes,
                                                              long long xt_plane_stride, int xt_pitch, int xt_coff,
                                                              const float* __restrict__ kv,
                                                              const float* __restrict__ bias_v,
@@ -330,18 +334,40 @@ __global__ void __launch_bounds__(256, 3) warp_attention_kernel(const __half* __
             float kk[8], vv[8], k0 = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; j++) { kk[j] = 0.f; vv[j] = bv[j]; }
+            if constexpr (WIDE) {
+                float4 q[4][4];
+                float k0c[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                if (t.off[i] < 0) continue;
-                const float* pxf = src + (size_t)t.off[i] * KVP;
-                const float4* px = reinterpret_cast<const float4*>(pxf + cg * 8);
-                const float4 k0v = __ldg(px), k1 = __ldg(px + 1), v0 = __ldg(px + C / 4), v1 = __ldg(px + C / 4 + 1);
-                const float wt = t.wt[i];
-                if (cg == 0) k0 += __ldg(pxf + 2 * C) * wt;
-                kk[0] += k0v.x * wt; kk[1] += k0v.y * wt; kk[2] += k0v.z * wt; kk[3] += k0v.w * wt;
-                kk[4] += k1.x * wt; kk[5] += k1.y * wt; kk[6] += k1.z * wt; kk[7] += k1.w * wt;
-                vv[0] += v0.x * wt; vv[1] += v0.y * wt; vv[2] += v0.z * wt; vv[3] += v0.w * wt;
-                vv[4] += v1.x * wt; vv[5] += v1.y * wt; vv[6] += v1.z * wt; vv[7] += v1.w * wt;
+                for (int i = 0; i < 4; i++) {
+                    const float* pxf = src + (size_t)(t.off[i] < 0 ? 0 : t.off[i]) * KVP;     // weight 0 when out of range
+                    const float4* px = reinterpret_cast<const float4*>(pxf + cg * 8);
+                    q[i][0] = __ldg(px); q[i][1] = __ldg(px + 1); q[i][2] = __ldg(px + C / 4); q[i][3] = __ldg(px + C / 4 + 1);
+                    k0c[i] = (cg == 0) ? __ldg(pxf + 2 * C) : 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (t.off[i] < 0) continue;
+                    const float wt = t.wt[i];
+                    k0 += k0c[i] * wt;
+                    kk[0] += q[i][0].x * wt; kk[1] += q[i][0].y * wt; kk[2] += q[i][0].z * wt; kk[3] += q[i][0].w * wt;
+                    kk[4] += q[i][1].x * wt; kk[5] += q[i][1].y * wt; kk[6] += q[i][1].z * wt; kk[7] += q[i][1].w * wt;
+                    vv[0] += q[i][2].x * wt; vv[1] += q[i][2].y * wt; vv[2] += q[i][2].z * wt; vv[3] += q[i][2].w * wt;
+                    vv[4] += q[i][3].x * wt; vv[5] += q[i][3].y * wt; vv[6] += q[i][3].z * wt; vv[7] += q[i][3].w * wt;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (t.off[i] < 0) continue;
+                    const float* pxf = src + (size_t)t.off[i] * KVP;
+                    const float4* px = reinterpret_cast<const float4*>(pxf + cg * 8);
+                    const float4 k0v = __ldg(px), k1 = __ldg(px + 1), v0 = __ldg(px + C / 4), v1 = __ldg(px + C / 4 + 1);
+                    const float wt = t.wt[i];
+                    if (cg == 0) k0 += __ldg(pxf + 2 * C) * wt;
+                    kk[0] += k0v.x * wt; kk[1] += k0v.y * wt; kk[2] += k0v.z * wt; kk[3] += k0v.w * wt;
+                    kk[4] += k1.x * wt; kk[5] += k1.y * wt; kk[6] += k1.z * wt; kk[7] += k1.w * wt;
+                    vv[0] += v0.x * wt; vv[1] += v0.y * wt; vv[2] += v0.z * wt; vv[3] += v0.w * wt;
+                    vv[4] += v1.x * wt; vv[5] += v1.y * wt; vv[6] += v1.z * wt; vv[7] += v1.w * wt;
+                }
             }
             float dot = k0;                                  // only the cg == 0 lane carries warp(k0)
 #pragma unroll
@@ -548,10 +574,19 @@ extern "C" int iper_warp_attention(const void* xt, int xt_planes, long long xt_p
     __half* o = reinterpret_cast<__half*>(out);
     const __half* x = reinterpret_cast<const __half*>(xt);
     cudaStream_t st = (cudaStream_t)stream;
+    const char* wide_env = getenv("IPER_ATT_WIDE");      // 1: hoisted gathers, 2 CTAs/SM (see warp_attention_kernel)
+    const int wide = wide_env ? atoi(wide_env) : 0;
 #define IPER_ATT(CV, NV)                                                                                             \
-    warp_attention_kernel<CV, NV><<<blocks, 256, 0, st>>>(x, xt_planes, xt_plane_stride, xt_pitch, xt_coff, kv, bias_v, \
-                                                          T, B, ns, h, w, o, out_planes, out_plane_stride, out_pitch,   \
-                                                          out_coff)
+    do {                                                                                                             \
+        if (wide)                                                                                                    \
+            warp_attention_kernel<CV, NV, 1><<<blocks, 256, 0, st>>>(x, xt_planes, xt_plane_stride, xt_pitch, xt_coff, kv, \
+                                                                     bias_v, T, B, ns, h, w, o, out_planes,             \
+                                                                     out_plane_stride, out_pitch, out_coff);           \
+        else                                                                                                         \
+            warp_attention_kernel<CV, NV, 0><<<blocks, 256, 0, st>>>(x, xt_planes, xt_plane_stride, xt_pitch, xt_coff, kv, \
+                                                                     bias_v, T, B, ns, h, w, o, out_planes,             \
+                                                                     out_plane_stride, out_pitch, out_coff);           \
+    } while (0)
 #define IPER_ATT_C(CV)                                                                                               \
     do {                                                                                                             \
         if (ns <= 2) IPER_ATT(CV, 2); else if (ns <= 4) IPER_ATT(CV, 4); else IPER_ATT(CV, 8);                       \
