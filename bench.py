@@ -301,14 +301,30 @@ def main():
                          dict(mode=mode, ksize=ksize, rows=rows, K=wpack.K, N=a.N, H=a.H, W=a.W, epi=epi,
                               cta_pair=kw.get("cta_pair", 0))))
 
+        other = []          # (name, e0, e1) of the non-conv launches of the same batch
+        OTHER_OPS = ("raster_frames", "conv_stem", "warp_attention", "flow_resize", "instnorm_finalize", "pred_to_u8")
+        saved = {k: getattr(ops, k) for k in OTHER_OPS if hasattr(ops, k)}
+
+        def wrap(name, fn):  # noqa: E306
+            def timed_other(*a_, **kw_):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); out = fn(*a_, **kw_); e1.record()
+                other.append((name, e0, e1))
+                return out
+            return timed_other
+
         with torch.cuda.stream(eng.compute):
             eng._step()
             ops.conv_gemm = timed_conv
+            for k, fn in saved.items():
+                setattr(ops, k, wrap(k, fn))
             try:
                 s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 s0.record(); eng._step(); s1.record()
             finally:
                 ops.conv_gemm = orig
+                for k, fn in saved.items():
+                    setattr(ops, k, fn)
             torch.cuda.synchronize(dev)
         conv_ms = sum(r[0].elapsed_time(r[1]) for r in recs)
         step_ms = s0.elapsed_time(s1)
@@ -316,8 +332,13 @@ def main():
         if args.dump_layers:     # per-launch table of the conv stack (ms, executed fp16-equivalent TFLOP/s)
             rows_ = [dict(r[3], ms=r[0].elapsed_time(r[1]), exec_tflops=2.0 * r[2] / (r[0].elapsed_time(r[1]) * 1e-3) / 1e12)
                      for r in recs]
+            agg = {}
+            for name, e0, e1 in other:
+                agg.setdefault(name, [0, 0.0]); agg[name][0] += 1; agg[name][1] += e0.elapsed_time(e1)
             with open(args.dump_layers, "w") as f:
                 json.dump(rows_, f, indent=0)
+            with open(args.dump_layers + ".other.json", "w") as f:
+                json.dump({k: dict(launches=v[0], ms=v[1]) for k, v in agg.items()}, f, indent=1)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

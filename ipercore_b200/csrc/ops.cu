@@ -592,8 +592,10 @@ extern "C" int iper_warp_attention(const void* xt, int xt_planes, long long xt_p
     __half* o = reinterpret_cast<__half*>(out);
     const __half* x = reinterpret_cast<const __half*>(xt);
     cudaStream_t st = (cudaStream_t)stream;
-    const char* wide_env = getenv("IPER_ATT_WIDE");      // 1: hoisted gathers, 2 CTAs/SM (see warp_attention_kernel)
-    const int wide = wide_env ? atoi(wide_env) : 0;
+    // gather schedule (see warp_attention_kernel): hoisted loads win only where the per-pixel maps are short (C = 64:
+    // 1.58 vs 1.73 ms per 50 frames at 256^2; C = 256: 0.39 vs 0.31 ms); IPER_ATT_WIDE=0/1 forces one
+    const char* wide_env = getenv("IPER_ATT_WIDE");
+    const int wide = wide_env ? atoi(wide_env) : (C == 64);
 #define IPER_ATT(CV, NV)                                                                                             \
     do {                                                                                                             \
         if (wide)                                                                                                    \
