@@ -90,20 +90,19 @@ __global__ void conv_direct_kernel(const DirectArgs d) {
 
 // ------------------------------------------------------------------------------------------------------------
 // Stem: Conv2d(Cin<=8 -> 64, 3x3, s2, p1)(+bias)+ReLU, NCHW fp32 image -> NHWC planes.  K = 9*Cin <= 72 is
-// tensor-core hostile; 0.45 GFLOP per 512^2 frame.  Block = 32x8 output pixels (128 threads); the 65x17 input halo and
-// the whole filter bank live in shared memory; each thread computes 2 pixels x 8 channels per pass.
+// tensor-core hostile; 0.45 GFLOP per 512^2 frame.  Block = 32x8 output pixels; the 65x17 input halo and the whole
+// filter bank live in shared memory; each thread computes 1 pixel x 8 channels per pass.  (A 2-pixels-per-thread
+// variant that halves the shared-memory filter reads per FMA was measured slower: 1.44 vs 1.34 ms per 50 frames.)
 // ------------------------------------------------------------------------------------------------------------
 constexpr int STEM_TW = 32, STEM_TH = 8, STEM_MAXC = 8;
 __host__ __device__ constexpr int stem_halo_floats(int cin) { return ((cin * (2 * STEM_TH + 1) * (2 * STEM_TW + 1) + 3) / 4) * 4; }
 
 template <int CIN>
-__global__ void __launch_bounds__(128, 4) conv_stem_kernel(const float* __restrict__ in, int N, int H, int W,
-                                                           const float* __restrict__ wgt, const float* __restrict__ bias,
-                                                           int Cout, __half* __restrict__ out, int out_planes,
-                                                           long long out_plane_stride, int out_pitch, int out_coff,
-                                                           double* __restrict__ stats_ws) {
-    // 128 threads, thread = TWO horizontally adjacent output pixels x 8 channels per pass: every filter value read from
-    // shared memory feeds two FMAs (the one-pixel version was bound by those reads, L1 77 %)
+__global__ void __launch_bounds__(256) conv_stem_kernel(const float* __restrict__ in, int N, int H, int W,
+                                                        const float* __restrict__ wgt, const float* __restrict__ bias,
+                                                        int Cout, __half* __restrict__ out, int out_planes,
+                                                        long long out_plane_stride, int out_pitch, int out_coff,
+                                                        double* __restrict__ stats_ws) {
     extern __shared__ __align__(16) float sm[];
     __shared__ float s_stat[2 * 128];
     constexpr int HALO_W = 2 * STEM_TW + 1, HALO_H = 2 * STEM_TH + 1;
@@ -112,73 +111,57 @@ __global__ void __launch_bounds__(128, 4) conv_stem_kernel(const float* __restri
     const int Ho = H / 2, Wo = W / 2;
     const int n = blockIdx.z, oy0 = blockIdx.y * STEM_TH, ox0 = blockIdx.x * STEM_TW;
     const int tid = threadIdx.x;
-    for (int i = tid; i < Cout * CIN * 9; i += 128) {
+    for (int i = tid; i < Cout * CIN * 9; i += 256) {
         const int co = i / (CIN * 9), r = i % (CIN * 9);        // source order (co, ci, ky, kx)
         s_w[r * Cout + co] = wgt[i];
     }
     const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;
-    for (int row = tid / 32; row < CIN * HALO_H; row += 4) {    // one warp per halo row: coalesced, no div/mod per element
-        const int c = row / HALO_H, iy = iy0 + row % HALO_H;
-        const float* src = in + (((size_t)n * CIN + c) * H + iy) * W;
-        for (int x = tid % 32; x < HALO_W; x += 32) {
-            const int ix = ix0 + x;
-            s_in[row * HALO_W + x] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(src + ix) : 0.f;
-        }
+    for (int i = tid; i < CIN * HALO_H * HALO_W; i += 256) {
+        const int c = i / (HALO_H * HALO_W), r = i % (HALO_H * HALO_W);
+        const int iy = iy0 + r / HALO_W, ix = ix0 + r % HALO_W;
+        float v = 0.f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) v = in[(((size_t)n * CIN + c) * H + iy) * W + ix];
+        s_in[i] = v;
     }
     __syncthreads();
-    const int lx = (tid % 16) * 2, ly = tid / 16;       // output pixels (lx, ly) and (lx + 1, ly) of the 32 x 8 tile
+    const int lx = tid % STEM_TW, ly = tid / STEM_TW;   // 32 x 8 output pixels per block
     const int oy = oy0 + ly, ox = ox0 + lx;
-    float patch[CIN][3][5];
+    float patch[CIN * 9];
 #pragma unroll
     for (int c = 0; c < CIN; c++)
 #pragma unroll
-        for (int ky = 0; ky < 3; ky++)
-#pragma unroll
-            for (int kx = 0; kx < 5; kx++) patch[c][ky][kx] = s_in[(c * HALO_H + 2 * ly + ky) * HALO_W + 2 * lx + kx];
-    const bool in0 = (oy < Ho) && (ox < Wo), in1 = (oy < Ho) && (ox + 1 < Wo);
+        for (int t = 0; t < 9; t++)
+            patch[c * 9 + t] = s_in[(c * HALO_H + 2 * ly + t / 3) * HALO_W + 2 * lx + t % 3];
+    const bool inside = (oy < Ho) && (ox < Wo);
     if (stats_ws) {
-        for (int i = tid; i < 2 * Cout; i += 128) s_stat[i] = 0.f;
+        for (int i = tid; i < 2 * Cout; i += 256) s_stat[i] = 0.f;
         __syncthreads();
-    } else if (!in0) {
+    } else if (!inside) {
         return;
     }
     const size_t obase = (((size_t)n * Ho + oy) * Wo + ox) * out_pitch + out_coff;
     for (int co0 = 0; co0 < Cout; co0 += 8) {
-        float a0[8], a1[8];
+        float acc[8];
 #pragma unroll
-        for (int j = 0; j < 8; j++) { a0[j] = 0.f; a1[j] = 0.f; }
+        for (int j = 0; j < 8; j++) acc[j] = 0.f;
 #pragma unroll
-        for (int c = 0; c < CIN; c++)
-#pragma unroll
-            for (int ky = 0; ky < 3; ky++)
-#pragma unroll
-                for (int kx = 0; kx < 3; kx++) {
-                    const int r = (c * 3 + ky) * 3 + kx;
-                    const float p0 = patch[c][ky][kx], p1 = patch[c][ky][kx + 2];
-                    const float4 w0 = *reinterpret_cast<const float4*>(&s_w[r * Cout + co0]);
-                    const float4 w1 = *reinterpret_cast<const float4*>(&s_w[r * Cout + co0 + 4]);
-                    a0[0] += p0 * w0.x; a0[1] += p0 * w0.y; a0[2] += p0 * w0.z; a0[3] += p0 * w0.w;
-                    a0[4] += p0 * w1.x; a0[5] += p0 * w1.y; a0[6] += p0 * w1.z; a0[7] += p0 * w1.w;
-                    a1[0] += p1 * w0.x; a1[1] += p1 * w0.y; a1[2] += p1 * w0.z; a1[3] += p1 * w0.w;
-                    a1[4] += p1 * w1.x; a1[5] += p1 * w1.y; a1[6] += p1 * w1.z; a1[7] += p1 * w1.w;
-                }
-        float o0[8], o1[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const float bj = bias ? bias[co0 + j] : 0.f;
-            o0[j] = fmaxf(a0[j] + bj, 0.f); o1[j] = fmaxf(a1[j] + bj, 0.f);
+        for (int r = 0; r < CIN * 9; r++) {
+            const float pv = patch[r];
+            const float4 w0 = *reinterpret_cast<const float4*>(&s_w[r * Cout + co0]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&s_w[r * Cout + co0 + 4]);
+            acc[0] += pv * w0.x; acc[1] += pv * w0.y; acc[2] += pv * w0.z; acc[3] += pv * w0.w;
+            acc[4] += pv * w1.x; acc[5] += pv * w1.y; acc[6] += pv * w1.z; acc[7] += pv * w1.w;
         }
-        if (in0) store_planes8(out, out_planes, out_plane_stride, obase + co0, o0);
-        if (in1) store_planes8(out, out_planes, out_plane_stride, obase + out_pitch + co0, o1);
+        float o8[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) o8[j] = fmaxf(acc[j] + (bias ? bias[co0 + j] : 0.f), 0.f);
+        if (inside) store_planes8(out, out_planes, out_plane_stride, obase + co0, o8);
         if (stats_ws) {
-            // fused instance-norm statistics: 8 channels x 64 pixels per warp -> exchange-and-halve (8 -> 4 -> 2 -> 1
+            // fused instance-norm statistics: 8 channels x 32 pixels per warp -> exchange-and-halve (8 -> 4 -> 2 -> 1
             // values, 7 shuffles) then two plain xor steps; lane l < 8 ends with the warp's sum of channel co0 + l
             float s1[8], s2[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const float v0 = in0 ? o0[j] : 0.f, v1 = in1 ? o1[j] : 0.f;
-                s1[j] = v0 + v1; s2[j] = v0 * v0 + v1 * v1;
-            }
+            for (int j = 0; j < 8; j++) { s1[j] = inside ? o8[j] : 0.f; s2[j] = s1[j] * s1[j]; }
             const int lane = tid & 31;
 #pragma unroll
             for (int half = 4; half >= 1; half >>= 1) {
@@ -201,7 +184,7 @@ __global__ void __launch_bounds__(128, 4) conv_stem_kernel(const float* __restri
     }
     if (stats_ws) {
         __syncthreads();
-        for (int i = tid; i < 2 * Cout; i += 128) atomicAdd(&stats_ws[(size_t)n * 2 * Cout + i], (double)s_stat[i]);
+        for (int i = tid; i < 2 * Cout; i += 256) atomicAdd(&stats_ws[(size_t)n * 2 * Cout + i], (double)s_stat[i]);
     }
 }
 
@@ -528,7 +511,7 @@ extern "C" int iper_conv_stem(const float* in_nchw, int N, int Cin, int H, int W
 #define IPER_STEM_CASE(CI)                                                                                              \
     case CI:                                                                                                            \
         IPER_CHECK_CUDA(cudaFuncSetAttribute(conv_stem_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        conv_stem_kernel<CI><<<grid, 128, smem, (cudaStream_t)stream>>>(in_nchw, N, H, W, w_f32, bias, Cout,              \
+        conv_stem_kernel<CI><<<grid, 256, smem, (cudaStream_t)stream>>>(in_nchw, N, H, W, w_f32, bias, Cout,              \
                                                                        reinterpret_cast<__half*>(out), out_planes,     \
                                                                        out_plane_stride, out_pitch, out_coff, stats_ws); \
         break;
