@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--frames", type=int, default=300)
-    ap.add_argument("--batch", type=int, default=50)
+    ap.add_argument("--batch", type=int, default=60)
     ap.add_argument("--ns", type=int, default=2)
     ap.add_argument("--precision", default="fp16x2", choices=["fp16x2", "fp16", "fp16f8"])
     ap.add_argument("--no-graph", action="store_true")
