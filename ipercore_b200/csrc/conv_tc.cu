@@ -1090,6 +1090,26 @@ static void build_halo_sched(HaloSched& hs, int mode, int Cin, int rows, int tw,
 
 using namespace iper;
 
+// Host-only: the tap program the halo kernel would run for a layer, flattened for inspection (tests/test_abi_cpu.py).
+// out[0] = number of A loads, out[1] = accumulator blocks, out[2] = box rows; then per load 4 ints {ox, oy, first, count};
+// then per entry 4 ints {a_row_off, b_row, b_k, acc}.  Returns the number of ints written (<= 3 + 12 + 64), or -1.
+extern "C" int iper_conv_halo_plan(int mode, int Cin, int rows, int32_t* out, int capacity) {
+    IPER_REQUIRE(out != nullptr && capacity >= 3 + 4 * HALO_MAX_LOADS + 4 * HALO_MAX_ENTRIES, "iper_conv_halo_plan: buffer too small");
+    IPER_REQUIRE(mode == IPER_CONV_S1 || mode == IPER_CONVT_4S2 || mode == IPER_CONV_ROW5, "iper_conv_halo_plan: mode %d has no halo form", mode);
+    const int tw = mode == IPER_CONV_ROW5 ? 32 : 16, th = BLOCK_M / tw;
+    HaloSched hs;
+    build_halo_sched(hs, mode, Cin, rows, tw, th);
+    int n = 0;
+    out[n++] = hs.n_loads; out[n++] = hs.acc_blocks; out[n++] = hs.box_rows;
+    int ne = 0;
+    for (int l = 0; l < hs.n_loads; l++) {
+        out[n++] = hs.ox[l]; out[n++] = hs.oy[l]; out[n++] = hs.first[l]; out[n++] = hs.count[l];
+        ne = hs.first[l] + hs.count[l];
+    }
+    for (int i = 0; i < ne; i++) { out[n++] = hs.e[i].a_row_off; out[n++] = hs.e[i].b_row; out[n++] = hs.e[i].b_k; out[n++] = hs.e[i].acc; }
+    return n;
+}
+
 extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream) {
     IPER_REQUIRE(d != nullptr, "iper_conv_gemm: null descriptor");
     IPER_REQUIRE(d->a && d->w, "iper_conv_gemm: null operand");
