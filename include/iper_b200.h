@@ -195,6 +195,11 @@ int iper_nhwc_f32_to_nchw(const float* in, int N, int C, int HW, int pitch, int 
  * (iPERCore/tools/utils/filesio/cv_utils.py:100-116) done on device so only 0.75 MB/frame crosses PCIe. */
 int iper_pred_to_u8(const float* pred, int B, int S, uint8_t* out, iper_stream_t stream);
 
+/* Mask morphology of source_setup — iPERCore/tools/utils/morphology/morph_ops.py: morph() :7-36 (mode 0 erode: border 1,
+ * box sum == ks*ks; mode 1 dilate: border 0, box sum >= 1) and soft_dilate() :39-61 (mode 2: border 0, sum >= ks*ks/2).
+ * mask, out (N,1,H,W) f32; ks odd, <= 63 (deploy.toml uses 3..51).  Exact for 0/1 masks. */
+int iper_morph(const float* mask, int N, int H, int W, int ks, int mode, float* out, iper_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,7 @@ SIGNATURES = {
     "iper_planes_to_nchw": [c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "iper_nhwc_f32_to_nchw": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "iper_pred_to_u8": [c_void_p, c_int, c_int, c_void_p, c_void_p],
+    "iper_morph": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
 }
 
 

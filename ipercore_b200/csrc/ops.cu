@@ -469,9 +469,63 @@ __global__ void pred_to_u8_kernel(const float* __restrict__ pred, int B, size_t 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Mask morphology of source_setup (iPERCore/tools/utils/morphology/morph_ops.py:7-61): ks x ks box sum of a
+// (N,1,H,W) mask with constant border padding, then a threshold.  One CTA per 32x32 output tile: the padded
+// (32+ks-1)^2 input patch lives in shared memory, a horizontal pass builds row sums, a vertical pass finishes —
+// O(ks) per pass instead of the reference's ks^2 dense convolution.  Exact for 0/1 masks (integer sums in fp32).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int MORPH_T = 32, MORPH_MAX_KS = 63;
+__global__ void __launch_bounds__(256) morph_kernel(const float* __restrict__ mask, int H, int W, int ks, int mode,
+                                                    float* __restrict__ out) {
+    extern __shared__ float msm[];
+    const int p = ks / 2, PW = MORPH_T + ks - 1;       // padded patch is PW x PW
+    float* s_in = msm;                                  // [PW][PW]
+    float* s_h = msm + PW * PW;                         // [PW][MORPH_T] horizontal sums
+    const int n = blockIdx.z, y0 = blockIdx.y * MORPH_T, x0 = blockIdx.x * MORPH_T;
+    const float padv = (mode == 0) ? 1.f : 0.f;         // erode pads with 1, dilate / soft dilate with 0
+    const float* src = mask + (size_t)n * H * W;
+    for (int i = threadIdx.x; i < PW * PW; i += 256) {
+        const int r = i / PW, c = i % PW, y = y0 + r - p, x = x0 + c - p;
+        s_in[i] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(src + (size_t)y * W + x) : padv;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < PW * MORPH_T; i += 256) {
+        const int r = i / MORPH_T, c = i % MORPH_T;
+        float acc = 0.f;
+        for (int k = 0; k < ks; k++) acc += s_in[r * PW + c + k];
+        s_h[i] = acc;
+    }
+    __syncthreads();
+    const float n_ks = (float)(ks * ks);
+    for (int i = threadIdx.x; i < MORPH_T * MORPH_T; i += 256) {
+        const int r = i / MORPH_T, c = i % MORPH_T, y = y0 + r, x = x0 + c;
+        if (y >= H || x >= W) continue;
+        float acc = 0.f;
+        for (int k = 0; k < ks; k++) acc += s_h[(r + k) * MORPH_T + c];
+        const bool on = mode == 0 ? (acc == n_ks) : (mode == 1 ? (acc >= 1.f) : (acc >= n_ks / 2));
+        out[(size_t)n * H * W + (size_t)y * W + x] = on ? 1.f : 0.f;
+    }
+}
+
 }  // namespace iper
 
 using namespace iper;
+
+extern "C" int iper_morph(const float* mask, int N, int H, int W, int ks, int mode, float* out, iper_stream_t stream) {
+    IPER_REQUIRE(N >= 0 && H > 0 && W > 0, "iper_morph: bad sizes");
+    IPER_REQUIRE(ks >= 1 && ks <= MORPH_MAX_KS && (ks & 1), "iper_morph: ks=%d must be odd and <= %d", ks, MORPH_MAX_KS);
+    IPER_REQUIRE(mode >= 0 && mode <= 2, "iper_morph: mode %d not in {0 erode, 1 dilate, 2 soft dilate}", mode);
+    if (N == 0) return 0;
+    IPER_REQUIRE(mask && out, "iper_morph: null pointer");
+    const int PW = MORPH_T + ks - 1;
+    const size_t smem = sizeof(float) * ((size_t)PW * PW + (size_t)PW * MORPH_T);
+    IPER_CHECK_CUDA(cudaFuncSetAttribute(morph_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((W + MORPH_T - 1) / MORPH_T, (H + MORPH_T - 1) / MORPH_T, N);
+    morph_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(mask, H, W, ks, mode, out);
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int iper_conv_direct(const iper_conv_gemm_desc* g, const float* w_f32, int Cout, iper_stream_t stream) {
     IPER_REQUIRE(g && w_f32 && g->a && g->out, "iper_conv_direct: null pointer");

@@ -294,6 +294,20 @@ def pred_to_u8(pred, out=None):
     return out
 
 
+MORPH_ERODE, MORPH_DILATE, MORPH_SOFT_DILATE = 0, 1, 2
+
+
+def morph(mask, ks, mode):
+    """morph_ops.morph / soft_dilate (morph_ops.py:7-61) on a (N,1,H,W) fp32 mask; mode MORPH_ERODE / _DILATE / _SOFT_DILATE."""
+    mask = _req(mask.contiguous(), torch.float32, "mask")
+    if mask.dim() != 4 or mask.shape[1] != 1:
+        raise ValueError("morph expects a (N,1,H,W) mask, got %s" % (tuple(mask.shape),))
+    N, _, H, W = mask.shape
+    out = torch.empty_like(mask)
+    check(lib.iper_morph(mask.data_ptr(), N, H, W, int(ks), int(mode), out.data_ptr(), _stream()), "morph")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # weight packing (one-time, at load): reference layouts -> K-major fp16 planes for the tcgen05 kernel
 # ------------------------------------------------------------------------------------------------------------------

@@ -9,6 +9,9 @@ What is replaced, at the reference's own seams:
       713-757, and the bs==3 loop :892-918) -> fused CUDA kernels; every other method and all buffers stay the reference's
   B3  ``NetworksFactory.get_by_name("AttLWB-SPADE", cfg=..., temporal=False)`` (networks/__init__.py:14-16)
       -> ipercore_b200.generator.AttentionLWBGenerator (loads the same checkpoints)
+  B2' ``iPERCore.tools.utils.morphology.morph / soft_dilate`` (morph_ops.py:7-61; source_setup masks,
+      flowcomposition.py:121,176-180,258) -> iper_morph (separable box sum + threshold); custom ``kernel=`` calls, CPU
+      tensors and even / > 63 sizes keep going to the reference implementation
   B4  ``Imitator.inference`` (models/imitator.py:327-382) -> batched FrameEngine when ``temporal`` is false and the
       generator is ours; same arguments, same ``pred_{:0>8}.png`` outputs / returned list.
 Nothing else of iPERCore is touched: options, preprocessing, personalisation, source_setup, video fusion stay upstream.
@@ -52,6 +55,31 @@ def install(precision="fp16x2", batch=16, patch_inference=True, device_lbs=True)
         cls.render_fim_wim = render_fim_wim
         cls.cal_bc_transform = cal_bc_transform
         cls.encode_fim = encode_fim
+
+    import iPERCore.tools.utils.morphology as morphology                   # B2': mask morphology of source_setup
+    from iPERCore.tools.utils.morphology import morph_ops
+    up_morph, up_soft = morph_ops.morph, morph_ops.soft_dilate
+
+    def _ours(m, ks, kernel):
+        return kernel is None and m.is_cuda and m.dim() == 4 and m.shape[1] == 1 and ks % 2 == 1 and ks <= 63
+
+    def morph(src_bg_mask, ks, mode="erode", kernel=None):
+        if not _ours(src_bg_mask, ks, kernel):
+            return up_morph(src_bg_mask, ks, mode=mode, kernel=kernel)
+        return ops.morph(src_bg_mask.float().contiguous(), ks, ops.MORPH_ERODE if mode == "erode" else ops.MORPH_DILATE)
+
+    def soft_dilate(src_bg_mask, ks, kernel=None):
+        if not _ours(src_bg_mask, ks, kernel):
+            return up_soft(src_bg_mask, ks, kernel=kernel)
+        return ops.morph(src_bg_mask.float().contiguous(), ks, ops.MORPH_SOFT_DILATE)
+
+    morph_ops.morph, morph_ops.soft_dilate = morph, soft_dilate
+    morphology.morph, morphology.soft_dilate = morph, soft_dilate
+    for modname in ("iPERCore.models.flowcomposition", "iPERCore.tools.human_digitalizer.deformers.sil_deformer",
+                    "iPERCore.tools.trainers.base"):      # modules that bound `morph` by name at import time
+        mod = sys.modules.get(modname)
+        if mod is not None and hasattr(mod, "morph"):
+            mod.morph = morph
 
     from iPERCore.models.networks import NetworksFactory                   # B3
     from .generator import AttentionLWBGenerator

@@ -119,3 +119,19 @@ def test_lbs_restatement_matches_reference(template, golden_dir):
     v72, _ = lbs_ref.smplh_forward(m, betas, pose[:, :72])
     full = np.concatenate([pose[:, :66], np.repeat(m["hands_mean"][None], 3, 0)], 1)
     np.testing.assert_array_equal(v72, lbs_ref.lbs(m, betas, full)[0])
+
+
+def test_morph_oracle_matches_reference_golden():
+    """oracle/morph_ref.py vs the outputs of the reference's morph()/soft_dilate() (tests/golden/morph.npz)."""
+    import os
+    import numpy as np
+    from oracle import morph_ref
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    src = open(os.path.join(here, "make_golden.py")).read()
+    ns = {"np": np}
+    exec(src[src.index("def morph_inputs"):src.index("def make_morph")], ns)
+    m = ns["morph_inputs"]()
+    gold = np.load(os.path.join(here, "morph.npz"))
+    for ks in (3, 11, 51):
+        for name, mode in (("erode", morph_ref.ERODE), ("dilate", morph_ref.DILATE), ("soft", morph_ref.SOFT_DILATE)):
+            assert np.array_equal(morph_ref.morph(m, ks, mode), gold["%s_%d" % (name, ks)].astype(np.float32)), (name, ks)

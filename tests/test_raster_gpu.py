@@ -115,3 +115,24 @@ def test_raster_workspace_too_small_fails_loudly():
     with pytest.raises(RuntimeError, match="workspace"):
         _lib.check(_lib.lib.iper_rasterize_faces(faces.data_ptr(), 1, 4, 32, 0.1, 100.0, fim.data_ptr(), wim.data_ptr(),
                                                  ws.data_ptr(), 8, None), "rasterize_faces")
+
+
+@pytest.mark.parametrize("ks", [3, 11, 51])
+def test_morph_matches_reference_golden(ks):
+    """iper_morph vs the reference's morph()/soft_dilate() outputs (tests/golden/morph.npz) and the oracle: bit-exact."""
+    from ipercore_b200 import ops
+    from oracle import morph_ref
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gold = np.load(os.path.join(here, "morph.npz"))
+    # the input masks are regenerated from the same seeded function the golden script used (no reference import needed)
+    src = open(os.path.join(here, "make_golden.py")).read()
+    ns = {"np": np}
+    exec(src[src.index("def morph_inputs"):src.index("def make_morph")], ns)
+    m = ns["morph_inputs"]()
+    md = torch.from_numpy(m).cuda()
+    for name, mode in (("erode", ops.MORPH_ERODE), ("dilate", ops.MORPH_DILATE), ("soft", ops.MORPH_SOFT_DILATE)):
+        got = ops.morph(md, ks, mode).cpu().numpy()
+        assert np.array_equal(got, gold["%s_%d" % (name, ks)].astype(np.float32)), (name, ks)
+        assert np.array_equal(got, morph_ref.morph(m, ks, mode))
+    with pytest.raises(RuntimeError, match="odd"):
+        ops.morph(md, 4, ops.MORPH_ERODE)
