@@ -629,10 +629,11 @@ extern "C" int iper_warp_attention(const void* xt, int xt_planes, long long xt_p
     __half* o = reinterpret_cast<__half*>(out);
     const __half* x = reinterpret_cast<const __half*>(xt);
     cudaStream_t st = (cudaStream_t)stream;
-    // gather schedule (see warp_attention_kernel): hoisted loads win only where the per-pixel maps are short (C = 64:
-    // 1.58 vs 1.73 ms per 50 frames at 256^2; C = 256: 0.39 vs 0.31 ms); IPER_ATT_WIDE=0/1 forces one
+    // gather schedule (see warp_attention_kernel).  Hoisting the 16 gathers only pays on dense synthetic flows at C = 64
+    // (1.58 vs 1.73 ms per 50 frames); on real frames most pixels are background whose taps the narrow schedule skips
+    // outright (ncu: 406 us narrow vs 542 us wide for the C = 64 stage of a 20-frame batch), so narrow is the default.
     const char* wide_env = getenv("IPER_ATT_WIDE");
-    const int wide = wide_env ? atoi(wide_env) : (C == 64);
+    const int wide = wide_env ? atoi(wide_env) : 0;
 #define IPER_ATT(CV, NV)                                                                                             \
     do {                                                                                                             \
         if (wide)                                                                                                    \
