@@ -27,6 +27,8 @@
 //                            only ~4 bits, so they run in kind::f8f6f4 (e4m3, 2x rate) into a second accumulator D2
 //                            with power-of-two pre-scaling (pass 1 over K — the MMA kinds are never interleaved);
 //                            the epilogue forms D1 + D2 * cross_scale (2 MMA-equivalents).
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -50,6 +52,7 @@ struct HaloSched {
     int n_loads, acc_blocks, box_rows;          // box_rows = (th + halo) * tw
     int na, nb, a_plane_bytes, tmem_cols;       // ring depths, bytes of one A box of a slot, TMEM columns to allocate
     int k8;                                     // format 3: e4m3 channels per step (128: 128-byte rows, 64: 64-byte rows)
+    int cat;                                    // heads, split fp16: weights concatenated along N ([w_hi ; w_lo]), see kernel
     int ox[HALO_MAX_LOADS], oy[HALO_MAX_LOADS], first[HALO_MAX_LOADS], count[HALO_MAX_LOADS];
     HaloEntry e[HALO_MAX_ENTRIES];
 };
@@ -177,6 +180,13 @@ IPER_DEVINL void epilogue_tile(const GemmArgs& a, const TileCoord& t, uint32_t t
                     if (hsel == 0) {
                         uint32_t r[32];
                         ld_acc(taddr, r);
+                        if (a.hs.cat) {          // N-concatenated split weights: columns [32,64) hold the hi*lo term
+                            uint32_t r2[32];
+                            tmem_ld32(taddr + 32, r2);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 20; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+                        }
 #pragma unroll
                         for (int i = 0; i < 20; i++) s_ex[row * 21 + i] = __uint_as_float(r[i]);
                     }
@@ -677,7 +687,12 @@ struct HaloWalk {
 template <int BN, int NS>
 __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const __grid_constant__ GemmArgs a) {
     constexpr int B_PLANE = (BN / 2) * 128;                    // this CTA's half of a weight tile, one box
-    constexpr int B_SLOT = 2 * B_PLANE;
+    // N-concatenated split weights (BN = 32 heads, NS = 2, hs.cat): with N = 32 an MMA is paced by reading its 128-row A
+    // operand from shared memory, so hi*hi and hi*lo share ONE read of a_hi: B = [w_hi ; w_lo] (N = 64, CTA r stages all
+    // 32 rows of plane r = region X) and only lo*hi runs as a separate N = 32 MMA (region Y = this CTA's half of w_hi).
+    // Two MMAs per K step instead of three; D holds [hi*hi + lo*hi | hi*lo] and the epilogue adds the halves.
+    constexpr bool CAT_OK = (BN == 32 && NS == 2);
+    constexpr int B_SLOT = (CAT_OK ? 3 : 2) * B_PLANE;
     extern __shared__ uint8_t smem_dyn[];
     __shared__ __align__(8) uint64_t a_full[HALO_MAX_NA];      // leader: 2 arrivals + bytes of both CTAs
     __shared__ __align__(8) uint64_t a_empty[HALO_MAX_NA];     // per CTA, multicast commit
@@ -715,7 +730,8 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const _
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
-    const int acc_cols = hs.acc_blocks * BN;
+    const bool cat = CAT_OK && hs.cat != 0;
+    const int acc_cols = hs.acc_blocks * BN * (cat ? 2 : 1);
 
     // work unit = (n tile, pair of consecutive M tiles); this CTA owns M tile 2*pair + rank (all phases of it)
     const int m_pairs = (a.m_tiles + 1) >> 1;
@@ -781,7 +797,14 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const _
                                 mbar_wait(&b_empty[slot], ph ^ 1);
                                 const int r = hs.e[i].b_row + brow;
                                 uint32_t bytes;
-                                if constexpr (NS == 2) {
+                                if (cat) {
+                                    // X = plane `rank`, all BN rows (two boxes of BN/2 rows); Y = this CTA's half of w_hi
+                                    const int r0 = hs.e[i].b_row + (u % a.n_tiles) * BN, k = hs.e[i].b_k + cc * 64;
+                                    tma_load_2d_2sm(sB(slot, 0), &a.mapB[rank], &b_full[slot], k, r0);
+                                    tma_load_2d_2sm(sB(slot, 1), &a.mapB[rank], &b_full[slot], k, r0 + BN / 2);
+                                    tma_load_2d_2sm(sB(slot, 2), &a.mapB[0], &b_full[slot], k, r);
+                                    bytes = 3 * B_PLANE;
+                                } else if constexpr (NS == 2) {
                                     for (int p = 0; p < 2; p++)
                                         tma_load_2d_2sm(sB(slot, p), &a.mapB[p], &b_full[slot], hs.e[i].b_k + cc * 64, r);
                                     bytes = 2 * B_PLANE;
@@ -831,8 +854,21 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const _
                                 const bool last_entry = (i == hs.first[l] + hs.count[l] - 1);
                                 if (elect_one()) {
                                     uint32_t first = (touched >> e.acc) & 1u;
-                                    const uint32_t d = d_pass + e.acc * BN;
-                                    if constexpr (NS == 2) {
+                                    const uint32_t d = d_pass + e.acc * BN * (cat ? 2 : 1);
+                                    if (cat) {
+                                        constexpr uint32_t idesc_cat = umma_idesc_f16(2 * BLOCK_M, 2 * BN);
+                                        const uint32_t ahi = smem_u32(sA(aslot, 0)) + (uint32_t)e.a_row_off * 128u;
+                                        const uint32_t alo = smem_u32(sA(aslot, 1)) + (uint32_t)e.a_row_off * 128u;
+                                        const uint32_t bx = smem_u32(sB(bslot, 0)), by = smem_u32(sB(bslot, 2));
+#pragma unroll
+                                        for (int k = 0; k < 4; k++) {       // [hi*hi | hi*lo] in one read of a_hi
+                                            umma_f16_2sm(d, umma_desc_sw128(ahi + k * 32), umma_desc_sw128(bx + k * 32), idesc_cat, first);
+                                            first = 1u;
+                                        }
+#pragma unroll
+                                        for (int k = 0; k < 4; k++)         // lo*hi into the first BN columns
+                                            umma_f16_2sm(d, umma_desc_sw128(alo + k * 32), umma_desc_sw128(by + k * 32), idesc, 1u);
+                                    } else if constexpr (NS == 2) {
                                         const int pa[3] = {1, 0, 0};      // lo*hi, hi*lo, hi*hi
                                         const int pb[3] = {0, 1, 0};
 #pragma unroll
@@ -932,7 +968,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const _
             }
             for (int blk = 0; blk < hs.acc_blocks; blk++) {
                 t.phase = blk;                  // transposed conv: accumulator block = output phase
-                epilogue_tile<BN, (NS == 3 ? 1 : NS)>(a, t, src + blk * BN, row, lane, tx, ty, 0, hsel, 2);
+                epilogue_tile<BN, (NS == 3 ? 1 : NS)>(a, t, src + blk * BN * (cat ? 2 : 1), row, lane, tx, ty, 0, hsel, 2);
             }
             release(&tmem_empty_bar[NS == 3 ? 1 : acc]);
         }
@@ -1027,7 +1063,7 @@ static int launch_gemm_pair(const GemmArgs& g, int max_ctas, cudaStream_t stream
 
 template <int BN, int NS>
 static int launch_gemm_halo(const GemmArgs& g, int max_ctas, cudaStream_t stream) {
-    const int a_slot = 2 * g.hs.a_plane_bytes, b_slot = 2 * (BN / 2) * 128;
+    const int a_slot = 2 * g.hs.a_plane_bytes, b_slot = ((BN == 32 && NS == 2) ? 3 : 2) * (BN / 2) * 128;
     int smem = g.hs.na * a_slot + g.hs.nb * b_slot + 1024;
     if (smem < 120 * 1024) smem = 120 * 1024;            // one CTA per SM (TMEM allocation)
     static int attr_smem = 0;
@@ -1189,13 +1225,16 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
         build_halo_sched(g.hs, d->mode, d->Cin, d->rows, g.tw, g.th);
         g.hs.a_plane_bytes = g.hs.box_rows * 128;
         g.hs.k8 = (d->Cin % 128 == 0) ? 128 : 64;
-        const int a_slot = 2 * g.hs.a_plane_bytes, b_slot = 2 * (d->block_n / 2) * 128;      // two boxes per slot
+        // heads in split fp16: N-concatenated weights (IPER_HEADS_CAT=0 keeps the three-MMA form for comparison)
+        const char* cat_env = getenv("IPER_HEADS_CAT");
+        g.hs.cat = (d->mode == IPER_CONV_ROW5 && d->block_n == 32 && fmt == 2 && !(cat_env && atoi(cat_env) == 0)) ? 1 : 0;
+        const int a_slot = 2 * g.hs.a_plane_bytes, b_slot = (d->block_n == 32 && fmt == 2 ? 3 : 2) * (d->block_n / 2) * 128;
         g.hs.na = (3 * a_slot + 6 * b_slot <= HALO_SMEM_BUDGET) ? 3 : 2;
         g.hs.nb = (HALO_SMEM_BUDGET - g.hs.na * a_slot) / b_slot;
         if (g.hs.nb > HALO_MAX_NB) g.hs.nb = HALO_MAX_NB;
         IPER_REQUIRE(g.hs.nb >= 3, "iper_conv_gemm: halo rings do not fit shared memory");
         int cols = 32;
-        while (cols < 2 * g.hs.acc_blocks * d->block_n) cols *= 2;
+        while (cols < 2 * g.hs.acc_blocks * d->block_n * (g.hs.cat ? 2 : 1)) cols *= 2;
         IPER_REQUIRE(cols <= 512, "iper_conv_gemm: halo accumulators exceed TMEM");
         g.hs.tmem_cols = cols;
     }

@@ -215,6 +215,16 @@ def test_conv_gemm_heads_epilogue(S, P):
         np.testing.assert_allclose(img2.cpu().numpy(), ei.numpy(), atol=tol, rtol=0)
         np.testing.assert_allclose(mask2.cpu().numpy(), em.numpy(), atol=tol, rtol=0)
         np.testing.assert_allclose(pred2.cpu().numpy(), (em * bgimg + (1 - em) * ei).numpy(), atol=1.5 * tol, rtol=0)
+        if P == 2:  # the default above concatenates [w_hi ; w_lo] along N (2 MMAs per K step); the 3-MMA form must agree
+            import os
+            os.environ["IPER_HEADS_CAT"] = "0"
+            try:
+                img3 = torch.full_like(img, 9.0)
+                ops.conv_gemm(a, wp, ops.IPER_CONV_ROW5, 5, 32, 32, ops.IPER_EPI_HEADS, heads=dict(img=img3), cta_pair=2)
+                torch.cuda.synchronize()
+            finally:
+                del os.environ["IPER_HEADS_CAT"]
+            np.testing.assert_allclose(img3.cpu().numpy(), img2.cpu().numpy(), atol=2e-6, rtol=0)
 
 
 def test_stem_and_attention_kernels():
