@@ -177,6 +177,19 @@ IPER_DEVINL void epilogue_tile(const GemmArgs& a, const TileCoord& t, uint32_t t
                 if constexpr (BN == 32) {
                     __shared__ float s_ex[BLOCK_M * 21];          // D[row][dx*4+o], 20 used columns (+1 pad)
                     const int nthr = 128 * nsplit;
+                    // horizontal taps: output x of a tw-pixel row segment needs D of x-2 .. x+2 (same image row = same
+                    // segment of s_ex rows), so the two outermost pixels either side are recomputed by the neighbour tile.
+                    // With two warps per pixel quarter, warp 0 writes img/pred channels 0-1, warp 1 channel 2 and the mask.
+                    const int xo = t.px0 + tx;
+                    const bool active = tx >= 2 && tx < a.tw - 2 && xo >= 0 && xo < a.Wo && n < a.N && y < a.Ho;
+                    const size_t hw = (size_t)a.oH * a.oW, p = (size_t)y * a.oW + xo;
+                    const int c_lo = (nsplit == 1) ? 0 : (hsel == 0 ? 0 : 2), c_hi = (nsplit == 1) ? 3 : (hsel == 0 ? 2 : 3);
+                    float bgv[3] = {0.f, 0.f, 0.f};     // background pixels for the composite: in flight during the exchange
+                    if (active && a.pred) {
+#pragma unroll
+                        for (int c = 0; c < 3; c++)
+                            if (c >= c_lo && c < c_hi) bgv[c] = __ldg(a.bg + (size_t)n * a.bg_batch_stride + c * hw + p);
+                    }
                     if (hsel == 0) {
                         uint32_t r[32];
                         ld_acc(taddr, r);
@@ -191,28 +204,21 @@ IPER_DEVINL void epilogue_tile(const GemmArgs& a, const TileCoord& t, uint32_t t
                         for (int i = 0; i < 20; i++) s_ex[row * 21 + i] = __uint_as_float(r[i]);
                     }
                     asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
-                    // horizontal taps: output x of a tw-pixel row segment needs D of x-2 .. x+2 (same image row = same
-                    // segment of s_ex rows), so the two outermost pixels either side are recomputed by the neighbour tile.
-                    // With two warps per pixel quarter, warp 0 writes img/pred channels 0-1, warp 1 channel 2 and the mask.
-                    const int xo = t.px0 + tx;
-                    if (tx >= 2 && tx < a.tw - 2 && xo >= 0 && xo < a.Wo && n < a.N && y < a.Ho) {
+                    if (active) {
                         auto head = [&](int o) {
                             float acc4 = 0.f;
 #pragma unroll
                             for (int dx = 0; dx < 5; dx++) acc4 += s_ex[(row + dx - 2) * 21 + dx * 4 + o];
                             return acc4;
                         };
-                        const size_t hw = (size_t)a.oH * a.oW, p = (size_t)y * a.oW + xo;
                         const float m = 1.f / (1.f + expf(-head(3)));
                         if (a.mask && hsel == nsplit - 1) a.mask[(size_t)n * hw + p] = m;
-                        const int c_lo = (nsplit == 1) ? 0 : (hsel == 0 ? 0 : 2), c_hi = (nsplit == 1) ? 3 : (hsel == 0 ? 2 : 3);
-                        for (int c = c_lo; c < c_hi; c++) {
+#pragma unroll
+                        for (int c = 0; c < 3; c++) {
+                            if (c < c_lo || c >= c_hi) continue;
                             const float v = tanhf(head(c));
                             if (a.img) a.img[((size_t)n * 3 + c) * hw + p] = v;
-                            if (a.pred) {
-                                const float bgv = a.bg[(size_t)n * a.bg_batch_stride + c * hw + p];
-                                a.pred[((size_t)n * 3 + c) * hw + p] = m * bgv + (1.f - m) * v;   // imitator.py:393
-                            }
+                            if (a.pred) a.pred[((size_t)n * 3 + c) * hw + p] = m * bgv[c] + (1.f - m) * v;   // imitator.py:393
                         }
                     }
                     asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");   // s_ex is reused by the next tile

@@ -298,9 +298,10 @@ IPER_DEVINL Taps bilinear_taps(float gx, float gy, int h, int w) {
 // With q = Wq x_t + bq and K_s = warp(Wk x_s) + bk:  K_s . q = warp(K'')_s . x_t + warp(k0)_s + (bk . q), and the last
 // term is the same for every source s, so it cancels in softmax_s — the per-frame q projection disappears.
 // WIDE = 1: the 16 128-bit gathers of a source (4 corners x {K'' lo, K'' hi, V' lo, V' hi}) are issued before any of them
-// is consumed (out-of-range corners read pixel 0 with weight 0), two CTAs per SM; WIDE = 0: corner by corner, three CTAs.
+// is consumed (out-of-range corners read pixel 0 with weight 0), two CTAs per SM; WIDE = 0: corner by corner, three CTAs;
+// WIDE = 2: corner by corner compiled for four CTAs per SM (64 registers, ~20 spilled values).
 template <int C, int NSMAX, int WIDE>
-__global__ void __launch_bounds__(256, WIDE ? 2 : 3) warp_attention_kernel(const __half* __restrict__ xt, int xt_planes,
+__global__ void __launch_bounds__(256, WIDE == 1 ? 2 : (WIDE == 2 ? 4 : 3)) warp_attention_kernel(const __half* __restrict__ xt, int xt_planes,
                                                              long long xt_plane_stride, int xt_pitch, int xt_coff,
                                                              const float* __restrict__ kv,
                                                              const float* __restrict__ bias_v,
@@ -312,9 +313,7 @@ __global__ void __launch_bounds__(256, WIDE ? 2 : 3) warp_attention_kernel(const
     const int lane = threadIdx.x & 31, cg = lane % LPP, sub = lane / LPP;
     const size_t hw = (size_t)h * w, total = (size_t)B * hw;
     const float inv_sqrt = 1.f / sqrtf((float)C);
-    float bv[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) bv[j] = __ldg(bias_v + cg * 8 + j);
+    const float4* bvp = reinterpret_cast<const float4*>(bias_v + cg * 8);   // re-read per source (L1 hit): 8 registers saved
     const size_t warps = (size_t)gridDim.x * 8;
     for (size_t wi = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5); wi * PPW < total; wi += warps) {
         const size_t pix = wi * PPW + sub;
@@ -333,9 +332,13 @@ __global__ void __launch_bounds__(256, WIDE ? 2 : 3) warp_attention_kernel(const
             const Taps t = bilinear_taps(g.x, g.y, h, w);
             const float* src = kv + (size_t)s * hw * KVP;
             float kk[8], vv[8], k0 = 0.f;
+            {
+                const float4 b0 = __ldg(bvp), b1 = __ldg(bvp + 1);
+                vv[0] = b0.x; vv[1] = b0.y; vv[2] = b0.z; vv[3] = b0.w; vv[4] = b1.x; vv[5] = b1.y; vv[6] = b1.z; vv[7] = b1.w;
+            }
 #pragma unroll
-            for (int j = 0; j < 8; j++) { kk[j] = 0.f; vv[j] = bv[j]; }
-            if constexpr (WIDE) {
+            for (int j = 0; j < 8; j++) kk[j] = 0.f;
+            if constexpr (WIDE == 1) {
                 float4 q[4][4];
                 float k0c[4];
 #pragma unroll
@@ -636,8 +639,12 @@ extern "C" int iper_warp_attention(const void* xt, int xt_planes, long long xt_p
     const int wide = wide_env ? atoi(wide_env) : 0;
 #define IPER_ATT(CV, NV)                                                                                             \
     do {                                                                                                             \
-        if (wide)                                                                                                    \
+        if (wide == 1)                                                                                               \
             warp_attention_kernel<CV, NV, 1><<<blocks, 256, 0, st>>>(x, xt_planes, xt_plane_stride, xt_pitch, xt_coff, kv, \
+                                                                     bias_v, T, B, ns, h, w, o, out_planes,             \
+                                                                     out_plane_stride, out_pitch, out_coff);           \
+        else if (wide == 2)                                                                                          \
+            warp_attention_kernel<CV, NV, 2><<<blocks, 256, 0, st>>>(x, xt_planes, xt_plane_stride, xt_pitch, xt_coff, kv, \
                                                                      bias_v, T, B, ns, h, w, o, out_planes,             \
                                                                      out_plane_stride, out_pitch, out_coff);           \
         else                                                                                                         \
