@@ -14,7 +14,11 @@
 // (D[p,(dx,o)] = sum_dy,c X[y+dy-2, p, c] W[o,c,dy,dx]) and the epilogue finishes the horizontal taps with a shift-add
 // out[x,o] = sum_dx D[x+dx-2,(dx,o)] through shared memory; tiles are 128-pixel row segments overlapping by 4.
 //
-// One persistent CTA per SM, warp-specialised:
+// Three kernels share the tile decode, the tap arithmetic and the epilogue:
+//   conv_halo_pair_kernel   (default wherever a layer qualifies) CTA pairs + vertical halo + tap program, 8 epilogue warps
+//   conv_gemm_pair_kernel   CTA pairs (cta_group::2), one TMA box per tap: stride-2 convs, wide transposed convs
+//   conv_gemm_kernel        one CTA per tile: small maps, N = 32/64 tiles, the non-halo layers of the fp16+e4m3 mode
+// conv_gemm_kernel — one persistent CTA per SM, warp-specialised:
 //   warp 0   : TMA producer (one lane)            smem ring of STAGES x {A planes, B planes}
 //   warp 1   : TMEM allocator + MMA issuer (one lane issues tcgen05.mma, tcgen05.commit frees ring slots)
 //   warps 2-5: epilogue — tcgen05.ld the fp32 accumulator (thread = pixel row), fused bias / ReLU / residual /
