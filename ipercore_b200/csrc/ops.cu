@@ -320,15 +320,34 @@ __global__ void __launch_bounds__(256, WIDE == 1 ? 2 : (WIDE == 2 ? 4 : 3)) warp
         const bool live = pix < total;
         const size_t pc = live ? pix : total - 1;           // keep the whole warp in the shuffles
         const size_t b = pc / hw, p = pc % hw;
+        // the flows of every source first: a pixel none of whose taps lands inside a source map (background, most of a
+        // frame) has logits 0 and value bias_v for every source, so its target features are never needed
+        float2 gs[NSMAX];
+        bool any_tap = false;
+#pragma unroll
+        for (int s = 0; s < NSMAX; s++) {
+            if (s < ns) {
+                gs[s] = __ldg(reinterpret_cast<const float2*>(T) + (b * ns + s) * hw + p);
+                const Taps t0 = bilinear_taps(gs[s].x, gs[s].y, h, w);
+                any_tap |= (t0.off[0] >= 0) | (t0.off[1] >= 0) | (t0.off[2] >= 0) | (t0.off[3] >= 0);
+            }
+        }
         float xv[8];
-        load_planes8(xt, xt_planes, xt_plane_stride, pc * xt_pitch + xt_coff + cg * 8, xv);
+        if (any_tap) {
+            load_planes8(xt, xt_planes, xt_plane_stride, pc * xt_pitch + xt_coff + cg * 8, xv);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) xv[j] = 0.f;
+        }
         // online softmax over the sources: running max m, denominator den and weighted value sum o8
         float m = -INFINITY, den = 0.f, o8[8];
 #pragma unroll
         for (int j = 0; j < 8; j++) o8[j] = 0.f;
 #pragma unroll 1
         for (int s = 0; s < ns; s++) {
-            const float2 g = __ldg(reinterpret_cast<const float2*>(T) + (b * ns + s) * hw + p);
+            float2 g = gs[0];
+#pragma unroll
+            for (int q = 1; q < NSMAX; q++) g = (s == q) ? gs[q] : g;      // register select, no local-memory indexing
             const Taps t = bilinear_taps(g.x, g.y, h, w);
             const float* src = kv + (size_t)s * hw * KVP;
             float kk[8], vv[8], k0 = 0.f;
