@@ -121,9 +121,10 @@ typedef struct {
 int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream);
 
 /* Host-only introspection of the cta_pair = 2 tap program for a layer (mode IPER_CONV_S1 3x3 / IPER_CONVT_4S2 /
- * IPER_CONV_ROW5): out = {n_loads, acc_blocks, box_rows, per load {ox, oy, first, count}, per entry {a_row_off, b_row,
- * b_k, acc}}; returns the number of ints written (capacity >= 79) or -1.  No device work. */
-int iper_conv_halo_plan(int mode, int Cin, int rows, int32_t* out, int capacity);
+ * IPER_CONV_ROW5; fuse_n = 1: the fused-N form of the transposed conv, several phases per MMA group):
+ * out = {n_loads, acc_blocks, box_rows, phase of block 0..3, per load {ox, oy, first, count}, per entry {a_row_off, b_row,
+ * b_k, acc, nblk, fb_row[2][2], fb_k[2][2]}}; returns the number of ints written (capacity >= 227) or -1.  No device work. */
+int iper_conv_halo_plan(int mode, int Cin, int rows, int fuse_n, int32_t* out, int capacity);
 
 /* CUDA-core direct convolution on the same operand formats — the on-device cross-check of iper_conv_gemm and
  * the path for tensor-core-hostile shapes.  Same descriptor; `w` is ignored, weights come as fp32 in the

@@ -81,7 +81,7 @@ def _load():
         fn = getattr(lib, name)          # AttributeError here = ABI drift; fail loudly
         fn.argtypes = argtypes
         fn.restype = c_int
-    lib.iper_conv_halo_plan.argtypes = [c_int, c_int, c_int, c_void_p, c_int]
+    lib.iper_conv_halo_plan.argtypes = [c_int, c_int, c_int, c_int, c_void_p, c_int]
     lib.iper_conv_halo_plan.restype = c_int
     lib.iper_raster_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.iper_raster_workspace_bytes.restype = c_size_t

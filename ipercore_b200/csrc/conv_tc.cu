@@ -51,12 +51,16 @@ constexpr int SMEM_BUDGET = 196 * 1024;   // ring buffer budget; keeps one CTA p
 // starts `a_row_off` smem rows down (a vertical tap = a 1024-byte-aligned offset into the same box), multiplies with the
 // weight tile at (K column b_k + chunk*64, row b_row + n_tile*BN) and accumulates into accumulator block `acc`.
 constexpr int HALO_MAX_LOADS = 3, HALO_MAX_ENTRIES = 16;
-struct HaloEntry { int a_row_off, b_row, b_k, acc; };
+// nblk > 1 (transposed conv, fused N): ONE MMA group of N = nblk * BN feeds the accumulator blocks [acc, acc + nblk) —
+// several output phases read the same view — and CTA r of the pair stages nblk/2 whole BN-row weight boxes
+// {fb_row[r][i], fb_k[r][i]} (its half of the concatenated N) instead of half a box.
+struct HaloEntry { int a_row_off, b_row, b_k, acc, nblk; int fb_row[2][2], fb_k[2][2]; };
 struct HaloSched {
     int n_loads, acc_blocks, box_rows;          // box_rows = (th + halo) * tw
     int na, nb, a_plane_bytes, tmem_cols;       // ring depths, bytes of one A box of a slot, TMEM columns to allocate
     int k8;                                     // format 3: e4m3 channels per step (128: 128-byte rows, 64: 64-byte rows)
     int cat;                                    // heads, split fp16: weights concatenated along N ([w_hi ; w_lo]), see kernel
+    int blk_phase[4];                           // transposed conv: output phase stored in accumulator block i
     int ox[HALO_MAX_LOADS], oy[HALO_MAX_LOADS], first[HALO_MAX_LOADS], count[HALO_MAX_LOADS];
     HaloEntry e[HALO_MAX_ENTRIES];
 };
@@ -64,6 +68,7 @@ struct HaloSched {
 struct alignas(64) GemmArgs {
     CUtensorMap mapA[3];
     CUtensorMap mapB[3];
+    CUtensorMap mapBf[2];    // halo kernel, fused-N entries: whole BN-row weight boxes of fp16 planes 0 / 1
     int mode, ksize;
     int N, Ho, Wo;           // grid the M tiles walk (conv: output grid; convT: input grid)
     int oH, oW;              // stored output spatial dims
@@ -696,7 +701,9 @@ struct HaloWalk {
 
 template <int BN, int NS>
 __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const __grid_constant__ GemmArgs a) {
-    constexpr int B_PLANE = (BN / 2) * 128;                    // this CTA's half of a weight tile, one box
+    // one weight box of a slot: this CTA's half of a weight tile; the BN = 64 build reserves 2*BN rows because the fused-N
+    // transposed conv stages up to two whole 64-row boxes per plane (its half of an N = 256 MMA)
+    constexpr int B_PLANE = (BN == 64 ? 2 * BN : BN / 2) * 128;
     // N-concatenated split weights (BN = 32 heads, NS = 2, hs.cat): with N = 32 an MMA is paced by reading its 128-row A
     // operand from shared memory, so hi*hi and hi*lo share ONE read of a_hi: B = [w_hi ; w_lo] (N = 64, CTA r stages all
     // 32 rows of plane r = region X) and only lo*hi runs as a separate N = 32 MMA (region Y = this CTA's half of w_hi).
@@ -807,22 +814,41 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const _
                                 mbar_wait(&b_empty[slot], ph ^ 1);
                                 const int r = hs.e[i].b_row + brow;
                                 uint32_t bytes;
-                                if (cat) {
+                                constexpr uint32_t HALF_BOX = (BN / 2) * 128, FULL_BOX = BN * 128;
+                                if (hs.e[i].nblk > 1) {
+                                    // fused N: this CTA's nblk/2 whole boxes, consecutive in every plane of the slot
+                                    const HaloEntry& e = hs.e[i];
+                                    const int nbx = e.nblk >> 1, nt = (u % a.n_tiles) * BN;
+                                    if constexpr (NS == 2) {
+                                        for (int p = 0; p < 2; p++)
+                                            for (int bx = 0; bx < nbx; bx++)
+                                                tma_load_2d_2sm(sB(slot, p) + bx * FULL_BOX, &a.mapBf[p], &b_full[slot],
+                                                                e.fb_k[rank][bx] + cc * 64, e.fb_row[rank][bx] + nt);
+                                        bytes = 2 * nbx * FULL_BOX;
+                                    } else {
+                                        const int nbox = (cin - cc * 128 >= 128) ? 2 : 1;
+                                        for (int h = 0; h < nbox; h++)
+                                            for (int bx = 0; bx < nbx; bx++)
+                                                tma_load_2d_2sm(sB(slot, h) + bx * FULL_BOX, &a.mapBf[0], &b_full[slot],
+                                                                e.fb_k[rank][bx] + cc * 128 + h * 64, e.fb_row[rank][bx] + nt);
+                                        bytes = nbox * nbx * FULL_BOX;
+                                    }
+                                } else if (cat) {
                                     // X = plane `rank`, all BN rows (two boxes of BN/2 rows); Y = this CTA's half of w_hi
                                     const int r0 = hs.e[i].b_row + (u % a.n_tiles) * BN, k = hs.e[i].b_k + cc * 64;
                                     tma_load_2d_2sm(sB(slot, 0), &a.mapB[rank], &b_full[slot], k, r0);
                                     tma_load_2d_2sm(sB(slot, 1), &a.mapB[rank], &b_full[slot], k, r0 + BN / 2);
                                     tma_load_2d_2sm(sB(slot, 2), &a.mapB[0], &b_full[slot], k, r);
-                                    bytes = 3 * B_PLANE;
+                                    bytes = 3 * HALF_BOX;
                                 } else if constexpr (NS == 2) {
                                     for (int p = 0; p < 2; p++)
                                         tma_load_2d_2sm(sB(slot, p), &a.mapB[p], &b_full[slot], hs.e[i].b_k + cc * 64, r);
-                                    bytes = 2 * B_PLANE;
+                                    bytes = 2 * HALF_BOX;
                                 } else if (pass == 0) {
                                     const int nbox = (cin - cc * 128 >= 128) ? 2 : 1;
                                     for (int h = 0; h < nbox; h++)
                                         tma_load_2d_2sm(sB(slot, h), &a.mapB[0], &b_full[slot], hs.e[i].b_k + cc * 128 + h * 64, r);
-                                    bytes = nbox * B_PLANE;
+                                    bytes = nbox * HALF_BOX;
                                 } else {
                                     for (int p = 0; p < 2; p++)
                                         tma_load_2d_2sm(sB(slot, p), &a.mapB[1 + p], &b_full[slot], hs.e[i].b_k + cc * walk.k8, r);
@@ -838,7 +864,6 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const _
     } else if (warp == 1) {
         // =========================== MMA issuer (leader CTA only) ===========================
         if (rank == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(2 * BLOCK_M, BN);
             constexpr uint32_t idesc8 = umma_idesc_e4m3(2 * BLOCK_M, BN);
             int aslot = 0, bslot = 0; uint32_t aph = 0, bph = 0; int it = 0;
             for (int u = cluster_id; u < units; u += num_clusters, it++) {
@@ -860,8 +885,10 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const _
                             for (int i = hs.first[l]; i < hs.first[l] + hs.count[l]; i++) {
                                 mbar_wait(&b_full[bslot], bph);
                                 tc_fence_after();
-                                const HaloEntry e = hs.e[i];
+                                const HaloEntry& e = hs.e[i];
                                 const bool last_entry = (i == hs.first[l] + hs.count[l] - 1);
+                                // fused-N entries (nblk > 1) issue N = nblk * BN; all their blocks are in the same state
+                                const uint32_t idesc = umma_idesc_f16(2 * BLOCK_M, (e.nblk > 1 ? e.nblk : 1) * BN);
                                 if (elect_one()) {
                                     uint32_t first = (touched >> e.acc) & 1u;
                                     const uint32_t d = d_pass + e.acc * BN * (cat ? 2 : 1);
@@ -927,7 +954,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const _
                                     if (last_entry && last_load) umma_commit_2sm(&tmem_full_bar[acc], 0x3);
                                 }
                                 __syncwarp();
-                                touched |= 1u << e.acc;
+                                touched |= ((1u << (e.nblk > 1 ? e.nblk : 1)) - 1u) << e.acc;
                                 if (++bslot == hs.nb) { bslot = 0; bph ^= 1; }
                             }
                             if (++aslot == hs.na) { aslot = 0; aph ^= 1; }
@@ -977,7 +1004,7 @@ __global__ void __launch_bounds__(HALO_THREADS, 1) conv_halo_pair_kernel(const _
                 src = lane_base + acc_cols;
             }
             for (int blk = 0; blk < hs.acc_blocks; blk++) {
-                t.phase = blk;                  // transposed conv: accumulator block = output phase
+                t.phase = hs.blk_phase[blk];    // transposed conv: the output phase this accumulator block holds
                 epilogue_tile<BN, (NS == 3 ? 1 : NS)>(a, t, src + blk * BN * (cat ? 2 : 1), row, lane, tx, ty, 0, hsel, 2);
             }
             release(&tmem_empty_bar[NS == 3 ? 1 : acc]);
@@ -1073,7 +1100,7 @@ static int launch_gemm_pair(const GemmArgs& g, int max_ctas, cudaStream_t stream
 
 template <int BN, int NS>
 static int launch_gemm_halo(const GemmArgs& g, int max_ctas, cudaStream_t stream) {
-    const int a_slot = 2 * g.hs.a_plane_bytes, b_slot = ((BN == 32 && NS == 2) ? 3 : 2) * (BN / 2) * 128;
+    const int a_slot = 2 * g.hs.a_plane_bytes, b_slot = ((BN == 32 && NS == 2) ? 3 : 2) * ((BN == 64 ? 2 * BN : BN / 2) * 128);
     int smem = g.hs.na * a_slot + g.hs.nb * b_slot + 1024;
     if (smem < 120 * 1024) smem = 120 * 1024;            // one CTA per SM (TMEM allocation)
     static int attr_smem = 0;
@@ -1101,32 +1128,87 @@ static int launch_gemm_halo(const GemmArgs& g, int max_ctas, cudaStream_t stream
     return 0;
 }
 
-// tap program of the halo kernel for one layer (see HaloSched)
-static void build_halo_sched(HaloSched& hs, int mode, int Cin, int rows, int tw, int th) {
+// transposed 4x4 s2 p1: spatial offset (oy, ox) of tap (ta, tb) of output phase (py, px) — same algebra as conv_gemm_kernel
+static void convt_tap_offset(int phase, int tap, int& oy, int& ox) {
+    const int py = phase >> 1, px = phase & 1, ta = tap >> 1, tb = tap & 1;
+    oy = py == 0 ? (ta == 0 ? 0 : -1) : (ta == 0 ? 1 : 0);
+    ox = px == 0 ? (tb == 0 ? 0 : -1) : (tb == 0 ? 1 : 0);
+}
+
+// tap program of the halo kernel for one layer (see HaloSched).  fuse_n (transposed conv, formats 1/2): the output phases
+// that read the same view share ONE MMA group (N = 2 or 4 blocks) — the accumulator blocks are ordered cyclically
+// [(0,0), (0,1), (1,1), (1,0)]; runs of 2 / 4 adjacent blocks that start on a multiple of their length are fused.
+static void build_halo_sched(HaloSched& hs, int mode, int Cin, int rows, int tw, int th, bool fuse_n) {
     hs = HaloSched{};
+    for (int i = 0; i < 4; i++) hs.blk_phase[i] = i;
     int ne = 0;
+    auto simple = [](int a_row_off, int b_row, int b_k, int acc) {
+        HaloEntry e = {};
+        e.a_row_off = a_row_off; e.b_row = b_row; e.b_k = b_k; e.acc = acc; e.nblk = 1;
+        return e;
+    };
     if (mode == IPER_CONV_S1) {                 // 3x3: one box per horizontal tap, three vertical views
         hs.n_loads = 3; hs.acc_blocks = 1; hs.box_rows = (th + 2) * tw;
         for (int dx = 0; dx < 3; dx++) {
             hs.ox[dx] = dx - 1; hs.oy[dx] = -1; hs.first[dx] = ne; hs.count[dx] = 3;
-            for (int dy = 0; dy < 3; dy++) hs.e[ne++] = HaloEntry{dy * tw, 0, (dy * 3 + dx) * Cin, 0};
+            for (int dy = 0; dy < 3; dy++) hs.e[ne++] = simple(dy * tw, 0, (dy * 3 + dx) * Cin, 0);
         }
     } else if (mode == IPER_CONV_ROW5) {        // heads: one box, five vertical views
         hs.n_loads = 1; hs.acc_blocks = 1; hs.box_rows = (th + 4) * tw;
         hs.ox[0] = 0; hs.oy[0] = -2; hs.first[0] = 0; hs.count[0] = 5;
-        for (int dy = 0; dy < 5; dy++) hs.e[ne++] = HaloEntry{dy * tw, 0, dy * Cin, 0};
-    } else {                                    // transposed 4x4 s2: phase (py,px), tap (ta,tb) as in conv_gemm_kernel
+        for (int dy = 0; dy < 5; dy++) hs.e[ne++] = simple(dy * tw, 0, dy * Cin, 0);
+    } else if (!fuse_n) {                       // transposed 4x4 s2: one entry per (phase, tap), block = phase
         hs.n_loads = 3; hs.acc_blocks = 4; hs.box_rows = (th + 2) * tw;
         for (int l = 0; l < 3; l++) {
             hs.ox[l] = l - 1; hs.oy[l] = -1; hs.first[l] = ne;
             for (int phase = 0; phase < 4; phase++)
                 for (int tap = 0; tap < 4; tap++) {
-                    const int py = phase >> 1, px = phase & 1, ta = tap >> 1, tb = tap & 1;
-                    const int oy = py == 0 ? (ta == 0 ? 0 : -1) : (ta == 0 ? 1 : 0);
-                    const int ox = px == 0 ? (tb == 0 ? 0 : -1) : (tb == 0 ? 1 : 0);
+                    int oy, ox;
+                    convt_tap_offset(phase, tap, oy, ox);
                     if (ox != l - 1) continue;
-                    hs.e[ne++] = HaloEntry{(oy + 1) * tw, phase * rows, tap * Cin, phase};
+                    hs.e[ne++] = simple((oy + 1) * tw, phase * rows, tap * Cin, phase);
                 }
+            hs.count[l] = ne - hs.first[l];
+        }
+    } else {                                    // transposed 4x4 s2, one entry per VIEW (dy, dx) and run of adjacent blocks
+        hs.n_loads = 3; hs.acc_blocks = 4; hs.box_rows = (th + 2) * tw;
+        const int order[4] = {0, 1, 3, 2};      // accumulator block -> phase
+        for (int i = 0; i < 4; i++) hs.blk_phase[i] = order[i];
+        const int load_ox[3] = {0, -1, 1};      // the centre view comes first: it initialises all four blocks at once
+        for (int l = 0; l < 3; l++) {
+            hs.ox[l] = load_ox[l]; hs.oy[l] = -1; hs.first[l] = ne;
+            const int dys[3] = {0, -1, 1};
+            for (int di = 0; di < 3; di++) {
+                const int dy = dys[di];
+                // blocks whose phase has a tap at this view, with that tap
+                int tap_of_blk[4];
+                for (int b = 0; b < 4; b++) {
+                    tap_of_blk[b] = -1;
+                    for (int tap = 0; tap < 4; tap++) {
+                        int oy, ox;
+                        convt_tap_offset(order[b], tap, oy, ox);
+                        if (oy == dy && ox == load_ox[l]) tap_of_blk[b] = tap;
+                    }
+                }
+                for (int b = 0; b < 4;) {           // maximal runs of adjacent blocks of length 4, 2 or 1
+                    if (tap_of_blk[b] < 0) { b++; continue; }
+                    int run = 1;
+                    while (b + run < 4 && tap_of_blk[b + run] >= 0) run++;
+                    // N must split evenly over the CTA pair, and a group's first TMEM column stays a multiple of its N
+                    run = (run == 4 && b == 0) ? 4 : ((run >= 2 && b % 2 == 0) ? 2 : 1);
+                    HaloEntry e = {};
+                    e.a_row_off = (dy + 1) * tw; e.acc = b; e.nblk = run;
+                    e.b_row = order[b] * rows; e.b_k = tap_of_blk[b] * Cin;
+                    if (run > 1)
+                        for (int r = 0; r < 2; r++)
+                            for (int i = 0; i < run / 2; i++) {
+                                const int blk = b + r * (run / 2) + i;
+                                e.fb_row[r][i] = order[blk] * rows; e.fb_k[r][i] = tap_of_blk[blk] * Cin;
+                            }
+                    hs.e[ne++] = e;
+                    b += run;
+                }
+            }
             hs.count[l] = ne - hs.first[l];
         }
     }
@@ -1137,22 +1219,29 @@ static void build_halo_sched(HaloSched& hs, int mode, int Cin, int rows, int tw,
 using namespace iper;
 
 // Host-only: the tap program the halo kernel would run for a layer, flattened for inspection (tests/test_abi_cpu.py).
-// out[0] = number of A loads, out[1] = accumulator blocks, out[2] = box rows; then per load 4 ints {ox, oy, first, count};
-// then per entry 4 ints {a_row_off, b_row, b_k, acc}.  Returns the number of ints written (<= 3 + 12 + 64), or -1.
-extern "C" int iper_conv_halo_plan(int mode, int Cin, int rows, int32_t* out, int capacity) {
-    IPER_REQUIRE(out != nullptr && capacity >= 3 + 4 * HALO_MAX_LOADS + 4 * HALO_MAX_ENTRIES, "iper_conv_halo_plan: buffer too small");
+// out[0] = number of A loads, out[1] = accumulator blocks, out[2] = box rows, out[3..6] = phase held by block 0..3; then per
+// load 4 ints {ox, oy, first, count}; then per entry 13 ints {a_row_off, b_row, b_k, acc, nblk, fb_row[2][2], fb_k[2][2]}.
+// fuse_n selects the fused-N form of the transposed conv.  Returns the number of ints written, or -1.
+extern "C" int iper_conv_halo_plan(int mode, int Cin, int rows, int fuse_n, int32_t* out, int capacity) {
+    IPER_REQUIRE(out != nullptr && capacity >= 7 + 4 * HALO_MAX_LOADS + 13 * HALO_MAX_ENTRIES, "iper_conv_halo_plan: buffer too small");
     IPER_REQUIRE(mode == IPER_CONV_S1 || mode == IPER_CONVT_4S2 || mode == IPER_CONV_ROW5, "iper_conv_halo_plan: mode %d has no halo form", mode);
     const int tw = mode == IPER_CONV_ROW5 ? 32 : 16, th = BLOCK_M / tw;
     HaloSched hs;
-    build_halo_sched(hs, mode, Cin, rows, tw, th);
+    build_halo_sched(hs, mode, Cin, rows, tw, th, fuse_n != 0 && mode == IPER_CONVT_4S2);
     int n = 0;
     out[n++] = hs.n_loads; out[n++] = hs.acc_blocks; out[n++] = hs.box_rows;
+    for (int i = 0; i < 4; i++) out[n++] = hs.blk_phase[i];
     int ne = 0;
     for (int l = 0; l < hs.n_loads; l++) {
         out[n++] = hs.ox[l]; out[n++] = hs.oy[l]; out[n++] = hs.first[l]; out[n++] = hs.count[l];
         ne = hs.first[l] + hs.count[l];
     }
-    for (int i = 0; i < ne; i++) { out[n++] = hs.e[i].a_row_off; out[n++] = hs.e[i].b_row; out[n++] = hs.e[i].b_k; out[n++] = hs.e[i].acc; }
+    for (int i = 0; i < ne; i++) {
+        const HaloEntry& e = hs.e[i];
+        out[n++] = e.a_row_off; out[n++] = e.b_row; out[n++] = e.b_k; out[n++] = e.acc; out[n++] = e.nblk;
+        for (int r = 0; r < 2; r++) for (int k = 0; k < 2; k++) out[n++] = e.fb_row[r][k];
+        for (int r = 0; r < 2; r++) for (int k = 0; k < 2; k++) out[n++] = e.fb_k[r][k];
+    }
     return n;
 }
 
@@ -1232,13 +1321,17 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
     g.n_tiles = d->rows / d->block_n;
     g.total_tiles = g.m_groups * g.n_tiles * g.phases;
     if (halo) {
-        build_halo_sched(g.hs, d->mode, d->Cin, d->rows, g.tw, g.th);
+        // transposed conv in formats 1/2: phases that read the same view share one MMA group (IPER_CONVT_FUSE_N=0 disables)
+        const char* fuse_env = getenv("IPER_CONVT_FUSE_N");
+        const bool fuse_n = d->mode == IPER_CONVT_4S2 && fmt != 3 && !(fuse_env && atoi(fuse_env) == 0);
+        build_halo_sched(g.hs, d->mode, d->Cin, d->rows, g.tw, g.th, fuse_n);
         g.hs.a_plane_bytes = g.hs.box_rows * 128;
         g.hs.k8 = (d->Cin % 128 == 0) ? 128 : 64;
         // heads in split fp16: N-concatenated weights (IPER_HEADS_CAT=0 keeps the three-MMA form for comparison)
         const char* cat_env = getenv("IPER_HEADS_CAT");
         g.hs.cat = (d->mode == IPER_CONV_ROW5 && d->block_n == 32 && fmt == 2 && !(cat_env && atoi(cat_env) == 0)) ? 1 : 0;
-        const int a_slot = 2 * g.hs.a_plane_bytes, b_slot = (d->block_n == 32 && fmt == 2 ? 3 : 2) * (d->block_n / 2) * 128;
+        const int b_plane = (d->block_n == 64 ? 2 * d->block_n : d->block_n / 2) * 128;       // as B_PLANE in the kernel
+        const int a_slot = 2 * g.hs.a_plane_bytes, b_slot = (d->block_n == 32 && fmt == 2 ? 3 : 2) * b_plane;
         g.hs.na = (3 * a_slot + 6 * b_slot <= HALO_SMEM_BUDGET) ? 3 : 2;
         g.hs.nb = (HALO_SMEM_BUDGET - g.hs.na * a_slot) / b_slot;
         if (g.hs.nb > HALO_MAX_NB) g.hs.nb = HALO_MAX_NB;
@@ -1311,8 +1404,14 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
         cuuint64_t wstr[1] = {ktot * esz};
         cuuint32_t wbox[2] = {(cuuint32_t)kbox, (cuuint32_t)(pair ? d->block_n / 2 : d->block_n)};
         if (int rc = encode_map(&g.mapB[p], wb, 2, wdims, wstr, wbox, u8, row_bytes)) return rc;
+        if (halo && !u8 && p < 2) {             // whole BN-row boxes for the fused-N entries
+            cuuint32_t fbox[2] = {(cuuint32_t)kbox, (cuuint32_t)d->block_n};
+            if (int rc = encode_map(&g.mapBf[p], wb, 2, wdims, wstr, fbox, false, row_bytes)) return rc;
+        }
     }
     for (int p = nmaps; p < 3; p++) { g.mapA[p] = g.mapA[0]; g.mapB[p] = g.mapB[0]; }
+    if (!halo) { g.mapBf[0] = g.mapB[0]; g.mapBf[1] = g.mapB[0]; }
+    else if (nmaps < 2 || fmt == 3) g.mapBf[1] = g.mapBf[0];
 
     cudaStream_t s = (cudaStream_t)stream;
     if (d->stats_ws) {

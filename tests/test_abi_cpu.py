@@ -117,54 +117,82 @@ print("OK")
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-2000:]
 
 
-def _halo_plan(mode, cin, rows):
+def _halo_plan(mode, cin, rows, fuse_n=0):
     import numpy as np
     from ipercore_b200 import _lib
-    buf = np.zeros(128, dtype=np.int32)
-    n = _lib.lib.iper_conv_halo_plan(mode, cin, rows, buf.ctypes.data, buf.size)
+    buf = np.zeros(256, dtype=np.int32)
+    n = _lib.lib.iper_conv_halo_plan(mode, cin, rows, fuse_n, buf.ctypes.data, buf.size)
     assert n > 0, _lib.lib.iper_last_error()
     n_loads, acc_blocks, box_rows = (int(v) for v in buf[:3])
-    loads = buf[3:3 + 4 * n_loads].reshape(n_loads, 4)
+    blk_phase = [int(v) for v in buf[3:7]]
+    loads = buf[7:7 + 4 * n_loads].reshape(n_loads, 4)
     ne = int(loads[-1, 2] + loads[-1, 3])
-    entries = buf[3 + 4 * n_loads:3 + 4 * n_loads + 4 * ne].reshape(ne, 4)
-    assert n == 3 + 4 * n_loads + 4 * ne
-    return acc_blocks, box_rows, loads, entries
+    entries = buf[7 + 4 * n_loads:7 + 4 * n_loads + 13 * ne].reshape(ne, 13)
+    assert n == 7 + 4 * n_loads + 13 * ne
+    return acc_blocks, box_rows, loads, entries, blk_phase
 
 
 def test_halo_tap_program_covers_every_tap_once():
     """Host logic of the halo kernel (conv_tc.cu build_halo_sched): every (phase, tap) of the layer appears exactly once,
     reads the view of the box that corresponds to its spatial offset, and the transposed conv's offsets agree with
-    ConvTranspose2d(4, 2, 1) index algebra (out = 2*in - 1 + k)."""
-    import numpy as np
+    ConvTranspose2d(4, 2, 1) index algebra (out = 2*in - 1 + k) — in the per-(phase, tap) form and in the fused-N form."""
     from ipercore_b200._lib import IPER_CONV_ROW5, IPER_CONV_S1, IPER_CONVT_4S2
     cin, rows, tw = 128, 64, 16
     # 3x3 stride 1: tap (dy, dx) at K column (dy*3+dx)*Cin must read input offset (dy-1, dx-1)
-    acc, box_rows, loads, ent = _halo_plan(IPER_CONV_S1, cin, rows)
+    acc, box_rows, loads, ent, _ = _halo_plan(IPER_CONV_S1, cin, rows)
     assert acc == 1 and box_rows == (8 + 2) * tw and len(ent) == 9
     seen = set()
     for ox, oy, first, count in loads:
-        for a_off, b_row, b_k, blk in ent[first:first + count]:
+        for a_off, b_row, b_k, blk, nblk in ent[first:first + count, :5]:
             tap = b_k // cin
             dy, dx = divmod(tap, 3)
-            assert b_k % cin == 0 and b_row == 0 and blk == 0
+            assert b_k % cin == 0 and b_row == 0 and blk == 0 and nblk == 1
             assert a_off % tw == 0 and oy + a_off // tw == dy - 1 and ox == dx - 1
             seen.add(tap)
     assert seen == set(range(9))
     # heads: five vertical taps of one 32 x (4+4) box
-    acc, box_rows, loads, ent = _halo_plan(IPER_CONV_ROW5, 64, 32)
+    acc, box_rows, loads, ent, _ = _halo_plan(IPER_CONV_ROW5, 64, 32)
     assert acc == 1 and box_rows == 8 * 32 and len(loads) == 1 and tuple(loads[0][:2]) == (0, -2)
     assert [(int(e[0]) // 32, int(e[2]) // 64) for e in ent] == [(d, d) for d in range(5)]
     # transposed 4x4 s2 p1: output (2y+py, 2x+px) gathers input (y+oy, x+ox) through kernel index k = (2y+py) - 2(y+oy) + 1
-    acc, box_rows, loads, ent = _halo_plan(IPER_CONVT_4S2, cin, rows)
-    assert acc == 4 and len(ent) == 16
     kidx = {0: (1, 3), 1: (0, 2)}          # pack_convT_weight: phase parity -> kernel indices of taps 0, 1
+
+    def check(phase, tap, iy, ix):
+        py, px, ta, tb = phase >> 1, phase & 1, tap >> 1, tap & 1
+        assert kidx[py][ta] == py - 2 * iy + 1 and kidx[px][tb] == px - 2 * ix + 1
+
+    acc, box_rows, loads, ent, blk_phase = _halo_plan(IPER_CONVT_4S2, cin, rows, fuse_n=0)
+    assert acc == 4 and len(ent) == 16 and blk_phase == [0, 1, 2, 3]
     seen = set()
     for ox, oy, first, count in loads:
-        for a_off, b_row, b_k, blk in ent[first:first + count]:
+        for a_off, b_row, b_k, blk, nblk in ent[first:first + count, :5]:
             phase, tap = b_row // rows, b_k // cin
-            assert b_row % rows == 0 and b_k % cin == 0 and blk == phase
-            py, px, ta, tb = phase >> 1, phase & 1, tap >> 1, tap & 1
-            iy, ix = oy + a_off // tw, ox
-            assert kidx[py][ta] == py - 2 * iy + 1 and kidx[px][tb] == px - 2 * ix + 1
+            assert b_row % rows == 0 and b_k % cin == 0 and blk == phase and nblk == 1
+            check(phase, tap, oy + a_off // tw, ox)
             seen.add((phase, tap))
     assert len(seen) == 16
+    # fused N: one entry per view and run of adjacent accumulator blocks; block b holds phase blk_phase[b]; CTA r of the
+    # pair stages the whole weight boxes of blocks [acc + r*nblk/2, acc + (r+1)*nblk/2)
+    acc, box_rows, loads, ent, blk_phase = _halo_plan(IPER_CONVT_4S2, cin, rows, fuse_n=1)
+    assert acc == 4 and sorted(blk_phase) == [0, 1, 2, 3] and len(ent) == 11
+    assert int(ent[0][4]) == 4 and int(ent[0][3]) == 0, "the first MMA group must initialise all four accumulator blocks"
+    seen = []
+    for ox, oy, first, count in loads:
+        for e in ent[first:first + count]:
+            a_off, b_row, b_k, blk, nblk = (int(v) for v in e[:5])
+            fb_row, fb_k = e[5:9].reshape(2, 2), e[9:13].reshape(2, 2)
+            assert nblk in (1, 2, 4) and blk + nblk <= 4 and blk % nblk == 0
+            iy = oy + a_off // tw
+            if nblk == 1:
+                assert b_row // rows == blk_phase[blk]
+                check(b_row // rows, b_k // cin, iy, ox)
+                seen.append((b_row // rows, b_k // cin))
+            else:
+                for r in range(2):
+                    for i in range(nblk // 2):
+                        b = blk + r * (nblk // 2) + i
+                        phase, tap = int(fb_row[r][i]) // rows, int(fb_k[r][i]) // cin
+                        assert phase == blk_phase[b]
+                        check(phase, tap, iy, ox)
+                        seen.append((phase, tap))
+    assert len(seen) == 16 and len(set(seen)) == 16
