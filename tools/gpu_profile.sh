@@ -14,6 +14,7 @@ timeout 1200 ncu --set full --clock-control none -k "regex:conv_gemm|conv_halo" 
     > gpurun_out/ncu_conv.log 2>&1
 echo "conv capture exit $?"
 python tools/ncu_extract.py /tmp/ncu/conv_all.ncu-rep gpurun_out/conv_gemm_ncu.csv
+if [ "${1:-}" = "quick" ]; then ls -la gpurun_out; exit 0; fi     # quick: launch list + conv capture only
 timeout 600 ncu --set full --clock-control none --import-source on -k "regex:conv_gemm|conv_halo" -s 69 -c 1 \
     -o gpurun_out/conv_res0b $BENCH > gpurun_out/ncu_conv1.log 2>&1
 timeout 600 ncu --set full --clock-control none -k "regex:raster_kernel|raster_setup_kernel|warp_attention_kernel|conv_stem_kernel|flow_resize_kernel|pred_to_u8_kernel" \
