@@ -84,3 +84,15 @@ def smooth_image(shape, seed):
     img = (a * (1 - fx) + b * fx) * (1 - fy) + (c * (1 - fx) + d * fx) * fy
     img = 0.9 * img + 0.1 * rng.uniform(-1, 1, size=img.shape)
     return img.astype(np.float32)
+
+
+def morph_masks(seed=5):
+    """Binary (3,1,96,80) test masks for the mask-morphology row: a blob, scattered speckles, a mask touching the border."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    m = np.zeros((3, 1, 96, 80), dtype=np.float32)
+    yy, xx = np.mgrid[0:96, 0:80]
+    m[0, 0] = ((yy - 50) ** 2 / 900.0 + (xx - 38) ** 2 / 400.0 < 1.0)
+    m[1, 0] = rng.random((96, 80)) < 0.03
+    m[2, 0, :40, :] = 1.0
+    m[2, 0, 40:, 60:] = rng.random((56, 20)) < 0.5
+    return m

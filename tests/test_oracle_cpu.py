@@ -126,11 +126,9 @@ def test_morph_oracle_matches_reference_golden():
     import os
     import numpy as np
     from oracle import morph_ref
+    from oracle import synth
     here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-    src = open(os.path.join(here, "make_golden.py")).read()
-    ns = {"np": np}
-    exec(src[src.index("def morph_inputs"):src.index("def make_morph")], ns)
-    m = ns["morph_inputs"]()
+    m = synth.morph_masks()
     gold = np.load(os.path.join(here, "morph.npz"))
     for ks in (3, 11, 51):
         for name, mode in (("erode", morph_ref.ERODE), ("dilate", morph_ref.DILATE), ("soft", morph_ref.SOFT_DILATE)):

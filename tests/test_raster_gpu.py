@@ -124,11 +124,7 @@ def test_morph_matches_reference_golden(ks):
     from oracle import morph_ref
     here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     gold = np.load(os.path.join(here, "morph.npz"))
-    # the input masks are regenerated from the same seeded function the golden script used (no reference import needed)
-    src = open(os.path.join(here, "make_golden.py")).read()
-    ns = {"np": np}
-    exec(src[src.index("def morph_inputs"):src.index("def make_morph")], ns)
-    m = ns["morph_inputs"]()
+    m = synth.morph_masks()          # the same seeded masks the golden script fed to the reference's functions
     md = torch.from_numpy(m).cuda()
     for name, mode in (("erode", ops.MORPH_ERODE), ("dilate", ops.MORPH_DILATE), ("soft", ops.MORPH_SOFT_DILATE)):
         got = ops.morph(md, ks, mode).cpu().numpy()
