@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--dump-layers", default="", help="write the per-launch conv timing table (JSON) to this path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=8)
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of sampled frames of the last step")
+    ap.add_argument("--no-strong", action="store_true", help="N>1: skip the strong-scaling pass (one clip split over ranks)")
     return ap.parse_args()
 
 
@@ -123,7 +125,9 @@ def host_cores():
     return n
 
 
-def cpu_frames_per_sec(args, wl, n_frames, repeats=1):
+def cpu_frames_per_sec(args, wl, n_frames, repeats=1, keep=None, frames=None):
+    """Oracle port over `frames` (default: the first n_frames of the clip).  `keep` (a dict) receives, per frame index,
+    the oracle's fim, float composite and uint8 BGR frame — what the `parity` block compares the GPU frames with."""
     import numpy as np
     import torch
     from oracle import flow_ref, generator_ref, weights
@@ -140,13 +144,16 @@ def cpu_frames_per_sec(args, wl, n_frames, repeats=1):
         times = []
         for _ in range(repeats):
             t0 = time.perf_counter()
-            for i in range(n_frames):
+            for i in (range(n_frames) if frames is None else frames):
                 fi = flow_ref.frame_inputs(wl["cams"][i:i + 1], wl["verts"][i:i + 1], tpl["faces"], tpl["map_fn"],
                                            tpl["f_uvs2img"], wl["uv_img"], src_f2pts, S)
                 img, mask = generator_ref.forward_tsf(sd, torch.from_numpy(fi["tsf_inputs"]), se, sr,
                                                       torch.from_numpy(fi["Tst"]))
                 pred = generator_ref.composite(img, mask, bg)
-                _ = ((pred + 1) / 2.0 * 255).clamp(0, 255).to(torch.uint8)
+                u8 = ((pred + 1) / 2.0 * 255).clamp(0, 255).to(torch.uint8)
+                if keep is not None:
+                    keep[int(i)] = dict(fim=fi["fim"][0], pred=pred[0].numpy(),
+                                        u8=u8[0].numpy()[::-1].transpose(1, 2, 0))      # BGR HWC like the engine's frames
             times.append(time.perf_counter() - t0)
     return n_frames / min(times), cores, times
 
@@ -285,6 +292,68 @@ def main():
     fps_e2e = world * T * args.steps / (ms_e2e * 1e-3)
     launches = eng.launches_per_batch * nb * args.steps if eng.graph else _lib.launch_count() - launches0
 
+    # ---- parity of the frames the timed e2e region just produced (rank 0): oracle port on a sample of frames ----------
+    # out_h holds every uint8 frame of the last e2e step; eng.last_pred the float composites of its last batch.
+    cpu, parity = None, None
+    if rank == 0 and not args.no_parity:
+        keep = {}
+        if world == 1 and not args.no_cpu_baseline:     # the cpu_baseline leg already runs the oracle: keep its frames
+            v, cores, _ = cpu_frames_per_sec(args, wl, args.cpu_frames, keep=keep)
+            cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                   "sample": "first %d frames of the 300-pose clip through the oracle port (CPU restatement of raster + "
+                             "flow + forward_tsf + composite, torch fp32, all host threads); source setup untimed" % args.cpu_frames}
+        last_lo = (nb - 1) * B
+        extra = sorted({last_lo, T - 1, min(B - 1, T - 1), min(B, T - 1)} - set(keep))   # batch edges + the last batch
+        cpu_frames_per_sec(args, wl, 0, keep=keep, frames=extra)
+        idx = sorted(keep)
+        got_u8 = out_h.numpy()
+        code = max(int(np.abs(got_u8[i].astype(np.int32) - keep[i]["u8"].astype(np.int32)).max()) for i in idx)
+        frac = float(np.mean([(got_u8[i] != keep[i]["u8"]).mean() for i in idx]))
+        sel = torch.tensor(idx, device=dev)
+        fi = render.frame_inputs(cams_d[sel].contiguous(), verts_d[sel].contiguous(), eng.src["uv_img"], eng.src["src_f2pts"],
+                                 want_fim=True)
+        fim_equal = all(np.array_equal(fi["fim"][k].cpu().numpy(), keep[i]["fim"]) for k, i in enumerate(idx))
+        lastp = eng.last_pred.float().cpu().numpy()      # composites of the last batch of the last e2e step
+        fl = [i for i in idx if i >= last_lo]
+        max_abs = max(float(np.abs(lastp[i - last_lo] - keep[i]["pred"]).max()) for i in fl)
+        parity = {"frames": len(idx), "frame_ids": idx, "max_abs": max_abs, "max_abs_frames": fl, "tolerance": 1e-3,
+                  "u8_max_code_diff": code, "u8_frac_differing": frac, "fim_equal": bool(fim_equal),
+                  "ok": bool(fim_equal and max_abs <= 1e-3 and code <= 1),
+                  "against": "oracle port (CPU restatement pinned to the reference's own modules by tests/golden) on the "
+                             "uint8 frames of the last timed e2e step (all sampled frames) and the float composites of its "
+                             "last batch; face-index maps re-rendered for the sampled frames"}
+        if not parity["ok"]:
+            sys.stderr.write("bench.py: PARITY FAILED %s\n" % json.dumps(parity))
+
+    # ---- strong scaling: ONE clip of T frames split over the ranks (engine.shard_range), batch sized to the shard -------
+    strong = None
+    if world > 1 and not args.no_strong:
+        from ipercore_b200.engine import balanced_batch, shard_range
+        wl0 = wl if rank == 0 else make_workload(args, 0)       # every rank takes a contiguous shard of rank 0's clip
+        lo_s, hi_s = shard_range(T, rank, world)
+        Bs = balanced_batch(hi_s - lo_s, B)
+        es = FrameEngine(gen, render, batch=Bs, use_graph=not args.no_graph, device=dev)
+        es.src = eng.src
+        cams_s, verts_s = t(wl0["cams"][lo_s:hi_s]), t(wl0["verts"][lo_s:hi_s])
+        n_s = hi_s - lo_s
+
+        def step_strong():
+            for b0 in range(0, n_s, Bs):
+                b1 = min(b0 + Bs, n_s)
+                u8 = es.run_batch_device(cams_s[b0:b1], verts_s[b0:b1])
+                with torch.cuda.stream(es.compute):
+                    out_d[b0:b1].copy_(u8[:b1 - b0], non_blocking=True)
+            cur.wait_stream(es.compute)
+
+        engines.append(es)
+        for _ in range(max(args.warmup, 1)):
+            step_strong()
+        ms_s, _ = timed(step_strong, args.steps)
+        engines.pop()
+        strong = {"value": T * args.steps / (ms_s * 1e-3), "unit": "frames/s", "frames_total": T, "frames_rank0": n_s,
+                  "batch": Bs, "ms_per_step": ms_s / args.steps,
+                  "note": "one %d-frame clip split contiguously over %d ranks, no collective; max over ranks" % (T, world)}
+
     # ---- roofline of the conv stack: CUDA events around every conv_gemm launch of one (un-graphed) batch ----
     roof = None
     if rank == 0:
@@ -365,8 +434,7 @@ def main():
                 "traffic_note": "dram__bytes_read+write of the batch's conv launches (profiles/conv_traffic.json, ncu --set full); "
                                 "the stack is tensor-bound, DRAM runs at ~1.4 TB/s"}
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if cpu is None and rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, cores, _ = cpu_frames_per_sec(args, wl, args.cpu_frames)
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
                "sample": "first %d frames of the 300-pose clip through the oracle port (CPU restatement of raster + "
@@ -382,6 +450,7 @@ def main():
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(cams_h.numel() * 4 + verts_h.numel() * 4),
                         "d2h_bytes_per_step": int(out_h.numel()), "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "parity": parity, "strong": strong,
                 "wall_s_timed_region": wall}
         print(json.dumps(line))
     if world > 1:

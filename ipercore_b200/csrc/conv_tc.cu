@@ -1047,21 +1047,50 @@ static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint
 
 static int floor_pow2(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 
+// Per-device launch state.  Function attributes (opt-in shared memory) and the SM count belong to a DEVICE, and a process
+// may drive several (one thread per GPU, or set_device between calls), so nothing here is cached per process: the slot of
+// the current device is looked up on every launch.  Slots only ever grow towards the same value, so racing threads that
+// both set an attribute are harmless.
+constexpr int MAX_DEVICES = 64;
+struct DeviceSlot { int dev, sms; };
+static int current_device(DeviceSlot& slot) {
+    static int sms[MAX_DEVICES] = {};
+    int dev = 0;
+    IPER_CHECK_CUDA(cudaGetDevice(&dev));
+    IPER_REQUIRE(dev >= 0 && dev < MAX_DEVICES, "device ordinal %d out of range", dev);
+    if (!sms[dev]) {
+        int n = 0;
+        IPER_CHECK_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        sms[dev] = n;
+    }
+    slot.dev = dev; slot.sms = sms[dev];
+    return 0;
+}
+// opt-in dynamic shared memory of `func` on the current device, raised at most once per (kernel, device, size)
+template <typename F>
+static int ensure_smem(F func, int (&have)[MAX_DEVICES], int dev, int bytes) {
+    if (bytes > have[dev]) {
+        IPER_CHECK_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        have[dev] = bytes;
+    }
+    return 0;
+}
+// process-wide experiment switches, read once (not on every launch)
+static bool env_flag_default_on(const char* name) {
+    const char* v = getenv(name);
+    return !(v && atoi(v) == 0);
+}
+static bool convt_fuse_n_enabled() { static const bool on = env_flag_default_on("IPER_CONVT_FUSE_N"); return on; }
+static bool heads_cat_enabled() { static const bool on = env_flag_default_on("IPER_HEADS_CAT"); return on; }
+
 template <int BN, int NS, int TM>
 static int launch_gemm(const GemmArgs& g, int max_ctas, cudaStream_t stream) {
     using C = Cfg<BN, NS, TM>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        IPER_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, NS, TM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             C::SMEM_BYTES));
-        attr_set = true;
-    }
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        IPER_CHECK_CUDA(cudaGetDevice(&dev));
-        IPER_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    static int have[MAX_DEVICES] = {};
+    DeviceSlot ds;
+    if (int rc = current_device(ds)) return rc;
+    if (int rc = ensure_smem(conv_gemm_kernel<BN, NS, TM>, have, ds.dev, C::SMEM_BYTES)) return rc;
+    const int num_sms = ds.sms;
     int grid = g.total_tiles < num_sms ? g.total_tiles : num_sms;
     if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
     conv_gemm_kernel<BN, NS, TM><<<grid, GEMM_THREADS, C::SMEM_BYTES, stream>>>(g);
@@ -1072,18 +1101,11 @@ static int launch_gemm(const GemmArgs& g, int max_ctas, cudaStream_t stream) {
 template <int BN, int NS>
 static int launch_gemm_pair(const GemmArgs& g, int max_ctas, cudaStream_t stream) {
     using C = Cfg2<BN, NS>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        IPER_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_pair_kernel<BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             C::SMEM_BYTES));
-        attr_set = true;
-    }
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        IPER_CHECK_CUDA(cudaGetDevice(&dev));
-        IPER_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    static int have[MAX_DEVICES] = {};
+    DeviceSlot ds;
+    if (int rc = current_device(ds)) return rc;
+    if (int rc = ensure_smem(conv_gemm_pair_kernel<BN, NS>, have, ds.dev, C::SMEM_BYTES)) return rc;
+    const int num_sms = ds.sms;
     const int units = ((g.m_tiles + 1) / 2) * g.n_tiles * g.phases;
     int clusters = num_sms / 2;
     if (max_ctas > 0 && clusters > max_ctas / 2) clusters = max_ctas / 2 > 0 ? max_ctas / 2 : 1;
@@ -1103,17 +1125,11 @@ static int launch_gemm_halo(const GemmArgs& g, int max_ctas, cudaStream_t stream
     const int a_slot = 2 * g.hs.a_plane_bytes, b_slot = ((BN == 32 && NS == 2) ? 3 : 2) * ((BN == 64 ? 2 * BN : BN / 2) * 128);
     int smem = g.hs.na * a_slot + g.hs.nb * b_slot + 1024;
     if (smem < 120 * 1024) smem = 120 * 1024;            // one CTA per SM (TMEM allocation)
-    static int attr_smem = 0;
-    if (smem > attr_smem) {
-        IPER_CHECK_CUDA(cudaFuncSetAttribute(conv_halo_pair_kernel<BN, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
-    }
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        IPER_CHECK_CUDA(cudaGetDevice(&dev));
-        IPER_CHECK_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    static int have[MAX_DEVICES] = {};
+    DeviceSlot ds;
+    if (int rc = current_device(ds)) return rc;
+    if (int rc = ensure_smem(conv_halo_pair_kernel<BN, NS>, have, ds.dev, smem)) return rc;
+    const int num_sms = ds.sms;
     const int units = ((g.m_tiles + 1) / 2) * g.n_tiles;
     int clusters = num_sms / 2;
     if (max_ctas > 0 && clusters > max_ctas / 2) clusters = max_ctas / 2 > 0 ? max_ctas / 2 : 1;
@@ -1322,14 +1338,12 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
     g.total_tiles = g.m_groups * g.n_tiles * g.phases;
     if (halo) {
         // transposed conv in formats 1/2: phases that read the same view share one MMA group (IPER_CONVT_FUSE_N=0 disables)
-        const char* fuse_env = getenv("IPER_CONVT_FUSE_N");
-        const bool fuse_n = d->mode == IPER_CONVT_4S2 && fmt != 3 && !(fuse_env && atoi(fuse_env) == 0);
+        const bool fuse_n = d->mode == IPER_CONVT_4S2 && fmt != 3 && convt_fuse_n_enabled();
         build_halo_sched(g.hs, d->mode, d->Cin, d->rows, g.tw, g.th, fuse_n);
         g.hs.a_plane_bytes = g.hs.box_rows * 128;
         g.hs.k8 = (d->Cin % 128 == 0) ? 128 : 64;
         // heads in split fp16: N-concatenated weights (IPER_HEADS_CAT=0 keeps the three-MMA form for comparison)
-        const char* cat_env = getenv("IPER_HEADS_CAT");
-        g.hs.cat = (d->mode == IPER_CONV_ROW5 && d->block_n == 32 && fmt == 2 && !(cat_env && atoi(cat_env) == 0)) ? 1 : 0;
+        g.hs.cat = (d->mode == IPER_CONV_ROW5 && d->block_n == 32 && fmt == 2 && heads_cat_enabled()) ? 1 : 0;
         const int b_plane = (d->block_n == 64 ? 2 * d->block_n : d->block_n / 2) * 128;       // as B_PLANE in the kernel
         const int a_slot = 2 * g.hs.a_plane_bytes, b_slot = (d->block_n == 32 && fmt == 2 ? 3 : 2) * b_plane;
         g.hs.na = (3 * a_slot + 6 * b_slot <= HALO_SMEM_BUDGET) ? 3 : 2;

@@ -22,6 +22,15 @@ def shard_range(n_items, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def balanced_batch(n_frames, max_batch):
+    """Batch size <= max_batch that splits n_frames into equally sized batches (the last one at most nb-1 frames short):
+    a 38-frame shard runs as one batch of 38 instead of a 60-frame graph with 22 idle slots."""
+    if n_frames <= 0:
+        return max(1, max_batch)
+    nb = -(-n_frames // max(1, max_batch))
+    return -(-n_frames // nb)
+
+
 class FrameEngine:
     def __init__(self, generator, renderer, batch=16, use_graph=True, device=None):
         self.gen, self.render = generator, renderer
@@ -56,22 +65,27 @@ class FrameEngine:
         self.u8_d = torch.empty((B, S, S, 3), dtype=torch.uint8, device=dev)
         self._nv = nv
 
-    def _step(self):
+    def _step(self, n=None):
+        """One batch on the static buffers; n < B (ragged last batch, eager only) processes just the first n frames."""
         s = self.src
-        fi = self.render.frame_inputs(self.cams_d, self.verts_d, s["uv_img"], s["src_f2pts"])
+        n = self.B if n is None else n
+        fi = self.render.frame_inputs(self.cams_d[:n], self.verts_d[:n], s["uv_img"], s["src_f2pts"])
         img, mask, pred = self.gen.forward_tsf(fi["tsf_inputs"], s["enc"], s["res"], fi["Tst"], bg_img=s["bg"],
                                                return_pred=True)
-        ops.pred_to_u8(pred, out=self.u8_d)
+        ops.pred_to_u8(pred, out=self.u8_d[:n])
         self.last_pred = pred
 
     def _ensure_ready(self, nv):
         if self.src is None:
             raise RuntimeError("FrameEngine.set_source must be called first")
         if self._nv != nv:
-            self._alloc_static(nv)
+            with torch.cuda.stream(self.compute):
+                self._alloc_static(nv)
             self.graph = None
         if self.graph is None:
             from . import _lib
+            # the warm-up / capture below reads the source cache produced on the caller's stream (set_source)
+            self.compute.wait_stream(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(self.compute):
                 n0 = _lib.launch_count()
                 self._step()                      # warm-up (also triggers the one-time weight repack)
@@ -94,11 +108,16 @@ class FrameEngine:
             n = cams_d.shape[0]
             self.cams_d[:n].copy_(cams_d, non_blocking=True)
             self.verts_d[:n].copy_(verts_d, non_blocking=True)
-            if self.graph:
-                self.graph.replay()
-            else:
-                self._step()
+            self._run(n)
         return self.u8_d
+
+    def _run(self, n):
+        """Replay the B-frame graph for a full batch; a ragged batch (n < B) runs eagerly on exactly n frames — no stale
+        frame of the previous batch is re-rendered."""
+        if n == self.B and self.graph:
+            self.graph.replay()
+        else:
+            self._step(n)
 
     # ---- public API: host in, host out (the call a run_imitator user makes) -----------------------------------------
     @torch.no_grad()
@@ -106,6 +125,7 @@ class FrameEngine:
         """cams (T,3), verts (T,nv,3) host tensors (pinned for async copies) -> uint8 (T,S,S,3) BGR frames on the host."""
         T, nv = verts.shape[0], verts.shape[1]
         B, S = self.B, self.S
+        self.compute.wait_stream(torch.cuda.current_stream(self.dev))
         self._ensure_ready(nv)
         if out is None:
             out = torch.empty((T, S, S, 3), dtype=torch.uint8).pin_memory()
@@ -138,16 +158,13 @@ class FrameEngine:
             sv, sc, so = self._stage[i % 2]
             with torch.cuda.stream(self.compute):
                 self.compute.wait_event(self._in_ready[i % 2])
-                self.cams_d.copy_(sc, non_blocking=True)
-                self.verts_d.copy_(sv, non_blocking=True)
+                self.cams_d[:hi - lo].copy_(sc[:hi - lo], non_blocking=True)
+                self.verts_d[:hi - lo].copy_(sv[:hi - lo], non_blocking=True)
                 self._in_consumed[i % 2].record(self.compute)
-                if self.graph:
-                    self.graph.replay()
-                else:
-                    self._step()
+                self._run(hi - lo)
                 if i >= 2:
                     self.compute.wait_event(self._out_done[i % 2])     # D2H of batch i-2 has drained this slot
-                so.copy_(self.u8_d, non_blocking=True)
+                so[:hi - lo].copy_(self.u8_d[:hi - lo], non_blocking=True)
                 self._out_ready[i % 2].record(self.compute)
             if i + 1 < nb:
                 upload(i + 1)       # overlaps batch i's compute (slot (i+1)%2 was consumed by batch i-1's d2d copy)

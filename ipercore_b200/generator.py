@@ -318,6 +318,20 @@ class AttentionLWBGenerator(nn.Module):
             raise NotImplementedError("temporal attention inputs are not supported on the B200 path (temporal=false)")
         pk = self._pack()
         B, ns, S, _, _ = Tst.shape
+        n_src = src_enc_outs[0].shape[0]
+        if n_src != ns:
+            # reference semantics (attlwb_spade_resunet.py:208-252): source features are (bs*ns, ...) and item b attends
+            # to ITS OWN ns sources.  The kernels share one source set across the batch (the run_imitator case, bs=1
+            # source set -> B target frames), so per-item source sets run item by item.
+            if n_src != B * ns:
+                raise ValueError("forward_tsf: %d source feature maps for Tst of (bs=%d, ns=%d)" % (n_src, B, ns))
+            outs = []
+            for b in range(B):
+                sl = lambda lst: [t[b * ns:(b + 1) * ns].contiguous() for t in lst]
+                bg_b = bg_img if bg_img is None or bg_img.shape[0] == 1 else bg_img[b:b + 1]
+                outs.append(self.forward_tsf(tsf_inputs[b:b + 1], sl(src_enc_outs), sl(src_res_outs), Tst[b:b + 1],
+                                             bg_img=bg_b, return_pred=return_pred))
+            return tuple(torch.cat(parts, 0) for parts in zip(*outs))
         P, dev = self.P, tsf_inputs.device
         tsf_inputs = tsf_inputs.float().contiguous(); Tst = Tst.float().contiguous()
         nf = self.num_filters

@@ -257,6 +257,9 @@ def warp_attention(xt, kv, bias_v, T, out):
     B, h, w, C = xt.N, xt.H, xt.W, xt.C
     ns = kv.shape[0]
     assert kv.shape[-1] == 2 * C + 64 and kv.dtype == torch.float32 and kv.is_contiguous()
+    if tuple(T.shape) != (B, ns, h, w, 2) or tuple(kv.shape[1:3]) != (h, w):
+        raise ValueError("warp_attention: flow %s does not match (B=%d, ns=%d, h=%d, w=%d, 2) — the ns source maps are "
+                         "shared by all B frames" % (tuple(T.shape), B, ns, h, w))
     check(lib.iper_warp_attention(xt.ptr(), xt.P, xt.plane_stride, xt.pitch, xt.coff, kv.data_ptr(), bias_v.data_ptr(),
                                   T.data_ptr(), B, ns, h, w, C, out.ptr(), out.P, out.plane_stride, out.pitch, out.coff,
                                   _stream()), "warp_attention")

@@ -34,16 +34,30 @@ class SMPLHDevice(nn.Module):
             self.hands_mean = None
         assert self.posedirs.shape == ((self.nj - 1) * 9, self.nv * 3)
         self._shape_key, self._shape_cache = None, None
+        self._pinned = False
 
     @classmethod
     def from_reference(cls, smplh):
         """Build from an instantiated reference ``SMPLH`` / ``SMPL`` module (its registered buffers)."""
-        return cls(smplh.v_template.cpu().numpy(), smplh.shapedirs.cpu().numpy(), smplh.posedirs.cpu().numpy(),
-                   smplh.J_regressor.cpu().numpy(), smplh.parents.cpu().numpy(), smplh.lbs_weights.cpu().numpy(),
-                   getattr(smplh, "hands_mean", None))
+        n = lambda t: None if t is None else (t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t))
+        return cls(n(smplh.v_template), n(smplh.shapedirs), n(smplh.posedirs), n(smplh.J_regressor), n(smplh.parents),
+                   n(smplh.lbs_weights), n(getattr(smplh, "hands_mean", None)))
 
     # ---- one-time per shape ----------------------------------------------------------------------------------------
+    def pin_shape(self, betas, offsets=0):
+        """Compute the shape-dependent quantities ONCE (one host read of the 10 betas) and keep them for every following
+        forward()/get_details() call until unpin_shape(): run_imitator poses every target frame with the SOURCE shape
+        (imitator.py:248-256), so the per-batch path then has no host synchronisation at all."""
+        self._pinned = False
+        self._shape(betas.reshape(-1, self.nb)[0], offsets)
+        self._pinned = True
+
+    def unpin_shape(self):
+        self._pinned = False
+
     def _shape(self, betas, offsets):
+        if self._pinned:
+            return self._shape_cache
         dev = self.v_template.device
         off = None
         if torch.is_tensor(offsets) and offsets.numel() > 1:
@@ -84,7 +98,7 @@ class SMPLHDevice(nn.Module):
             theta = torch.cat([theta[:, :66], self.hands_mean[None].expand(N, -1)], dim=1)
         if theta.shape[1] != self.nj * 3:
             raise ValueError("pose has %d dims, model has %d joints" % (theta.shape[1], self.nj))
-        if beta.dim() == 2 and beta.shape[0] > 1 and not bool((beta == beta[0:1]).all()):
+        if not self._pinned and beta.dim() == 2 and beta.shape[0] > 1 and not bool((beta == beta[0:1]).all()):
             raise NotImplementedError("the device path shares one shape across the batch (run_imitator uses the source shape)")
         v_shaped, J, _ = self._shape(beta.reshape(-1, self.nb)[0], offsets)
         theta = theta.contiguous()

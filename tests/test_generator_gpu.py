@@ -38,7 +38,7 @@ def test_forward_src_tsf_matches_reference(S, precision, tol, golden_dir):
     e_mask = np.abs(mask.cpu().numpy() - g["tsf_mask"]).max()
     print("S=%d %s: max-abs err src_enc2 %.2e src_res5 %.2e tsf_img %.2e tsf_mask %.2e" % (S, precision, e_enc, e_res, e_img, e_mask))
     assert e_img <= tol and e_mask <= tol, (e_img, e_mask)
-    assert e_enc <= 10 * tol and e_res <= 10 * tol
+    assert e_enc <= tol and e_res <= tol, (e_enc, e_res)      # measured 2e-5 / 7e-5 in fp16x2
 
 
 def test_batched_frames_equal_single_frames(golden_dir):
