@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=8)
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of sampled frames of the last step")
+    ap.add_argument("--no-lib-baseline", action="store_true", help="skip the reference-generator-on-cuDNN side leg")
+    ap.add_argument("--no-png", action="store_true", help="skip the e2e pass that also writes the PNG files")
     ap.add_argument("--no-strong", action="store_true", help="N>1: skip the strong-scaling pass (one clip split over ranks)")
     return ap.parse_args()
 
@@ -159,26 +161,99 @@ def cpu_frames_per_sec(args, wl, n_frames, repeats=1, keep=None, frames=None):
 
 
 def run_reference(args):
+    """Reference arm: the reference's OWN classes on the host cores when the staged tree (oracle/_ref) is present —
+    iPERCore.models.imitator.Imitator.source_setup (untimed, once) + .inference over a bounded sample of target poses per
+    step — otherwise the oracle port.  No kernel, model or engine of ipercore_b200 is on this path."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    wl = make_workload(args, 0)
+    import torch
+    from oracle import ref_runtime as rr
+    cores = int(os.environ.get("IPER_CPU_THREADS", "0")) or host_cores()
+    torch.set_num_threads(cores)
     sample = 2 if args.size >= 512 else 4
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_frames_per_sec(args, wl, 1)
-    t0 = time.perf_counter()
-    _, cores, times = cpu_frames_per_sec(args, wl, sample, repeats=max(args.steps, 1))
+    t_start = time.perf_counter()
+    if rr.available():
+        import contextlib
+        import tempfile
+        work = tempfile.mkdtemp(prefix="iper_ref_")
+        opt, model = rr.make_opt(work, image_size=args.size, num_source=args.ns)
+        with contextlib.redirect_stdout(sys.stderr):      # the reference prints progress to stdout; ours is ONE json line
+            im = rr.build_imitator(opt, "cpu")
+        src_smpl, tgt = rr.synthetic_clip(model, sample, ns=args.ns)
+        im.source_setup(rr.write_source_images(work, args.ns, args.size), src_smpl, masks=None, bg_img=None, offsets=0,
+                        links_ids=None)
+        times = []
+        for it in range(max(args.warmup, 0) + max(args.steps, 1)):
+            t0 = time.perf_counter()
+            outs = im.inference(tgt, cam_strategy="smooth", output_dir="", prefix="pred_", verbose=False)
+            if it >= max(args.warmup, 0):
+                times.append(time.perf_counter() - t0)
+        assert len(outs) == sample and outs[0].shape == (3, args.size, args.size)
+        kind = "reference"
+        desc = ("the reference's own iPERCore Imitator.inference (staged tree oracle/_ref: SMPLH LBS, SMPLRenderer + "
+                "FlowComposition, AttentionLWBGenerator, torch fp32 on %d host threads; neural_renderer's rasteriser = host C "
+                "oracle; synthetic SMPLH pkl / checkpoint), %d target poses per step, source_setup untimed" % (cores, sample))
+    else:
+        wl = make_workload(args, 0)
+        for _ in range(max(args.warmup, 0) and 1):
+            cpu_frames_per_sec(args, wl, 1)
+        _, cores, times = cpu_frames_per_sec(args, wl, sample, repeats=max(args.steps, 1))
+        kind = "port"
+        desc = "oracle port (CPU restatement of raster+flow+AttLWB-SPADE forward_tsf, torch fp32), %d frames of the " \
+               "300-pose clip per step" % sample
     fps = sample * len(times) / sum(times)
-    desc = "oracle port (CPU restatement of raster+flow+AttLWB-SPADE forward_tsf, torch fp32), %d frames of the " \
-           "300-pose clip per step" % sample
     line = {"impl": "reference", "metric": "motion_imitation_frames_per_sec", "value": fps, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_block(args, 0),
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": desc},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t_start}
     print(json.dumps(line))
+
+
+def gpu_library_baseline(args, dev, wl, render, src_inputs, src_f2pts):
+    """The kernels to beat: the reference's own AttentionLWBGenerator.forward_tsf on torch/cuDNN on this GPU (staged tree),
+    in the reference's bs=1 per-frame loop (imitator.py:341-380) and batched, TF32 (torch default), bf16 autocast and strict
+    fp32.  Generator only — the reference's rasteriser extension is not available; untimed side leg, rank 0."""
+    import torch
+    from oracle import ref_runtime as rr
+    if not rr.available():
+        return {"unavailable": "reference tree not staged (oracle/_ref)"}
+    net = rr.reference_generator(0, dev)
+    S, ns = args.size, args.ns
+    t = lambda a: torch.from_numpy(a).to(dev)
+    fi = render.frame_inputs(t(wl["cams"][:16]), t(wl["verts"][:16]), t(wl["uv_img"]), src_f2pts)
+    out = {"what": "reference AttentionLWBGenerator.forward_tsf (torch %s / cuDNN), %dx%d, ns=%d, generator only" %
+                   (torch.__version__, S, S, ns)}
+    with torch.no_grad():
+        enc, res = net.forward_src(src_inputs, only_enc=True)
+
+        def loop(bs, iters, autocast):
+            e = [x.repeat(bs, 1, 1, 1) for x in enc]; r = [x.repeat(bs, 1, 1, 1) for x in res]
+            ti, Ts = fi["tsf_inputs"][:bs].contiguous(), fi["Tst"][:bs].contiguous()
+            def once():
+                if autocast:
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        return net.forward_tsf(ti, e, r, Ts)
+                return net.forward_tsf(ti, e, r, Ts)
+            for _ in range(3):
+                once()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(dev); e0.record()
+            for _ in range(iters):
+                once()
+            e1.record(); torch.cuda.synchronize(dev)
+            return bs * iters / (e0.elapsed_time(e1) * 1e-3)
+
+        for name, tf32, ac in (("tf32", True, False), ("bf16_autocast", True, True), ("fp32", False, False)):
+            torch.backends.cudnn.allow_tf32 = tf32; torch.backends.cuda.matmul.allow_tf32 = tf32
+            out[name] = {"bs1_loop_fps": loop(1, 20, ac), "bs16_fps": loop(16, 3, ac)}
+        torch.backends.cudnn.allow_tf32 = True
+    del net
+    torch.cuda.empty_cache()
+    return out
 
 
 def config_block(args, launches):
@@ -325,6 +400,32 @@ def main():
         if not parity["ok"]:
             sys.stderr.write("bench.py: PARITY FAILED %s\n" % json.dumps(parity))
 
+    # ---- output stage: the same e2e pass with PNG files written like Imitator.inference does (pred_%08d.png), encodes
+    #      overlapped with the next batch (engine.synthesize_stream + patch.FrameWriter); rank 0, one pass ----------------
+    e2e_png = None
+    if rank == 0 and world == 1 and not args.no_png:
+        import shutil
+        import tempfile
+        from ipercore_b200.patch import FrameWriter
+        out_dir = tempfile.mkdtemp(prefix="iper_png_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            def feed(lo, hi):
+                return cams_h[lo:hi].to(dev, non_blocking=True), verts_h[lo:hi].to(dev, non_blocking=True)
+            for rep in range(2):                  # first pass warms the pool / page cache
+                writer = FrameWriter(T, out_dir, "pred_", workers=host_cores())
+                torch.cuda.synchronize(dev)
+                w0 = time.perf_counter()
+                eng.synthesize_stream(T, feed, writer.sink)
+                paths = writer.close()
+                torch.cuda.synchronize(dev)
+                w_png = time.perf_counter() - w0
+            nbytes = sum(os.path.getsize(p_) for p_ in paths)
+            e2e_png = {"value": T / w_png, "unit": "frames/s", "frames": T, "workers": host_cores(),
+                       "png_bytes_per_frame": nbytes // T, "timing": "host wall clock around one whole clip incl. the last file",
+                       "files": "pred_%08d.png (cv2.imwrite, uint8 BGR), " + ("tmpfs" if out_dir.startswith("/dev/shm") else "tmp dir")}
+        finally:
+            shutil.rmtree(out_dir, ignore_errors=True)
+
     # ---- strong scaling: ONE clip of T frames split over the ranks (engine.shard_range), batch sized to the shard -------
     strong = None
     if world > 1 and not args.no_strong:
@@ -353,6 +454,13 @@ def main():
         strong = {"value": T * args.steps / (ms_s * 1e-3), "unit": "frames/s", "frames_total": T, "frames_rank0": n_s,
                   "batch": Bs, "ms_per_step": ms_s / args.steps,
                   "note": "one %d-frame clip split contiguously over %d ranks, no collective; max over ranks" % (T, world)}
+
+    lib_base = None
+    if rank == 0 and world == 1 and not args.no_lib_baseline:
+        try:
+            lib_base = gpu_library_baseline(args, dev, wl, render, src_inputs, src_f2pts)
+        except Exception as exc:   # a side leg must never take the bench line down
+            lib_base = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
 
     # ---- roofline of the conv stack: CUDA events around every conv_gemm launch of one (un-graphed) batch ----
     roof = None
@@ -450,7 +558,8 @@ def main():
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(cams_h.numel() * 4 + verts_h.numel() * 4),
                         "d2h_bytes_per_step": int(out_h.numel()), "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                "parity": parity, "strong": strong,
+                "parity": parity, "strong": strong, "e2e_png": e2e_png,
+                "gpu_library_baseline": lib_base,
                 "wall_s_timed_region": wall}
         print(json.dumps(line))
     if world > 1:

@@ -119,6 +119,57 @@ class FrameEngine:
         else:
             self._step(n)
 
+    # ---- streaming API: batches flow feed -> synthesize -> pinned ring -> sink, all three overlapped ------------------
+    @torch.no_grad()
+    def synthesize_stream(self, T, feed, sink, ring=3):
+        """Synthesize T frames batch by batch with the OUTPUT STAGE overlapped.
+
+        feed(lo, hi) -> (cams (n,3), verts (n,nv,3)) device tensors; it is called inside ``torch.cuda.stream(self.compute)``
+            so whatever it launches (device LBS, an H2D copy from pinned memory) is ordered before the batch's kernels.
+        sink(lo, hi, frames) is called on the calling thread as soon as the batch's uint8 BGR frames (n,S,S,3) are in
+            pinned host memory — while the GPU already runs the next batch.  It may return futures (e.g. PNG encodes on a
+            thread pool) that still read `frames`; the ring slot is not reused before they are done.
+        Host memory is a bounded ring of `ring` pinned (B,S,S,3) buffers, not T frames."""
+        B, S = self.B, self.S
+        ring = max(2, int(ring))
+        if not hasattr(self, "_ring") or len(self._ring) != ring or self._ring[0].shape[0] != B:
+            self._ring = [torch.empty((B, S, S, 3), dtype=torch.uint8).pin_memory() for _ in range(ring)]
+        done = [torch.cuda.Event() for _ in range(ring)]
+        busy = [None] * ring                    # futures of the sink still reading slot r
+        cur = torch.cuda.current_stream(self.dev)
+        self.compute.wait_stream(cur)
+        nb = (T + B - 1) // B
+
+        def drain(i):                           # batch i's frames are on the host: hand them to the sink
+            lo, hi = i * B, min((i + 1) * B, T)
+            r = i % ring
+            done[r].synchronize()
+            busy[r] = sink(lo, hi, self._ring[r][:hi - lo])
+
+        for i in range(nb):
+            lo, hi = i * B, min((i + 1) * B, T)
+            r = i % ring
+            if busy[r]:
+                for f in busy[r]:
+                    f.result()
+                busy[r] = None
+            with torch.cuda.stream(self.compute):
+                cams_d, verts_d = feed(lo, hi)
+                self._ensure_ready(verts_d.shape[1])
+                self.cams_d[:hi - lo].copy_(cams_d, non_blocking=True)
+                self.verts_d[:hi - lo].copy_(verts_d, non_blocking=True)
+                self._run(hi - lo)
+                self._ring[r][:hi - lo].copy_(self.u8_d[:hi - lo], non_blocking=True)
+                done[r].record(self.compute)
+            if i >= 1:
+                drain(i - 1)                    # overlaps batch i on the GPU
+        if nb:
+            drain(nb - 1)
+        for fs in busy:
+            for f in fs or ():
+                f.result()
+        cur.wait_stream(self.compute)
+
     # ---- public API: host in, host out (the call a run_imitator user makes) -----------------------------------------
     @torch.no_grad()
     def synthesize(self, cams, verts, out=None):

@@ -110,31 +110,72 @@ def install(precision="fp16x2", batch=16, patch_inference=True, device_lbs=True)
     _INSTALLED = True
 
 
+def _source_key(src):
+    """Identity of the per-source cache the captured graph reads: same tensors (and versions) -> the graph is reused."""
+    enc, res = src["feats"]
+    ts = list(enc) + list(res) + [src["uv_img"], src["bg"], src["f2pts"]]
+    return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts)
+
+
+class FrameWriter:
+    """Output stage of Imitator.inference (imitator.py:365-379 -> cv_utils.save_cv2_img, cv_utils.py:100-116): PNG encodes
+    run on a thread pool (cv2.imwrite releases the GIL) batch by batch as the frames land in pinned memory, instead of
+    after the whole clip.  Without an output directory the reference returns float CHW arrays in [-1, 1]."""
+
+    def __init__(self, T, output_dir, prefix, workers=None):
+        import cv2
+        from concurrent.futures import ThreadPoolExecutor
+        self.cv2, self.dir, self.T = cv2, output_dir, T
+        self.paths = [os.path.join(output_dir, prefix + "{:0>8}.png".format(t)) for t in range(T)] if output_dir else None
+        self.arrays = None if output_dir else [None] * T
+        self.pool = ThreadPoolExecutor(max_workers=workers or min(16, os.cpu_count() or 4))
+
+    def _one(self, t, frame):
+        if self.paths is not None:
+            if not self.cv2.imwrite(self.paths[t], frame):
+                raise IOError("cv2.imwrite failed for %s" % self.paths[t])
+        else:
+            f = frame[:, :, ::-1].astype(np.float32) / 255.0 * 2.0 - 1.0
+            self.arrays[t] = np.ascontiguousarray(f.transpose(2, 0, 1))
+
+    def sink(self, lo, hi, frames):
+        arr = frames.numpy()                   # uint8 BGR HWC (cv_utils.save_cv2_img semantics), pinned ring slot
+        return [self.pool.submit(self._one, lo + k, arr[k]) for k in range(hi - lo)]
+
+    def close(self):
+        self.pool.shutdown(wait=True)
+        return self.paths if self.paths is not None else self.arrays
+
+
 @torch.no_grad()
 def batched_inference(imitator, tgt_smpls, cam_strategy="smooth", output_dir="", prefix="pred_", batch=16):
     """Imitator.inference (models/imitator.py:327-382) with the bs=1 loop replaced by the batched engine.
 
     Per-sequence host pre-pass exactly as upstream (:337-339, :298-305): stabilise, first_cam, cam swap; the SMPL body
     model produces the vertices in chunks of `batch` frames — on the device LBS kernels (ipercore_b200.smpl, built from
-    the reference body model's buffers) unless install(device_lbs=False) or the model uses hand PCA; frames then go through
-    FrameEngine and are written with the reference's file names.  Returns the list of paths (or of CHW float arrays when output_dir is empty)."""
+    the reference body model's buffers) unless install(device_lbs=False) or the model uses hand PCA.  Every batch is
+    issued on the engine's stream (cam swap -> LBS -> raster -> generator -> uint8 -> D2H into a bounded pinned ring) and
+    its PNG files are encoded on a thread pool while the GPU runs the next batch.  The CUDA graph is captured once per
+    source set, not per call.  Returns the list of paths (or of CHW float arrays when output_dir is empty)."""
     from .engine import FrameEngine
-    import cv2
     dev, opt, src = imitator.device, imitator._opt, imitator.src_info
-    tgt = torch.tensor(tgt_smpls).float().to(dev)
+    tgt = torch.as_tensor(np.asarray(tgt_smpls), dtype=torch.float32).to(dev)
     if cam_strategy == "smooth":
         tgt = imitator.weak_cam_swapper.stabilize(tgt)
     imitator.first_cam = tgt[0:1, 0:3].clone() if cam_strategy == "smooth" else None
     eng = getattr(imitator, "_iper_engine", None)
-    if eng is None or eng.B != batch:
+    if eng is None or eng.B != batch or eng.gen is not imitator.generator:
         eng = FrameEngine(imitator.generator, _EngineRenderer(imitator.flow_comp.render), batch=batch, device=dev)
+        eng._src_key = None
         imitator._iper_engine = eng
-    eng.gen = imitator.generator
-    enc, res = src["feats"]
-    eng.src = dict(enc=enc, res=res, uv_img=src["uv_img"].float().contiguous(),
-                   bg=src["bg"].float().reshape(1, 3, opt.image_size, opt.image_size).contiguous(),
-                   src_f2pts=src["f2pts"].float().contiguous())
-    eng.graph = None
+    key = _source_key(src)
+    if eng._src_key != key:                       # new source set: new cache, re-capture on first use
+        enc, res = src["feats"]
+        eng.src = dict(enc=enc, res=res, uv_img=src["uv_img"].float().contiguous(),
+                       bg=src["bg"].float().reshape(1, 3, opt.image_size, opt.image_size).contiguous(),
+                       src_f2pts=src["f2pts"].float().contiguous())
+        eng.graph = None
+        eng._src_key = key
     from .smpl import SMPLHDevice
     body = imitator.body_rec
     if (_DEVICE_LBS and not isinstance(body, SMPLHDevice) and not getattr(body, "use_pca", False)
@@ -142,36 +183,29 @@ def batched_inference(imitator, tgt_smpls, cam_strategy="smooth", output_dir="",
         if getattr(imitator, "_iper_smpl", None) is None:
             imitator._iper_smpl = SMPLHDevice.from_reference(body).to(dev)
         body = imitator._iper_smpl
-    T, S = tgt.shape[0], opt.image_size
-    frames = torch.empty((T, S, S, 3), dtype=torch.uint8).pin_memory()
-    cur = torch.cuda.current_stream(dev)
-    for lo in range(0, T, batch):
-        t = tgt[lo:lo + batch]
-        n = t.shape[0]
-        cam = imitator.weak_cam_swapper.cam_swap(src["cam"][0:1].expand(n, -1), t[:, 0:3],
-                                                 imitator.first_cam.expand(n, -1) if imitator.first_cam is not None else None,
-                                                 cam_strategy)
-        ref_smpl = torch.cat([cam, t[:, 3:-10], src["shape"][0:1].expand(n, -1)], dim=1)
-        eng.compute.wait_stream(cur)
-        with torch.cuda.stream(eng.compute):
-            # everything of a batch is issued on the engine's stream (LBS -> raster -> generator -> u8 -> D2H), so the
-            # vertices never leave the device and no tensor crosses streams
-            info = body.get_details(ref_smpl, src["offsets"], links_ids=src["links_ids"])
-            u8 = eng.run_batch_device(info["cam"].float().contiguous(), info["verts"].float().contiguous())
-            frames[lo:lo + n].copy_(u8[:n], non_blocking=True)
-    eng.compute.synchronize()
-    outputs = []
-    if output_dir:
-        # PNG encode off the GPU's critical path: a small thread pool (cv2.imwrite releases the GIL)
-        from concurrent.futures import ThreadPoolExecutor
-        paths = [os.path.join(output_dir, prefix + "{:0>8}.png".format(t)) for t in range(T)]
-        with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 4)) as pool:
-            list(pool.map(lambda a: cv2.imwrite(a[0], a[1]), ((paths[t], frames[t].numpy()) for t in range(T))))
-        outputs = paths                                      # frames are uint8 BGR HWC (cv_utils.save_cv2_img semantics)
-    else:
-        for t in range(T):
-            f = frames[t].numpy()[:, :, ::-1].astype(np.float32) / 255.0 * 2.0 - 1.0
-            outputs.append(np.ascontiguousarray(f.transpose(2, 0, 1)))
+    pinned = isinstance(body, SMPLHDevice)
+    if pinned:                                    # every target frame is posed with the SOURCE shape (imitator.py:248-256)
+        body.pin_shape(src["shape"][0], src["offsets"])
+    T = tgt.shape[0]
+    src_cam, src_shape, first_cam = src["cam"][0:1], src["shape"][0:1], imitator.first_cam
+
+    def feed(lo, hi):
+        # runs on the engine's stream: every tensor of the batch is created, consumed and freed on that one stream
+        t = tgt[lo:hi]
+        n = hi - lo
+        cam = imitator.weak_cam_swapper.cam_swap(src_cam.expand(n, -1), t[:, 0:3],
+                                                 first_cam.expand(n, -1) if first_cam is not None else None, cam_strategy)
+        ref_smpl = torch.cat([cam, t[:, 3:-10], src_shape.expand(n, -1)], dim=1)
+        info = body.get_details(ref_smpl, src["offsets"], links_ids=src["links_ids"])
+        return info["cam"].float().contiguous(), info["verts"].float().contiguous()
+
+    writer = FrameWriter(T, output_dir, prefix)
+    try:
+        eng.synthesize_stream(T, feed, writer.sink)
+    finally:
+        outputs = writer.close()
+        if pinned:
+            body.unpin_shape()
     return outputs
 
 
