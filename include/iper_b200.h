@@ -34,6 +34,13 @@ int iper_abi_version(void);
  * owns it so the library never allocates — it may be reused by the next call on the same stream.
  * ---------------------------------------------------------------------------------------------------------- */
 size_t iper_raster_workspace_bytes(int B, int nf, int from_verts);
+/* Rounding model of the rasteriser arithmetic, process-wide.  The upstream extension is built by nvcc, whose default
+ * -fmad=true may contract a*b+c; which model the installed fork follows can only be checked against a real build of it:
+ *   0 (default) every float op rounded separately — bit-exact with oracle/raster_ref.c
+ *   1           fused where nvcc would contract upstream's source — bit-exact with the oracle's -DORACLE_FMA variant
+ * Also selectable by the environment variable IPER_RASTER_FMA=1 (read at the first launch). */
+int iper_raster_set_contraction(int mode);
+int iper_raster_get_contraction(void);
 int iper_rasterize_faces(const float* faces, int B, int nf, int S, float near_, float far_, int32_t* fim, float* wim,
                          void* workspace, size_t workspace_bytes, iper_stream_t stream);
 
@@ -57,6 +64,15 @@ int iper_raster_frames(const float* verts, const float* cams, const int32_t* fac
  * f2pts[s] (f2pts_per_item=0, shape (nsrc,nf,3,2)) or f2pts[b] (f2pts_per_item=1, nsrc must be 1). */
 int iper_flow_from_fim_wim(const float* f2pts, int f2pts_per_item, const int32_t* fim, const float* wim, int nb,
                            int nsrc, int nf, int S, float* T, iper_stream_t stream);
+
+/* SMPLRenderer.get_vis_f2pts (nmr.py:639-681): faces that appear in fim — except the smallest unique value of the map, which
+ * `fim.unique()[1:]` drops: the background -1 when present, else the lowest visible face id — plus their top_k UV-nearest
+ * neighbours (face_k_nearest (nf, top_k) int64, the reference buffer) keep their corner coordinates, all other faces become -2.
+ * f2pts / out (B, nf, elems_per_face) f32 (elems 6 = (3,2) or 9 = (3,3)); fim (B,S,S) i32.  workspace: byte flags,
+ * iper_vis_f2pts_workspace_bytes(B, nf).  No host synchronisation (the reference sorts twice per item with torch.unique). */
+size_t iper_vis_f2pts_workspace_bytes(int B, int nf);
+int iper_vis_f2pts(const float* f2pts, int elems_per_face, const int32_t* fim, const int64_t* face_k_nearest, int top_k, int B,
+                   int nf, int S, float* out, void* workspace, size_t workspace_bytes, iper_stream_t stream);
 
 /* SMPLRenderer.encode_fim (nmr.py:390-401): out = map_fn[fim] (fim == -1 -> row nf); transpose -> (nb,ch,S,S). */
 int iper_encode_fim(const int32_t* fim, const float* map_fn, int nb, int nf, int ch, int S, int transpose, float* out,

@@ -46,6 +46,7 @@ SIGNATURES = {
                            c_void_p, c_void_p, c_size_t, c_void_p],
     "iper_flow_from_fim_wim": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "iper_encode_fim": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "iper_vis_f2pts": [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
     "iper_flow_resize": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "iper_conv_gemm": [ctypes.POINTER(ConvGemmDesc), c_void_p],
     "iper_conv_direct": [ctypes.POINTER(ConvGemmDesc), c_void_p, c_int, c_void_p],
@@ -83,6 +84,12 @@ def _load():
         fn.restype = c_int
     lib.iper_conv_halo_plan.argtypes = [c_int, c_int, c_int, c_int, c_void_p, c_int]
     lib.iper_conv_halo_plan.restype = c_int
+    lib.iper_raster_set_contraction.argtypes = [c_int]
+    lib.iper_raster_set_contraction.restype = c_int
+    lib.iper_raster_get_contraction.argtypes = []
+    lib.iper_raster_get_contraction.restype = c_int
+    lib.iper_vis_f2pts_workspace_bytes.argtypes = [c_int, c_int]
+    lib.iper_vis_f2pts_workspace_bytes.restype = c_size_t
     lib.iper_raster_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.iper_raster_workspace_bytes.restype = c_size_t
     lib.iper_last_error.argtypes = []

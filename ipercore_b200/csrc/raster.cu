@@ -23,6 +23,8 @@
 // Parity contract: every float operation below that feeds the inside test, the weights or the depth is an
 // explicitly rounded binary32 op (__fmul_rn/__fadd_rn/__fdiv_rn — never contracted into FMA) in the same order
 // as oracle/raster_ref.c, including the two places where upstream's double literals promote to double.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "iper_b200.h"
 
@@ -45,32 +47,48 @@ IPER_DEVINL bool is_backface(const float* f) {
            __fmul_rn(__fsub_rn(f[4], f[1]), __fsub_rn(f[6], f[0]));
 }
 
+// Rounding model of the contraction-sensitive expressions (see oracle/raster_ref.c): `fma` = 0 rounds every product
+// (source-level IEEE semantics, the default), `fma` = 1 fuses exactly where nvcc -fmad=true would contract upstream's
+// source (the oracle's -DORACLE_FMA variant).  Selected per process by iper_raster_set_contraction / IPER_RASTER_FMA.
+IPER_DEVINL float mul_add(float a, float b, float c, int fma) {            // a*b + c
+    return fma ? __fmaf_rn(a, b, c) : __fadd_rn(__fmul_rn(a, b), c);
+}
+IPER_DEVINL float mul_sub2(float a, float b, float c, float d, int fma) {  // a*b - c*d
+    return fma ? __fmaf_rn(a, b, -__fmul_rn(c, d)) : __fsub_rn(__fmul_rn(a, b), __fmul_rn(c, d));
+}
+
 // upstream kernel 1: pixel-space corners and the adjugate/determinant inverse
-IPER_DEVINL void face_inverse(const float* f, int is, float* inv) {
+IPER_DEVINL void face_inverse(const float* f, int is, float* inv, int fma) {
     float p[3][2];
     const float fis = (float)is;
 #pragma unroll
     for (int n = 0; n < 3; n++)
 #pragma unroll
         for (int d = 0; d < 2; d++) {
-            float t = __fmul_rn(f[3 * n + d], fis);
-            t = __fadd_rn(t, fis);
+            float t = mul_add(f[3 * n + d], fis, fis, fma);
             t = __fsub_rn(t, 1.0f);
             p[n][d] = __fmul_rn(0.5f, t);  // exact
         }
     float a[9];
     a[0] = __fsub_rn(p[1][1], p[2][1]);
     a[1] = __fsub_rn(p[2][0], p[1][0]);
-    a[2] = __fsub_rn(__fmul_rn(p[1][0], p[2][1]), __fmul_rn(p[2][0], p[1][1]));
+    a[2] = mul_sub2(p[1][0], p[2][1], p[2][0], p[1][1], fma);
     a[3] = __fsub_rn(p[2][1], p[0][1]);
     a[4] = __fsub_rn(p[0][0], p[2][0]);
-    a[5] = __fsub_rn(__fmul_rn(p[2][0], p[0][1]), __fmul_rn(p[0][0], p[2][1]));
+    a[5] = mul_sub2(p[2][0], p[0][1], p[0][0], p[2][1], fma);
     a[6] = __fsub_rn(p[0][1], p[1][1]);
     a[7] = __fsub_rn(p[1][0], p[0][0]);
-    a[8] = __fsub_rn(__fmul_rn(p[0][0], p[1][1]), __fmul_rn(p[1][0], p[0][1]));
-    float den = __fmul_rn(p[2][0], __fsub_rn(p[0][1], p[1][1]));
-    den = __fadd_rn(den, __fmul_rn(p[0][0], __fsub_rn(p[1][1], p[2][1])));
-    den = __fadd_rn(den, __fmul_rn(p[1][0], __fsub_rn(p[2][1], p[0][1])));
+    a[8] = mul_sub2(p[0][0], p[1][1], p[1][0], p[0][1], fma);
+    float den;
+    if (fma) {      // m1 + m2 + m3 -> fma(x3, y3, fma(x1, y1, x2*y2))
+        den = __fmul_rn(p[0][0], __fsub_rn(p[1][1], p[2][1]));
+        den = __fmaf_rn(p[2][0], __fsub_rn(p[0][1], p[1][1]), den);
+        den = __fmaf_rn(p[1][0], __fsub_rn(p[2][1], p[0][1]), den);
+    } else {
+        den = __fmul_rn(p[2][0], __fsub_rn(p[0][1], p[1][1]));
+        den = __fadd_rn(den, __fmul_rn(p[0][0], __fsub_rn(p[1][1], p[2][1])));
+        den = __fadd_rn(den, __fmul_rn(p[1][0], __fsub_rn(p[2][1], p[0][1])));
+    }
 #pragma unroll
     for (int k = 0; k < 9; k++) inv[k] = __fdiv_rn(a[k], den);
 }
@@ -92,13 +110,12 @@ IPER_DEVINL bool inside_face(const float* f, float xp, float yp) {
 
 // clamped + renormalised barycentric weights and perspective-correct depth; returns false when rejected
 IPER_DEVINL bool weights_depth(const float* f, const float* inv, int xi, int yi, float near_, float far_, float* w,
-                               float& zp) {
+                               float& zp, int fma) {
     const float fx = (float)xi, fy = (float)yi;
     float ws = 0.f;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        float t = __fmul_rn(inv[3 * k + 0], fx);
-        t = __fadd_rn(t, __fmul_rn(inv[3 * k + 1], fy));
+        float t = mul_add(inv[3 * k + 0], fx, __fmul_rn(inv[3 * k + 1], fy), fma);
         t = __fadd_rn(t, inv[3 * k + 2]);
         double d = fmax((double)t, 0.0);  // min(max(w, 0.), 1.) — NaN -> 0 like upstream's fmax/fmin
         d = fmin(d, 1.0);
@@ -149,6 +166,7 @@ struct RasterArgs {
     const float* face_verts;  // (B, nf, 3, 3): given (seam B1) or written by the setup kernel into the workspace
     const uint32_t* bins;     // (B, nf) packed tile ranges from the setup kernel (0xFFFFFFFF = culled)
     int B, nv, nf, S;
+    int fma;               // rounding model of the rasteriser arithmetic (0: every op rounded, 1: nvcc -fmad contraction)
     float near_, far_, eye_z;
     // outputs (any may be null)
     int32_t* fim;  // (B,S,S)
@@ -294,14 +312,14 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(const RasterArgs
             int x0, x1, y0, y1;
             face_range(g, x0, x1, y0, y1);
             float inv[9];
-            face_inverse(g.v, S, inv);
+            face_inverse(g.v, S, inv, a.fma);
             const int bw = x1 - x0 + 1, npx = bw * (y1 - y0 + 1);
             for (int i = lane; i < npx; i += 32) {
                 const int xi = x0 + i % bw, yi = y0 + i / bw;
                 const float xp = s_xp[xi - tx0], yp = s_yp[(S - 1 - yi) - r0];
                 if (!inside_face(g.v, xp, yp)) continue;
                 float w[3], zp;
-                if (!weights_depth(g.v, inv, xi, yi, a.near_, a.far_, w, zp)) continue;
+                if (!weights_depth(g.v, inv, xi, yi, a.near_, a.far_, w, zp, a.fma)) continue;
                 const unsigned long long key = ((unsigned long long)__float_as_uint(zp) << 32) | (unsigned)f;
                 atomicMin(&zbuf[(S - 1 - yi - r0) * TILE_W + (xi - tx0)], key);
             }
@@ -322,8 +340,8 @@ __global__ void __launch_bounds__(RASTER_THREADS) raster_kernel(const RasterArgs
             FaceGeom g;
             load_face(fn, g);
             float inv[9], zp;
-            face_inverse(g.v, S, inv);
-            weights_depth(g.v, inv, xi, S - 1 - row, a.near_, a.far_, w, zp);
+            face_inverse(g.v, S, inv, a.fma);
+            weights_depth(g.v, inv, xi, S - 1 - row, a.near_, a.far_, w, zp, a.fma);
         }
         const size_t pix = (size_t)row * S + xi;
         if (a.fim) a.fim[(size_t)b * SS + pix] = fn;
@@ -424,13 +442,60 @@ __global__ void flow_resize_kernel(const float* __restrict__ T, int n, int S, in
     }
 }
 
+// ---- SMPLRenderer.get_vis_f2pts (nmr.py:639-681) ---------------------------------------------------------------------
+// faces visible in fim, minus the SMALLEST unique value of the map (`fim.unique()[1:]`: the background -1 when present,
+// otherwise the lowest visible face id), together with their top_k UV-nearest neighbours keep their corner coordinates;
+// every other face is set to -2.  Three passes over byte flags instead of two torch.unique sorts with host syncs.
+__global__ void vis_mark_kernel(const int32_t* __restrict__ fim, int nf, size_t SS, unsigned char* __restrict__ vis,
+                                int* __restrict__ min_id) {
+    const int b = blockIdx.y;
+    int local_min = 0x7fffffff;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < SS; i += (size_t)gridDim.x * blockDim.x) {
+        const int fn = __ldg(fim + (size_t)b * SS + i);
+        local_min = min(local_min, fn);
+        if (fn >= 0 && fn < nf) vis[(size_t)b * nf + fn] = 1;
+    }
+    for (int o = 16; o > 0; o >>= 1) local_min = min(local_min, __shfl_xor_sync(0xffffffffu, local_min, o));
+    if ((threadIdx.x & 31) == 0) atomicMin(min_id + b, local_min);
+}
+__global__ void vis_spread_kernel(const unsigned char* __restrict__ vis, const int* __restrict__ min_id,
+                                  const long long* __restrict__ nearest, int top_k, int nf, unsigned char* __restrict__ keep) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (f >= nf || !vis[(size_t)b * nf + f] || f == min_id[b]) return;
+    for (int k = 0; k < top_k; k++) {
+        const long long nb = __ldg(nearest + (size_t)f * top_k + k);
+        if (nb >= 0 && nb < nf) keep[(size_t)b * nf + nb] = 1;
+    }
+}
+__global__ void vis_apply_kernel(const float* __restrict__ f2pts, const unsigned char* __restrict__ keep, int elems, size_t total,
+                                 float* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = keep[i / elems] ? f2pts[i] : -2.0f;
+}
+
+static size_t vis_ws_bytes(int B, int nf) {
+    // min_id (B) ints, padded to 16 bytes, then vis (B, nf) and keep (B, nf) byte flags
+    return (((size_t)B * sizeof(int) + 15) & ~(size_t)15) + 2 * (size_t)B * nf;
+}
+
 static size_t raster_ws_bytes(int B, int nf, bool from_verts) {
     // bins (B, nf) u32, then — when the corners are computed here — face corners (B, nf, 9) f32
     return (size_t)B * nf * sizeof(uint32_t) + (from_verts ? (size_t)B * nf * 9 * sizeof(float) : 0);
 }
 
+// process-wide rounding model: -1 = not chosen yet (first launch reads IPER_RASTER_FMA, default 0)
+static int g_raster_fma = -1;
+static int raster_fma_mode() {
+    if (g_raster_fma < 0) {
+        const char* v = getenv("IPER_RASTER_FMA");
+        g_raster_fma = (v && atoi(v) != 0) ? 1 : 0;
+    }
+    return g_raster_fma;
+}
+
 static int launch_raster(RasterArgs a, bool from_verts, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     const int S = a.S;
+    a.fma = raster_fma_mode();
     const int tiles_x = (S + TILE_W - 1) / TILE_W, tiles_y = (S + TILE_H - 1) / TILE_H;
     IPER_REQUIRE(tiles_x <= 256 && tiles_y <= 256, "rasteriser: image size %d exceeds the 8-bit tile index range", S);
     IPER_REQUIRE(a.nf <= (1 << 24), "rasteriser: too many faces (%d)", a.nf);
@@ -457,6 +522,45 @@ static int launch_raster(RasterArgs a, bool from_verts, void* workspace, size_t 
 }  // namespace iper
 
 using namespace iper;
+
+extern "C" size_t iper_vis_f2pts_workspace_bytes(int B, int nf) {
+    if (B <= 0 || nf <= 0) return 0;
+    return vis_ws_bytes(B, nf);
+}
+
+extern "C" int iper_vis_f2pts(const float* f2pts, int elems_per_face, const int32_t* fim, const int64_t* face_k_nearest,
+                              int top_k, int B, int nf, int S, float* out, void* workspace, size_t workspace_bytes,
+                              iper_stream_t stream) {
+    IPER_REQUIRE(B >= 0 && nf > 0 && S > 0 && top_k > 0 && elems_per_face > 0, "iper_vis_f2pts: bad sizes");
+    if (B == 0) return 0;
+    IPER_REQUIRE(f2pts && fim && face_k_nearest && out, "iper_vis_f2pts: null pointer");
+    IPER_REQUIRE(workspace && workspace_bytes >= vis_ws_bytes(B, nf), "iper_vis_f2pts: workspace of %zu bytes needed, got %zu",
+                 vis_ws_bytes(B, nf), workspace_bytes);
+    cudaStream_t st = (cudaStream_t)stream;
+    int* min_id = reinterpret_cast<int*>(workspace);
+    const size_t head = ((size_t)B * sizeof(int) + 15) & ~(size_t)15;
+    unsigned char* vis = reinterpret_cast<unsigned char*>(workspace) + head;
+    unsigned char* keep = vis + (size_t)B * nf;
+    IPER_CHECK_CUDA(cudaMemsetAsync(min_id, 0x7f, head, st));                    // 0x7f7f7f7f: larger than any face id
+    IPER_CHECK_CUDA(cudaMemsetAsync(vis, 0, 2 * (size_t)B * nf, st));
+    const size_t SS = (size_t)S * S;
+    vis_mark_kernel<<<dim3((unsigned)min((SS + 255) / 256, (size_t)64), B), 256, 0, st>>>(fim, nf, SS, vis, min_id);
+    IPER_CHECK_CUDA(cudaGetLastError());
+    vis_spread_kernel<<<dim3((nf + 255) / 256, B), 256, 0, st>>>(vis, min_id, reinterpret_cast<const long long*>(face_k_nearest),
+                                                                top_k, nf, keep);
+    IPER_CHECK_CUDA(cudaGetLastError());
+    const size_t total = (size_t)B * nf * elems_per_face;
+    vis_apply_kernel<<<(unsigned)min((total + 255) / 256, (size_t)148 * 16), 256, 0, st>>>(f2pts, keep, elems_per_face, total, out);
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int iper_raster_set_contraction(int mode) {
+    IPER_REQUIRE(mode == 0 || mode == 1, "iper_raster_set_contraction: mode %d not in {0 = every op rounded, 1 = fmad model}", mode);
+    g_raster_fma = mode;
+    return 0;
+}
+extern "C" int iper_raster_get_contraction(void) { return raster_fma_mode(); }
 
 extern "C" size_t iper_raster_workspace_bytes(int B, int nf, int from_verts) {
     if (B <= 0 || nf <= 0) return 0;

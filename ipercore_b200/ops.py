@@ -147,6 +147,25 @@ def encode_fim(fim, map_fn, transpose=True):
     return out
 
 
+def vis_f2pts(f2pts, fims, face_k_nearest):
+    """SMPLRenderer.get_vis_f2pts (nmr.py:639-681) on (bs,nf,3,2|3) / (nf,3,2|3) corners and (bs,S,S) / (S,S) face maps."""
+    single = f2pts.dim() == 3
+    if single:
+        f2pts, fims = f2pts[None], fims[None]
+    f2pts = _req(f2pts.float().contiguous(), torch.float32, "f2pts")
+    fims = _req(fims.int().contiguous(), torch.int32, "fims")
+    nb = _req(face_k_nearest.long().contiguous(), torch.int64, "face_k_nearest")
+    B, nf = f2pts.shape[:2]
+    S = fims.shape[-1]
+    if fims.shape[0] != B or tuple(nb.shape[:1]) != (nf,):
+        raise ValueError("vis_f2pts: f2pts %s, fims %s, face_k_nearest %s do not match" % (tuple(f2pts.shape), tuple(fims.shape), tuple(nb.shape)))
+    out = torch.empty_like(f2pts)
+    ws = torch.empty((max(int(lib.iper_vis_f2pts_workspace_bytes(B, nf)), 1),), dtype=torch.uint8, device=f2pts.device)
+    check(lib.iper_vis_f2pts(f2pts.data_ptr(), f2pts[0, 0].numel(), fims.data_ptr(), nb.data_ptr(), nb.shape[1], B, nf, S,
+                             out.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "vis_f2pts")
+    return out[0] if single else out
+
+
 def flow_resize(T, h, w):
     """LWB.resize_trans (attlwb_spade_resunet.py:175-182) on (..., S, S, 2) -> (..., h, w, 2)."""
     T = _req(T.contiguous(), torch.float32, "T")

@@ -5,8 +5,9 @@
 
 What is replaced, at the reference's own seams:
   B1  ``sys.modules["neural_renderer"]``  -> ipercore_b200.neural_renderer  (nmr.py:8 imports it as ``nr``)
-  B2  ``BaseSMPLRenderer/SMPLRenderer.render_fim_wim``, ``cal_bc_transform``, ``encode_fim`` (nmr.py:319-342, 390-401,
-      713-757, and the bs==3 loop :892-918) -> fused CUDA kernels; every other method and all buffers stay the reference's
+  B2  ``BaseSMPLRenderer/SMPLRenderer.render_fim_wim``, ``cal_bc_transform``, ``encode_fim``, ``get_vis_f2pts`` (nmr.py:319-342,
+      390-401, 639-681, 713-757, and the bs==3 loop :892-918) -> CUDA kernels; every other method and all buffers stay the
+      reference's
   B3  ``NetworksFactory.get_by_name("AttLWB-SPADE", cfg=..., temporal=False)`` (networks/__init__.py:14-16)
       -> ipercore_b200.generator.AttentionLWBGenerator (loads the same checkpoints)
   B2' ``iPERCore.tools.utils.morphology.morph / soft_dilate`` (morph_ops.py:7-61; source_setup masks,
@@ -51,10 +52,14 @@ def install(precision="fp16x2", batch=16, patch_inference=True, device_lbs=True)
         assert (cam is not None and vertices is not None) or fim is not None
         return ops.encode_fim(fim.int(), (self.map_fn if map_fn is None else map_fn).float(), transpose), fim
 
+    def get_vis_f2pts(self, f2pts, fims):                                  # nmr.py:639-681 (two torch.unique + host syncs)
+        return ops.vis_f2pts(f2pts, fims, self.face_k_nearest)
+
     for cls in (nmr.BaseSMPLRenderer, nmr.SMPLRenderer):
         cls.render_fim_wim = render_fim_wim
         cls.cal_bc_transform = cal_bc_transform
         cls.encode_fim = encode_fim
+        cls.get_vis_f2pts = get_vis_f2pts
 
     import iPERCore.tools.utils.morphology as morphology                   # B2': mask morphology of source_setup
     from iPERCore.tools.utils.morphology import morph_ops

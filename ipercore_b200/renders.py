@@ -111,27 +111,9 @@ class SMPLRenderer(nn.Module):
         return self.f_uvs2img.repeat(bs, 1, 1, 1)
 
     def get_vis_f2pts(self, f2pts, fims):
-        """nmr.py:639-681 (only consumed when only_vis=true, default false): visible faces and their UV-nearest
-        neighbours keep their coordinates, the rest are set to -2.  Tensor ops, no host sync."""
-        single = f2pts.dim() == 3
-        if single:
-            f2pts, fims = f2pts[None], fims[None]
-        bs, nf = f2pts.shape[:2]
-        vis = torch.zeros((bs, nf + 1), dtype=torch.bool, device=f2pts.device)
-        idx = fims.reshape(bs, -1).long()
-        # the reference drops the smallest unique value (`fim.unique()[1:]`): the background -1 when present,
-        # otherwise the lowest visible face id
-        has_bg = (idx == -1).any(dim=1)
-        low = torch.where(has_bg, torch.full_like(idx[:, 0], nf), idx.clamp(min=0).min(dim=1).values)
-        vis.scatter_(1, torch.where(idx < 0, torch.full_like(idx, nf), idx), True)
-        vis[torch.arange(bs, device=vis.device), low] = False
-        vis = vis[:, :nf]
-        nb = self.face_k_nearest.to(f2pts.device)
-        src = vis[:, :, None].expand(-1, -1, nb.shape[1]).reshape(bs, -1)
-        keep = torch.zeros((bs, nf), dtype=torch.int32, device=f2pts.device)
-        keep.scatter_add_(1, nb.reshape(1, -1).expand(bs, -1), src.int())
-        out = torch.where((keep > 0)[:, :, None, None], f2pts, torch.full_like(f2pts, -2.0))
-        return out[0] if single else out
+        """nmr.py:639-681: visible faces (minus the smallest unique value of the map, as `fim.unique()[1:]` does) and their
+        UV-nearest neighbours keep their coordinates, the rest are set to -2 — iper_vis_f2pts, no host sync."""
+        return ops.vis_f2pts(f2pts, fims, self.face_k_nearest)
 
     # ---- fused engine entry point -------------------------------------------------------------------------------
     def frame_inputs(self, cam, vertices, uv_img, src_f2pts, want_fim=False):

@@ -16,6 +16,18 @@
  * (no FMA contraction; build with -ffp-contract=off), and the places where upstream's double literals
  * (`2.`, `0.5`, `1.`, `0.`) promote an expression to double are evaluated in double and rounded once.
  *
+ * CONTRACTION VARIANT (-DORACLE_FMA, symbols suffixed _fma): upstream is compiled by nvcc, whose default -fmad=true lets
+ * the compiler contract a*b+c into one fused multiply-add, so the shipped extension most likely does NOT round every
+ * product.  Which products fuse is the compiler's choice; the variant models the LLVM/NVPTX DAG-combiner rules
+ * (fadd(fmul x y, z) -> fma(x,y,z), fsub(fmul x y, z) -> fma(x,y,-z), no reassociation) on upstream's expressions:
+ *   p          = 0.5 * (fma(v, is, is) - 1)
+ *   adjugate   a*b - c*d        -> fma(a, b, -(c*d))
+ *   determinant m1 + m2 + m3    -> fma(x3, y3, fma(x1, y1, x2*y2))
+ *   weights    i0*xi + i1*yi + i2 -> fma(i0, xi, i1*yi) + i2
+ * Comparisons of two products (back-face and edge tests) and the divisions have no add to fuse and are unchanged.  It
+ * cannot be checked here either (the extension is absent); it exists so that the CUDA rasteriser's matching switch
+ * (iper_raster_set_contraction) can be validated against a real build of the fork later.  tests/ run both.
+ *
  * Semantics:
  *   kernel 1, per face : skip when back-facing; pixel-space corners p = 0.5*(v*is + is - 1);
  *                        face_inv = inverse of [[x0,x1,x2],[y0,y1,y2],[1,1,1]] (adjugate / determinant).
@@ -32,6 +44,16 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifdef ORACLE_FMA
+#define NAME(x) x##_fma
+#define MULADD(a, b, c) fmaf((a), (b), (c))                 /* a*b + c, fused        */
+#define MULSUB2(a, b, c, d) fmaf((a), (b), -((c) * (d)))    /* a*b - c*d             */
+#else
+#define NAME(x) x
+#define MULADD(a, b, c) ((a) * (b) + (c))                   /* separately rounded (-ffp-contract=off) */
+#define MULSUB2(a, b, c, d) ((a) * (b) - (c) * (d))
+#endif
+
 static inline int backface(const float *f)
 {
     return (f[7] - f[1]) * (f[3] - f[0]) < (f[4] - f[1]) * (f[6] - f[0]);
@@ -44,18 +66,23 @@ static void face_setup(const float *f, int is, float *inv)
     for (int n = 0; n < 3; n++)
         for (int d = 0; d < 2; d++) {
             /* 0.5 * (face * is + is - 1): float chain, the final 0.5* is exact in either precision */
-            float t = f[3 * n + d] * (float)is;
-            t = t + (float)is;
+            float t = MULADD(f[3 * n + d], (float)is, (float)is);
             t = t - 1.0f;
             p[n][d] = (float)(0.5 * (double)t);
         }
     float a[9] = {
-        p[1][1] - p[2][1], p[2][0] - p[1][0], p[1][0] * p[2][1] - p[2][0] * p[1][1],
-        p[2][1] - p[0][1], p[0][0] - p[2][0], p[2][0] * p[0][1] - p[0][0] * p[2][1],
-        p[0][1] - p[1][1], p[1][0] - p[0][0], p[0][0] * p[1][1] - p[1][0] * p[0][1]};
+        p[1][1] - p[2][1], p[2][0] - p[1][0], MULSUB2(p[1][0], p[2][1], p[2][0], p[1][1]),
+        p[2][1] - p[0][1], p[0][0] - p[2][0], MULSUB2(p[2][0], p[0][1], p[0][0], p[2][1]),
+        p[0][1] - p[1][1], p[1][0] - p[0][0], MULSUB2(p[0][0], p[1][1], p[1][0], p[0][1])};
+#ifdef ORACLE_FMA
+    float den = p[0][0] * (p[1][1] - p[2][1]);
+    den = fmaf(p[2][0], p[0][1] - p[1][1], den);
+    den = fmaf(p[1][0], p[2][1] - p[0][1], den);
+#else
     float den = p[2][0] * (p[0][1] - p[1][1]);
     den = den + p[0][0] * (p[1][1] - p[2][1]);
     den = den + p[1][0] * (p[2][1] - p[0][1]);
+#endif
     for (int k = 0; k < 9; k++) inv[k] = a[k] / den;
 }
 
@@ -72,7 +99,7 @@ static inline float clamp01(float w)
  * fim   : (bs, is, is) int32     wim : (bs, is, is, 3) float32
  * returns 0
  */
-int oracle_rasterize_fim_wim(const float *faces, int bs, int nf, int is, float near_, float far_,
+int NAME(oracle_rasterize_fim_wim)(const float *faces, int bs, int nf, int is, float near_, float far_,
                              int32_t *fim, float *wim)
 {
     float *inv = (float *)calloc((size_t)bs * nf * 9, sizeof(float));
@@ -104,8 +131,7 @@ int oracle_rasterize_fim_wim(const float *faces, int bs, int nf, int is, float n
                 const float *fi = ib + 9 * fn;
                 float w[3];
                 for (int k = 0; k < 3; k++) {
-                    float t = fi[3 * k + 0] * (float)xi;
-                    t = t + fi[3 * k + 1] * (float)yi;
+                    float t = MULADD(fi[3 * k + 0], (float)xi, fi[3 * k + 1] * (float)yi);
                     t = t + fi[3 * k + 2];
                     w[k] = t;
                 }
@@ -139,7 +165,7 @@ int oracle_rasterize_fim_wim(const float *faces, int bs, int nf, int is, float n
  * orders of magnitude below one pixel).  Used by the CPU baseline and by large-size tests; the plain loop
  * above is the definition and tests/ checks the two against each other.
  */
-int oracle_rasterize_fim_wim_fast(const float *faces, int bs, int nf, int is, float near_, float far_,
+int NAME(oracle_rasterize_fim_wim_fast)(const float *faces, int bs, int nf, int is, float near_, float far_,
                                   int32_t *fim, float *wim)
 {
     const size_t npix = (size_t)is * is;
@@ -177,8 +203,7 @@ int oracle_rasterize_fim_wim_fast(const float *faces, int bs, int nf, int is, fl
                         continue;
                     float w[3];
                     for (int k = 0; k < 3; k++) {
-                        float t = inv[3 * k + 0] * (float)xi;
-                        t = t + inv[3 * k + 1] * (float)yi;
+                        float t = MULADD(inv[3 * k + 0], (float)xi, inv[3 * k + 1] * (float)yi);
                         t = t + inv[3 * k + 2];
                         w[k] = t;
                     }

@@ -133,3 +133,30 @@ def test_morph_oracle_matches_reference_golden():
     for ks in (3, 11, 51):
         for name, mode in (("erode", morph_ref.ERODE), ("dilate", morph_ref.DILATE), ("soft", morph_ref.SOFT_DILATE)):
             assert np.array_equal(morph_ref.morph(m, ks, mode), gold["%s_%d" % (name, ks)].astype(np.float32)), (name, ks)
+
+
+def test_raster_contraction_variant(template):
+    """The -DORACLE_FMA variant (nvcc -fmad=true model of the upstream source, oracle/raster_ref.c header): same rules on the
+    known answers, fast == definition, and on a real mesh it may differ from the separately-rounded variant only on pixels
+    that sit on a face edge / depth tie (a handful), with weights equal to float rounding elsewhere."""
+    S = 4
+    tri = np.array([[-1, -1, 1], [3, -1, 1], [-1, 3, 1]], np.float32)
+    for t in (tri, tri[[0, 2, 1]]):
+        a, _ = raster.rasterize_fim_wim(t[None, None], S, fast=False)
+        b, _ = raster.rasterize_fim_wim(t[None, None], S, fast=False, fma=True)
+        np.testing.assert_array_equal(a, b)
+    cams, verts = synth.pose_sweep(template, 2, total=7)
+    fv = flow_ref.vertices_to_faces(flow_ref.project(cams, verts), template["faces"])
+    fim_d, wim_d = raster.rasterize_fim_wim(fv, 48, fast=False, fma=True)
+    fim_f, wim_f = raster.rasterize_fim_wim(fv, 48, fast=True, fma=True)
+    np.testing.assert_array_equal(fim_d, fim_f)
+    np.testing.assert_array_equal(wim_d, wim_f)
+    fim0, wim0 = raster.rasterize_fim_wim(fv, 128)
+    fim1, wim1 = raster.rasterize_fim_wim(fv, 128, fma=True)
+    differ = (fim0 != fim1)
+    assert differ.mean() < 1e-3, "contraction may only flip pixels that sit exactly on an edge or a depth tie"
+    # upstream's pixel-space adjugate cancels catastrophically on small faces, so the WEIGHTS are sensitive to the rounding
+    # model far above float epsilon (measured: median 8e-5, p99 2.5e-3, max 1e-1 at 512^2) — the reason the switch exists
+    d = np.abs(wim0 - wim1).max(-1)[(fim0 >= 0) & ~differ]
+    assert np.median(d) < 1e-3 and np.percentile(d, 99) < 2e-2
+    assert (wim0 != wim1).any(), "the two rounding models must not be the same build"

@@ -32,6 +32,48 @@ def test_raster_frames_bit_exact(S, n, template):
     np.testing.assert_array_equal(out["f2pts"].cpu().numpy(), f2pts_o)
 
 
+def test_raster_contraction_switch_bit_exact(template):
+    """iper_raster_set_contraction(1): the nvcc -fmad=true rounding model, bit-exact against the oracle's -DORACLE_FMA variant
+    (and switching back restores the default model) — the re-validation switch for when the fork can be built."""
+    from ipercore_b200 import _lib, ops
+    S = 256
+    cams, verts = synth.pose_sweep(template, 2, total=7)
+    fv = flow_ref.vertices_to_faces(flow_ref.project(cams, verts), template["faces"])
+    fim1, wim1 = raster.rasterize_fim_wim(fv, S, fma=True)
+    fim0, wim0 = raster.rasterize_fim_wim(fv, S, fma=False)
+    assert _lib.lib.iper_raster_get_contraction() == 0
+    try:
+        _lib.check(_lib.lib.iper_raster_set_contraction(1), "set_contraction")
+        out = ops.raster_frames(_t(verts), _t(cams), _t(template["faces"]), S)
+        np.testing.assert_array_equal(out["fim"].cpu().numpy(), fim1)
+        np.testing.assert_array_equal(out["wim"].cpu().numpy(), wim1)
+    finally:
+        _lib.check(_lib.lib.iper_raster_set_contraction(0), "set_contraction")
+    out = ops.raster_frames(_t(verts), _t(cams), _t(template["faces"]), S)
+    np.testing.assert_array_equal(out["fim"].cpu().numpy(), fim0)
+    np.testing.assert_array_equal(out["wim"].cpu().numpy(), wim0)
+    assert (wim0 != wim1).any()
+
+
+def test_vis_f2pts_matches_reference_golden(template, golden_dir):
+    """iper_vis_f2pts vs keep-masks produced by the reference's own SMPLRenderer.get_vis_f2pts (tests/golden/vis.npz): maps
+    with background (drops -1) and a map without background (drops the LOWEST visible face id, as `unique()[1:]` does)."""
+    import make_golden
+    from ipercore_b200 import ops
+    v = np.load(os.path.join(golden_dir, "vis.npz"))
+    g = np.load(os.path.join(golden_dir, "flow_S128.npz"))
+    nb = _t(template["face_k_nearest"].astype(np.int64))
+    for tag, f2pts, fim in (("s128", g["f2pts"], g["fim"]), ("nobg", g["f2pts"][:1], make_golden.vis_inputs())):
+        want = np.where(v["keep_" + tag][:, :, None, None], f2pts, np.float32(-2.0))
+        got = ops.vis_f2pts(_t(f2pts), _t(fim), nb)
+        np.testing.assert_array_equal(got.cpu().numpy(), want)
+        got1 = ops.vis_f2pts(_t(f2pts[0]), _t(fim[0]), nb)                 # the 3-D form of the reference signature
+        np.testing.assert_array_equal(got1.cpu().numpy(), want[0])
+    f3 = np.concatenate([g["f2pts"], np.ones_like(g["f2pts"][..., :1])], -1)   # (bs, nf, 3, 3) corners
+    got3 = ops.vis_f2pts(_t(f3), _t(g["fim"]), nb)
+    np.testing.assert_array_equal(got3.cpu().numpy(), np.where(v["keep_s128"][:, :, None, None], f3, np.float32(-2.0)))
+
+
 def test_rasterize_faces_seam_any_batch(template):
     """Seam B1 incl. batch size 3 (the upstream bug the reference loops around, nmr.py:892-918) and empty batch."""
     from ipercore_b200 import ops
