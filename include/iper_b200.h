@@ -217,6 +217,34 @@ int iper_pred_to_u8(const float* pred, int B, int S, uint8_t* out, iper_stream_t
  * mask, out (N,1,H,W) f32; ks odd, <= 63 (deploy.toml uses 3..51).  Exact for 0/1 masks. */
 int iper_morph(const float* mask, int N, int H, int W, int ks, int mode, float* out, iper_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * One-time-per-source kernels of Imitator.source_setup (iPERCore/models/imitator.py:177-246 ->
+ * FlowComposition.process_source, iPERCore/models/flowcomposition.py:452-512).
+ *
+ * iper_canny_edges — CannyFilter.forward(img, low, high, hysteresis=True) for a 1-channel map
+ *   (iPERCore/tools/utils/morphology/canny_ops.py:129-192): gaussian 3x3 -> sobel x/y -> magnitude + orientation ->
+ *   directional non-maximum suppression -> double threshold -> hysteresis; edges (N,H,W) in {0,1} = its `thin_edges`.
+ *   gaussian_w[9], sobel_x_w[9] (sobel_y = transpose), directional_w[8*9] are HOST arrays (the module's constant
+ *   filter taps, passed by value to the kernels); mag_ws/tri_ws (N*H*W f32) and ori_ws (N*H*W bytes) are device scratch.
+ * iper_morph_image — make_morph_image / cal_top_k_ids / morph_image (flowcomposition.py:264-386) with top_k = 3:
+ *   uncertain pixels (outpad_sil*(1-confidant_sil) != 0) take sum_k (d_k / sum d) * src[nn_k] over their 3 nearest edge
+ *   pixels (squared pixel distance; ties -> lowest row-major index), every other pixel src * confidant_sil.
+ *   src_img/out (N,3,H,W), sils/edges (N,H,W); count_ws (N) and list_ws (N*H*W) int32 device scratch.
+ * iper_uv_warp + iper_uv_merge — make_uv_img (flowcomposition.py:87-137): per source, T = cal_bc_transform(f2pts, uv_fim,
+ *   uv_wim) fused with grid_sample(src, T) -> src_warp (N,3,H,W) and grid_sample(ones, T_vis) -> vis_warp (N,H,W); the caller
+ *   dilates vis_warp (iper_morph, ks 13) and iper_uv_merge blends the primary source with the others -> uv_img (bs,3,H,W).
+ *   uv_fim (H,W) i32 / uv_wim (H,W,3): the constant UV-layout maps of render_uv_fim_wim; f2pts (N,nf,3,2), N = bs*ns.
+ * ---------------------------------------------------------------------------------------------------------- */
+int iper_canny_edges(const float* img, int N, int H, int W, const float* gaussian_w, const float* sobel_x_w,
+                     const float* directional_w, float hysteresis_w, float low, float high, float* mag_ws, int8_t* ori_ws,
+                     float* tri_ws, float* edges, iper_stream_t stream);
+int iper_morph_image(const float* src_img, const float* confidant_sil, const float* outpad_sil, const float* edges, int N,
+                     int H, int W, int32_t* count_ws, int32_t* list_ws, float* out, iper_stream_t stream);
+int iper_uv_warp(const float* src_img, const float* f2pts, const float* vis_f2pts, const int32_t* uv_fim, const float* uv_wim,
+                 int N, int nf, int H, int W, float* src_warp, float* vis_warp, iper_stream_t stream);
+int iper_uv_merge(const float* src_warp, const float* vis_dilated, int bs, int ns, int H, int W, float* uv_img,
+                  iper_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,11 @@ SIGNATURES = {
     "iper_nhwc_f32_to_nchw": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "iper_pred_to_u8": [c_void_p, c_int, c_int, c_void_p, c_void_p],
     "iper_morph": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "iper_canny_edges": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p,
+                         c_void_p, c_void_p, c_void_p, c_void_p],
+    "iper_morph_image": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    "iper_uv_warp": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
+    "iper_uv_merge": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
 }
 
 

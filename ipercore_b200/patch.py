@@ -13,6 +13,8 @@ What is replaced, at the reference's own seams:
   B2' ``iPERCore.tools.utils.morphology.morph / soft_dilate`` (morph_ops.py:7-61; source_setup masks,
       flowcomposition.py:121,176-180,258) -> iper_morph (separable box sum + threshold); custom ``kernel=`` calls, CPU
       tensors and even / > 63 sizes keep going to the reference implementation
+  B2" ``FlowComposition.make_morph_image`` / ``make_uv_img`` (flowcomposition.py:87-137, 264-386; CannyFilter of
+      canny_ops.py) -> ipercore_b200.source_ops (Canny, top-3 nearest-boundary colour fill, UV merge kernels)
   B4  ``Imitator.inference`` (models/imitator.py:327-382) -> batched FrameEngine when ``temporal`` is false and the
       generator is ours; same arguments, same ``pred_{:0>8}.png`` outputs / returned list.
 Nothing else of iPERCore is touched: options, preprocessing, personalisation, source_setup, video fusion stay upstream.
@@ -85,6 +87,25 @@ def install(precision="fp16x2", batch=16, patch_inference=True, device_lbs=True)
         mod = sys.modules.get(modname)
         if mod is not None and hasattr(mod, "morph"):
             mod.morph = morph
+
+    from iPERCore.models import flowcomposition as fcm                     # B2'': one-time-per-source stage of source_setup
+    from . import source_ops
+    up_morph_image, up_uv_img = fcm.FlowComposition.make_morph_image, fcm.FlowComposition.make_uv_img
+
+    def make_morph_image(self, src_img, src_info, erode_ks=3, dilate_ks=11):      # flowcomposition.py:335-386
+        if not src_img.is_cuda:
+            return up_morph_image(self, src_img, src_info, erode_ks=erode_ks, dilate_ks=dilate_ks)
+        return source_ops.make_morph_image(src_img, src_info["confidant_sil"], src_info["outpad_sil"], erode_ks, dilate_ks)
+
+    def make_uv_img(self, src_img, src_info):                                     # flowcomposition.py:87-137
+        if not src_img.is_cuda:
+            return up_uv_img(self, src_img, src_info)
+        n = src_img.shape[0] * src_img.shape[1]
+        return source_ops.make_uv_img(src_img, src_info["obj_f2pts"], src_info["only_vis_obj_f2pts"], self.uv_fim[0:n],
+                                      self.uv_wim[0:n])
+
+    fcm.FlowComposition.make_morph_image = make_morph_image
+    fcm.FlowComposition.make_uv_img = make_uv_img
 
     from iPERCore.models.networks import NetworksFactory                   # B3
     from .generator import AttentionLWBGenerator

@@ -160,3 +160,27 @@ def test_raster_contraction_variant(template):
     d = np.abs(wim0 - wim1).max(-1)[(fim0 >= 0) & ~differ]
     assert np.median(d) < 1e-3 and np.percentile(d, 99) < 2e-2
     assert (wim0 != wim1).any(), "the two rounding models must not be the same build"
+
+
+def test_source_stage_restatement_matches_reference_golden(golden_dir):
+    """oracle/source_ref.py vs outputs of the reference's own make_morph_image / make_uv_img / CannyFilter captured in a real
+    Imitator.source_setup run (tests/golden/source_S96.npz)."""
+    import importlib.util
+    from oracle import source_ref
+    g = np.load(os.path.join(golden_dir, "source_S96.npz"))
+    # filter taps: the product's constant table (no CUDA needed to read it)
+    src = open(os.path.join(os.path.dirname(golden_dir), "..", "ipercore_b200", "source_ops.py")).read()
+    ns = {}
+    exec("import numpy as np\n" + src[src.index("def canny_constants"):src.index("_CANNY = None")], ns)
+    consts = ns["canny_constants"]()
+    conf, outp, edges = (g[k].astype(np.float32) for k in ("confidant_sil", "outpad_sil", "thin_edges"))
+    e = source_ref.canny_edges(conf[:, 0], consts)
+    diff = e != edges[:, 0]
+    assert diff.sum() <= 0.12 * edges.sum()          # NMS on exact float ties: the reference differs from itself by this much
+    for i in range(conf.shape[0]):
+        m = source_ref.morph_image(g["src_img"][i], conf[i, 0], outp[i, 0], edges[i, 0])
+        d = np.abs(m - g["morph_img"][i]).max(0)
+        unc = (outp[i, 0] * (1 - conf[i, 0])) != 0
+        assert d[~unc].max() == 0 and d[g["unique3"][i, 0]].max() <= 1e-6
+    uv = source_ref.make_uv_img(g["morph_img"], g["obj_f2pts"], g["only_vis_obj_f2pts"], g["uv_fim"], g["uv_wim"])
+    assert np.abs(uv - g["uv_img"][0]).max() <= 1e-5
