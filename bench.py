@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--batch", type=int, default=60)
     ap.add_argument("--ns", type=int, default=2)
-    ap.add_argument("--precision", default="fp16x2", choices=["fp16x2", "fp16", "fp16f8"])
+    ap.add_argument("--precision", default="fp16x2", choices=["fp16x2", "fp16", "fp16f8", "mixed"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--streams", type=int, default=1, help="engines replaying alternate batches on separate streams")
     ap.add_argument("--dump-layers", default="", help="write the per-launch conv timing table (JSON) to this path")
@@ -479,7 +479,7 @@ def main():
                               cta_pair=kw.get("cta_pair", 0))))
 
         other = []          # (name, e0, e1) of the non-conv launches of the same batch
-        OTHER_OPS = ("raster_frames", "conv_stem", "warp_attention", "flow_resize", "instnorm_finalize", "pred_to_u8")
+        OTHER_OPS = ("raster_frames", "conv_stem", "stem_im2col", "warp_attention", "flow_resize", "instnorm_finalize", "pred_to_u8")
         saved = {k: getattr(ops, k) for k in OTHER_OPS if hasattr(ops, k)}
 
         def wrap(name, fn):  # noqa: E306
@@ -553,7 +553,8 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": {"fp16x2": "f16x2 (split fp16 operands, fp32 accumulate)", "fp16": "f16 (fp32 accumulate)",
-                          "fp16f8": "f16 + e4m3 cross terms (fp32 accumulate)"}[args.precision],
+                          "fp16f8": "f16 + e4m3 cross terms (fp32 accumulate)",
+                          "mixed": "f16x2, SPADE convs single-pass f16 (opt-in, outside the parity tolerance)"}[args.precision],
                 "data": "synthetic", "config": config_block(args, launches),
                 "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": int(cams_h.numel() * 4 + verts_h.numel() * 4),
                         "d2h_bytes_per_step": int(out_h.numel()), "ms_per_step": ms_e2e / args.steps},

@@ -153,6 +153,12 @@ int iper_conv_stem(const float* in_nchw, int N, int Cin, int H, int W, const flo
                    void* out, int out_planes, long long out_plane_stride, int out_pitch, int out_coff,
                    double* stats_ws /* optional (N,Cout,2) fp64 sums, cleared by the call */, iper_stream_t stream);
 
+/* The same stem as a tensor-core GEMM: im2col of the 3x3 / s2 / p1 patches of (N,Cin<=7,H,W) fp32 into NHWC planes
+ * (N,H/2,W/2,64), channel k = (ky*3+kx)*Cin + ci, zero-padded to 64; the stem is then iper_conv_gemm(IPER_CONV_S1, ksize 1,
+ * Cin 64) on weights packed (Cout, 64) in the same (tap, ci) order. */
+int iper_stem_im2col(const float* in_nchw, int N, int Cin, int H, int W, void* out, int out_planes,
+                     long long out_plane_stride, int out_pitch, int out_coff, iper_stream_t stream);
+
 /* nn.InstanceNorm2d(affine=False) statistics (attlwb_spade_resunet.py:62, eps 1e-5, biased variance):
  * mean_rstd (N,C,2) = (mean, 1/sqrt(var+eps)) of an NHWC planes tensor.  workspace: N*C*2 doubles (fp64 sums,
  * cleared and filled by the call; two launches + one memset on the stream). */
@@ -216,6 +222,40 @@ int iper_pred_to_u8(const float* pred, int B, int S, uint8_t* out, iper_stream_t
  * box sum == ks*ks; mode 1 dilate: border 0, box sum >= 1) and soft_dilate() :39-61 (mode 2: border 0, sum >= ks*ks/2).
  * mask, out (N,1,H,W) f32; ks odd, <= 63 (deploy.toml uses 3..51).  Exact for 0/1 masks. */
 int iper_morph(const float* mask, int N, int H, int W, int ks, int mode, float* out, iper_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Stand-alone generator handle — runs the AttLWB-SPADE per-frame network from C alone: weight repacking, layer graph and
+ * workspace planning live in the library (csrc/generator.cu), so a non-Python host needs nothing but this header.
+ * Replaces NetworksFactory.get_by_name("AttLWB-SPADE", ...) + load_state_dict (iPERCore/models/networks/__init__.py:14-16,
+ * iPERCore/models/imitator.py:155-175) and BaseAttentionLWBGenerator.forward_src(only_enc=True) / forward_tsf
+ * (attlwb_spade_resunet.py:450-535) + the composite of Imitator.forward (imitator.py:384-395).
+ *
+ *   iper_gen_create(num_filters[3] = {64,128,256}, n_res_block, precision 1 (fp16) | 2 (split fp16), mixed_spade, &gen)
+ *   iper_gen_load_weight(gen, "tsf_net_enc.layers.0.0.weight", dev_ptr, shape, ndim)   for every state_dict tensor: reference
+ *        fp32 layouts on the DEVICE, kept by pointer until iper_gen_pack; a "module." prefix is stripped (base_model.py:56-65);
+ *        tensors the hot path does not use (bg_net.*, src_net.decoders.*, src_net.*_reg) are accepted and ignored
+ *   iper_gen_packed_bytes(gen) -> size of the packed-weights buffer (0 + iper_last_error() while tensors are missing)
+ *   iper_gen_pack(gen, packed, bytes, stream)        repack on the device into the caller's 256-byte aligned buffer
+ *   iper_gen_src_cache_bytes / iper_gen_src_workspace_bytes / iper_gen_tsf_workspace_bytes -> caller-owned buffers
+ *   iper_gen_forward_src(gen, src_inputs (ns,6,S,S) f32, ns, S, src_cache, ..)        once per source set
+ *   iper_gen_forward_tsf(gen, tsf_inputs (B,6,S,S), Tst (B,ns,S,S,2), src_cache, ns, B, S, bg ((1|B),3,S,S) or NULL,
+ *        bg_batched, img (B,3,S,S), mask (B,1,S,S), pred (B,3,S,S) [any may be NULL], workspace, ..)   per batch of frames
+ * The library never allocates device memory and never synchronises; the handle is a host object.  Not thread-safe per handle.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct iper_gen iper_gen;
+int iper_gen_create(const int* num_filters, int n_res_block, int precision, int mixed_spade, iper_gen** out);
+void iper_gen_destroy(iper_gen* gen);
+int iper_gen_load_weight(iper_gen* gen, const char* name, const float* dev_ptr, const int64_t* shape, int ndim);
+size_t iper_gen_packed_bytes(iper_gen* gen);
+int iper_gen_pack(iper_gen* gen, void* packed, size_t packed_bytes, iper_stream_t stream);
+size_t iper_gen_src_cache_bytes(iper_gen* gen, int ns, int S);
+size_t iper_gen_src_workspace_bytes(iper_gen* gen, int ns, int S);
+size_t iper_gen_tsf_workspace_bytes(iper_gen* gen, int ns, int B, int S);
+int iper_gen_forward_src(iper_gen* gen, const float* src_inputs, int ns, int S, void* src_cache, size_t src_cache_bytes,
+                         void* workspace, size_t workspace_bytes, iper_stream_t stream);
+int iper_gen_forward_tsf(iper_gen* gen, const float* tsf_inputs, const float* Tst, const void* src_cache, int ns, int B, int S,
+                         const float* bg, int bg_batched, float* img, float* mask, float* pred, void* workspace,
+                         size_t workspace_bytes, iper_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * One-time-per-source kernels of Imitator.source_setup (iPERCore/models/imitator.py:177-246 ->

@@ -52,6 +52,7 @@ SIGNATURES = {
     "iper_conv_direct": [ctypes.POINTER(ConvGemmDesc), c_void_p, c_int, c_void_p],
     "iper_conv_stem": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_ll, c_int,
                        c_int, c_void_p, c_void_p],
+    "iper_stem_im2col": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p],
     "iper_instnorm_finalize": [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p],
     "iper_instnorm_stats": [c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                             c_void_p],
@@ -69,11 +70,33 @@ SIGNATURES = {
     "iper_nhwc_f32_to_nchw": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "iper_pred_to_u8": [c_void_p, c_int, c_int, c_void_p, c_void_p],
     "iper_morph": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "iper_gen_create": [c_void_p, c_int, c_int, c_int, c_void_p],
+    "iper_gen_load_weight": [c_void_p, ctypes.c_char_p, c_void_p, c_void_p, c_int],
+    "iper_gen_pack": [c_void_p, c_void_p, c_size_t, c_void_p],
+    "iper_gen_forward_src": [c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p],
+    "iper_gen_forward_tsf": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_size_t, c_void_p],
     "iper_canny_edges": [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p,
                          c_void_p, c_void_p, c_void_p, c_void_p],
     "iper_morph_image": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     "iper_uv_warp": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p],
     "iper_uv_merge": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+}
+
+
+# entry points whose return type is not the int status: name -> (restype, argtypes)
+OTHER_SIGNATURES = {
+    "iper_last_error": (ctypes.c_char_p, []),
+    "iper_conv_halo_plan": (c_int, [c_int, c_int, c_int, c_int, c_void_p, c_int]),
+    "iper_raster_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "iper_raster_set_contraction": (c_int, [c_int]),
+    "iper_raster_get_contraction": (c_int, []),
+    "iper_vis_f2pts_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "iper_gen_destroy": (None, [c_void_p]),
+    "iper_gen_packed_bytes": (c_size_t, [c_void_p]),
+    "iper_gen_src_cache_bytes": (c_size_t, [c_void_p, c_int, c_int]),
+    "iper_gen_src_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
+    "iper_gen_tsf_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
 }
 
 
@@ -87,18 +110,10 @@ def _load():
         fn = getattr(lib, name)          # AttributeError here = ABI drift; fail loudly
         fn.argtypes = argtypes
         fn.restype = c_int
-    lib.iper_conv_halo_plan.argtypes = [c_int, c_int, c_int, c_int, c_void_p, c_int]
-    lib.iper_conv_halo_plan.restype = c_int
-    lib.iper_raster_set_contraction.argtypes = [c_int]
-    lib.iper_raster_set_contraction.restype = c_int
-    lib.iper_raster_get_contraction.argtypes = []
-    lib.iper_raster_get_contraction.restype = c_int
-    lib.iper_vis_f2pts_workspace_bytes.argtypes = [c_int, c_int]
-    lib.iper_vis_f2pts_workspace_bytes.restype = c_size_t
-    lib.iper_raster_workspace_bytes.argtypes = [c_int, c_int, c_int]
-    lib.iper_raster_workspace_bytes.restype = c_size_t
-    lib.iper_last_error.argtypes = []
-    lib.iper_last_error.restype = ctypes.c_char_p
+    for name, (restype, argtypes) in OTHER_SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
     return lib
 
 

@@ -1264,14 +1264,17 @@ extern "C" int iper_conv_halo_plan(int mode, int Cin, int rows, int fuse_n, int3
 extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream) {
     IPER_REQUIRE(d != nullptr, "iper_conv_gemm: null descriptor");
     IPER_REQUIRE(d->a && d->w, "iper_conv_gemm: null operand");
-    IPER_REQUIRE(d->a_planes == d->w_planes && d->a_planes >= 1 && d->a_planes <= 3,
-                 "iper_conv_gemm: a_planes (%d) and w_planes (%d) must be the same format 1, 2 or 3", d->a_planes, d->w_planes);
+    // a_planes == w_planes, or split-fp16 activations with single-plane weights: a single-pass layer of a mixed-precision
+    // plan reads only the hi plane of its input (1 MMA per K step) — the tensor stays usable by split-precision consumers
+    const bool hi_only = d->a_planes == 2 && d->w_planes == 1;
+    IPER_REQUIRE((d->a_planes == d->w_planes || hi_only) && d->a_planes >= 1 && d->a_planes <= 3,
+                 "iper_conv_gemm: a_planes (%d) and w_planes (%d) must be the same format 1, 2 or 3 (or 2 with 1)", d->a_planes, d->w_planes);
     IPER_REQUIRE(d->a_planes != 3 || (d->w8 && d->wl8 && d->cross_scale > 0.f && d->a_pitch % 16 == 0 && d->a_coff % 16 == 0),
                  "iper_conv_gemm: format 3 needs w8, wl8, cross_scale and a 16-aligned channel window");
     IPER_REQUIRE(d->Cin > 0 && d->Cin % 64 == 0, "iper_conv_gemm: Cin=%d must be a multiple of 64", d->Cin);
     // tiles_m = 2: two M tiles per CTA share one weight tile (32-channel K stages).  Measured SLOWER on B200 than one
     // tile with 64-channel stages (64-byte TMA rows deliver fewer bytes per request), so auto = 1; kept selectable.
-    const int fmt = d->a_planes;
+    const int fmt = hi_only ? 1 : d->a_planes;
     const int TMv = (d->tiles_m == 2 && fmt != 3) ? 2 : 1;
     // cta_pair: 2-CTA clusters (cta_group::2) — each CTA stages its own A tile and half of the weight tile
     const bool halo = d->cta_pair == 2;

@@ -188,6 +188,37 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(const float* __restrict_
     }
 }
 
+// Stem as a tensor-core GEMM: explicit im2col of the 3x3 / stride-2 / pad-1 patches of a (N, CIN <= 7, H, W) fp32 image into
+// NHWC planes (N, H/2, W/2, 64) with channel k = (ky*3 + kx)*CIN + ci (zeros from 9*CIN up), so that the stem becomes a
+// K = 64 "1x1 convolution" on the tcgen05 path (fused bias / ReLU / instance-norm statistics epilogue) instead of 54-term
+// FMA chains fed by shared-memory filter reads.  8 lanes cover one output pixel (8 channels = one 128-bit store per plane).
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ in, int N, int CIN, int H, int W,
+                                                          __half* __restrict__ out, int out_planes, long long out_plane_stride,
+                                                          int out_pitch, int out_coff) {
+    const int Ho = H / 2, Wo = W / 2;
+    const size_t total = (size_t)N * Ho * Wo * 8;
+    const int kmax = 9 * CIN;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        const int cg = (int)(i & 7);
+        const size_t pix = i >> 3;
+        const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho);
+        const size_t n = pix / ((size_t)Wo * Ho);
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int k = cg * 8 + j;
+            float val = 0.f;
+            if (k < kmax) {
+                const int tap = k / CIN, ci = k - tap * CIN;
+                const int iy = 2 * oy - 1 + tap / 3, ix = 2 * ox - 1 + tap % 3;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < W) val = __ldg(in + ((n * CIN + ci) * H + iy) * W + ix);
+            }
+            v[j] = val;
+        }
+        store_planes8(out, out_planes, out_plane_stride, pix * out_pitch + out_coff + cg * 8, v);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Instance-norm statistics over an NHWC planes tensor, two launches:
 //   partial: grid (splits, N), block 256; a thread owns 8 consecutive channels (one 128-bit load per plane),
@@ -409,6 +440,131 @@ __global__ void __launch_bounds__(256, WIDE == 1 ? 2 : (WIDE == 2 ? 4 : 3)) warp
 #pragma unroll
         for (int j = 0; j < 8; j++) o8[j] *= rden;
         if (live) store_planes8(out, out_planes, out_plane_stride, pix * out_pitch + out_coff + cg * 8, o8);
+    }
+}
+
+
+// Chunked schedule (default): a warp takes 32 CONSECUTIVE pixels.  Lane i reads the flows of pixel i (coalesced) and classifies
+// it; the ballot splits the chunk into background pixels (no tap of any source lands inside a map: their output is the same
+// constant for every such pixel — softmax over equal logits of the value bias — so the warp just streams that row out, no
+// dependent chain) and foreground pixels, which run the gather / online-softmax path PPW at a time with their flows
+// broadcast by shuffle.  On real frames ~85-90 % of the pixels are background: the per-pixel latency chain of the
+// pixel-per-warp schedule (flow load -> taps -> [gathers] -> shuffles -> exp -> store) is paid only where it is needed.
+template <int C, int NSMAX>
+__global__ void __launch_bounds__(256, 3) warp_attention_chunk_kernel(const __half* __restrict__ xt, int xt_planes,
+                                                                      long long xt_plane_stride, int xt_pitch, int xt_coff,
+                                                                      const float* __restrict__ kv,
+                                                                      const float* __restrict__ bias_v,
+                                                                      const float* __restrict__ T, int B, int ns, int h, int w,
+                                                                      __half* __restrict__ out, int out_planes,
+                                                                      long long out_plane_stride, int out_pitch, int out_coff) {
+    constexpr int LPP = C / 8, PPW = 32 / LPP, KVP = 2 * C + 64;
+    const int lane = threadIdx.x & 31, cg = lane % LPP, sub = lane / LPP;
+    const size_t hw = (size_t)h * w, total = (size_t)B * hw;
+    const float inv_sqrt = 1.f / sqrtf((float)C);
+    const float4* bvp = reinterpret_cast<const float4*>(bias_v + cg * 8);
+    float bv8[8];
+    {
+        const float4 b0 = __ldg(bvp), b1 = __ldg(bvp + 1);
+        bv8[0] = b0.x; bv8[1] = b0.y; bv8[2] = b0.z; bv8[3] = b0.w; bv8[4] = b1.x; bv8[5] = b1.y; bv8[6] = b1.z; bv8[7] = b1.w;
+    }
+    // background row: the same online-softmax arithmetic as the foreground path with logit 0 and value bias_v for every source
+    float bg8[8];
+    {
+        float m = -INFINITY, den = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) bg8[j] = 0.f;
+        for (int s = 0; s < ns; s++) {
+            const float m_new = fmaxf(m, 0.f);
+            const float scale = expf(m - m_new), e = expf(0.f - m_new);
+            den = den * scale + e;
+#pragma unroll
+            for (int j = 0; j < 8; j++) bg8[j] = bg8[j] * scale + e * bv8[j];
+            m = m_new;
+        }
+        const float rden = 1.f / den;
+#pragma unroll
+        for (int j = 0; j < 8; j++) bg8[j] *= rden;
+    }
+    const size_t nchunks = (total + 31) / 32, warps = (size_t)gridDim.x * 8;
+    for (size_t ch = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5); ch < nchunks; ch += warps) {
+        const size_t pix_l = ch * 32 + lane;
+        const bool live_l = pix_l < total;
+        const size_t pl = live_l ? pix_l : total - 1;
+        const size_t b_l = pl / hw, p_l = pl % hw;
+        float2 gs[NSMAX];
+        bool any_l = false;
+#pragma unroll
+        for (int s = 0; s < NSMAX; s++) {
+            gs[s] = make_float2(-2.f, -2.f);
+            if (s < ns) {
+                gs[s] = __ldg(reinterpret_cast<const float2*>(T) + (b_l * ns + s) * hw + p_l);
+                const Taps t0 = bilinear_taps(gs[s].x, gs[s].y, h, w);
+                any_l |= (t0.off[0] >= 0) | (t0.off[1] >= 0) | (t0.off[2] >= 0) | (t0.off[3] >= 0);
+            }
+        }
+        const unsigned live_mask = __ballot_sync(0xffffffffu, live_l);
+        const unsigned fg_mask = __ballot_sync(0xffffffffu, live_l && any_l);
+        const unsigned bg_mask = live_mask & ~fg_mask;
+        // ---- background: stream the constant row, PPW pixels per store instruction ----
+        const int nbg = __popc(bg_mask);
+        for (int k = sub; k < nbg; k += PPW) {
+            const int j = __fns(bg_mask, 0, k + 1);
+            store_planes8(out, out_planes, out_plane_stride, (ch * 32 + j) * out_pitch + out_coff + cg * 8, bg8);
+        }
+        // ---- foreground: PPW pixels at a time (every lane takes part in the shuffles) ----
+        const int nfg = __popc(fg_mask);
+        for (int k0 = 0; k0 < nfg; k0 += PPW) {
+            const int k = k0 + sub;
+            const bool act = k < nfg;
+            const int j = act ? __fns(fg_mask, 0, k + 1) : __ffs(fg_mask) - 1;      // idle sub-groups shadow a valid pixel
+            const size_t pix = ch * 32 + j;
+            float xv[8];
+            load_planes8(xt, xt_planes, xt_plane_stride, pix * xt_pitch + xt_coff + cg * 8, xv);
+            float m = -INFINITY, den = 0.f, o8[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) o8[q] = 0.f;
+#pragma unroll
+            for (int s = 0; s < NSMAX; s++) {
+                if (s < ns) {                                   // ns is warp-uniform
+                    const float gx = __shfl_sync(0xffffffffu, gs[s].x, j), gy = __shfl_sync(0xffffffffu, gs[s].y, j);
+                    const Taps t = bilinear_taps(gx, gy, h, w);
+                    const float* src = kv + (size_t)s * hw * KVP;
+                    float kk[8], vv[8], k0v = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) { kk[q] = 0.f; vv[q] = bv8[q]; }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        if (t.off[i] < 0) continue;
+                        const float* pxf = src + (size_t)t.off[i] * KVP;
+                        const float4* px = reinterpret_cast<const float4*>(pxf + cg * 8);
+                        const float4 ka = __ldg(px), kb = __ldg(px + 1), va = __ldg(px + C / 4), vb = __ldg(px + C / 4 + 1);
+                        const float wt = t.wt[i];
+                        if (cg == 0) k0v += __ldg(pxf + 2 * C) * wt;
+                        kk[0] += ka.x * wt; kk[1] += ka.y * wt; kk[2] += ka.z * wt; kk[3] += ka.w * wt;
+                        kk[4] += kb.x * wt; kk[5] += kb.y * wt; kk[6] += kb.z * wt; kk[7] += kb.w * wt;
+                        vv[0] += va.x * wt; vv[1] += va.y * wt; vv[2] += va.z * wt; vv[3] += va.w * wt;
+                        vv[4] += vb.x * wt; vv[5] += vb.y * wt; vv[6] += vb.z * wt; vv[7] += vb.w * wt;
+                    }
+                    float dot = k0v;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) dot += kk[q] * xv[q];
+#pragma unroll
+                    for (int o = LPP / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+                    const float logit = dot * inv_sqrt;
+                    const float m_new = fmaxf(m, logit);
+                    const float scale = expf(m - m_new), e = expf(logit - m_new);
+                    den = den * scale + e;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) o8[q] = o8[q] * scale + e * vv[q];
+                    m = m_new;
+                }
+            }
+            const float rden = 1.f / den;
+#pragma unroll
+            for (int q = 0; q < 8; q++) o8[q] *= rden;
+            if (act) store_planes8(out, out_planes, out_plane_stride, pix * out_pitch + out_coff + cg * 8, o8);
+        }
     }
 }
 
@@ -654,11 +810,17 @@ extern "C" int iper_warp_attention(const void* xt, int xt_planes, long long xt_p
     // gather schedule (see warp_attention_kernel).  Hoisting the 16 gathers only pays on dense synthetic flows at C = 64
     // (1.58 vs 1.73 ms per 50 frames); on real frames most pixels are background whose taps the narrow schedule skips
     // outright (ncu: 406 us narrow vs 542 us wide for the C = 64 stage of a 20-frame batch), so narrow is the default.
-    const char* wide_env = getenv("IPER_ATT_WIDE");
-    const int wide = wide_env ? atoi(wide_env) : 0;
+    // default: the chunked schedule (warp_attention_chunk_kernel); IPER_ATT_WIDE = 0 / 1 / 2 select the pixel-per-warp
+    // schedules above for comparison (read once)
+    static const int wide = [] { const char* v = getenv("IPER_ATT_WIDE"); return v ? atoi(v) : 3; }();
 #define IPER_ATT(CV, NV)                                                                                             \
     do {                                                                                                             \
-        if (wide == 1)                                                                                               \
+        if (wide == 3) {                                                                                             \
+            const int cblocks = (int)min((size_t)148 * 12, ((total + 31) / 32 + 7) / 8);                              \
+            warp_attention_chunk_kernel<CV, NV><<<cblocks, 256, 0, st>>>(x, xt_planes, xt_plane_stride, xt_pitch, xt_coff, kv, \
+                                                                         bias_v, T, B, ns, h, w, o, out_planes,         \
+                                                                         out_plane_stride, out_pitch, out_coff);       \
+        } else if (wide == 1)                                                                                               \
             warp_attention_kernel<CV, NV, 1><<<blocks, 256, 0, st>>>(x, xt_planes, xt_plane_stride, xt_pitch, xt_coff, kv, \
                                                                      bias_v, T, B, ns, h, w, o, out_planes,             \
                                                                      out_plane_stride, out_pitch, out_coff);           \
@@ -678,6 +840,22 @@ extern "C" int iper_warp_attention(const void* xt, int xt_planes, long long xt_p
     if (C == 64) IPER_ATT_C(64); else if (C == 128) IPER_ATT_C(128); else IPER_ATT_C(256);
 #undef IPER_ATT_C
 #undef IPER_ATT
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int iper_stem_im2col(const float* in_nchw, int N, int Cin, int H, int W, void* out, int out_planes,
+                                long long out_plane_stride, int out_pitch, int out_coff, iper_stream_t stream) {
+    IPER_REQUIRE(in_nchw && out, "iper_stem_im2col: null pointer");
+    IPER_REQUIRE(N >= 0 && Cin >= 1 && 9 * Cin <= 64 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0,
+                 "iper_stem_im2col: needs Cin <= 7 and even H, W (got Cin=%d, %dx%d)", Cin, H, W);
+    IPER_REQUIRE(out_pitch % 8 == 0 && out_coff % 8 == 0 && out_coff + 64 <= out_pitch, "iper_stem_im2col: bad output channel window");
+    IPER_REQUIRE(out_planes == 1 || out_planes == 2, "iper_stem_im2col: output format %d not in {1,2}", out_planes);
+    const size_t total = (size_t)N * (H / 2) * (W / 2) * 8;
+    if (total == 0) return 0;
+    const int blocks = (int)min((size_t)148 * 16, (total + 255) / 256);
+    stem_im2col_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in_nchw, N, Cin, H, W, reinterpret_cast<__half*>(out), out_planes,
+                                                                 out_plane_stride, out_pitch, out_coff);
     IPER_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

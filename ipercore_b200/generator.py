@@ -15,6 +15,10 @@ Precision modes (``precision=``):
   "fp16f8"            fp16 main term + the two small cross terms in e4m3 (kind::f8f6f4, 2x rate): 2 MMA-equivalents per
                       K step; also inside the 1e-3 target (measured on the golden cases, see tests);
   "fp16"              single fp16 plane, 1 MMA per K step (≈ TF32-grade operands; ~3e-3 max-abs on the golden case).
+  "mixed"             fp16x2 everywhere except the SPADE convolutions (mlp_shared, gamma|beta: 36 % of the FLOPs), which run
+                      single-pass on the hi plane with single-plane weights and single-plane intermediates.  Opt-in: the
+                      CPU emulation (tools/precision_plan.py) puts it at 6.6e-4 .. 1.8e-3 max-abs depending on weights and
+                      pose — NOT reliably inside the 1e-3 target, so it is never the default or the headline.
 
 Algebraic restructuring used (SURVEY.md §8a note): fk/fv are 1x1 convs of a bilinear warp of constant source features,
 and warp is linear, so  fk(warp(x)) = warp(Wk x) + bk; moreover  K_s.q = warp(Wq^T Wk x_s).x_t + warp(Wk^T bq . x_s) + bk.q
@@ -142,6 +146,7 @@ class AttentionLWBGenerator(nn.Module):
         # halo variant of the CTA-pair kernel (vertical taps share one TMA box; fused transposed-conv phases) wherever
         # a layer qualifies: 3x3 stride-1 convs, the 128->64 transposed conv, the 5x5 heads
         self.halo = self.cta_pair and os.environ.get("IPER_HALO", "1") != "0"
+        self.stem_direct = os.environ.get("IPER_STEM", "tc") == "direct"
         if temporal:
             raise NotImplementedError("temporal=True (TemporalFIFO recurrence, default false in deploy.toml:40) is not "
                                       "on the B200 hot path yet")
@@ -170,15 +175,20 @@ class AttentionLWBGenerator(nn.Module):
 
     # -------------------------------------------------------------------------------------------------------------
     def set_precision(self, precision):
-        fmts = {"fp16": 1, "fp16x2": 2, "fp16f8": 3}
+        fmts = {"fp16": 1, "fp16x2": 2, "fp16f8": 3, "mixed": 2}
         if precision not in fmts:
             raise ValueError("precision must be one of %s" % sorted(fmts))
         self.precision = precision
         self.P = fmts[precision]
+        # per-layer-group operand format overrides (weights and the group's private intermediates); see the module docstring
+        self.plan = {"spade_shared": 1, "spade_gb": 1} if precision == "mixed" else {}
         self._packed_key = None
 
+    def _fmt(self, group):
+        return self.plan.get(group, self.P)
+
     def _key(self):
-        return (self.P, tuple((p.data_ptr(), p._version) for p in self.parameters()))
+        return (self.P, tuple(sorted(self.plan.items())), tuple((p.data_ptr(), p._version) for p in self.parameters()))
 
     def _pack(self):
         """One-time repack of the reference-layout fp32 weights into K-major fp16 planes (redone if params change)."""
@@ -192,8 +202,8 @@ class AttentionLWBGenerator(nn.Module):
             raise RuntimeError("ipercore_b200.AttentionLWBGenerator runs on CUDA only; call .to('cuda') first")
         pk = {}
 
-        def conv(name, bias=True):
-            pk[name] = (ops.pack_conv_weight(sd[name + ".weight"], P), sd.get(name + ".bias") if bias else None)
+        def conv(name, bias=True, fmt=None):
+            pk[name] = (ops.pack_conv_weight(sd[name + ".weight"], fmt or P), sd.get(name + ".bias") if bias else None)
 
         def convT(name):
             pk[name] = (ops.pack_convT_weight(sd[name + ".weight"], P), sd.get(name + ".bias"))
@@ -204,13 +214,18 @@ class AttentionLWBGenerator(nn.Module):
                                               sd[prefix + ".fv.weight"])
             pk[prefix + ".kv"] = (ops.pack_conv_weight(wkv, P), None)
             pk[prefix + ".bv"] = sd[prefix + ".fv.bias"]
-            conv(prefix + ".spade.mlp_shared.0")
+            conv(prefix + ".spade.mlp_shared.0", fmt=self._fmt("spade_shared"))
             pk[prefix + ".spade.gb"] = ops.pack_spade_weight(
                 sd[prefix + ".spade.mlp_gamma.weight"], sd[prefix + ".spade.mlp_gamma.bias"],
-                sd[prefix + ".spade.mlp_beta.weight"], sd[prefix + ".spade.mlp_beta.bias"], P, _bn_for(2 * c))
+                sd[prefix + ".spade.mlp_beta.weight"], sd[prefix + ".spade.mlp_beta.bias"], self._fmt("spade_gb"),
+                _bn_for(2 * c))
 
         for net in ("src_net.encoders", "tsf_net_enc"):
             pk[net + ".stem"] = (sd[net + ".layers.0.0.weight"], sd.get(net + ".layers.0.0.bias"))
+            # tensor-core form of the stem: im2col (K = 54 -> 64) + 1x1 GEMM; always split fp16 — the first layer is the most
+            # precision-sensitive one (tools/precision_plan.py: "enc x1" 3e-3)
+            pk[net + ".stem_tc"] = (ops.pack_stem_weight(sd[net + ".layers.0.0.weight"], 2 if P != 1 else 1),
+                                    sd.get(net + ".layers.0.0.bias"))
             for i in (1, 2):
                 conv("%s.layers.%d.0" % (net, i))
         for i in range(self.n_res):
@@ -256,6 +271,21 @@ class AttentionLWBGenerator(nn.Module):
                 return 2
         return int(self.P != 3 and rows >= 128 and mode != ops.IPER_CONV_ROW5)     # plain CTA pairs: formats 1/2 only
 
+    def _stem(self, pk, net, x_in, out, stats_ws=None):
+        """Encoder.layers[0] (attlwb_spade_resunet.py:268-271): conv3x3 s2 (Cin = 6) + ReLU.  Default: im2col + tcgen05 1x1 GEMM
+        (IPER_STEM=direct selects the CUDA-core kernel, kept as the cross-check)."""
+        if self.stem_direct or out.P == 3:
+            w, b = pk[net + ".stem"]
+            ops.conv_stem(x_in, w, b, out, stats_ws=stats_ws)
+            return out
+        w, b = pk[net + ".stem_tc"]
+        N, _, H, W = x_in.shape
+        col = Planes.empty(w.fmt, N, H // 2, W // 2, 64, x_in.device)
+        ops.stem_im2col(x_in, col)
+        ops.conv_gemm(col, w, IPER_CONV_S1, 1, w.rows_total, 64, IPER_EPI_PLANES, bias=b, relu=True, out=out, stats_ws=stats_ws,
+                      cta_pair=0)
+        return out
+
     def _project_kv(self, pk, prefix, feat):
         """source maps [(Wq^T Wk) x | Wv x | (Wk^T bq).x | pad] of source features: Planes (ns,h,w,C) -> fp32 (ns,h,w,2C+64)."""
         w, _ = pk[prefix + ".kv"]
@@ -279,10 +309,9 @@ class AttentionLWBGenerator(nn.Module):
         bs, ns, _, S, _ = src_inputs.shape
         x_in = src_inputs.reshape(bs * ns, -1, S, S).float().contiguous()
         N, P, dev = bs * ns, self.P, src_inputs.device
-        w, b = pk["src_net.encoders.stem"]
         feats = []
         x = Planes.empty(P, N, S // 2, S // 2, 64, dev)
-        ops.conv_stem(x_in, w, b, x)
+        self._stem(pk, "src_net.encoders", x_in, x)
         feats.append(x)
         for i, c in ((1, 128), (2, 256)):
             y = Planes.empty(P, N, x.H // 2, x.W // 2, c, dev)
@@ -350,9 +379,10 @@ class AttentionLWBGenerator(nn.Module):
             """SelfAttentionLWB.forward (attlwb_spade_resunet.py:208-252); `ws` = fp64 sums of x from its producer."""
             C, h = x.C, x.H
             stats = ops.instnorm_finalize(ws, h * h)
-            a = Planes.empty(P, B, h, h, C, dev)
+            # `a` feeds only mlp_shared and `actv` only gamma|beta: a single-pass consumer needs one plane of them
+            a = Planes.empty(min(P, self._fmt("spade_shared")), B, h, h, C, dev)
             ops.warp_attention(x, self._kv_for(pk, prefix, src_x), pk[prefix + ".bv"], flow_at(h), a)
-            actv = Planes.empty(P, B, h, h, 128, dev)
+            actv = Planes.empty(min(P, self._fmt("spade_gb")), B, h, h, 128, dev)
             self._conv(pk, prefix + ".spade.mlp_shared.0", a, IPER_CONV_S1, 3, actv, relu=True)
             wgb, bgb = pk[prefix + ".spade.gb"]
             if out is None:
@@ -362,10 +392,9 @@ class AttentionLWBGenerator(nn.Module):
             return out
 
         # 1. encoder (:507-519)
-        w, b = pk["tsf_net_enc.stem"]
         x = Planes.empty(P, B, S // 2, S // 2, nf[0], dev)
         ws = ops.stats_workspace(B, nf[0], dev)
-        ops.conv_stem(tsf_inputs, w, b, x, stats_ws=ws)          # instance-norm statistics fused into every producer
+        self._stem(pk, "tsf_net_enc", tsf_inputs, x, stats_ws=ws)   # instance-norm statistics fused into every producer
         for i in range(3):
             if i > 0:
                 y = Planes.empty(P, B, x.H // 2, x.W // 2, nf[i], dev)

@@ -231,6 +231,22 @@ def conv_stem(x_nchw, w_f32, bias, out, stats_ws=None):
                              out.P, out.plane_stride, out.pitch, out.coff, _ptr(stats_ws), _stream()), "conv_stem")
 
 
+def stem_im2col(x_nchw, out):
+    """(N,Cin<=7,H,W) fp32 -> Planes (N,H/2,W/2,64): 3x3/s2/p1 patches, channel k = (ky*3+kx)*Cin + ci (iper_stem_im2col)."""
+    x_nchw = _req(x_nchw, torch.float32, "x")
+    N, Cin, H, W = x_nchw.shape
+    check(lib.iper_stem_im2col(x_nchw.data_ptr(), N, Cin, H, W, out.ptr(), out.P, out.plane_stride, out.pitch, out.coff,
+                               _stream()), "stem_im2col")
+    return out
+
+
+def pack_stem_weight(w, P):
+    """Conv2d(Cin<=7 -> Cout, 3x3) weight -> (P, Cout, 64), K = (ky*3+kx)*Cin + ci zero-padded to 64 (matches stem_im2col)."""
+    Cout, Cin = w.shape[:2]
+    m = w.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).float()
+    return PackedW(torch.cat([m, m.new_zeros(Cout, 64 - 9 * Cin)], 1), P)
+
+
 def stats_workspace(N, C, device):
     return torch.empty((N, C, 2), dtype=torch.float64, device=device)
 
