@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="imitate", choices=["imitate", "train"],
+                    help="imitate = BASELINE.json configs[1] (the headline); train = configs[4], one G + D + VGG training step per rank")
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--frames", type=int, default=300)
     ap.add_argument("--batch", type=int, default=60)
@@ -256,6 +258,71 @@ def gpu_library_baseline(args, dev, wl, render, src_inputs, src_f2pts):
     return out
 
 
+def run_train(args):
+    """BASELINE.json configs[4]: 512x512 training step (G + D + VGG perceptual) in bf16, one sample per rank, gradients averaged with
+    bucketed flat NCCL all-reduces overlapped with backward (ipercore_b200/train.py).  A side benchmark: the driver's headline
+    is the default --config imitate.  value = training samples per second over all ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ipercore_b200 import _lib, train
+    from ipercore_b200.generator import AttentionLWBGenerator
+    from oracle import weights
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    S, ns = args.size, args.ns
+    net = AttentionLWBGenerator(CFG)
+    net.load_state_dict(weights.synth_state_dict(0), strict=True)
+    step = train.LWGTrainStep(net, dev, distributed=world > 1)
+    g = torch.Generator().manual_seed(100 + rank)
+    r = lambda *s: (torch.rand(*s, generator=g) * 2 - 1).to(dev)
+    batch = dict(bg_inputs=torch.cat([r(1, 1, 3, S, S), (r(1, 1, 1, S, S) > 0).float()], 2), src_inputs=r(1, ns, 6, S, S),
+                 tsf_inputs=r(1, 1, 6, S, S), Tst=r(1, 1, ns, S, S, 2), real_src=r(1, ns, 3, S, S), real_tsf=r(1, 1, 3, S, S),
+                 real_bg=r(1, 3, S, S), body_mask=(r(1, ns + 1, 1, S, S) > 0).float())
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 1)):
+        out = step.step(batch)
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.start()
+    e0.record()
+    for _ in range(args.steps):
+        out = step.step(batch)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        n_g = sum(p.numel() for p in step.G.parameters()); n_d = sum(p.numel() for p in step.D.parameters())
+        line = {"metric": "lwg_training_samples_per_sec", "value": world * args.steps / (ms * 1e-3), "unit": "samples/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "LWG training step %dx%d: G (AttLWB-SPADE) + D (patch_global) + VGG19 perceptual, batch 1 per GPU, "
+                                       "ns=%d, nt=1 (BASELINE.json configs[4])" % (S, S, ns),
+                           "kernels": "3x3/s1 convs (fwd, dgrad, wgrad) on tcgen05 bf16; the rest of the step is PyTorch bf16",
+                           "allreduce": "bucketed flat NCCL all-reduce of %d G + %d D gradients, overlapped with backward" % (n_g, n_d)},
+                "gpu_launches": int(_lib.launch_count() - n0), "clocks": clocks,
+                "losses": {k: float(v) for k, v in out.items()}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def config_block(args, launches):
     return {"workload": "run_imitator %dx%d: 1 source set (ns=%d) -> %d synthetic target SMPL poses per GPU "
                         "(BASELINE.json configs[1])" % (args.size, args.size, args.ns, args.frames),
@@ -270,6 +337,8 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == "train":
+        return run_train(args)
     import numpy as np
     import torch
     import torch.distributed as dist

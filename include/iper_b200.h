@@ -285,6 +285,22 @@ int iper_uv_warp(const float* src_img, const float* f2pts, const float* vis_f2pt
 int iper_uv_merge(const float* src_warp, const float* vis_dilated, int bs, int ns, int H, int W, float* uv_img,
                   iper_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Training-step kernels (BASELINE.json configs[4]): the 3x3 / stride-1 / pad-1 convolutions of the
+ * generator in bf16 on the tensor cores — forward, data gradient and weight gradient — which the reference trains through
+ * cuDNN (iPERCore/tools/trainers/lwg_trainer.py:699-833 on attlwb_spade_resunet.py:14-25, 80-93, 316-357).
+ *   iper_conv3x3_bf16        y (N,H,W,Cout) = conv(x (N,H,W,Cin) NHWC bf16 = torch channels_last, w_packed (Cout, 9*Cin) bf16 with
+ *                            K = (ky*3+kx)*Cin + ci) [+ bias fp32] [ReLU].  dgrad = the same call on dY with the weights
+ *                            rotated by 180 degrees and in/out transposed: w'(ci, (2-ky, 2-kx), co) = w(co, ci, ky, kx).
+ *   iper_conv3x3_wgrad_bf16  dW (Cout, 9, Cin) fp32 = sum over pixels of dY (N,Cout,H,W) x X (N,Cin,H,W) shifted by the tap; both
+ *                            operands NCHW bf16 (pixels contiguous = K-major rows for the pixel contraction), W %% 64 == 0.
+ * Cin, Cout multiples of 64 (one of them of 128 for wgrad); H >= 8, W >= 16.
+ * ---------------------------------------------------------------------------------------------------------- */
+int iper_conv3x3_bf16(const void* x_nhwc, int N, int H, int W, int Cin, const void* w_packed, int Cout, const float* bias,
+                      int relu, void* out_nhwc, iper_stream_t stream);
+int iper_conv3x3_wgrad_bf16(const void* x_nchw, const void* dy_nchw, int N, int H, int W, int Cin, int Cout, float* dW,
+                            iper_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

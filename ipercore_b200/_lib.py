@@ -70,6 +70,8 @@ SIGNATURES = {
     "iper_nhwc_f32_to_nchw": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "iper_pred_to_u8": [c_void_p, c_int, c_int, c_void_p, c_void_p],
     "iper_morph": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "iper_conv3x3_bf16": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p],
+    "iper_conv3x3_wgrad_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "iper_gen_create": [c_void_p, c_int, c_int, c_int, c_void_p],
     "iper_gen_load_weight": [c_void_p, ctypes.c_char_p, c_void_p, c_void_p, c_int],
     "iper_gen_pack": [c_void_p, c_void_p, c_size_t, c_void_p],
