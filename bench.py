@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--dump-layers", default="", help="write the per-launch conv timing table (JSON) to this path")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=8)
+    ap.add_argument("--profile-batch", action="store_true",
+                    help="for ncu --profile-from-start off: warm up, then run exactly ONE eager batch between cudaProfilerStart/Stop and exit")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of sampled frames of the last step")
     ap.add_argument("--no-lib-baseline", action="store_true", help="skip the reference-generator-on-cuDNN side leg")
     ap.add_argument("--no-png", action="store_true", help="skip the e2e pass that also writes the PNG files")
@@ -423,6 +425,16 @@ def main():
             ms = float(tt)
         return ms, wall
 
+    if args.profile_batch:
+        eng.use_graph = False
+        eng.run_batch_device(cams_d[:B], verts_d[:B])          # warm-up (packs weights, fills caches)
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
+        eng.run_batch_device(cams_d[:B], verts_d[:B])
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profile_batch": B, "launches_per_batch": eng.launches_per_batch}))
+        return
     for _ in range(max(args.warmup, 1)):
         step_device()
     sampler = ClockSampler(local) if rank == 0 else None
