@@ -452,34 +452,37 @@ def main():
     # out_h holds every uint8 frame of the last e2e step; eng.last_pred the float composites of its last batch.
     cpu, parity = None, None
     if rank == 0 and not args.no_parity:
-        keep = {}
-        if world == 1 and not args.no_cpu_baseline:     # the cpu_baseline leg already runs the oracle: keep its frames
-            v, cores, _ = cpu_frames_per_sec(args, wl, args.cpu_frames, keep=keep)
-            cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
-                   "sample": "first %d frames of the 300-pose clip through the oracle port (CPU restatement of raster + "
-                             "flow + forward_tsf + composite, torch fp32, all host threads); source setup untimed" % args.cpu_frames}
-        last_lo = (nb - 1) * B
-        extra = sorted({last_lo, T - 1, min(B - 1, T - 1), min(B, T - 1)} - set(keep))   # batch edges + the last batch
-        cpu_frames_per_sec(args, wl, 0, keep=keep, frames=extra)
-        idx = sorted(keep)
-        got_u8 = out_h.numpy()
-        code = max(int(np.abs(got_u8[i].astype(np.int32) - keep[i]["u8"].astype(np.int32)).max()) for i in idx)
-        frac = float(np.mean([(got_u8[i] != keep[i]["u8"]).mean() for i in idx]))
-        sel = torch.tensor(idx, device=dev)
-        fi = render.frame_inputs(cams_d[sel].contiguous(), verts_d[sel].contiguous(), eng.src["uv_img"], eng.src["src_f2pts"],
-                                 want_fim=True)
-        fim_equal = all(np.array_equal(fi["fim"][k].cpu().numpy(), keep[i]["fim"]) for k, i in enumerate(idx))
-        lastp = eng.last_pred.float().cpu().numpy()      # composites of the last batch of the last e2e step
-        fl = [i for i in idx if i >= last_lo]
-        max_abs = max(float(np.abs(lastp[i - last_lo] - keep[i]["pred"]).max()) for i in fl)
-        parity = {"frames": len(idx), "frame_ids": idx, "max_abs": max_abs, "max_abs_frames": fl, "tolerance": 1e-3,
-                  "u8_max_code_diff": code, "u8_frac_differing": frac, "fim_equal": bool(fim_equal),
-                  "ok": bool(fim_equal and max_abs <= 1e-3 and code <= 1),
-                  "against": "oracle port (CPU restatement pinned to the reference's own modules by tests/golden) on the "
-                             "uint8 frames of the last timed e2e step (all sampled frames) and the float composites of its "
-                             "last batch; face-index maps re-rendered for the sampled frames"}
-        if not parity["ok"]:
-            sys.stderr.write("bench.py: PARITY FAILED %s\n" % json.dumps(parity))
+        try:
+            keep = {}
+            if world == 1 and not args.no_cpu_baseline:     # the cpu_baseline leg already runs the oracle: keep its frames
+                v, cores, _ = cpu_frames_per_sec(args, wl, args.cpu_frames, keep=keep)
+                cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port",
+                       "sample": "first %d frames of the 300-pose clip through the oracle port (CPU restatement of raster + "
+                                 "flow + forward_tsf + composite, torch fp32, all host threads); source setup untimed" % args.cpu_frames}
+            last_lo = (nb - 1) * B
+            extra = sorted({last_lo, T - 1, min(B - 1, T - 1), min(B, T - 1)} - set(keep))   # batch edges + the last batch
+            cpu_frames_per_sec(args, wl, 0, keep=keep, frames=extra)
+            idx = sorted(keep)
+            got_u8 = out_h.numpy()
+            code = max(int(np.abs(got_u8[i].astype(np.int32) - keep[i]["u8"].astype(np.int32)).max()) for i in idx)
+            frac = float(np.mean([(got_u8[i] != keep[i]["u8"]).mean() for i in idx]))
+            sel = torch.tensor(idx, device=dev)
+            fi = render.frame_inputs(cams_d[sel].contiguous(), verts_d[sel].contiguous(), eng.src["uv_img"], eng.src["src_f2pts"],
+                                     want_fim=True)
+            fim_equal = all(np.array_equal(fi["fim"][k].cpu().numpy(), keep[i]["fim"]) for k, i in enumerate(idx))
+            lastp = eng.last_pred.float().cpu().numpy()      # composites of the last batch of the last e2e step
+            fl = [i for i in idx if i >= last_lo]
+            max_abs = max(float(np.abs(lastp[i - last_lo] - keep[i]["pred"]).max()) for i in fl)
+            parity = {"frames": len(idx), "frame_ids": idx, "max_abs": max_abs, "max_abs_frames": fl, "tolerance": 1e-3,
+                      "u8_max_code_diff": code, "u8_frac_differing": frac, "fim_equal": bool(fim_equal),
+                      "ok": bool(fim_equal and max_abs <= 1e-3 and code <= 1),
+                      "against": "oracle port (CPU restatement pinned to the reference's own modules by tests/golden) on the "
+                                 "uint8 frames of the last timed e2e step (all sampled frames) and the float composites of its "
+                                 "last batch; face-index maps re-rendered for the sampled frames"}
+            if not parity["ok"]:
+                sys.stderr.write("bench.py: PARITY FAILED %s\n" % json.dumps(parity))
+        except Exception as exc:     # a checker failure must be visible in the line, never lose the measurement
+            parity = {"ok": False, "error": "%s: %s" % (type(exc).__name__, exc)}
 
     # ---- output stage: the same e2e pass with PNG files written like Imitator.inference does (pred_%08d.png), encodes
     #      overlapped with the next batch (engine.synthesize_stream + patch.FrameWriter); rank 0, one pass ----------------
@@ -504,6 +507,8 @@ def main():
             e2e_png = {"value": T / w_png, "unit": "frames/s", "frames": T, "workers": host_cores(),
                        "png_bytes_per_frame": nbytes // T, "timing": "host wall clock around one whole clip incl. the last file",
                        "files": "pred_%08d.png (cv2.imwrite, uint8 BGR), " + ("tmpfs" if out_dir.startswith("/dev/shm") else "tmp dir")}
+        except Exception as exc:
+            e2e_png = {"error": "%s: %s" % (type(exc).__name__, exc)}
         finally:
             shutil.rmtree(out_dir, ignore_errors=True)
 
