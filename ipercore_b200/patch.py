@@ -179,7 +179,7 @@ def batched_inference(imitator, tgt_smpls, cam_strategy="smooth", output_dir="",
 
     Per-sequence host pre-pass exactly as upstream (:337-339, :298-305): stabilise, first_cam, cam swap; the SMPL body
     model produces the vertices in chunks of `batch` frames — on the device LBS kernels (ipercore_b200.smpl, built from
-    the reference body model's buffers) unless install(device_lbs=False) or the model uses hand PCA.  Every batch is
+    the reference body model's buffers, hand-pose PCA included) unless install(device_lbs=False).  Every batch is
     issued on the engine's stream (cam swap -> LBS -> raster -> generator -> uint8 -> D2H into a bounded pinned ring) and
     its PNG files are encoded on a thread pool while the GPU runs the next batch.  The CUDA graph is captured once per
     source set, not per call.  Returns the list of paths (or of CHW float arrays when output_dir is empty)."""
@@ -204,7 +204,7 @@ def batched_inference(imitator, tgt_smpls, cam_strategy="smooth", output_dir="",
         eng._src_key = key
     from .smpl import SMPLHDevice
     body = imitator.body_rec
-    if (_DEVICE_LBS and not isinstance(body, SMPLHDevice) and not getattr(body, "use_pca", False)
+    if (_DEVICE_LBS and not isinstance(body, SMPLHDevice)
             and not (hasattr(src["links_ids"], "ndim") and src["links_ids"].ndim == 3)):
         if getattr(imitator, "_iper_smpl", None) is None:
             imitator._iper_smpl = SMPLHDevice.from_reference(body).to(dev)

@@ -7,7 +7,7 @@ path reads (cam, pose, shape, verts, j3d, j2d, theta).  Shape-dependent quantiti
 (betas, offsets): in run_imitator every target frame uses the SOURCE shape (imitator.py:248-256).
 
 Model parameters come from the user's SMPL pkl (through the reference's own loader) or from arrays; the hand-pose PCA
-path (use_pca) is not on the default path and not supported.
+path (``use_pca``: 78-dim poses, batch_smplh.py:160-168) is expanded with the model's PCA components before the kernels.
 """
 import numpy as np
 import torch
@@ -18,7 +18,8 @@ from .ops import _ptr, _stream
 
 
 class SMPLHDevice(nn.Module):
-    def __init__(self, v_template, shapedirs, posedirs, J_regressor, parents, lbs_weights, hands_mean=None):
+    def __init__(self, v_template, shapedirs, posedirs, J_regressor, parents, lbs_weights, hands_mean=None,
+                 left_hand_components=None, right_hand_components=None, use_pca=False):
         super().__init__()
         f = lambda a: torch.as_tensor(np.asarray(a), dtype=torch.float32).contiguous()
         self.nv, self.nj, self.nb = int(v_template.shape[0]), int(J_regressor.shape[0]), int(shapedirs.shape[-1])
@@ -32,6 +33,15 @@ class SMPLHDevice(nn.Module):
             self.register_buffer("hands_mean", f(hands_mean))
         else:
             self.hands_mean = None
+        # hand-pose PCA (batch_smplh.py:25-26, 105-131, 160-168): 78-dim poses = 66 body + 6 + 6 PCA coefficients
+        self.use_pca = bool(use_pca)
+        if left_hand_components is not None and right_hand_components is not None:
+            self.register_buffer("left_hand_components", f(left_hand_components))
+            self.register_buffer("right_hand_components", f(right_hand_components))
+        else:
+            self.left_hand_components = self.right_hand_components = None
+        if self.use_pca and self.left_hand_components is None:
+            raise ValueError("use_pca needs the left/right hand PCA components")
         assert self.posedirs.shape == ((self.nj - 1) * 9, self.nv * 3)
         self._shape_key, self._shape_cache = None, None
         self._pinned = False
@@ -41,7 +51,8 @@ class SMPLHDevice(nn.Module):
         """Build from an instantiated reference ``SMPLH`` / ``SMPL`` module (its registered buffers)."""
         n = lambda t: None if t is None else (t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t))
         return cls(n(smplh.v_template), n(smplh.shapedirs), n(smplh.posedirs), n(smplh.J_regressor), n(smplh.parents),
-                   n(smplh.lbs_weights), n(getattr(smplh, "hands_mean", None)))
+                   n(smplh.lbs_weights), n(getattr(smplh, "hands_mean", None)), n(getattr(smplh, "left_hand_components", None)),
+                   n(getattr(smplh, "right_hand_components", None)), use_pca=bool(getattr(smplh, "use_pca", False)))
 
     # ---- one-time per shape ----------------------------------------------------------------------------------------
     def pin_shape(self, betas, offsets=0):
@@ -96,6 +107,10 @@ class SMPLHDevice(nn.Module):
             if self.hands_mean is None:
                 raise ValueError("72-dim pose needs hands_mean (SMPLH)")
             theta = torch.cat([theta[:, :66], self.hands_mean[None].expand(N, -1)], dim=1)
+        if self.use_pca:        # batch_smplh.py:160-168: the last 12 values are PCA coefficients of the two hands
+            lh = theta[:, -12:-6] @ self.left_hand_components
+            rh = theta[:, -6:] @ self.right_hand_components
+            theta = torch.cat([theta[:, :-12], lh, rh], dim=1)
         if theta.shape[1] != self.nj * 3:
             raise ValueError("pose has %d dims, model has %d joints" % (theta.shape[1], self.nj))
         if not self._pinned and beta.dim() == 2 and beta.shape[0] > 1 and not bool((beta == beta[0:1]).all()):

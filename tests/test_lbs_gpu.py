@@ -54,3 +54,31 @@ def test_lbs_batch_and_get_details(template):
     z, _, _ = dev(torch.from_numpy(beta).cuda(), torch.zeros(1, 156).cuda())
     vs = m["v_template"] + np.einsum("l,mkl->mk", beta[0], m["shapedirs"])
     np.testing.assert_allclose(z[0].cpu().numpy(), vs, atol=2e-6, rtol=0)
+
+
+def test_hand_pca_and_from_reference_cuda_module(template):
+    """use_pca (batch_smplh.py:160-168): 78-dim poses expand through the PCA components exactly like the full 156-dim pose;
+    from_reference() accepts a CUDA-resident module (every buffer, hands_mean included, is a device tensor there)."""
+    import types
+    from ipercore_b200.smpl import SMPLHDevice
+    from oracle import lbs_ref, synth
+    m = lbs_ref.synthetic_smplh(template=synth.base_verts(template).astype(np.float32))
+    rng = np.random.Generator(np.random.PCG64(11))
+    comps_l = np.linalg.qr(rng.standard_normal((45, 45)))[0][:6].astype(np.float32)
+    comps_r = np.linalg.qr(rng.standard_normal((45, 45)))[0][:6].astype(np.float32)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    ref_module = types.SimpleNamespace(v_template=t(m["v_template"]), shapedirs=t(m["shapedirs"]), posedirs=t(m["posedirs"]),
+                                       J_regressor=t(m["J_regressor"]), parents=t(m["parents"]), lbs_weights=t(m["lbs_weights"]),
+                                       hands_mean=t(m["hands_mean"]), left_hand_components=t(comps_l), right_hand_components=t(comps_r),
+                                       use_pca=True)
+    body = SMPLHDevice.from_reference(ref_module).to(dev)
+    assert body.use_pca and body.hands_mean is not None
+    betas = (rng.standard_normal((1, 10)) * 0.5).astype(np.float32)
+    pose78 = (rng.standard_normal((3, 78)) * 0.3).astype(np.float32)
+    v_pca, j_pca, full = body(t(betas), t(pose78))
+    full_np = np.concatenate([pose78[:, :66], pose78[:, 66:72] @ comps_l, pose78[:, 72:78] @ comps_r], 1)
+    np.testing.assert_allclose(full.cpu().numpy(), full_np, atol=1e-6)
+    v_ref, j_ref = lbs_ref.lbs(m, np.repeat(betas, 3, 0), full_np)
+    np.testing.assert_allclose(v_pca.cpu().numpy(), v_ref, atol=2e-5)
+    np.testing.assert_allclose(j_pca.cpu().numpy(), j_ref, atol=2e-5)
