@@ -147,14 +147,13 @@ class AttentionLWBGenerator(nn.Module):
         # a layer qualifies: 3x3 stride-1 convs, the 128->64 transposed conv, the 5x5 heads
         self.halo = self.cta_pair and os.environ.get("IPER_HALO", "1") != "0"
         self.stem_direct = os.environ.get("IPER_STEM", "tc") == "direct"
-        if temporal:
-            raise NotImplementedError("temporal=True (TemporalFIFO recurrence, default false in deploy.toml:40) is not "
-                                      "on the B200 hot path yet")
         get = (lambda o, k: o[k]) if isinstance(cfg, dict) else getattr
         self._name = get(cfg, "name") if (isinstance(cfg, dict) and "name" in cfg) or hasattr(cfg, "name") else "AttLWB-SPADE"
         bg, sid, tsf = get(cfg, "BGNet"), get(cfg, "SIDNet"), get(cfg, "TSFNet")
         nf = list(get(tsf, "num_filters")); n_res = get(tsf, "n_res_block")
-        self.temporal = False
+        # temporal attention (SelfAttentionLWB.forward :208-252 with temp_x / Ttt): the previous frames' features are extra
+        # attention sources with their own flow; the parameters are the same, only forward_tsf's inputs differ
+        self.temporal = bool(temporal)
         self.num_filters, self.n_res = nf, n_res
         self.bg_net = _BGNetParams(get(bg, "cond_nc"), list(get(bg, "num_filters")), get(bg, "n_res_block"))
         self.src_net = _SIDNetParams(get(sid, "cond_nc"), list(get(sid, "num_filters")), get(sid, "n_res_block"))
@@ -343,11 +342,19 @@ class AttentionLWBGenerator(nn.Module):
 
         With ``bg_img`` ((1|bs),3,S,S) and ``return_pred`` the heads epilogue also writes the composite
         ``mask*bg + (1-mask)*img`` of Imitator.forward (models/imitator.py:393) and returns it as a third value."""
-        if temp_enc_outs is not None or Ttt is not None:
-            raise NotImplementedError("temporal attention inputs are not supported on the B200 path (temporal=false)")
+        temporal = self.temporal and temp_enc_outs is not None and temp_res_outs is not None and Ttt is not None
         pk = self._pack()
         B, ns, S, _, _ = Tst.shape
-        n_src = src_enc_outs[0].shape[0]
+        if temporal:
+            # attlwb_spade_resunet.py:230-246: K/V of the nt previous frames are concatenated to the ns sources.  The frame loop
+            # is a recurrence (TemporalFIFO, imitator.py:18-127), so this mode runs one frame at a time
+            if B != 1:
+                raise NotImplementedError("temporal attention is a frame recurrence: forward_tsf takes bs = 1 in this mode")
+            Tst = torch.cat([Tst.float(), Ttt.float().reshape(B, -1, S, S, 2)], dim=1).contiguous()
+            src_enc_outs = [(s_, t_) for s_, t_ in zip(src_enc_outs, temp_enc_outs)]
+            src_res_outs = [(s_, t_) for s_, t_ in zip(src_res_outs, temp_res_outs)]
+            ns = Tst.shape[1]
+        n_src = ns if temporal else src_enc_outs[0].shape[0]
         if n_src != ns:
             # reference semantics (attlwb_spade_resunet.py:208-252): source features are (bs*ns, ...) and item b attends
             # to ITS OWN ns sources.  The kernels share one source set across the batch (the run_imitator case, bs=1
@@ -381,7 +388,11 @@ class AttentionLWBGenerator(nn.Module):
             stats = ops.instnorm_finalize(ws, h * h)
             # `a` feeds only mlp_shared and `actv` only gamma|beta: a single-pass consumer needs one plane of them
             a = Planes.empty(min(P, self._fmt("spade_shared")), B, h, h, C, dev)
-            ops.warp_attention(x, self._kv_for(pk, prefix, src_x), pk[prefix + ".bv"], flow_at(h), a)
+            if isinstance(src_x, tuple):       # temporal: (source features, previous-frame features) -> one list of maps
+                kv = torch.cat([self._kv_for(pk, prefix, t_) for t_ in src_x], dim=0)
+            else:
+                kv = self._kv_for(pk, prefix, src_x)
+            ops.warp_attention(x, kv, pk[prefix + ".bv"], flow_at(h), a)
             actv = Planes.empty(min(P, self._fmt("spade_gb")), B, h, h, 128, dev)
             self._conv(pk, prefix + ".spade.mlp_shared.0", a, IPER_CONV_S1, 3, actv, relu=True)
             wgb, bgb = pk[prefix + ".spade.gb"]

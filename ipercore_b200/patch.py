@@ -8,8 +8,9 @@ What is replaced, at the reference's own seams:
   B2  ``BaseSMPLRenderer/SMPLRenderer.render_fim_wim``, ``cal_bc_transform``, ``encode_fim``, ``get_vis_f2pts`` (nmr.py:319-342,
       390-401, 639-681, 713-757, and the bs==3 loop :892-918) -> CUDA kernels; every other method and all buffers stay the
       reference's
-  B3  ``NetworksFactory.get_by_name("AttLWB-SPADE", cfg=..., temporal=False)`` (networks/__init__.py:14-16)
-      -> ipercore_b200.generator.AttentionLWBGenerator (loads the same checkpoints)
+  B3  ``NetworksFactory.get_by_name("AttLWB-SPADE", cfg=..., temporal=...)`` (networks/__init__.py:14-16)
+      -> ipercore_b200.generator.AttentionLWBGenerator (loads the same checkpoints); with ``temporal=true`` the upstream bs=1
+      loop (TemporalFIFO recurrence) drives it frame by frame
   B2' ``iPERCore.tools.utils.morphology.morph / soft_dilate`` (morph_ops.py:7-61; source_setup masks,
       flowcomposition.py:121,176-180,258) -> iper_morph (separable box sum + threshold); custom ``kernel=`` calls, CPU
       tensors and even / > 63 sizes keep going to the reference implementation
@@ -112,7 +113,7 @@ def install(precision="fp16x2", batch=16, patch_inference=True, device_lbs=True)
     upstream_get = NetworksFactory.get_by_name
 
     def get_by_name(network_name, *args, **kwargs):
-        if network_name == "AttLWB-SPADE" and not kwargs.get("temporal", False):
+        if network_name == "AttLWB-SPADE":
             net = AttentionLWBGenerator(*args, precision=precision, **kwargs)
             print("Network %s was created (ipercore_b200, %s)" % (network_name, precision))
             return net

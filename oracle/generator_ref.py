@@ -56,13 +56,18 @@ def spade(sd, prefix, x, cond):
     return normalized * (1 + gamma) + beta
 
 
-def self_attention_lwb(sd, prefix, tsf_x, src_x, Tst):
-    """SelfAttentionLWB.forward (attlwb_spade_resunet.py:208-252), temporal branch off."""
+def self_attention_lwb(sd, prefix, tsf_x, src_x, Tst, temp_x=None, Ttt=None):
+    """SelfAttentionLWB.forward (attlwb_spade_resunet.py:208-252); temp_x / Ttt = the temporal branch (:230-246)."""
     bs, ns, H, W, _ = Tst.shape
     h, w = tsf_x.shape[-2:]
     src_warp = lwb_transform(src_x, Tst.reshape(bs * ns, H, W, 2))
     k = _conv(sd, prefix + ".fk", src_warp).view(bs, ns, -1, h, w)
     v = _conv(sd, prefix + ".fv", src_warp).view(bs, ns, -1, h, w)
+    if temp_x is not None and Ttt is not None:
+        nt = Ttt.shape[1]
+        temp_warp = lwb_transform(temp_x, Ttt.reshape(bs * nt, H, W, 2))
+        k = torch.cat([k, _conv(sd, prefix + ".fk", temp_warp).view(bs, nt, -1, h, w)], dim=1)
+        v = torch.cat([v, _conv(sd, prefix + ".fv", temp_warp).view(bs, nt, -1, h, w)], dim=1)
     q = _conv(sd, prefix + ".fq", tsf_x)
     x = attention(q, k, v)
     return spade(sd, prefix + ".spade", tsf_x, x)
@@ -83,8 +88,9 @@ def forward_src(sd, src_inputs, n_res=6):
     return enc_outs, res_outs
 
 
-def forward_tsf(sd, tsf_inputs, src_enc_outs, src_res_outs, Tst, n_res=6, taps=None):
-    """BaseAttentionLWBGenerator.forward_tsf (attlwb_spade_resunet.py:480-535), temporal off.
+def forward_tsf(sd, tsf_inputs, src_enc_outs, src_res_outs, Tst, n_res=6, taps=None, temp_enc_outs=None, temp_res_outs=None,
+                Ttt=None):
+    """BaseAttentionLWBGenerator.forward_tsf (attlwb_spade_resunet.py:480-535); temp_* / Ttt = temporal attention inputs.
 
     ``taps`` (optional dict) collects intermediates for layer-wise debugging of the CUDA path."""
     x = tsf_inputs
@@ -93,13 +99,15 @@ def forward_tsf(sd, tsf_inputs, src_enc_outs, src_res_outs, Tst, n_res=6, taps=N
         x = F.relu(_conv(sd, "tsf_net_enc.layers.%d.0" % i, x, stride=2, padding=1))
         if taps is not None:
             taps["enc%d_conv" % i] = x
-        x = self_attention_lwb(sd, "enc_attlwbs.%d" % i, x, src_enc_outs[i], Tst)
+        x = self_attention_lwb(sd, "enc_attlwbs.%d" % i, x, src_enc_outs[i], Tst,
+                               None if temp_enc_outs is None else temp_enc_outs[i], Ttt)
         if taps is not None:
             taps["enc%d" % i] = x
         enc_outs.append(x)
     for i in range(n_res):
         x = residual_block(sd, "res_blocks.%d" % i, x)
-        x = self_attention_lwb(sd, "res_attlwbs.%d" % i, x, src_res_outs[i], Tst)
+        x = self_attention_lwb(sd, "res_attlwbs.%d" % i, x, src_res_outs[i], Tst,
+                               None if temp_res_outs is None else temp_res_outs[i], Ttt)
         if taps is not None:
             taps["res%d" % i] = x
     # SkipDecoder.forward (attlwb_spade_resunet.py:348-357)

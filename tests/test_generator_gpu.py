@@ -106,3 +106,25 @@ def test_generic_sizes_and_source_counts(S, ns, B, template):
             err = max(err, float((img[i:i + 1].cpu() - ei).abs().max()), float((mask[i:i + 1].cpu() - em).abs().max()))
     print("S=%d ns=%d: max-abs err %.2e" % (S, ns, err))
     assert err <= 1e-3
+
+
+def test_temporal_attention_matches_reference_golden(golden_dir):
+    """temporal=True (attlwb_spade_resunet.py:208-252, 480-535): the previous frame's features are extra attention sources with
+    their own flow Ttt — vs the reference generator built with temporal=True (tests/golden/gen_S64_temporal.npz)."""
+    import make_golden
+    from ipercore_b200.generator import AttentionLWBGenerator
+    from oracle.weights import synth_state_dict
+    S = 64
+    g = np.load(os.path.join(golden_dir, "gen_S%d_temporal.npz" % S))
+    inp = {k: torch.from_numpy(v).to("cuda:0") for k, v in make_golden.gen_inputs(S).items()}
+    prev, Ttt = (torch.from_numpy(a).to("cuda:0") for a in make_golden.temporal_inputs(S))
+    net = AttentionLWBGenerator(CFG, temporal=True); net.load_state_dict(synth_state_dict(0), strict=True); net = net.to("cuda:0").eval()
+    enc, res = net.forward_src(inp["src_inputs"], only_enc=True)
+    tenc, tres = net.forward_src(prev, only_enc=True)
+    img, mask = net.forward_tsf(inp["tsf_inputs"], enc, res, inp["Tst"], tenc, tres, Ttt)
+    e = max(np.abs(img.cpu().numpy() - g["tsf_img"]).max(), np.abs(mask.cpu().numpy() - g["tsf_mask"]).max())
+    img0, _ = net.forward_tsf(inp["tsf_inputs"], enc, res, inp["Tst"])
+    print("temporal forward_tsf vs reference: %.2e (the temporal source moves the output by %.2f)" % (e, float((img - img0).abs().max())))
+    assert e <= 1e-3 and float((img - img0).abs().max()) > 0.05
+    with pytest.raises(NotImplementedError, match="bs = 1"):
+        net.forward_tsf(inp["tsf_inputs"].repeat(2, 1, 1, 1), enc, res, inp["Tst"].repeat(2, 1, 1, 1, 1), tenc, tres, Ttt.repeat(2, 1, 1, 1, 1))

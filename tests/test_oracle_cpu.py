@@ -184,3 +184,19 @@ def test_source_stage_restatement_matches_reference_golden(golden_dir):
         assert d[~unc].max() == 0 and d[g["unique3"][i, 0]].max() <= 1e-6
     uv = source_ref.make_uv_img(g["morph_img"], g["obj_f2pts"], g["only_vis_obj_f2pts"], g["uv_fim"], g["uv_wim"])
     assert np.abs(uv - g["uv_img"][0]).max() <= 1e-5
+
+
+def test_generator_restatement_temporal_branch(golden_dir):
+    """oracle/generator_ref.py's temporal attention branch vs the reference generator built with temporal=True."""
+    import make_golden
+    S = 64
+    g = np.load(os.path.join(golden_dir, "gen_S%d_temporal.npz" % S))
+    sd = weights.synth_state_dict(0)
+    inp = make_golden.gen_inputs(S)
+    prev, Ttt = make_golden.temporal_inputs(S)
+    with torch.no_grad():
+        se, sr = generator_ref.forward_src(sd, torch.from_numpy(inp["src_inputs"]))
+        te, tr = generator_ref.forward_src(sd, torch.from_numpy(prev))
+        img, mask = generator_ref.forward_tsf(sd, torch.from_numpy(inp["tsf_inputs"]), se, sr, torch.from_numpy(inp["Tst"]),
+                                              temp_enc_outs=te, temp_res_outs=tr, Ttt=torch.from_numpy(Ttt))
+    assert np.abs(img.numpy() - g["tsf_img"]).max() <= 1e-5 and np.abs(mask.numpy() - g["tsf_mask"]).max() <= 1e-5
