@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--device", default="cuda:0")
     ap.add_argument("--ns", type=int, default=2)
+    ap.add_argument("--temporal", type=int, default=0)
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -35,6 +36,7 @@ def main():
         import ipercore_b200.patch as b200
         b200.install(precision="fp16x2", batch=a.batch)           # BEFORE iPERCore.models is imported
     opt, model = rr.make_opt(a.work, image_size=a.size, num_source=a.ns)
+    opt.temporal = bool(a.temporal)           # deploy.toml:40; true = TemporalFIFO recurrence through the upstream bs=1 loop
     out_dir = os.path.join(a.work, "patched" if a.patched else "stock")
     os.makedirs(out_dir, exist_ok=True)
     im = rr.build_imitator(opt, a.device)

@@ -19,24 +19,27 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
-def _run(patched, work, size, frames, batch):
+def _run(patched, work, size, frames, batch, temporal=0):
     cmd = [sys.executable, os.path.join(ROOT, "tests", "ref_run_imitator.py"), "--patched", str(patched), "--work", work,
-           "--size", str(size), "--frames", str(frames), "--batch", str(batch)]
+           "--size", str(size), "--frames", str(frames), "--batch", str(batch), "--temporal", str(temporal)]
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
     assert p.returncode == 0, p.stdout[-4000:]
     d = os.path.join(work, "patched" if patched else "stock")
     return d, json.load(open(os.path.join(d, "run.json")))
 
 
-def test_real_imitator_patched_equals_stock(tmp_path):
+@pytest.mark.parametrize("temporal", [0, 1])
+def test_real_imitator_patched_equals_stock(temporal, tmp_path):
+    """temporal=0: the batched engine replaces Imitator.inference; temporal=1: the upstream bs=1 loop with its TemporalFIFO
+    recurrence (imitator.py:18-127, 341-380) drives the B200 generator / renderer frame by frame."""
     from oracle import ref_runtime as rr
     if not rr.available():
         pytest.skip("reference tree not staged (oracle/build_ref.py needs /root/reference once)")
     import cv2
     S, T, B = 256, 5, 2                       # 2 + 2 + 1 frames: CUDA-graph batches and a ragged tail
     work = str(tmp_path)
-    d0, r0 = _run(0, work, S, T, B)
-    d1, r1 = _run(1, work, S, T, B)
+    d0, r0 = _run(0, work, S, T, B, temporal)
+    d1, r1 = _run(1, work, S, T, B, temporal)
     assert r0["generator"].startswith("iPERCore.") and r0["nr_is_stub"]
     assert r1["generator"] == "ipercore_b200.generator" and r1["renderer_nr"] == "ipercore_b200.neural_renderer"
     assert r0["outputs"] == r1["outputs"] == ["pred_%08d.png" % i for i in range(T)]
