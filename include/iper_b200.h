@@ -131,6 +131,11 @@ typedef struct {
      * horizontal tap (3x3 stride-1, block_n >= 64; 5x5 heads as IPER_CONV_ROW5 with 32x4 tiles), and the transposed
      * conv runs its four phases fused from the same boxes (block_n 64); needs a map of >= 16x8 (heads 32x4) pixels.  */
     int cta_pair;
+    /* Optional DEVICE scalar 1/s (formats 1/2).  fp16 planes have fp16 RANGE: the lo plane of a weight below ~1e-3 is subnormal
+     * and the split degrades towards a single fp16.  Packing the weights as w * s with s a power of two (e.g. max|w| * s in
+     * [128, 256)) and passing 1/s here keeps both planes normal; the epilogue multiplies the accumulator by 1/s before bias —
+     * exact (power of two), so results are bit-identical to s = 1 wherever s = 1 was not losing bits.  NULL = 1. */
+    const float* w_scale_inv;
 } iper_conv_gemm_desc;
 
 /* tcgen05/TMEM implicit-GEMM convolution with TMA im2col tile loads (conv_tc.cu). */

@@ -33,6 +33,7 @@ class ConvGemmDesc(ctypes.Structure):
         ("max_ctas", c_int),
         ("w8", c_void_p), ("wl8", c_void_p), ("cross_scale", c_float), ("tiles_m", c_int),
         ("stats_ws", c_void_p), ("cta_pair", c_int),
+        ("w_scale_inv", c_void_p),
     ]
 
 

@@ -85,6 +85,7 @@ struct alignas(64) GemmArgs {
     const float* bg; long long bg_batch_stride; float* img; float* mask; float* pred;
     float cross_scale;
     double* stats_ws;        // optional (N, Cout, 2) fp64 sums of the stored output (instance-norm statistics)
+    const float* w_scale_inv;   // optional device scalar 1/s: the packed weights hold w * s (s a power of two), see iper_b200.h
     HaloSched hs;            // conv_halo_pair_kernel only
 };
 
@@ -162,6 +163,9 @@ IPER_DEVINL void load_planes32(const __half* x, int fmt, long long plane_stride,
 template <int BN, int NS>
 IPER_DEVINL void epilogue_tile(const GemmArgs& a, const TileCoord& t, uint32_t taddr, int row, int lane, int tx, int ty,
                                int tni, int hsel = 0, int nsplit = 1) {
+    // weights are packed as w * s with s a power of two that lifts small weights (and their lo plane) out of fp16's
+    // subnormal range; the accumulator is scaled back here — exact, so in-range layers are bit-identical to s = 1
+    const float wsc = a.w_scale_inv ? __ldg(a.w_scale_inv) : 1.f;
     // accumulator chunk: 32 fp32 columns of D1 (+ the matching columns of the fp8 cross-term accumulator D2)
     auto ld_acc = [&](uint32_t taddr_col, uint32_t (&r)[32]) {
         tmem_ld32(taddr_col, r);
@@ -174,6 +178,10 @@ IPER_DEVINL void epilogue_tile(const GemmArgs& a, const TileCoord& t, uint32_t t
                 r[i] = __float_as_uint(fmaf(__uint_as_float(r2[i]), a.cross_scale, __uint_as_float(r[i])));
         } else {
             tmem_ld_wait();
+            if (wsc != 1.f) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) * wsc);
+            }
         }
     };
             const int n = t.pn0 + tni, y = t.py0 + ty, xx = t.px0 + tx;
@@ -207,7 +215,7 @@ IPER_DEVINL void epilogue_tile(const GemmArgs& a, const TileCoord& t, uint32_t t
                             tmem_ld32(taddr + 32, r2);
                             tmem_ld_wait();
 #pragma unroll
-                            for (int i = 0; i < 20; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]));
+                            for (int i = 0; i < 20; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) + __uint_as_float(r2[i]) * wsc);
                         }
 #pragma unroll
                         for (int i = 0; i < 20; i++) s_ex[row * 21 + i] = __uint_as_float(r[i]);
@@ -1371,6 +1379,8 @@ extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream
     g.bg = d->bg; g.bg_batch_stride = d->bg_batch_stride; g.img = d->img; g.mask = d->mask; g.pred = d->pred;
     g.cross_scale = d->cross_scale;
     g.stats_ws = d->stats_ws;
+    g.w_scale_inv = d->w_scale_inv;
+    IPER_REQUIRE(!(d->w_scale_inv && fmt == 3), "iper_conv_gemm: w_scale_inv is not supported with format 3");
 
     // ---- epilogue-specific validation ----
     if (d->epi == IPER_EPI_HEADS) {

@@ -32,9 +32,25 @@ struct PackArgs {
     int Cout, Cin, ks;   // source dims
     int cb;              // PK_SPADE: channels per tile half
     __half* hi; __half* lo;   // lo may be null (single plane)
+    // power-of-two pre-scale (iper_conv_gemm_desc.w_scale_inv): slot = {max|w| bits, s, 1/s}; measure = 1: only fill the max
+    uint32_t* slot; int measure;
 };
+// s = 2^floor(log2(256 / max|w|)): max|w| * s in [128, 256); exact via frexp
+__global__ void pack_scale_kernel(uint32_t* slot) {
+    const float mx = __uint_as_float(slot[0]);
+    float s = 1.f;
+    if (mx > 0.f && mx < 3.0e38f) {
+        int e;
+        const float m = frexpf(mx, &e);             // mx = m * 2^e, m in [0.5, 1)
+        s = ldexpf(1.f, (m == 0.5f ? 9 : 8) - e);
+    }
+    reinterpret_cast<float*>(slot)[1] = s;
+    reinterpret_cast<float*>(slot)[2] = 1.f / s;
+}
 __global__ void pack_kernel(PackArgs a) {
     const size_t total = (size_t)a.rows * a.K;
+    const float scale = a.measure ? 1.f : reinterpret_cast<const float*>(a.slot)[1];
+    float local_max = 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const int r = (int)(i / a.K), k = (int)(i % a.K);
         float v = 0.f;
@@ -68,10 +84,13 @@ __global__ void pack_kernel(PackArgs a) {
         } else {   // PK_MATRIX
             v = a.src[i];
         }
+        if (a.measure) { local_max = fmaxf(local_max, fabsf(v)); continue; }
+        v *= scale;
         const __half h = __float2half_rn(v);
         a.hi[i] = h;
         if (a.lo) a.lo[i] = __float2half_rn(v - __half2float(h));
     }
+    if (a.measure && local_max > 0.f) atomicMax(a.slot, __float_as_uint(local_max));     // non-negative floats order like their bits
 }
 // spade bias in the same tile interleave: [gamma bias cb | beta bias cb] per tile
 __global__ void spade_bias_kernel(const float* __restrict__ bg, const float* __restrict__ bb, int C, int cb, float* __restrict__ out) {
@@ -107,6 +126,7 @@ struct PlanesT {           // NHWC planes tensor (ops.py: Planes)
 
 struct Packed {            // one packed weight matrix inside the caller's packed-weights buffer
     size_t off = 0; int fmt = 0, rows = 0, K = 0;
+    size_t slot_off = (size_t)-1;     // {max bits, s, 1/s} of the power-of-two pre-scale, or -1
     size_t bias_off = (size_t)-1;     // fp32 bias inside the packed buffer (copied / interleaved), or -1
 };
 
@@ -207,15 +227,25 @@ static int pack_all(iper_gen* g, Bump& b, cudaStream_t st) {
         p.fmt = fmt; p.rows = rows; p.K = K;
         const size_t plane = (size_t)rows * K * sizeof(__half);
         p.off = b.take_off((fmt == 2 ? 2 : 1) * plane);
+        p.slot_off = b.take_off(16);
         PackArgs a = {};
         a.rows = rows; a.K = K;
-        if (!b.dry) { a.hi = (__half*)(b.base + p.off); a.lo = fmt == 2 ? (__half*)(b.base + p.off + plane) : nullptr; }
+        if (!b.dry) {
+            a.hi = (__half*)(b.base + p.off); a.lo = fmt == 2 ? (__half*)(b.base + p.off + plane) : nullptr;
+            a.slot = (uint32_t*)(b.base + p.slot_off);
+        }
         return a;
     };
-    auto launch = [&](const PackArgs& a) -> int {
+    auto launch = [&](PackArgs a) -> int {          // measure max|w| -> power-of-two scale -> write the scaled planes
         if (b.dry) return 0;
         const size_t total = (size_t)a.rows * a.K;
-        pack_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(a);
+        const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 8);
+        IPER_CHECK_CUDA(cudaMemsetAsync(a.slot, 0, 16, st));
+        a.measure = 1;
+        pack_kernel<<<grid, 256, 0, st>>>(a);
+        pack_scale_kernel<<<1, 1, 0, st>>>(a.slot);
+        a.measure = 0;
+        pack_kernel<<<grid, 256, 0, st>>>(a);
         IPER_CHECK_CUDA(cudaGetLastError());
         return 0;
     };
@@ -378,6 +408,7 @@ void fill(iper_conv_gemm_desc& d, Ctx& c, const PlanesT& a, const Packed& w, int
     d.N = a.N; d.H = a.H; d.W = a.W; d.a_pitch = a.pitch; d.a_coff = a.coff; d.Cin = a.C;
     d.mode = mode; d.ksize = ksize;
     d.w = c.wptr(w); d.w_planes = w.fmt; d.w_plane_stride = (long long)w.rows * w.K;
+    if (w.slot_off != (size_t)-1) d.w_scale_inv = reinterpret_cast<const float*>(c.g->packed + w.slot_off) + 2;
     d.rows = rows; d.block_n = block_n; d.epi = epi;
 }
 void set_out(iper_conv_gemm_desc& d, const PlanesT& o) {

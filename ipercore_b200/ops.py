@@ -212,6 +212,10 @@ def conv_gemm(a, wpack, mode, ksize, rows, block_n, epi, **kw):
     """tcgen05 implicit-GEMM convolution (conv_tc.cu). `wpack` = PackedW from the pack_* helpers below."""
     d = _fill_desc(a, mode, ksize, rows, block_n, epi, **kw)
     d.w = wpack.w.data_ptr(); d.w_planes = wpack.fmt; d.w_plane_stride = wpack.w[0].numel()
+    if wpack.scale != 1.0:
+        if wpack.scale_inv.device != wpack.w.device:
+            wpack.scale_inv = wpack.scale_inv.to(wpack.w.device)
+        d.w_scale_inv = wpack.scale_inv.data_ptr()
     if wpack.fmt == FMT_H8:
         d.w8 = wpack.w8.data_ptr(); d.wl8 = wpack.wl8.data_ptr(); d.cross_scale = wpack.cross_scale
     check(lib.iper_conv_gemm(d, _stream()), "conv_gemm")
@@ -376,6 +380,14 @@ class PackedW:
     def __init__(self, m, fmt):
         m = m.float().contiguous()
         self.fmt, self.rows_total, self.K = fmt, m.shape[0], m.shape[1]
+        # power-of-two pre-scale (formats 1/2): max|w| * s in [128, 256) keeps hi AND lo planes of small weights out of fp16's
+        # subnormal range; the conv epilogue multiplies the accumulator by 1/s (exact).  See iper_conv_gemm_desc.w_scale_inv
+        self.scale = 1.0
+        mx = float(m.abs().max()) if m.numel() else 0.0
+        if fmt in (FMT_H, FMT_HL) and mx > 0 and math.isfinite(mx):
+            self.scale = 2.0 ** math.floor(math.log2(256.0 / mx))
+        self.scale_inv = torch.tensor([1.0 / self.scale], dtype=torch.float32, device=m.device)
+        m = m * self.scale
         self.w = split_planes(m, fmt)
         self.w8 = self.wl8 = None
         self.cross_scale = 0.0
@@ -390,17 +402,18 @@ class PackedW:
 
     def to(self, device):
         self.w = self.w.to(device)
+        self.scale_inv = self.scale_inv.to(device)
         if self.w8 is not None:
             self.w8, self.wl8 = self.w8.to(device), self.wl8.to(device)
         return self
 
     def effective(self):
         """(w_main, w_for_lo_term, wlo_term) fp32 matrices the three MMA groups multiply with (test helper)."""
-        hi = self.w[0].float().cpu()
+        hi = self.w[0].float().cpu() / self.scale            # de-scaled: the values the layer effectively multiplies with
         if self.fmt == 1:
             return hi, None, None
         if self.fmt == 2:
-            return hi, hi, self.w[1].float().cpu()
+            return hi, hi, self.w[1].float().cpu() / self.scale
         return hi, self.w8.cpu().view(torch.float8_e4m3fn).float() / self.sW, \
             self.wl8.cpu().view(torch.float8_e4m3fn).float() / (self.sW * 2048.0)
 

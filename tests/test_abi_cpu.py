@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_descriptor_struct_matches_header():
     from ipercore_b200._lib import ConvGemmDesc
-    assert ctypes.sizeof(ConvGemmDesc) == 280 and ConvGemmDesc.cta_pair.offset == 272 and ConvGemmDesc.tiles_m.offset == 260 and ConvGemmDesc.stats_ws.offset == 264 and ConvGemmDesc.max_ctas.offset == 232 and ConvGemmDesc.cross_scale.offset == 256
+    assert ctypes.sizeof(ConvGemmDesc) == 288 and ConvGemmDesc.w_scale_inv.offset == 280 and ConvGemmDesc.cta_pair.offset == 272 and ConvGemmDesc.tiles_m.offset == 260 and ConvGemmDesc.stats_ws.offset == 264 and ConvGemmDesc.max_ctas.offset == 232 and ConvGemmDesc.cross_scale.offset == 256
 
 
 def test_argument_validation_reports_errors():
@@ -64,12 +64,14 @@ def test_weight_packing_layouts():
     p = ops.pack_conv_weight(w, 2)
     assert p.w.shape == (2, 2, 27) and p.fmt == 2 and p.rows_total == 2 and p.K == 27
     # K order is (tap, cin): element (co=1, tap=4 (ky=1,kx=1), ci=2)
-    assert float(p.w[0, 1, 4 * 3 + 2]) + float(p.w[1, 1, 4 * 3 + 2]) == float(w[1, 2, 1, 1])
+    # (the planes hold w * 2^k with max|w| * 2^k in [128, 256), undone exactly by the conv epilogue's w_scale_inv)
+    assert 128.0 <= float(w.abs().max()) * p.scale < 256.0 and float(p.scale_inv) * p.scale == 1.0
+    assert (float(p.w[0, 1, 4 * 3 + 2]) + float(p.w[1, 1, 4 * 3 + 2])) / p.scale == float(w[1, 2, 1, 1])
     wt = torch.randn(4, 5, 4, 4)
     pt = ops.pack_convT_weight(wt, 1)
     assert pt.w.shape == (1, 4 * 5, 4 * 4)
     # phase (py=1,px=0), tap (ta=0,tb=1): ky=0, kx=3
-    torch.testing.assert_close(pt.w[0, 2 * 5 + 3, (0 * 2 + 1) * 4 + 2].float(), wt[2, 3, 0, 3], atol=2e-3, rtol=2e-3)
+    torch.testing.assert_close(pt.w[0, 2 * 5 + 3, (0 * 2 + 1) * 4 + 2].float() / pt.scale, wt[2, 3, 0, 3], atol=2e-3, rtol=2e-3)
     hi_lo = ops.split_planes(torch.tensor([1.0001234, -3.14159265]), 2).float()
     torch.testing.assert_close(hi_lo.sum(0), torch.tensor([1.0001234, -3.14159265]), atol=1e-6, rtol=0)
     # format 3: e4m3 planes reproduce w and (w - fp16(w)) to ~2^-4 relative, with a power-of-two scale

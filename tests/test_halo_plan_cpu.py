@@ -62,8 +62,9 @@ def test_plan_reproduces_conv3x3():
     cin, cout, H, W = 128, 64, 11, 21
     x, w = _rand((H, W, cin), 1), _rand((cout, cin, 3, 3), 2)
     wm = torch.from_numpy(w).permute(0, 2, 3, 1).reshape(cout, -1).numpy()          # fp64 copy of pack_conv_weight's layout
-    real = ops.pack_conv_weight(torch.from_numpy(w).float(), 1).w[0].float().numpy()
-    np.testing.assert_allclose(real, wm.astype(np.float32).astype(np.float16).astype(np.float32), rtol=0, atol=0)   # same layout as the real packer
+    pw = ops.pack_conv_weight(torch.from_numpy(w).float(), 1)
+    real = pw.w[0].float().numpy() / pw.scale                                     # the packer stores w * 2^k (exact)
+    np.testing.assert_allclose(real, wm.astype(np.float32), rtol=2.0 ** -10, atol=0)   # same layout as the real packer (fp16 of w * 2^k)
     got, _ = _run_plan(x, wm, IPER_CONV_S1, cin, cout, cout, 16, 8)
     exp = F.conv2d(torch.from_numpy(x).permute(2, 0, 1)[None], torch.from_numpy(w), padding=1)[0].permute(1, 2, 0).numpy()
     np.testing.assert_allclose(got[:, :, 0], exp, atol=1e-9)
@@ -85,8 +86,9 @@ def test_plan_reproduces_transposed_conv_both_forms():
     cin, cout, H, W = 128, 64, 9, 19
     x, w = _rand((H, W, cin), 3), _rand((cin, cout, 4, 4), 4)
     wm = _packT(w)
-    real = ops.pack_convT_weight(torch.from_numpy(w).float(), 1).w[0].float().numpy()
-    np.testing.assert_allclose(real, wm.astype(np.float32).astype(np.float16).astype(np.float32), rtol=0, atol=0)   # same layout as the real packer
+    pw = ops.pack_convT_weight(torch.from_numpy(w).float(), 1)
+    real = pw.w[0].float().numpy() / pw.scale
+    np.testing.assert_allclose(real, wm.astype(np.float32), rtol=2.0 ** -10, atol=0)   # same layout as the real packer (fp16 of w * 2^k)
     exp = F.conv_transpose2d(torch.from_numpy(x).permute(2, 0, 1)[None], torch.from_numpy(w), stride=2, padding=1)[0]
     exp = exp.permute(1, 2, 0).numpy()
     for fuse in (0, 1):
