@@ -162,7 +162,7 @@ IPER_DEVINL void load_planes32(const __half* x, int fmt, long long plane_stride,
 // the halo kernel); warp `hsel` of them takes the 32-column chunks j with j % nsplit == hsel.
 template <int BN, int NS>
 IPER_DEVINL void epilogue_tile(const GemmArgs& a, const TileCoord& t, uint32_t taddr, int row, int lane, int tx, int ty,
-                               int tni, int hsel = 0, int nsplit = 1) {
+                               int tni, int hsel = 0, int nsplit = 1, double* pend = nullptr) {
     // weights are packed as w * s with s a power of two that lifts small weights (and their lo plane) out of fp16's
     // subnormal range; the accumulator is scaled back here — exact, so in-range layers are bit-identical to s = 1
     const float wsc = a.w_scale_inv ? __ldg(a.w_scale_inv) : 1.f;
@@ -306,7 +306,10 @@ IPER_DEVINL void epilogue_tile(const GemmArgs& a, const TileCoord& t, uint32_t t
                             for (int i = 0; i < 32; i++) { o[i] = valid ? o[i] : 0.f; sq[i] = o[i] * o[i]; }
                             const float s1 = warp_transpose_sum32(o, lane), s2 = warp_transpose_sum32(sq, lane);
                             const int nw = __shfl_sync(0xffffffffu, n, 0);
-                            if (nw < a.N) {
+                            if (pend) {         // this warp's running sums of the current image (flushed by the caller)
+                                pend[(c0 + lane) * 2] += (double)s1;
+                                pend[(c0 + lane) * 2 + 1] += (double)s2;
+                            } else if (nw < a.N) {
                                 atomicAdd(a.stats_ws + ((size_t)nw * a.rows + c0 + lane) * 2, (double)s1);
                                 atomicAdd(a.stats_ws + ((size_t)nw * a.rows + c0 + lane) * 2 + 1, (double)s2);
                             }
@@ -331,8 +334,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
     __shared__ __align__(8) uint64_t tmem_full_bar[2];
     __shared__ __align__(8) uint64_t tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_slot;
+    // per-epilogue-warp running instance-norm sums of the image being processed (single-N-tile layers): a CTA walks a
+    // CONTIGUOUS range of tiles, so almost all of them belong to one image and the fp64 atomics on the (N, C, 2) workspace are
+    // issued once per image per warp instead of once per tile (the K = 64 stem GEMM has 512 tiles per image on 128 addresses)
+    __shared__ double s_pend[4][BN][2];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // contiguous tile range of this CTA
+    const int tile_lo = (int)((long long)a.total_tiles * blockIdx.x / gridDim.x);
+    const int tile_hi = (int)((long long)a.total_tiles * (blockIdx.x + 1) / gridDim.x);
     // 1024-byte aligned ring buffer (swizzle atoms are 1024 B / 512 B)
     const uint32_t ring = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     uint8_t* ring_ptr = smem_dyn + (ring - smem_u32(smem_dyn));
@@ -367,7 +377,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         // =========================== TMA producer ===========================
         if (lane == 0) {
             int stage = 0; uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+            for (int tile = tile_lo; tile < tile_hi; tile++) {
                 TileCoord tc[TM];
 #pragma unroll
                 for (int t = 0; t < TM; t++) tc[t] = decode_tile<TM>(a, tile, t);
@@ -421,7 +431,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         constexpr uint32_t idesc = umma_idesc_f16(BLOCK_M, BN);
         constexpr uint32_t idesc8 = umma_idesc_e4m3(BLOCK_M, BN);
         int stage = 0; uint32_t ph = 0; int it = 0;
-        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, it++) {
+        for (int tile = tile_lo; tile < tile_hi; tile++, it++) {
             const int acc = it % C::NACC; const uint32_t acc_ph = (it / C::NACC) & 1;
             mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
             tc_fence_after();
@@ -480,7 +490,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
         const int row = q * 32 + lane;          // accumulator row = pixel index inside the patch
         const int tx = row % a.tw, ty = (row / a.tw) % a.th, tni = row / (a.tw * a.th);
         int it = 0;
-        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, it++) {
+        // pending statistics: only when the layer has one N tile (channel = accumulator column) and a warp's 32 rows lie in
+        // one image, so that the warp's sums belong to exactly one (image, channel) set at a time
+        double* pend = (a.stats_ws != nullptr && a.n_tiles == 1 && (a.tw * a.th) % 32 == 0) ? &s_pend[q][0][0] : nullptr;
+        int pend_n = -1;
+        auto flush = [&]() {
+            if (pend_n >= 0 && pend_n < a.N)
+                for (int c = lane; c < BN; c += 32) {
+                    atomicAdd(a.stats_ws + ((size_t)pend_n * a.rows + c) * 2, pend[c * 2]);
+                    atomicAdd(a.stats_ws + ((size_t)pend_n * a.rows + c) * 2 + 1, pend[c * 2 + 1]);
+                }
+            for (int c = lane; c < BN; c += 32) { pend[c * 2] = 0.0; pend[c * 2 + 1] = 0.0; }
+            __syncwarp();
+        };
+        if (pend) flush();
+        for (int tile = tile_lo; tile < tile_hi; tile++, it++) {
             const int acc = it % C::NACC; const uint32_t acc_ph = (it / C::NACC) & 1;
             mbar_wait(&tmem_full_bar[acc], acc_ph);
             tc_fence_after();
@@ -488,13 +512,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) conv_gemm_kernel(const __grid
             for (int tm = 0; tm < TM; tm++) {
             const TileCoord t = decode_tile<TM>(a, tile, tm);
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS + tm * BN;
-            epilogue_tile<BN, NS>(a, t, taddr, row, lane, tx, ty, tni);
+            if (pend) {
+                const int nw = t.pn0 + (q * 32) / (a.tw * a.th);        // image of this warp's rows
+                if (nw != pend_n) { flush(); pend_n = nw; }
+            }
+            epilogue_tile<BN, NS>(a, t, taddr, row, lane, tx, ty, tni, 0, 1, pend);
             }  // tm
             // accumulators drained: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
+        if (pend) flush();
     }
 
     tc_fence_before();
