@@ -86,11 +86,22 @@ class _Conv3x3(torch.autograd.Function):
         return dx, dw, db
 
 
+def _torch_conv(x, weight, bias, stride=1, padding=0, transposed=False):
+    """The PyTorch side of the step.  Layers with fewer than 8 input or output channels (6-channel stems, the 3- / 1-channel
+    heads, the discriminator's ends) run in fp32: cuDNN has no bf16 channels_last engine for some of their gradients
+    ("GET was unable to find an engine"), and they are a rounding error of the step's FLOPs."""
+    tiny = min(weight.shape[0], weight.shape[1]) < 8
+    dt = torch.float32 if tiny else x.dtype
+    fn = F.conv_transpose2d if transposed else F.conv2d
+    y = fn(x.to(dt), weight.to(dt), None if bias is None else bias.to(dt), stride=stride, padding=padding)
+    return y if tiny else y
+
+
 def conv3x3(x, weight, bias=None):
     """3x3 / s1 / p1 convolution: tcgen05 bf16 kernels (forward, dgrad, wgrad) when the layer qualifies, torch otherwise."""
     if _eligible(x, weight):
         return _Conv3x3.apply(x, weight, bias)
-    return F.conv2d(x, weight.to(x.dtype), None if bias is None else bias.to(x.dtype), padding=1)
+    return _torch_conv(x, weight, bias, padding=1)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -115,11 +126,11 @@ class TrainableGenerator(nn.Module):
         w, b = self._p(name + ".weight"), self._p(name + ".bias")
         if w.shape[-1] == 3 and stride == 1 and padding == 1:
             return conv3x3(x, w, b)
-        return F.conv2d(x, w.to(x.dtype), None if b is None else b.to(x.dtype), stride=stride, padding=padding)
+        return _torch_conv(x, w, b, stride=stride, padding=padding)
 
     def _ct(self, name, x):
         w, b = self._p(name + ".weight"), self._p(name + ".bias")
-        return F.conv_transpose2d(x, w.to(x.dtype), None if b is None else b.to(x.dtype), stride=2, padding=1)
+        return _torch_conv(x, w, b, stride=2, padding=1, transposed=True)
 
     def _res(self, prefix, x, second):
         y = F.relu(self._c("%s.main.0" % prefix, x, padding=1))
@@ -130,7 +141,7 @@ class TrainableGenerator(nn.Module):
         bs, ns, _, h, w = bg_inputs.shape
         x = bg_inputs.reshape(bs * ns, -1, h, w).to(BF16)
         inorm = lambda t: F.instance_norm(t.float(), eps=1e-5).to(BF16)
-        x = F.relu(inorm(self._c("bg_net.main.0", x, padding=3)))
+        x = F.relu(inorm(self._c("bg_net.main.0", x, padding=3)))       # 4 -> 64 (fp32 conv, see _torch_conv); inorm returns bf16
         idx = 3
         for _ in range(3):
             x = F.relu(inorm(self._c("bg_net.main.%d" % idx, x, stride=2, padding=1))); idx += 3
@@ -147,7 +158,7 @@ class TrainableGenerator(nn.Module):
         x = src_inputs.reshape(bs * ns, -1, h, w).to(BF16)
         enc = []
         for i in range(3):
-            x = F.relu(self._c("src_net.encoders.layers.%d.0" % i, x, stride=2, padding=1)); enc.append(x)
+            x = F.relu(self._c("src_net.encoders.layers.%d.0" % i, x, stride=2, padding=1)).to(BF16); enc.append(x)
         res = []
         for i in range(self.n_res):
             x = self._res("src_net.res_blocks.%d" % i, x, 2); res.append(x)
@@ -183,7 +194,7 @@ class TrainableGenerator(nn.Module):
         x = tsf_inputs.to(BF16)
         enc = []
         for i in range(3):
-            x = F.relu(self._c("tsf_net_enc.layers.%d.0" % i, x, stride=2, padding=1))
+            x = F.relu(self._c("tsf_net_enc.layers.%d.0" % i, x, stride=2, padding=1)).to(BF16)
             x = self._att("enc_attlwbs.%d" % i, x, src_enc[i], Tst); enc.append(x)
         for i in range(self.n_res):
             x = self._res("res_blocks.%d" % i, x, 2)
@@ -251,7 +262,7 @@ class VGG19Features(nn.Module):
         for hi in self.CUTS:
             for layer in self.features[lo:hi]:
                 # frozen 3x3 convs: the same tcgen05 kernels (forward + data gradient; no weight gradient is requested)
-                x = F.relu(conv3x3(x, layer.weight, layer.bias)) if isinstance(layer, nn.Conv2d) else \
+                x = F.relu(conv3x3(x, layer.weight, layer.bias)).to(BF16) if isinstance(layer, nn.Conv2d) else \
                     (x if isinstance(layer, nn.ReLU) else layer(x))
             outs.append(x); lo = hi
         return outs
@@ -364,8 +375,7 @@ class LWGTrainStep:
         tsf_cond = b["tsf_inputs"][:, :, -3:].reshape(bs * nt, 3, h, w)
         f_tsf = fake_tsf.reshape(bs * nt, 3, h, w)
         r_tsf = b["real_tsf"].reshape(bs * nt, 3, h, w)
-        with torch.autocast("cuda", dtype=BF16):
-            d_fake = self.D(torch.cat([f_tsf, tsf_cond], dim=1))
+        d_fake = self.D(torch.cat([f_tsf, tsf_cond], dim=1))       # D runs in fp32/TF32: its ends have 6 and 1 channels (see _torch_conv)
         l_adv = lsgan(d_fake, 0.0) * self.lam["adv"]
         l_rec = (F.l1_loss(fake_src, b["real_src"]) + F.l1_loss(fake_bg.reshape(-1, 3, h, w), b["real_bg"])) / 2 * self.lam["rec"]
         l_tsf = vgg_loss(self.vgg, f_tsf, r_tsf) * self.lam["tsf"]
@@ -381,8 +391,7 @@ class LWGTrainStep:
         # ---- D step (optimize_D :797-834) ----
         real_in = torch.cat([r_tsf, tsf_cond], dim=1)
         fake_in = torch.cat([f_tsf.detach(), tsf_cond], dim=1)
-        with torch.autocast("cuda", dtype=BF16):
-            loss_D = lsgan(self.D(real_in), 1.0) + lsgan(self.D(fake_in), -1.0)
+        loss_D = lsgan(self.D(real_in), 1.0) + lsgan(self.D(fake_in), -1.0)
         self._zero(self.opt_D, self.bk_D)
         loss_D.backward()
         if self.bk_D is not None:
