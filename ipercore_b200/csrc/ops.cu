@@ -192,12 +192,13 @@ __global__ void __launch_bounds__(256) conv_stem_kernel(const float* __restrict_
 // NHWC planes (N, H/2, W/2, 64) with channel k = (ky*3 + kx)*CIN + ci (zeros from 9*CIN up), so that the stem becomes a
 // K = 64 "1x1 convolution" on the tcgen05 path (fused bias / ReLU / instance-norm statistics epilogue) instead of 54-term
 // FMA chains fed by shared-memory filter reads.  8 lanes cover one output pixel (8 channels = one 128-bit store per plane).
-__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ in, int N, int CIN, int H, int W,
+template <int CIN>
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ in, int N, int H, int W,
                                                           __half* __restrict__ out, int out_planes, long long out_plane_stride,
                                                           int out_pitch, int out_coff) {
     const int Ho = H / 2, Wo = W / 2;
     const size_t total = (size_t)N * Ho * Wo * 8;
-    const int kmax = 9 * CIN;
+    constexpr int kmax = 9 * CIN;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
         const int cg = (int)(i & 7);
         const size_t pix = i >> 3;
@@ -459,6 +460,9 @@ __global__ void __launch_bounds__(256, 3) warp_attention_chunk_kernel(const __ha
                                                                       __half* __restrict__ out, int out_planes,
                                                                       long long out_plane_stride, int out_pitch, int out_coff) {
     constexpr int LPP = C / 8, PPW = 32 / LPP, KVP = 2 * C + 64;
+    // pixels per chunk: a foreground pixel costs a full gather chain of PPW-wide steps, so the wider a pixel is in lanes the
+    // fewer pixels a warp takes (more warps share the foreground of a region): 32 / 16 / 8 for C = 64 / 128 / 256
+    constexpr int CH = 8 * PPW;
     const int lane = threadIdx.x & 31, cg = lane % LPP, sub = lane / LPP;
     const size_t hw = (size_t)h * w, total = (size_t)B * hw;
     const float inv_sqrt = 1.f / sqrtf((float)C);
@@ -486,10 +490,10 @@ __global__ void __launch_bounds__(256, 3) warp_attention_chunk_kernel(const __ha
 #pragma unroll
         for (int j = 0; j < 8; j++) bg8[j] *= rden;
     }
-    const size_t nchunks = (total + 31) / 32, warps = (size_t)gridDim.x * 8;
+    const size_t nchunks = (total + CH - 1) / CH, warps = (size_t)gridDim.x * 8;
     for (size_t ch = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5); ch < nchunks; ch += warps) {
-        const size_t pix_l = ch * 32 + lane;
-        const bool live_l = pix_l < total;
+        const size_t pix_l = ch * CH + lane;
+        const bool live_l = lane < CH && pix_l < total;
         const size_t pl = live_l ? pix_l : total - 1;
         const size_t b_l = pl / hw, p_l = pl % hw;
         float2 gs[NSMAX];
@@ -510,7 +514,7 @@ __global__ void __launch_bounds__(256, 3) warp_attention_chunk_kernel(const __ha
         const int nbg = __popc(bg_mask);
         for (int k = sub; k < nbg; k += PPW) {
             const int j = __fns(bg_mask, 0, k + 1);
-            store_planes8(out, out_planes, out_plane_stride, (ch * 32 + j) * out_pitch + out_coff + cg * 8, bg8);
+            store_planes8(out, out_planes, out_plane_stride, (ch * CH + j) * out_pitch + out_coff + cg * 8, bg8);
         }
         // ---- foreground: PPW pixels at a time (every lane takes part in the shuffles) ----
         const int nfg = __popc(fg_mask);
@@ -518,7 +522,7 @@ __global__ void __launch_bounds__(256, 3) warp_attention_chunk_kernel(const __ha
             const int k = k0 + sub;
             const bool act = k < nfg;
             const int j = act ? __fns(fg_mask, 0, k + 1) : __ffs(fg_mask) - 1;      // idle sub-groups shadow a valid pixel
-            const size_t pix = ch * 32 + j;
+            const size_t pix = ch * CH + j;
             float xv[8];
             load_planes8(xt, xt_planes, xt_plane_stride, pix * xt_pitch + xt_coff + cg * 8, xv);
             float m = -INFINITY, den = 0.f, o8[8];
@@ -816,7 +820,8 @@ extern "C" int iper_warp_attention(const void* xt, int xt_planes, long long xt_p
 #define IPER_ATT(CV, NV)                                                                                             \
     do {                                                                                                             \
         if (wide == 3) {                                                                                             \
-            const int cblocks = (int)min((size_t)148 * 12, ((total + 31) / 32 + 7) / 8);                              \
+            const size_t cpx = (size_t)(CV == 256 ? 8 : (CV == 128 ? 16 : 32));       /* pixels per warp chunk */       \
+            const int cblocks = (int)min((size_t)148 * 12, ((total + cpx - 1) / cpx + 7) / 8);                        \
             warp_attention_chunk_kernel<CV, NV><<<cblocks, 256, 0, st>>>(x, xt_planes, xt_plane_stride, xt_pitch, xt_coff, kv, \
                                                                          bias_v, T, B, ns, h, w, o, out_planes,         \
                                                                          out_plane_stride, out_pitch, out_coff);       \
@@ -854,8 +859,14 @@ extern "C" int iper_stem_im2col(const float* in_nchw, int N, int Cin, int H, int
     const size_t total = (size_t)N * (H / 2) * (W / 2) * 8;
     if (total == 0) return 0;
     const int blocks = (int)min((size_t)148 * 16, (total + 255) / 256);
-    stem_im2col_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in_nchw, N, Cin, H, W, reinterpret_cast<__half*>(out), out_planes,
-                                                                 out_plane_stride, out_pitch, out_coff);
+#define IPER_IM2COL(CV)                                                                                                     \
+    stem_im2col_kernel<CV><<<blocks, 256, 0, (cudaStream_t)stream>>>(in_nchw, N, H, W, reinterpret_cast<__half*>(out), out_planes, \
+                                                                     out_plane_stride, out_pitch, out_coff)
+    switch (Cin) {
+        case 1: IPER_IM2COL(1); break; case 2: IPER_IM2COL(2); break; case 3: IPER_IM2COL(3); break; case 4: IPER_IM2COL(4); break;
+        case 5: IPER_IM2COL(5); break; case 6: IPER_IM2COL(6); break; default: IPER_IM2COL(7); break;
+    }
+#undef IPER_IM2COL
     IPER_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
