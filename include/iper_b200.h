@@ -298,13 +298,16 @@ int iper_uv_merge(const float* src_warp, const float* vis_dilated, int bs, int n
  *                            K = (ky*3+kx)*Cin + ci) [+ bias fp32] [ReLU].  dgrad = the same call on dY with the weights
  *                            rotated by 180 degrees and in/out transposed: w'(ci, (2-ky, 2-kx), co) = w(co, ci, ky, kx).
  *   iper_conv3x3_wgrad_bf16  dW (Cout, 9, Cin) fp32 = sum over pixels of dY (N,Cout,H,W) x X (N,Cin,H,W) shifted by the tap; both
- *                            operands NCHW bf16 (pixels contiguous = K-major rows for the pixel contraction), W %% 64 == 0.
+ *                            operands NCHW bf16 (pixels contiguous = K-major rows for the pixel contraction), W %% 64 == 0; the
+ *                            horizontal tap shift is served from three x-shifted copies of X the call writes into the workspace
+ *                            (a TMA box may not start at a 2-byte offset in its innermost dimension).
  * Cin, Cout multiples of 64 (one of them of 128 for wgrad); H >= 8, W >= 16.
  * ---------------------------------------------------------------------------------------------------------- */
 int iper_conv3x3_bf16(const void* x_nhwc, int N, int H, int W, int Cin, const void* w_packed, int Cout, const float* bias,
                       int relu, void* out_nhwc, iper_stream_t stream);
+size_t iper_conv3x3_wgrad_workspace_bytes(int N, int H, int W, int Cin);   /* three x-shifted copies of X (TMA alignment) */
 int iper_conv3x3_wgrad_bf16(const void* x_nchw, const void* dy_nchw, int N, int H, int W, int Cin, int Cout, float* dW,
-                            iper_stream_t stream);
+                            void* workspace, size_t workspace_bytes, iper_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -72,7 +72,7 @@ SIGNATURES = {
     "iper_pred_to_u8": [c_void_p, c_int, c_int, c_void_p, c_void_p],
     "iper_morph": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "iper_conv3x3_bf16": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p],
-    "iper_conv3x3_wgrad_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "iper_conv3x3_wgrad_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
     "iper_gen_create": [c_void_p, c_int, c_int, c_int, c_void_p],
     "iper_gen_load_weight": [c_void_p, ctypes.c_char_p, c_void_p, c_void_p, c_int],
     "iper_gen_pack": [c_void_p, c_void_p, c_size_t, c_void_p],
@@ -95,6 +95,7 @@ OTHER_SIGNATURES = {
     "iper_raster_set_contraction": (c_int, [c_int]),
     "iper_raster_get_contraction": (c_int, []),
     "iper_vis_f2pts_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "iper_conv3x3_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "iper_gen_destroy": (None, [c_void_p]),
     "iper_gen_packed_bytes": (c_size_t, [c_void_p]),
     "iper_gen_src_cache_bytes": (c_size_t, [c_void_p, c_int, c_int]),

@@ -9,9 +9,14 @@
 //                    kernel on the 180-degree-rotated, in/out-transposed weights.
 //   wgrad            dW[co, tap, ci] = sum_{n,y,x} dY[n,co,y,x] X[n,ci,y+dy,x+dx]: the contraction runs over PIXELS, so both
 //                    operands are read from NCHW tensors, where a row segment of 64 pixels of one channel is a K-major
-//                    128-byte row: A = 128 channels of dY, B = BN channels of X shifted by the tap (TMA zero fill again is
-//                    the padding).  One CTA per (row tile, column tile, tap, K split); fp32 atomics combine the splits.
+//                    128-byte row: A = 128 channels of dY, B = BN channels of X shifted by the tap.  The vertical shift is a
+//                    TMA coordinate (zero fill = padding); the horizontal one cannot be — the innermost TMA coordinate must
+//                    stay 16-byte aligned (a +-1 pixel start faults) — so a small pre-pass writes the three x-shifted copies
+//                    [X(x-1) | X | X(x+1)] into a caller-owned workspace and the tap picks its copy through a 5th tensor
+//                    dimension.  One CTA per (row tile, column tile, tap, K split); fp32 atomics combine the splits.
 // One CTA per output tile, 192 threads: warp 0 TMA producer, warp 1 MMA issuer (single thread), warps 2-5 epilogue.
+#include <algorithm>
+
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cudaTypedefs.h>
@@ -100,13 +105,13 @@ __global__ void __launch_bounds__(TR_THREADS, 1) train_gemm_kernel(const __grid_
                 } else {
                     const int j = k0 + i;
                     const int xc = j % a.rc, y = (j / a.rc) % a.H, n = j / (a.rc * a.H);
-                    const int dx = tap % 3 - 1, dy = tap / 3 - 1;
+                    const int dxi = tap % 3, dy = tap / 3 - 1;       // dxi selects the x-shifted copy of X (5th dimension)
                     if (a.a_shift == 0) {
-                        tma_load_4d(sA(s), &a.mapA, &full_bar[s], xc * 64, y, row0, n);
-                        tma_load_4d(sB(s), &a.mapB, &full_bar[s], xc * 64 + dx, y + dy, col0, n);
+                        tma_load_5d(sA(s), &a.mapA, &full_bar[s], xc * 64, y, row0, n, 0);
+                        tma_load_5d(sB(s), &a.mapB, &full_bar[s], xc * 64, y + dy, col0, n, dxi);
                     } else {
-                        tma_load_4d(sA(s), &a.mapA, &full_bar[s], xc * 64 + dx, y + dy, row0, n);
-                        tma_load_4d(sB(s), &a.mapB, &full_bar[s], xc * 64, y, col0, n);
+                        tma_load_5d(sA(s), &a.mapA, &full_bar[s], xc * 64, y + dy, row0, n, dxi);
+                        tma_load_5d(sB(s), &a.mapB, &full_bar[s], xc * 64, y, col0, n, 0);
                     }
                 }
                 if (++s == TR_STAGES) { s = 0; ph ^= 1; }
@@ -178,6 +183,17 @@ __global__ void __launch_bounds__(TR_THREADS, 1) train_gemm_kernel(const __grid_
     if (warp == 1) tmem_dealloc(tmem, TCOLS);
 }
 
+// [X(x-1) | X | X(x+1)] with zero fill at the row ends, NCHW bf16: ws (3, N*C*H*W)
+__global__ void shift3_kernel(const __nv_bfloat16* __restrict__ x, size_t total, int W, __nv_bfloat16* __restrict__ ws) {
+    const __nv_bfloat16 zero = __float2bfloat16(0.f);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int xx = (int)(i % W);
+        ws[i] = xx > 0 ? x[i - 1] : zero;
+        ws[total + i] = x[i];
+        ws[2 * total + i] = xx < W - 1 ? x[i + 1] : zero;
+    }
+}
+
 static PFN_cuTensorMapEncodeTiled_v12000 train_encode_fn() {
     static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
     if (!fn) {
@@ -192,7 +208,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 train_encode_fn() {
 static int bf16_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box) {
     auto fn = train_encode_fn();
     IPER_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
-    cuuint32_t es[4] = {1, 1, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -243,14 +259,25 @@ extern "C" int iper_conv3x3_bf16(const void* x_nhwc, int N, int H, int W, int Ci
     return BN == 128 ? launch_train<128>(t, grid, (cudaStream_t)stream) : launch_train<64>(t, grid, (cudaStream_t)stream);
 }
 
+extern "C" size_t iper_conv3x3_wgrad_workspace_bytes(int N, int H, int W, int Cin) {
+    if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0) return 0;
+    return (size_t)3 * N * Cin * H * W * sizeof(__nv_bfloat16);
+}
+
 extern "C" int iper_conv3x3_wgrad_bf16(const void* x_nchw, const void* dy_nchw, int N, int H, int W, int Cin, int Cout,
-                                       float* dW, iper_stream_t stream) {
-    IPER_REQUIRE(x_nchw && dy_nchw && dW, "iper_conv3x3_wgrad_bf16: null pointer");
+                                       float* dW, void* workspace, size_t workspace_bytes, iper_stream_t stream) {
+    IPER_REQUIRE(x_nchw && dy_nchw && dW && workspace, "iper_conv3x3_wgrad_bf16: null pointer");
+    IPER_REQUIRE(workspace_bytes >= iper_conv3x3_wgrad_workspace_bytes(N, H, W, Cin) && ((uintptr_t)workspace & 15) == 0,
+                 "iper_conv3x3_wgrad_bf16: workspace of %zu bytes (16-byte aligned) needed", iper_conv3x3_wgrad_workspace_bytes(N, H, W, Cin));
     IPER_REQUIRE(N > 0 && H > 0 && W % 64 == 0 && Cin % 64 == 0 && Cout % 64 == 0,
                  "iper_conv3x3_wgrad_bf16: needs W %% 64 == 0, Cin %% 64 == 0, Cout %% 64 == 0 (got %dx%d, %d -> %d)", H, W, Cin, Cout);
     IPER_REQUIRE(Cin % 128 == 0 || Cout % 128 == 0, "iper_conv3x3_wgrad_bf16: one of Cin, Cout must be a multiple of 128");
     cudaStream_t st = (cudaStream_t)stream;
     IPER_CHECK_CUDA(cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)Cout * 9 * Cin, st));
+    const size_t xtotal = (size_t)N * Cin * H * W;
+    shift3_kernel<<<(unsigned)std::min<size_t>((xtotal + 255) / 256, 148 * 16), 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x_nchw), xtotal, W, reinterpret_cast<__nv_bfloat16*>(workspace));
+    IPER_CHECK_CUDA(cudaGetLastError());
     TrainArgs t = {};
     t.mode = 1; t.N = N; t.H = H; t.W = W; t.Cin = Cin; t.Cout = Cout; t.dW = dW;
     t.rc = W / 64; t.ksteps = N * H * t.rc;
@@ -263,15 +290,17 @@ extern "C" int iper_conv3x3_wgrad_bf16(const void* x_nchw, const void* dy_nchw, 
     if (sk > t.ksteps) sk = t.ksteps;
     if (sk < 1) sk = 1;
     t.splitk = sk;
-    const void* rows_t = t.a_shift == 0 ? dy_nchw : x_nchw; const void* cols_t = t.a_shift == 0 ? x_nchw : dy_nchw;
-    cuuint64_t rd[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)rowsC, (cuuint64_t)N};
-    cuuint64_t rs[3] = {(cuuint64_t)W * 2, (cuuint64_t)H * W * 2, (cuuint64_t)rowsC * H * W * 2};
-    cuuint32_t rb[4] = {64, 1, 128, 1};
-    if (int rc = bf16_map(&t.mapA, rows_t, 4, rd, rs, rb)) return rc;
-    cuuint64_t cd[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)colsC, (cuuint64_t)N};
-    cuuint64_t cs[3] = {(cuuint64_t)W * 2, (cuuint64_t)H * W * 2, (cuuint64_t)colsC * H * W * 2};
-    cuuint32_t cb[4] = {64, 1, (cuuint32_t)BN, 1};
-    if (int rc = bf16_map(&t.mapB, cols_t, 4, cd, cs, cb)) return rc;
+    // 5-D maps (W, H, C, N, copy): X lives in the workspace as three x-shifted copies, dY has a single "copy"
+    const void* rows_t = t.a_shift == 0 ? dy_nchw : (const void*)workspace; const void* cols_t = t.a_shift == 0 ? (const void*)workspace : dy_nchw;
+    const cuuint64_t rcopies = t.a_shift == 0 ? 1 : 3, ccopies = t.a_shift == 0 ? 3 : 1;
+    cuuint64_t rd[5] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)rowsC, (cuuint64_t)N, rcopies};
+    cuuint64_t rs[4] = {(cuuint64_t)W * 2, (cuuint64_t)H * W * 2, (cuuint64_t)rowsC * H * W * 2, (cuuint64_t)N * rowsC * H * W * 2};
+    cuuint32_t rb[5] = {64, 1, 128, 1, 1};
+    if (int rc = bf16_map(&t.mapA, rows_t, 5, rd, rs, rb)) return rc;
+    cuuint64_t cd[5] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)colsC, (cuuint64_t)N, ccopies};
+    cuuint64_t cs[4] = {(cuuint64_t)W * 2, (cuuint64_t)H * W * 2, (cuuint64_t)colsC * H * W * 2, (cuuint64_t)N * colsC * H * W * 2};
+    cuuint32_t cb[5] = {64, 1, (cuuint32_t)BN, 1, 1};
+    if (int rc = bf16_map(&t.mapB, cols_t, 5, cd, cs, cb)) return rc;
     const int grid = items * sk;
     return BN == 128 ? launch_train<128>(t, grid, st) : launch_train<64>(t, grid, st);
 }

@@ -78,8 +78,9 @@ class _Conv3x3(torch.autograd.Function):
             x_nchw = x_cl.contiguous()                      # pixels contiguous per channel: K-major rows for the pixel contraction
             dy_nchw = dy_cl.contiguous()
             g = torch.empty((co, 9, ci), dtype=torch.float32, device=x_cl.device)
-            check(lib.iper_conv3x3_wgrad_bf16(x_nchw.data_ptr(), dy_nchw.data_ptr(), n, h, w, ci, co, g.data_ptr(), _stream()),
-                  "conv3x3_wgrad_bf16")
+            ws = torch.empty((lib.iper_conv3x3_wgrad_workspace_bytes(n, h, w, ci),), dtype=torch.uint8, device=x_cl.device)
+            check(lib.iper_conv3x3_wgrad_bf16(x_nchw.data_ptr(), dy_nchw.data_ptr(), n, h, w, ci, co, g.data_ptr(), ws.data_ptr(),
+                                              ws.numel(), _stream()), "conv3x3_wgrad_bf16")
             dw = g.view(co, 3, 3, ci).permute(0, 3, 1, 2).to(weight.dtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy_cl.float().sum(dim=(0, 2, 3))
