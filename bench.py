@@ -565,7 +565,7 @@ def main():
                               cta_pair=kw.get("cta_pair", 0))))
 
         other = []          # (name, e0, e1) of the non-conv launches of the same batch
-        OTHER_OPS = ("raster_frames", "conv_stem", "stem_im2col", "warp_attention", "flow_resize", "instnorm_finalize", "pred_to_u8")
+        OTHER_OPS = ("raster_frames", "conv_stem", "conv_stem_tc", "stem_im2col", "warp_attention", "flow_resize", "instnorm_finalize", "pred_to_u8")
         saved = {k: getattr(ops, k) for k in OTHER_OPS if hasattr(ops, k)}
 
         def wrap(name, fn):  # noqa: E306

@@ -164,6 +164,14 @@ int iper_conv_stem(const float* in_nchw, int N, int Cin, int H, int W, const flo
 int iper_stem_im2col(const float* in_nchw, int N, int Cin, int H, int W, void* out, int out_planes,
                      long long out_plane_stride, int out_pitch, int out_coff, iper_stream_t stream);
 
+/* The stem on the tensor cores WITHOUT the im2col round trip (default): builder warps stage the image patch of every 16x8 output
+ * tile in shared memory and write the [128 px x 64] split-fp16 A operand directly in the swizzled layout UMMA reads; weights
+ * w_packed = (w_planes, Cout = 64, 64) fp16 planes with K = (ky*3+kx)*Cin + ci zero-padded to 64 (and optionally pre-scaled, see
+ * iper_conv_gemm_desc.w_scale_inv); epilogue = bias + ReLU + planes store + optional instance-norm sums (stats_ws (N,64,2) fp64). */
+int iper_conv_stem_tc(const float* in_nchw, int N, int Cin, int H, int W, const void* w_packed, int w_planes,
+                      long long w_plane_stride, const float* w_scale_inv, const float* bias, void* out, int out_planes,
+                      long long out_plane_stride, int out_pitch, int out_coff, double* stats_ws, iper_stream_t stream);
+
 /* nn.InstanceNorm2d(affine=False) statistics (attlwb_spade_resunet.py:62, eps 1e-5, biased variance):
  * mean_rstd (N,C,2) = (mean, 1/sqrt(var+eps)) of an NHWC planes tensor.  workspace: N*C*2 doubles (fp64 sums,
  * cleared and filled by the call; two launches + one memset on the stream). */

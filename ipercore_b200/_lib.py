@@ -53,6 +53,8 @@ SIGNATURES = {
     "iper_conv_direct": [ctypes.POINTER(ConvGemmDesc), c_void_p, c_int, c_void_p],
     "iper_conv_stem": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_ll, c_int,
                        c_int, c_void_p, c_void_p],
+    "iper_conv_stem_tc": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int,
+                          c_int, c_void_p, c_void_p],
     "iper_stem_im2col": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_ll, c_int, c_int, c_void_p],
     "iper_instnorm_finalize": [c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p],
     "iper_instnorm_stats": [c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,

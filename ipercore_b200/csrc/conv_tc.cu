@@ -1267,6 +1267,175 @@ static void build_halo_sched(HaloSched& hs, int mode, int Cin, int rows, int tw,
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Stem on the tensor cores without an im2col round trip: Conv2d(CIN <= 7 -> 64, 3x3, s2, p1) + bias + ReLU (+ instance-norm
+// statistics) from the fp32 NCHW image (attlwb_spade_resunet.py:268-271).  K = 9*CIN <= 63 is padded to ONE 64-channel
+// K step, so a tile is a single [128 px x 64] A operand that no tensor map can describe (9 taps x 6 channels of 9 different
+// pixels): four BUILDER warps stage the tile's (33 x 17 x CIN) input patch in shared memory and write the A operand — split
+// into fp16 hi / lo — straight into the 128-byte-swizzled K-major layout UMMA reads (16-byte chunk c of row r lives at
+// r*128 + ((c ^ (r & 7)) << 4)), make it visible to the async proxy (fence.proxy.async) and arrive on the stage's mbarrier.
+// Warp 4 issues the three split-fp16 MMA groups (N = 64) into a double-buffered TMEM accumulator; warps 5-8 run the shared
+// epilogue (bias, ReLU, planes store, per-warp running statistics).  The 16 KB weight tile is loaded once per CTA by TMA.
+// Per frame this reads the 6.3 MB image once and writes the 33.6 MB output; the im2col + GEMM form (iper_stem_im2col) moved
+// another 67 MB through HBM and the CUDA-core stem was shared-memory-LSU bound.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int STEM_TC_THREADS = 288;      // warps 0-3 builders, 4 MMA issuer, 5-8 epilogue
+struct StemTcArgs {
+    const float* in; int CIN, H, W;       // input (N, CIN, H, W) fp32
+};
+
+template <int NS>
+__global__ void __launch_bounds__(STEM_TC_THREADS, 1) conv_stem_tc_kernel(const __grid_constant__ GemmArgs a, const StemTcArgs sa) {
+    constexpr int BN = 64, A_PLANE = BLOCK_M * 128, B_PLANE = BN * 128;
+    constexpr int PW = 33, PH = 17;                        // input patch of a 16 x 8 output tile (stride 2, 3x3)
+    extern __shared__ uint8_t smem_dyn[];
+    __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], tmem_full_bar[2], tmem_empty_bar[2], w_bar;
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ double s_pend[4][BN][2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ring = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    uint8_t* base = smem_dyn + (ring - smem_u32(smem_dyn));
+    uint8_t* sB = base;                                    // [NS planes][64 rows x 128 B]
+    auto sA = [&](int stage, int p) -> uint8_t* { return base + NS * B_PLANE + (stage * NS + p) * A_PLANE; };
+    float* patch = reinterpret_cast<float*>(base + NS * B_PLANE + 2 * NS * A_PLANE);      // [CIN][PH][PW]
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&full_bar[i], 128); mbar_init(&empty_bar[i], 1); mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4);
+        }
+        mbar_init(&w_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(&tmem_base_slot, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    const int tile_lo = (int)((long long)a.total_tiles * blockIdx.x / gridDim.x);
+    const int tile_hi = (int)((long long)a.total_tiles * (blockIdx.x + 1) / gridDim.x);
+    auto coord = [&](int tile) -> TileCoord {
+        TileCoord c; c.phase = 0; c.n_tile = 0;
+        c.px0 = (tile % a.tiles_x) * 16; c.py0 = ((tile / a.tiles_x) % a.tiles_y) * 8; c.pn0 = tile / (a.tiles_x * a.tiles_y);
+        return c;
+    };
+
+    if (warp < 4) {
+        // =========================== builders: image patch -> swizzled split-fp16 A operand ===========================
+        const int r = threadIdx.x;                        // A row = pixel of the tile
+        const int tx = r & 15, ty = r >> 4;
+        const int CIN = sa.CIN, KMAX = 9 * CIN;
+        int stage = 0; uint32_t ph = 0;
+        for (int tile = tile_lo; tile < tile_hi; tile++) {
+            const TileCoord t = coord(tile);
+            const int iy0 = 2 * t.py0 - 1, ix0 = 2 * t.px0 - 1;
+            const float* img = sa.in + (size_t)t.pn0 * CIN * sa.H * sa.W;
+            asm volatile("bar.sync 1, 128;" ::: "memory");             // previous tile's reads of the patch are done
+            for (int i = r; i < CIN * PH * PW; i += 128) {
+                const int c = i / (PH * PW), rem = i - c * (PH * PW), py = rem / PW, px = rem - py * PW;
+                const int iy = iy0 + py, ix = ix0 + px;
+                patch[i] = (iy >= 0 && iy < sa.H && ix >= 0 && ix < sa.W) ? __ldg(img + ((size_t)c * sa.H + iy) * sa.W + ix) : 0.f;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&empty_bar[stage], ph ^ 1);                       // the MMAs that read this stage have retired
+            uint8_t* ahi = sA(stage, 0) + r * 128;
+            uint8_t* alo = (NS == 2) ? sA(stage, 1) + r * 128 : nullptr;
+#pragma unroll 1
+            for (int c = 0; c < 8; c++) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    float v[2];
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const int k = c * 8 + 2 * j + e;
+                        float val = 0.f;
+                        if (k < KMAX) {
+                            const int tap = k / CIN, ci = k - tap * CIN;
+                            val = patch[(ci * PH + 2 * ty + tap / 3) * PW + 2 * tx + tap % 3];
+                        }
+                        v[e] = val;
+                    }
+                    const __half h0 = __float2half_rn(v[0]), h1 = __float2half_rn(v[1]);
+                    hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                    lo[j] = (uint32_t)__half_as_ushort(__float2half_rn(v[0] - __half2float(h0))) |
+                            ((uint32_t)__half_as_ushort(__float2half_rn(v[1] - __half2float(h1))) << 16);
+                }
+                const int sw = (c ^ (r & 7)) << 4;                       // SWIZZLE_128B: chunk index xor row-in-atom
+                *reinterpret_cast<uint4*>(ahi + sw) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                if (NS == 2) *reinterpret_cast<uint4*>(alo + sw) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            fence_proxy_async();                                        // generic-proxy stores -> visible to tcgen05.mma
+            mbar_arrive(&full_bar[stage]);
+            if (++stage == 2) { stage = 0; ph ^= 1; }
+        }
+    } else if (warp == 4) {
+        // =========================== weights (TMA, once) + MMA issuer ===========================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&w_bar, NS * B_PLANE);
+            for (int p = 0; p < NS; p++) tma_load_2d(sB + p * B_PLANE, &a.mapB[p], &w_bar, 0, 0);
+        }
+        mbar_wait(&w_bar, 0);
+        constexpr uint32_t idesc = umma_idesc_f16(BLOCK_M, BN);
+        int stage = 0; uint32_t ph = 0; int it = 0;
+        for (int tile = tile_lo; tile < tile_hi; tile++, it++) {
+            const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
+            mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
+            mbar_wait(&full_bar[stage], ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d = tmem_base + acc * BN;
+                constexpr int NPAIR = (NS == 2) ? 3 : 1;
+                const int pa[3] = {NS == 2 ? 1 : 0, 0, 0}, pb[3] = {0, NS == 2 ? 1 : 0, 0};      // lo*hi, hi*lo, hi*hi
+                uint32_t first = 0u;
+#pragma unroll
+                for (int q = 0; q < NPAIR; q++) {
+                    const uint32_t ab = smem_u32(sA(stage, pa[q])), bb = smem_u32(sB + pb[q] * B_PLANE);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        umma_f16(d, umma_desc_sw128(ab + k * 32), umma_desc_sw128(bb + k * 32), idesc, first);
+                        first = 1u;
+                    }
+                }
+                umma_commit(&empty_bar[stage]);
+                umma_commit(&tmem_full_bar[acc]);
+            }
+            __syncwarp();
+            if (++stage == 2) { stage = 0; ph ^= 1; }
+        }
+    } else {
+        // =========================== epilogue (warps 5..8) ===========================
+        const int q = warp & 3, row = q * 32 + lane;
+        const int tx = row % 16, ty = row / 16;
+        double* pend = a.stats_ws ? &s_pend[q][0][0] : nullptr;
+        int pend_n = -1, it = 0;
+        auto flush = [&]() {
+            if (pend_n >= 0 && pend_n < a.N)
+                for (int c = lane; c < BN; c += 32) {
+                    atomicAdd(a.stats_ws + ((size_t)pend_n * a.rows + c) * 2, pend[c * 2]);
+                    atomicAdd(a.stats_ws + ((size_t)pend_n * a.rows + c) * 2 + 1, pend[c * 2 + 1]);
+                }
+            for (int c = lane; c < BN; c += 32) { pend[c * 2] = 0.0; pend[c * 2 + 1] = 0.0; }
+            __syncwarp();
+        };
+        if (pend) flush();
+        for (int tile = tile_lo; tile < tile_hi; tile++, it++) {
+            const int acc = it & 1; const uint32_t acc_ph = (it >> 1) & 1;
+            mbar_wait(&tmem_full_bar[acc], acc_ph);
+            tc_fence_after();
+            const TileCoord t = coord(tile);
+            if (pend && t.pn0 != pend_n) { flush(); pend_n = t.pn0; }
+            epilogue_tile<BN, NS>(a, t, tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN, row, lane, tx, ty, 0, 0, 1, pend);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        if (pend) flush();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, 2 * BN);
+}
+
 }  // namespace iper
 
 using namespace iper;
@@ -1296,6 +1465,53 @@ extern "C" int iper_conv_halo_plan(int mode, int Cin, int rows, int fuse_n, int3
         for (int r = 0; r < 2; r++) for (int k = 0; k < 2; k++) out[n++] = e.fb_k[r][k];
     }
     return n;
+}
+
+extern "C" int iper_conv_stem_tc(const float* in_nchw, int N, int Cin, int H, int W, const void* w_packed, int w_planes,
+                                 long long w_plane_stride, const float* w_scale_inv, const float* bias, void* out, int out_planes,
+                                 long long out_plane_stride, int out_pitch, int out_coff, double* stats_ws, iper_stream_t stream) {
+    IPER_REQUIRE(in_nchw && w_packed && out, "iper_conv_stem_tc: null pointer");
+    IPER_REQUIRE(N > 0 && Cin >= 1 && 9 * Cin <= 64 && H % 2 == 0 && W % 2 == 0 && H >= 2 && W >= 2,
+                 "iper_conv_stem_tc: needs Cin <= 7 and even H, W (got Cin=%d, %dx%d)", Cin, H, W);
+    IPER_REQUIRE(w_planes == 1 || w_planes == 2, "iper_conv_stem_tc: weight format %d not in {1,2}", w_planes);
+    IPER_REQUIRE(out_pitch % 8 == 0 && out_coff % 8 == 0 && out_coff + 64 <= out_pitch, "iper_conv_stem_tc: bad output channel window");
+    IPER_REQUIRE(((uintptr_t)w_packed & 15) == 0, "iper_conv_stem_tc: weights must be 16-byte aligned");
+    GemmArgs g = {};
+    g.mode = IPER_CONV_S1; g.ksize = 1;
+    g.N = N; g.Ho = H / 2; g.Wo = W / 2; g.oH = g.Ho; g.oW = g.Wo;
+    g.tw = 16; g.th = 8; g.tn = 1;
+    g.tiles_x = (g.Wo + 15) / 16; g.tiles_y = (g.Ho + 7) / 8; g.tiles_nb = N;
+    g.m_tiles = g.tiles_x * g.tiles_y * N; g.m_groups = g.m_tiles; g.n_tiles = 1; g.phases = 1; g.total_tiles = g.m_tiles;
+    g.rows = 64; g.epi = IPER_EPI_PLANES; g.relu = 1; g.bias = bias;
+    g.out = out; g.out_planes = out_planes; g.out_plane_stride = out_plane_stride; g.out_pitch = out_pitch; g.out_coff = out_coff;
+    g.stats_ws = stats_ws; g.w_scale_inv = w_scale_inv;
+    for (int p = 0; p < w_planes; p++) {
+        cuuint64_t wdims[2] = {64, 64};
+        cuuint64_t wstr[1] = {64 * 2};
+        cuuint32_t wbox[2] = {64, 64};
+        if (int rc = encode_map(&g.mapB[p], reinterpret_cast<const __half*>(w_packed) + (size_t)p * w_plane_stride, 2, wdims, wstr, wbox, false, 128)) return rc;
+    }
+    for (int p = w_planes; p < 3; p++) g.mapB[p] = g.mapB[0];
+    for (int p = 0; p < 3; p++) g.mapA[p] = g.mapB[0];
+    g.mapBf[0] = g.mapB[0]; g.mapBf[1] = g.mapB[0];
+    StemTcArgs sa = {in_nchw, Cin, H, W};
+    cudaStream_t s = (cudaStream_t)stream;
+    if (stats_ws) IPER_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * (size_t)N * 64, s));
+    DeviceSlot ds;
+    if (int rc = current_device(ds)) return rc;
+    const int smem = w_planes * (64 * 128) + 2 * w_planes * (BLOCK_M * 128) + Cin * 17 * 33 * 4 + 1024;
+    const int grid = g.total_tiles < ds.sms ? g.total_tiles : ds.sms;
+    if (w_planes == 2) {
+        static int have[MAX_DEVICES] = {};
+        if (int rc = ensure_smem(conv_stem_tc_kernel<2>, have, ds.dev, smem)) return rc;
+        conv_stem_tc_kernel<2><<<grid, STEM_TC_THREADS, smem, s>>>(g, sa);
+    } else {
+        static int have[MAX_DEVICES] = {};
+        if (int rc = ensure_smem(conv_stem_tc_kernel<1>, have, ds.dev, smem)) return rc;
+        conv_stem_tc_kernel<1><<<grid, STEM_TC_THREADS, smem, s>>>(g, sa);
+    }
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
 }
 
 extern "C" int iper_conv_gemm(const iper_conv_gemm_desc* d, iper_stream_t stream) {

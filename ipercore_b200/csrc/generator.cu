@@ -433,14 +433,10 @@ int conv(Ctx& c, const std::string& name, const PlanesT& a, int mode, int ksize,
 }
 int stem(Ctx& c, const std::string& name, const float* in_nchw, int N, int S, const PlanesT& out, double* stats) {
     const Packed& w = c.P(name);
-    PlanesT col = c.planes(w.fmt, N, S / 2, S / 2, 64);
     if (c.ws.dry) return 0;
-    if (int rc = iper_stem_im2col(in_nchw, N, 6, S, S, col.p, col.fmt, col.plane_stride(), col.pitch, 0, (iper_stream_t)c.st)) return rc;
-    iper_conv_gemm_desc d;
-    fill(d, c, col, w, IPER_CONV_S1, 1, 64, 64, IPER_EPI_PLANES);
-    d.bias = c.bias(w); d.relu = 1; d.stats_ws = stats;
-    set_out(d, out);
-    return iper_conv_gemm(&d, (iper_stream_t)c.st);
+    const float* wsi = w.slot_off != (size_t)-1 ? reinterpret_cast<const float*>(c.g->packed + w.slot_off) + 2 : nullptr;
+    return iper_conv_stem_tc(in_nchw, N, 6, S, S, c.wptr(w), w.fmt, (long long)w.rows * w.K, wsi, c.bias(w), out.p, out.fmt,
+                             out.plane_stride(), out.pitch, out.coff, stats, (iper_stream_t)c.st);
 }
 }  // namespace
 

@@ -146,7 +146,7 @@ class AttentionLWBGenerator(nn.Module):
         # halo variant of the CTA-pair kernel (vertical taps share one TMA box; fused transposed-conv phases) wherever
         # a layer qualifies: 3x3 stride-1 convs, the 128->64 transposed conv, the 5x5 heads
         self.halo = self.cta_pair and os.environ.get("IPER_HALO", "1") != "0"
-        self.stem_direct = os.environ.get("IPER_STEM", "tc") == "direct"
+        self.stem_mode = os.environ.get("IPER_STEM", "tc")           # "tc" (fused, default) | "im2col" | "direct" (CUDA cores)
         get = (lambda o, k: o[k]) if isinstance(cfg, dict) else getattr
         self._name = get(cfg, "name") if (isinstance(cfg, dict) and "name" in cfg) or hasattr(cfg, "name") else "AttLWB-SPADE"
         bg, sid, tsf = get(cfg, "BGNet"), get(cfg, "SIDNet"), get(cfg, "TSFNet")
@@ -271,13 +271,16 @@ class AttentionLWBGenerator(nn.Module):
         return int(self.P != 3 and rows >= 128 and mode != ops.IPER_CONV_ROW5)     # plain CTA pairs: formats 1/2 only
 
     def _stem(self, pk, net, x_in, out, stats_ws=None):
-        """Encoder.layers[0] (attlwb_spade_resunet.py:268-271): conv3x3 s2 (Cin = 6) + ReLU.  Default: im2col + tcgen05 1x1 GEMM
-        (IPER_STEM=direct selects the CUDA-core kernel, kept as the cross-check)."""
-        if self.stem_direct or out.P == 3:
+        """Encoder.layers[0] (attlwb_spade_resunet.py:268-271): conv3x3 s2 (Cin = 6) + ReLU.  Default: tcgen05 with the A operand
+        built in shared memory (iper_conv_stem_tc); IPER_STEM=im2col: im2col through HBM + 1x1 GEMM; IPER_STEM=direct: the
+        CUDA-core kernel, kept as the cross-check."""
+        if self.stem_mode == "direct" or out.P == 3:
             w, b = pk[net + ".stem"]
             ops.conv_stem(x_in, w, b, out, stats_ws=stats_ws)
             return out
         w, b = pk[net + ".stem_tc"]
+        if self.stem_mode != "im2col":
+            return ops.conv_stem_tc(x_in, w, b, out, stats_ws=stats_ws)
         N, _, H, W = x_in.shape
         col = Planes.empty(w.fmt, N, H // 2, W // 2, 64, x_in.device)
         ops.stem_im2col(x_in, col)

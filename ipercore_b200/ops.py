@@ -235,6 +235,18 @@ def conv_stem(x_nchw, w_f32, bias, out, stats_ws=None):
                              out.P, out.plane_stride, out.pitch, out.coff, _ptr(stats_ws), _stream()), "conv_stem")
 
 
+def conv_stem_tc(x_nchw, wpack, bias, out, stats_ws=None):
+    """First encoder layer on the tensor cores, A operand built in shared memory (iper_conv_stem_tc); wpack = pack_stem_weight."""
+    x_nchw = _req(x_nchw, torch.float32, "x")
+    N, Cin, H, W = x_nchw.shape
+    if wpack.scale != 1.0 and wpack.scale_inv.device != wpack.w.device:
+        wpack.scale_inv = wpack.scale_inv.to(wpack.w.device)
+    check(lib.iper_conv_stem_tc(x_nchw.data_ptr(), N, Cin, H, W, wpack.w.data_ptr(), wpack.fmt, wpack.w[0].numel(),
+                                wpack.scale_inv.data_ptr() if wpack.scale != 1.0 else 0, _ptr(bias), out.ptr(), out.P,
+                                out.plane_stride, out.pitch, out.coff, _ptr(stats_ws), _stream()), "conv_stem_tc")
+    return out
+
+
 def stem_im2col(x_nchw, out):
     """(N,Cin<=7,H,W) fp32 -> Planes (N,H/2,W/2,64): 3x3/s2/p1 patches, channel k = (ky*3+kx)*Cin + ci (iper_stem_im2col)."""
     x_nchw = _req(x_nchw, torch.float32, "x")
