@@ -318,3 +318,39 @@ def test_split_fp16_range_and_small_values():
     assert rel <= 2e-6
     over = Planes.from_nchw(torch.full((1, 8, 8, 8), 7.0e4, device=DEV), 2).to_nchw()
     assert torch.isinf(over).all()                       # saturation is loud, not silent
+
+
+@pytest.mark.parametrize("N,H,W,P", [(2, 64, 64, 2), (3, 40, 72, 2), (1, 16, 32, 1), (5, 512, 512, 2)])
+def test_stem_tensor_core_forms(N, H, W, P):
+    """First encoder layer (Conv2d(6, 64, 3, s2, p1) + bias + ReLU, attlwb_spade_resunet.py:268-271) in its three forms:
+    iper_conv_stem_tc (A operand built in shared memory by builder warps — the default), im2col + 1x1 GEMM, and the CUDA-core
+    kernel, against torch fp32; partial tiles (20x36 output), a 256^2 output with several images per CTA range, single plane;
+    the fused instance-norm sums against a separate statistics pass."""
+    from ipercore_b200 import ops
+    from ipercore_b200.ops import Planes
+    x = _rand((N, 6, H, W), 71); w = _rand((64, 6, 3, 3), 72, 0.2); b = _rand((64,), 73, 0.1)
+    exp = F.relu(F.conv2d(x, w, b, stride=2, padding=1))
+    tol = 1e-5 if P == 2 else 5e-3
+    wp = ops.pack_stem_weight(w.to(DEV), P)
+    out = Planes.empty(P, N, H // 2, W // 2, 64, DEV)
+    ws = ops.stats_workspace(N, 64, DEV)
+    ops.conv_stem_tc(x.to(DEV), wp, b.to(DEV), out, stats_ws=ws)
+    got = _planes_value(out)
+    print("stem tc %s P=%d: max err %.2e" % ((N, H, W), P, float((got - exp).abs().max())))
+    np.testing.assert_allclose(got.numpy(), exp.numpy(), atol=tol, rtol=0)
+    f, a = ops.instnorm_finalize(ws, (H // 2) * (W // 2)), ops.instnorm_stats(out)
+    torch.testing.assert_close(f[..., 0], a[..., 0], atol=2e-6, rtol=0)
+    torch.testing.assert_close(f[..., 1], a[..., 1], atol=0, rtol=2e-5)
+    if H <= 128:
+        col = Planes.empty(P, N, H // 2, W // 2, 64, DEV)
+        ops.stem_im2col(x.to(DEV), col)
+        out2 = Planes.empty(P, N, H // 2, W // 2, 64, DEV)
+        ws2 = ops.stats_workspace(N, 64, DEV)
+        ops.conv_gemm(col, wp, ops.IPER_CONV_S1, 1, 64, 64, ops.IPER_EPI_PLANES, bias=b.to(DEV), relu=True, out=out2, stats_ws=ws2)
+        np.testing.assert_allclose(_planes_value(out2).numpy(), exp.numpy(), atol=tol, rtol=0)
+        f2 = ops.instnorm_finalize(ws2, (H // 2) * (W // 2))     # per-warp running sums of conv_gemm_kernel
+        torch.testing.assert_close(f2[..., 0], a[..., 0], atol=2e-6, rtol=0)
+        torch.testing.assert_close(f2[..., 1], a[..., 1], atol=0, rtol=2e-5)
+        out3 = Planes.empty(P, N, H // 2, W // 2, 64, DEV)
+        ops.conv_stem(x.to(DEV), w.to(DEV), b.to(DEV), out3)
+        np.testing.assert_allclose(_planes_value(out3).numpy(), exp.numpy(), atol=tol, rtol=0)
