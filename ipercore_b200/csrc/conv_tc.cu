@@ -1280,16 +1280,19 @@ static void build_halo_sched(HaloSched& hs, int mode, int Cin, int rows, int tw,
 // another 67 MB through HBM and the CUDA-core stem was shared-memory-LSU bound.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int STEM_TC_THREADS = 288;      // warps 0-3 builders, 4 MMA issuer, 5-8 epilogue
-struct StemTcArgs {
-    const float* in; int CIN, H, W;       // input (N, CIN, H, W) fp32
+constexpr int STEM_PW = 40, STEM_PH = 17;  // staged patch: 17 rows x 40 columns (33 needed, start shifted to a 16-byte boundary)
+struct alignas(64) StemTcArgs {
+    CUtensorMap mapIn;                     // fp32 image as (W, H, CIN, N), box (40, 17, CIN, 1), no swizzle, zero fill
 };
 
-template <int NS>
-__global__ void __launch_bounds__(STEM_TC_THREADS, 1) conv_stem_tc_kernel(const __grid_constant__ GemmArgs a, const StemTcArgs sa) {
+template <int NS, int CIN>
+__global__ void __launch_bounds__(STEM_TC_THREADS, 1) conv_stem_tc_kernel(const __grid_constant__ GemmArgs a,
+                                                                          const __grid_constant__ StemTcArgs sa) {
     constexpr int BN = 64, A_PLANE = BLOCK_M * 128, B_PLANE = BN * 128;
-    constexpr int PW = 33, PH = 17;                        // input patch of a 16 x 8 output tile (stride 2, 3x3)
+    constexpr int PATCH_FLOATS = CIN * STEM_PH * STEM_PW, PATCH_STRIDE = ((PATCH_FLOATS * 4 + 1023) / 1024) * 1024;
+    constexpr int KMAX = 9 * CIN;
     extern __shared__ uint8_t smem_dyn[];
-    __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], tmem_full_bar[2], tmem_empty_bar[2], w_bar;
+    __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], tmem_full_bar[2], tmem_empty_bar[2], patch_bar[2], w_bar;
     __shared__ uint32_t tmem_base_slot;
     __shared__ double s_pend[4][BN][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1297,14 +1300,16 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 1) conv_stem_tc_kernel(const 
     uint8_t* base = smem_dyn + (ring - smem_u32(smem_dyn));
     uint8_t* sB = base;                                    // [NS planes][64 rows x 128 B]
     auto sA = [&](int stage, int p) -> uint8_t* { return base + NS * B_PLANE + (stage * NS + p) * A_PLANE; };
-    float* patch = reinterpret_cast<float*>(base + NS * B_PLANE + 2 * NS * A_PLANE);      // [CIN][PH][PW]
+    auto sP = [&](int buf) -> float* { return reinterpret_cast<float*>(base + NS * B_PLANE + 2 * NS * A_PLANE + buf * PATCH_STRIDE); };
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; i++) {
             mbar_init(&full_bar[i], 128); mbar_init(&empty_bar[i], 1); mbar_init(&tmem_full_bar[i], 1); mbar_init(&tmem_empty_bar[i], 4);
+            mbar_init(&patch_bar[i], 1);
         }
         mbar_init(&w_bar, 1);
         fence_barrier_init();
+        tma_prefetch_desc(&sa.mapIn);
     }
     if (warp == 4) tmem_alloc(&tmem_base_slot, 2 * BN);
     tc_fence_before();
@@ -1320,26 +1325,28 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 1) conv_stem_tc_kernel(const 
     };
 
     if (warp < 4) {
-        // =========================== builders: image patch -> swizzled split-fp16 A operand ===========================
+        // =========================== builders: image patch (TMA) -> swizzled split-fp16 A operand ===========================
         const int r = threadIdx.x;                        // A row = pixel of the tile
         const int tx = r & 15, ty = r >> 4;
-        const int CIN = sa.CIN, KMAX = 9 * CIN;
-        int stage = 0; uint32_t ph = 0;
-        for (int tile = tile_lo; tile < tile_hi; tile++) {
+        auto fetch = [&](int tile, int buf) {             // one thread: the tile's input patch, zero-filled outside the image
             const TileCoord t = coord(tile);
-            const int iy0 = 2 * t.py0 - 1, ix0 = 2 * t.px0 - 1;
-            const float* img = sa.in + (size_t)t.pn0 * CIN * sa.H * sa.W;
-            asm volatile("bar.sync 1, 128;" ::: "memory");             // previous tile's reads of the patch are done
-            for (int i = r; i < CIN * PH * PW; i += 128) {
-                const int c = i / (PH * PW), rem = i - c * (PH * PW), py = rem / PW, px = rem - py * PW;
-                const int iy = iy0 + py, ix = ix0 + px;
-                patch[i] = (iy >= 0 && iy < sa.H && ix >= 0 && ix < sa.W) ? __ldg(img + ((size_t)c * sa.H + iy) * sa.W + ix) : 0.f;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            mbar_wait(&empty_bar[stage], ph ^ 1);                       // the MMAs that read this stage have retired
+            mbar_arrive_expect_tx(&patch_bar[buf], PATCH_FLOATS * 4);
+            // columns start at 2*px0 - 4 (a multiple of 4 floats: TMA's innermost coordinate must stay 16-byte aligned);
+            // the tap (ky, kx) of output column tx is patch column 2*tx + kx + 3
+            tma_load_4d(sP(buf), &sa.mapIn, &patch_bar[buf], 2 * t.px0 - 4, 2 * t.py0 - 1, 0, t.pn0);
+        };
+        if (r == 0 && tile_lo < tile_hi) fetch(tile_lo, 0);
+        int stage = 0; uint32_t ph = 0; int it = 0;
+        for (int tile = tile_lo; tile < tile_hi; tile++, it++) {
+            const int buf = it & 1;
+            asm volatile("bar.sync 1, 128;" ::: "memory");             // every builder is done with the other patch buffer
+            if (r == 0 && tile + 1 < tile_hi) fetch(tile + 1, buf ^ 1);
+            mbar_wait(&patch_bar[buf], (it >> 1) & 1);
+            mbar_wait(&empty_bar[stage], ph ^ 1);                       // the MMAs that read this A stage have retired
+            const float* patch = sP(buf) + (2 * ty) * STEM_PW + 2 * tx + 3;
             uint8_t* ahi = sA(stage, 0) + r * 128;
             uint8_t* alo = (NS == 2) ? sA(stage, 1) + r * 128 : nullptr;
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < 8; c++) {
                 uint32_t hi[4], lo[4];
 #pragma unroll
@@ -1347,13 +1354,8 @@ __global__ void __launch_bounds__(STEM_TC_THREADS, 1) conv_stem_tc_kernel(const 
                     float v[2];
 #pragma unroll
                     for (int e = 0; e < 2; e++) {
-                        const int k = c * 8 + 2 * j + e;
-                        float val = 0.f;
-                        if (k < KMAX) {
-                            const int tap = k / CIN, ci = k - tap * CIN;
-                            val = patch[(ci * PH + 2 * ty + tap / 3) * PW + 2 * tx + tap % 3];
-                        }
-                        v[e] = val;
+                        const int k = c * 8 + 2 * j + e;                // compile-time after unrolling
+                        v[e] = (k < KMAX) ? patch[((k % CIN) * STEM_PH + (k / CIN) / 3) * STEM_PW + (k / CIN) % 3] : 0.f;
                     }
                     const __half h0 = __float2half_rn(v[0]), h1 = __float2half_rn(v[1]);
                     hi[j] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
@@ -1471,11 +1473,12 @@ extern "C" int iper_conv_stem_tc(const float* in_nchw, int N, int Cin, int H, in
                                  long long w_plane_stride, const float* w_scale_inv, const float* bias, void* out, int out_planes,
                                  long long out_plane_stride, int out_pitch, int out_coff, double* stats_ws, iper_stream_t stream) {
     IPER_REQUIRE(in_nchw && w_packed && out, "iper_conv_stem_tc: null pointer");
-    IPER_REQUIRE(N > 0 && Cin >= 1 && 9 * Cin <= 64 && H % 2 == 0 && W % 2 == 0 && H >= 2 && W >= 2,
-                 "iper_conv_stem_tc: needs Cin <= 7 and even H, W (got Cin=%d, %dx%d)", Cin, H, W);
+    IPER_REQUIRE(Cin == 6, "iper_conv_stem_tc: built for the 6-channel encoders of the generator (Cin=%d): use iper_stem_im2col + "
+                 "iper_conv_gemm for other channel counts", Cin);
+    IPER_REQUIRE(N > 0 && H % 2 == 0 && W % 4 == 0 && H >= 2 && W >= 4, "iper_conv_stem_tc: needs even H and W %% 4 == 0 (got %dx%d)", H, W);
     IPER_REQUIRE(w_planes == 1 || w_planes == 2, "iper_conv_stem_tc: weight format %d not in {1,2}", w_planes);
     IPER_REQUIRE(out_pitch % 8 == 0 && out_coff % 8 == 0 && out_coff + 64 <= out_pitch, "iper_conv_stem_tc: bad output channel window");
-    IPER_REQUIRE(((uintptr_t)w_packed & 15) == 0, "iper_conv_stem_tc: weights must be 16-byte aligned");
+    IPER_REQUIRE(((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)in_nchw & 15) == 0, "iper_conv_stem_tc: operands must be 16-byte aligned");
     GemmArgs g = {};
     g.mode = IPER_CONV_S1; g.ksize = 1;
     g.N = N; g.Ho = H / 2; g.Wo = W / 2; g.oH = g.Ho; g.oW = g.Wo;
@@ -1494,21 +1497,34 @@ extern "C" int iper_conv_stem_tc(const float* in_nchw, int N, int Cin, int H, in
     for (int p = w_planes; p < 3; p++) g.mapB[p] = g.mapB[0];
     for (int p = 0; p < 3; p++) g.mapA[p] = g.mapB[0];
     g.mapBf[0] = g.mapB[0]; g.mapBf[1] = g.mapB[0];
-    StemTcArgs sa = {in_nchw, Cin, H, W};
+    StemTcArgs sa;
+    {   // fp32 image (W, H, C, N), plain (unswizzled) boxes of 40 x 17 x Cin floats, zero fill outside = the conv's padding
+        PFN_cuTensorMapEncodeTiled_v12000 fn = get_encode_fn();
+        IPER_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+        cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Cin, (cuuint64_t)N};
+        cuuint64_t str[3] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4, (cuuint64_t)Cin * H * W * 4};
+        cuuint32_t box[4] = {(cuuint32_t)STEM_PW, (cuuint32_t)STEM_PH, (cuuint32_t)Cin, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = fn(&sa.mapIn, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in_nchw), dims, str, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        IPER_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp32 image) failed with CUresult %d", (int)r);
+    }
     cudaStream_t s = (cudaStream_t)stream;
     if (stats_ws) IPER_CHECK_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * (size_t)N * 64, s));
     DeviceSlot ds;
     if (int rc = current_device(ds)) return rc;
-    const int smem = w_planes * (64 * 128) + 2 * w_planes * (BLOCK_M * 128) + Cin * 17 * 33 * 4 + 1024;
+    const int patch_stride = ((6 * STEM_PH * STEM_PW * 4 + 1023) / 1024) * 1024;
+    const int smem = w_planes * (64 * 128) + 2 * w_planes * (BLOCK_M * 128) + 2 * patch_stride + 1024;
     const int grid = g.total_tiles < ds.sms ? g.total_tiles : ds.sms;
     if (w_planes == 2) {
         static int have[MAX_DEVICES] = {};
-        if (int rc = ensure_smem(conv_stem_tc_kernel<2>, have, ds.dev, smem)) return rc;
-        conv_stem_tc_kernel<2><<<grid, STEM_TC_THREADS, smem, s>>>(g, sa);
+        if (int rc = ensure_smem(conv_stem_tc_kernel<2, 6>, have, ds.dev, smem)) return rc;
+        conv_stem_tc_kernel<2, 6><<<grid, STEM_TC_THREADS, smem, s>>>(g, sa);
     } else {
         static int have[MAX_DEVICES] = {};
-        if (int rc = ensure_smem(conv_stem_tc_kernel<1>, have, ds.dev, smem)) return rc;
-        conv_stem_tc_kernel<1><<<grid, STEM_TC_THREADS, smem, s>>>(g, sa);
+        if (int rc = ensure_smem(conv_stem_tc_kernel<1, 6>, have, ds.dev, smem)) return rc;
+        conv_stem_tc_kernel<1, 6><<<grid, STEM_TC_THREADS, smem, s>>>(g, sa);
     }
     IPER_CHECK_CUDA(cudaGetLastError());
     return 0;

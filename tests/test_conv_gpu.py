@@ -315,7 +315,7 @@ def test_split_fp16_range_and_small_values():
     ref = F.conv2d(xa.double(), w.double(), padding=1).float()
     rel = float((out.to_nchw().cpu() - ref).abs().max() / ref.abs().max())
     print("conv over |x| ~ 3e4: relative error %.2e" % rel)
-    assert rel <= 2e-6
+    assert rel <= 4e-6          # 2.4e-5 without the power-of-two weight pre-scale (the lo plane of 1e-3 weights is subnormal)
     over = Planes.from_nchw(torch.full((1, 8, 8, 8), 7.0e4, device=DEV), 2).to_nchw()
     assert torch.isinf(over).all()                       # saturation is loud, not silent
 
@@ -338,9 +338,11 @@ def test_stem_tensor_core_forms(N, H, W, P):
     got = _planes_value(out)
     print("stem tc %s P=%d: max err %.2e" % ((N, H, W), P, float((got - exp).abs().max())))
     np.testing.assert_allclose(got.numpy(), exp.numpy(), atol=tol, rtol=0)
+    # fused sums are taken from the fp32 values before the planes store; a single fp16 plane (P = 1) then differs by its rounding
+    sa, sr = (2e-6, 2e-5) if P == 2 else (1e-4, 1e-3)
     f, a = ops.instnorm_finalize(ws, (H // 2) * (W // 2)), ops.instnorm_stats(out)
-    torch.testing.assert_close(f[..., 0], a[..., 0], atol=2e-6, rtol=0)
-    torch.testing.assert_close(f[..., 1], a[..., 1], atol=0, rtol=2e-5)
+    torch.testing.assert_close(f[..., 0], a[..., 0], atol=sa, rtol=0)
+    torch.testing.assert_close(f[..., 1], a[..., 1], atol=0, rtol=sr)
     if H <= 128:
         col = Planes.empty(P, N, H // 2, W // 2, 64, DEV)
         ops.stem_im2col(x.to(DEV), col)
@@ -349,8 +351,8 @@ def test_stem_tensor_core_forms(N, H, W, P):
         ops.conv_gemm(col, wp, ops.IPER_CONV_S1, 1, 64, 64, ops.IPER_EPI_PLANES, bias=b.to(DEV), relu=True, out=out2, stats_ws=ws2)
         np.testing.assert_allclose(_planes_value(out2).numpy(), exp.numpy(), atol=tol, rtol=0)
         f2 = ops.instnorm_finalize(ws2, (H // 2) * (W // 2))     # per-warp running sums of conv_gemm_kernel
-        torch.testing.assert_close(f2[..., 0], a[..., 0], atol=2e-6, rtol=0)
-        torch.testing.assert_close(f2[..., 1], a[..., 1], atol=0, rtol=2e-5)
+        torch.testing.assert_close(f2[..., 0], a[..., 0], atol=sa, rtol=0)
+        torch.testing.assert_close(f2[..., 1], a[..., 1], atol=0, rtol=sr)
         out3 = Planes.empty(P, N, H // 2, W // 2, 64, DEV)
         ops.conv_stem(x.to(DEV), w.to(DEV), b.to(DEV), out3)
         np.testing.assert_allclose(_planes_value(out3).numpy(), exp.numpy(), atol=tol, rtol=0)
