@@ -294,7 +294,7 @@ def test_fused_instnorm_statistics(N, H, W, Cin, Cout, mode):
 def test_split_fp16_range_and_small_values():
     """VERDICT r01 weak point 9: the hi/lo planes have fp16 RANGE.  Documented behaviour, probed with adversarial scales:
     values up to 6e4 survive the planes round trip and a convolution at ~22 bits; tiny values are kept to an ABSOLUTE error of
-    one fp16 subnormal step (3e-8) — the lo plane underflows, the hi plane does not; beyond 65504 the planes saturate to inf
+    one fp16 subnormal step (3e-8) — the lo plane underflows, the hi plane does not; beyond 65504 the planes go non-finite
     (the kernels do not clamp: an instance-normalised network never gets there, and a silent clamp would hide a real bug)."""
     from ipercore_b200 import ops
     from ipercore_b200.ops import Planes
@@ -317,7 +317,7 @@ def test_split_fp16_range_and_small_values():
     print("conv over |x| ~ 3e4: relative error %.2e" % rel)
     assert rel <= 4e-6          # 2.4e-5 without the power-of-two weight pre-scale (the lo plane of 1e-3 weights is subnormal)
     over = Planes.from_nchw(torch.full((1, 8, 8, 8), 7.0e4, device=DEV), 2).to_nchw()
-    assert torch.isinf(over).all()                       # saturation is loud, not silent
+    assert not torch.isfinite(over).any()                # loud, not silent: hi = inf, lo = x - inf -> the value reads back non-finite
 
 
 @pytest.mark.parametrize("N,H,W,P", [(2, 64, 64, 2), (3, 40, 72, 2), (1, 16, 32, 1), (5, 512, 512, 2)])
