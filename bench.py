@@ -279,7 +279,7 @@ def run_train(args):
     S, ns = args.size, args.ns
     net = AttentionLWBGenerator(CFG)
     net.load_state_dict(weights.synth_state_dict(0), strict=True)
-    step = train.LWGTrainStep(net, dev, distributed=world > 1)
+    step = train.LWGTrainStep(net, dev, distributed=world > 1, graph=not args.no_graph)
     g = torch.Generator().manual_seed(100 + rank)
     r = lambda *s: (torch.rand(*s, generator=g) * 2 - 1).to(dev)
     batch = dict(bg_inputs=torch.cat([r(1, 1, 3, S, S), (r(1, 1, 1, S, S) > 0).float()], 2), src_inputs=r(1, ns, 6, S, S),
@@ -292,7 +292,7 @@ def run_train(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    for _ in range(max(args.warmup, 1)):
+    for _ in range(max(args.warmup, 1) + (3 if not args.no_graph else 0)):     # graph mode: 2 eager steps + the capture come first
         out = step.step(batch)
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
@@ -316,9 +316,12 @@ def run_train(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "LWG training step %dx%d: G (AttLWB-SPADE) + D (patch_global) + VGG19 perceptual, batch 1 per GPU, "
                                        "ns=%d, nt=1 (BASELINE.json configs[4])" % (S, S, ns),
-                           "kernels": "3x3/s1 convs (fwd, dgrad, wgrad) on tcgen05 bf16; the rest of the step is PyTorch bf16",
+                           "kernels": "every stride-1 convolution of G and VGG19 (1x1, 3x3, 5x5, 7x7: fwd, dgrad, wgrad, bias grad) on tcgen05 bf16, "
+                                      "fused Adam + weight repack; strided / transposed convs, D, norms, warp, losses are PyTorch",
+                           "cuda_graph": not args.no_graph,
                            "allreduce": "bucketed flat NCCL all-reduce of %d G + %d D gradients, overlapped with backward" % (n_g, n_d)},
-                "gpu_launches": int(_lib.launch_count() - n0), "clocks": clocks,
+                "gpu_launches": int(args.steps * step.launches_per_step) if step._graph is not None else int(_lib.launch_count() - n0),
+                "clocks": clocks,
                 "losses": {k: float(v) for k, v in out.items()}}
         print(json.dumps(line))
     if world > 1:

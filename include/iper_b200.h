@@ -298,24 +298,47 @@ int iper_uv_warp(const float* src_img, const float* f2pts, const float* vis_f2pt
 int iper_uv_merge(const float* src_warp, const float* vis_dilated, int bs, int ns, int H, int W, float* uv_img,
                   iper_stream_t stream);
 
-/* ------------------------------------------------------------------------------------------------------------
- * Training-step kernels (BASELINE.json configs[4]): the 3x3 / stride-1 / pad-1 convolutions of the
- * generator in bf16 on the tensor cores — forward, data gradient and weight gradient — which the reference trains through
- * cuDNN (iPERCore/tools/trainers/lwg_trainer.py:699-833 on attlwb_spade_resunet.py:14-25, 80-93, 316-357).
- *   iper_conv3x3_bf16        y (N,H,W,Cout) = conv(x (N,H,W,Cin) NHWC bf16 = torch channels_last, w_packed (Cout, 9*Cin) bf16 with
- *                            K = (ky*3+kx)*Cin + ci) [+ bias fp32] [ReLU].  dgrad = the same call on dY with the weights
- *                            rotated by 180 degrees and in/out transposed: w'(ci, (2-ky, 2-kx), co) = w(co, ci, ky, kx).
- *   iper_conv3x3_wgrad_bf16  dW (Cout, 9, Cin) fp32 = sum over pixels of dY (N,Cout,H,W) x X (N,Cin,H,W) shifted by the tap; both
- *                            operands NCHW bf16 (pixels contiguous = K-major rows for the pixel contraction), W %% 64 == 0; the
- *                            horizontal tap shift is served from three x-shifted copies of X the call writes into the workspace
- *                            (a TMA box may not start at a 2-byte offset in its innermost dimension).
- * Cin, Cout multiples of 64 (one of them of 128 for wgrad); H >= 8, W >= 16.
+/* ----------------------------------------------------------------------------------------------------------
+ * Training-step kernels (BASELINE.json configs[4]): the stride-1 "same" convolutions of the step in bf16 on
+ * the tensor cores — forward, data gradient, weight gradient, bias gradient — and the fused Adam + weight-repack pass.  The
+ * reference trains these layers through cuDNN and torch.optim.Adam (iPERCore/tools/trainers/lwg_trainer.py:326-352, 699-833 on
+ * attlwb_spade_resunet.py:14-25, 80-93, 208-252, 316-357, 605-613; bg_inpaintor.py:24-60).  Everything is NHWC bf16 (= torch
+ * channels_last); channel counts are multiples of 64 (callers zero-pad the 1/3/4/6-channel ends).
+ *   iper_conv_bf16        y (N,H,W,Cout) = conv_kxk(x (N,H,W,Cin), stride 1, padding k/2; k in {1,3,5,7}) with w_packed (Cout, k*k*Cin)
+ *                         bf16, K = (ky*k+kx)*Cin + ci  [+ bias fp32] [+ add_nhwc, a residual of the output's shape] [ReLU].
+ *                         dgrad = the same call on dY with the weights rotated by 180 degrees and in/out transposed:
+ *                         w'(ci, (k-1-ky, k-1-kx), co) = w(co, ci, ky, kx).
+ *   iper_conv_wgrad_bf16  dW[co*stride_co + ci*stride_ci + tap*stride_tap] += sum over pixels dY[p, co] * X[p + tap - k/2, ci]
+ *                         (fp32 atomics: the caller zeroes dW, or lets several calls accumulate).  Reads both operands in NHWC
+ *                         (MN-major tcgen05 operands; no transposed or shifted copies).  Only co < co_valid, ci < ci_valid are
+ *                         written (zero-padded ends).  (co, tap, ci) layout: strides (k*k*Cin, 1, Cin); the parameter's own
+ *                         (co, ci, ky, kx) layout: strides (Cin_real*k*k, k*k, 1).
+ *   iper_bias_grad_bf16   db[c] += sum over pixels dY[p, c], c < C (fp32 atomics), `pitch` channels per pixel.
+ *   iper_adam_pack        torch.optim.Adam's update (betas, eps, no weight decay; bias correction from the device-side step
+ *                         counter *step_dev, so the call can be captured in a CUDA graph) over flat fp32 buffers, described by a
+ *                         device-resident segment table + chunk table ((segment, first element) pairs of <= chunk_elems elements),
+ *                         gradients pre-multiplied by grad_scale (1 / world size); for segments with taps > 0 (convolution weights
+ *                         (co, ci, ky, kx)) it also writes the bf16 forward packing (co_pad, taps, ci_pad) at fwd_offset and, when
+ *                         dgrad_offset >= 0, the dgrad packing (ci_pad, taps reversed, co_pad) — padding entries are never written
+ *                         (the caller zeroes the pack buffers once).  update = 0 only repacks.
+ * H >= 8, W >= 16 for iper_conv_bf16.
  * ---------------------------------------------------------------------------------------------------------- */
-int iper_conv3x3_bf16(const void* x_nhwc, int N, int H, int W, int Cin, const void* w_packed, int Cout, const float* bias,
-                      int relu, void* out_nhwc, iper_stream_t stream);
-size_t iper_conv3x3_wgrad_workspace_bytes(int N, int H, int W, int Cin);   /* three x-shifted copies of X (TMA alignment) */
-int iper_conv3x3_wgrad_bf16(const void* x_nchw, const void* dy_nchw, int N, int H, int W, int Cin, int Cout, float* dW,
-                            void* workspace, size_t workspace_bytes, iper_stream_t stream);
+typedef struct iper_adam_seg {
+    long long offset, numel;        /* position in the flat buffers */
+    int co, ci, taps;               /* convolution weight (co, ci, ky, kx) with taps = k*k; taps = 0: not a packed weight */
+    int co_pad, ci_pad, reserved;   /* channel counts of the packings (multiples of 64) */
+    long long fwd_offset, dgrad_offset;   /* element offsets into pack_fwd / pack_dgrad (dgrad_offset < 0: none) */
+} iper_adam_seg;
+
+int iper_conv_bf16(const void* x_nhwc, int N, int H, int W, int Cin, const void* w_packed, int Cout, int ksize, const float* bias,
+                   int relu, const void* add_nhwc, void* out_nhwc, iper_stream_t stream);
+int iper_conv_wgrad_bf16(const void* x_nhwc, const void* dy_nhwc, int N, int H, int W, int Cin, int Cout, int ksize, float* dW,
+                         long long stride_co, long long stride_ci, long long stride_tap, int co_valid, int ci_valid,
+                         iper_stream_t stream);
+int iper_bias_grad_bf16(const void* dy_nhwc, long long pixels, int C, int pitch, float* db, iper_stream_t stream);
+int iper_adam_pack(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const iper_adam_seg* segs_dev,
+                   const int* chunks_dev, int n_chunks, int chunk_elems, float lr, float beta1, float beta2, float eps,
+                   float grad_scale, const float* step_dev, int update, void* pack_fwd, void* pack_dgrad, iper_stream_t stream);
 
 #ifdef __cplusplus
 }

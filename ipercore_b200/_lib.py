@@ -37,6 +37,12 @@ class ConvGemmDesc(ctypes.Structure):
     ]
 
 
+class AdamSeg(ctypes.Structure):
+    """Mirror of iper_adam_seg (include/iper_b200.h)."""
+    _fields_ = [("offset", c_ll), ("numel", c_ll), ("co", c_int), ("ci", c_int), ("taps", c_int), ("co_pad", c_int),
+                ("ci_pad", c_int), ("reserved", c_int), ("fwd_offset", c_ll), ("dgrad_offset", c_ll)]
+
+
 # name -> argtypes; every function returns int status except iper_last_error
 SIGNATURES = {
     "iper_abi_version": [],
@@ -73,8 +79,12 @@ SIGNATURES = {
     "iper_nhwc_f32_to_nchw": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "iper_pred_to_u8": [c_void_p, c_int, c_int, c_void_p, c_void_p],
     "iper_morph": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
-    "iper_conv3x3_bf16": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p],
-    "iper_conv3x3_wgrad_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p],
+    "iper_conv_bf16": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    "iper_conv_wgrad_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_ll, c_ll, c_int, c_int,
+                             c_void_p],
+    "iper_bias_grad_bf16": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p],
+    "iper_adam_pack": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float,
+                       c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     "iper_gen_create": [c_void_p, c_int, c_int, c_int, c_void_p],
     "iper_gen_load_weight": [c_void_p, ctypes.c_char_p, c_void_p, c_void_p, c_int],
     "iper_gen_pack": [c_void_p, c_void_p, c_size_t, c_void_p],
@@ -97,7 +107,6 @@ OTHER_SIGNATURES = {
     "iper_raster_set_contraction": (c_int, [c_int]),
     "iper_raster_get_contraction": (c_int, []),
     "iper_vis_f2pts_workspace_bytes": (c_size_t, [c_int, c_int]),
-    "iper_conv3x3_wgrad_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "iper_gen_destroy": (None, [c_void_p]),
     "iper_gen_packed_bytes": (c_size_t, [c_void_p]),
     "iper_gen_src_cache_bytes": (c_size_t, [c_void_p, c_int, c_int]),

@@ -31,78 +31,148 @@ CL = torch.channels_last
 USE_KERNELS = True          # tests flip this to compare against the all-torch formulation
 
 
-def _eligible(x, weight):
-    """forward / dgrad need 64-aligned channels and a map of at least 8x16; the weight gradient (trainable layers only) also
-    needs W % 64 == 0 (64-pixel K rows) and one channel count that is a multiple of 128 (its 128-row operand)."""
+def _pad64(c):
+    return (c + 63) // 64 * 64
+
+
+def _eligible(x, weight, stride=1, padding=None):
+    """Stride-1 "same" convolutions with an odd kernel <= 7 on maps of at least 8x16 run on the tcgen05 kernels; channel counts
+    that are not multiples of 64 (the 1/3/4/6-channel ends) are zero-padded by the caller below."""
     co, ci, kh, kw = weight.shape
-    n, _, h, w = x.shape
-    if not (USE_KERNELS and x.is_cuda and kh == 3 and kw == 3 and ci % 64 == 0 and co % 64 == 0 and h >= 8 and w >= 16):
-        return False
-    return (not weight.requires_grad) or (w % 64 == 0 and (ci % 128 == 0 or co % 128 == 0))
+    h, w = x.shape[-2:]
+    if padding is None:
+        padding = kh // 2
+    return bool(USE_KERNELS and x.is_cuda and kh == kw and kh in (1, 3, 5, 7) and stride == 1 and padding == kh // 2 and h >= 8 and w >= 16)
 
 
-def _conv_fwd(x_cl, w_packed, cout, bias, relu=False):
+def pack_weight(weight):
+    """(co, ci, k, k) fp32 -> (forward (co_pad, k*k*ci_pad), dgrad (ci_pad, k*k*co_pad)) bf16, K = (tap, channel); the dgrad
+    packing holds the 180-degree-rotated, in/out-transposed filter.  The torch formulation of csrc/train.cu adam_pack_kernel's
+    repacking (used for frozen weights and by the tests; trainable weights are repacked by the fused Adam pass)."""
+    co, ci, k, _ = weight.shape
+    cop, cip = _pad64(co), _pad64(ci)
+    w = weight.detach()
+    f = torch.zeros((cop, k * k, cip), dtype=BF16, device=w.device)
+    f[:co, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, k * k, ci)
+    d = torch.zeros((cip, k * k, cop), dtype=BF16, device=w.device)
+    d[:ci, :, :co] = w.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, k * k, co)
+    return f.view(cop, -1), d.view(cip, -1)
+
+
+def _packs(weight):
+    pk = getattr(weight, "_iper_pack", None)            # maintained by ParamStore (trainable) ...
+    if pk is None:
+        if weight.requires_grad:
+            return pack_weight(weight)
+        pk = weight._iper_pack = pack_weight(weight)    # ... or packed once (frozen weights: VGG)
+    return pk
+
+
+def _to_cl(x, cpad):
+    """-> bf16 channels_last with the channel count zero-padded to cpad."""
+    x = x.to(BF16)
+    if x.shape[1] != cpad:
+        x = F.pad(x, (0, 0, 0, 0, 0, cpad - x.shape[1]))
+    return x.contiguous(memory_format=CL)
+
+
+def _conv_call(x_cl, w_packed, cout, ksize, bias=None, relu=False, add=None):
     n, cin, h, w = x_cl.shape
     y = torch.empty((n, cout, h, w), dtype=BF16, device=x_cl.device, memory_format=CL)
-    check(lib.iper_conv3x3_bf16(x_cl.data_ptr(), n, h, w, cin, w_packed.data_ptr(), cout, 0 if bias is None else bias.data_ptr(),
-                                int(relu), y.data_ptr(), _stream()), "conv3x3_bf16")
+    check(lib.iper_conv_bf16(x_cl.data_ptr(), n, h, w, cin, w_packed.data_ptr(), cout, ksize, 0 if bias is None else bias.data_ptr(),
+                             int(relu), 0 if add is None else add.data_ptr(), y.data_ptr(), _stream()), "conv_bf16")
     return y
 
 
-class _Conv3x3(torch.autograd.Function):
-    """y = conv2d(x, weight, bias, stride 1, padding 1) in bf16 on the tcgen05 kernels; x any layout, y channels_last."""
+class _Conv(torch.autograd.Function):
+    """y = [relu]( conv2d(x, weight, bias, stride 1, padding k/2) [+ add] ) in bf16 on the tcgen05 kernels; x any layout, y
+    channels_last.  Weight / bias gradients go straight into the parameter's flat fp32 gradient when the parameter has a sink
+    (ParamStore), otherwise they are returned to autograd."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
-        x_cl = x.to(BF16).contiguous(memory_format=CL)
-        co, ci = weight.shape[:2]
-        wp = weight.detach().permute(0, 2, 3, 1).reshape(co, 9 * ci).to(BF16).contiguous()      # K = (tap, ci)
-        b = None if bias is None else bias.detach().float().contiguous()
-        y = _conv_fwd(x_cl, wp, co, b)
-        ctx.save_for_backward(x_cl, weight)
-        ctx.has_bias = bias is not None
-        return y
+    def forward(ctx, x, weight, bias, relu, add):
+        co, ci, k, _ = weight.shape
+        cop, cip = _pad64(co), _pad64(ci)
+        x_cl = _to_cl(x, cip)
+        wf, _ = _packs(weight)
+        b = None
+        if bias is not None:
+            b = bias.detach().float()
+            b = (F.pad(b, (0, cop - co)) if co != cop else b).contiguous()
+        a = None if add is None else _to_cl(add, cop)
+        y = _conv_call(x_cl, wf, cop, k, b, relu, a)
+        ctx.save_for_backward(x_cl, weight, y if relu else None)
+        ctx.has_bias, ctx.relu, ctx.has_add, ctx.bias_ref = bias is not None, relu, add is not None, bias
+        if weight.requires_grad and torch.is_grad_enabled():
+            weight._iper_uses = getattr(weight, "_iper_uses", 0) + 1
+        return y if co == cop else y[:, :co]
 
     @staticmethod
     def backward(ctx, dy):
-        x_cl, weight = ctx.saved_tensors
-        co, ci = weight.shape[:2]
+        x_cl, weight, y = ctx.saved_tensors
+        co, ci, k, _ = weight.shape
+        cop, cip = _pad64(co), _pad64(ci)
         n, _, h, w = x_cl.shape
-        dy_cl = dy.to(BF16).contiguous(memory_format=CL)
-        dx = dw = db = None
+        dy_cl = _to_cl(dy, cop)
+        if ctx.relu:
+            dy_cl = torch.ops.aten.threshold_backward(dy_cl, y, 0).contiguous(memory_format=CL)
+        dx = dw = db = dadd = None
+        st = _stream()
         if ctx.needs_input_grad[0]:
-            # dX = conv(dY, w') with w'(ci, (2-ky, 2-kx), co) = w(co, ci, ky, kx)
-            wd = weight.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(ci, 9 * co).to(BF16).contiguous()
-            dx = _conv_fwd(dy_cl, wd, ci, None)
+            _, wd = _packs(weight)
+            dx = _conv_call(dy_cl, wd, cip, k)
+            if ci != cip:
+                dx = dx[:, :ci]
+        weight._iper_uses = getattr(weight, "_iper_uses", 1) - 1
         if ctx.needs_input_grad[1]:
-            x_nchw = x_cl.contiguous()                      # pixels contiguous per channel: K-major rows for the pixel contraction
-            dy_nchw = dy_cl.contiguous()
-            g = torch.empty((co, 9, ci), dtype=torch.float32, device=x_cl.device)
-            ws = torch.empty((lib.iper_conv3x3_wgrad_workspace_bytes(n, h, w, ci),), dtype=torch.uint8, device=x_cl.device)
-            check(lib.iper_conv3x3_wgrad_bf16(x_nchw.data_ptr(), dy_nchw.data_ptr(), n, h, w, ci, co, g.data_ptr(), ws.data_ptr(),
-                                              ws.numel(), _stream()), "conv3x3_wgrad_bf16")
-            dw = g.view(co, 3, 3, ci).permute(0, 3, 1, 2).to(weight.dtype)
+            sink = getattr(weight, "_iper_sink", None)
+            if sink is not None:                         # accumulate into the flat gradient, parameter layout (co, ci, ky, kx)
+                g, strides = sink.grad, (ci * k * k, k * k, 1)
+            else:
+                g = torch.zeros((co, k * k, ci), dtype=torch.float32, device=x_cl.device)
+                strides = (k * k * ci, 1, ci)
+            check(lib.iper_conv_wgrad_bf16(x_cl.data_ptr(), dy_cl.data_ptr(), n, h, w, cip, cop, k, g.data_ptr(), strides[0], strides[1],
+                                           strides[2], co, ci, st), "conv_wgrad_bf16")
+            if sink is None:
+                dw = g.view(co, k, k, ci).permute(0, 3, 1, 2).to(weight.dtype)
+            elif weight._iper_uses == 0:
+                sink.ready()
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy_cl.float().sum(dim=(0, 2, 3))
-        return dx, dw, db
+            bias = ctx.bias_ref
+            sink = getattr(bias, "_iper_sink", None)
+            g = sink.grad if sink is not None else torch.zeros((co,), dtype=torch.float32, device=x_cl.device)
+            check(lib.iper_bias_grad_bf16(dy_cl.data_ptr(), n * h * w, co, cop, g.data_ptr(), st), "bias_grad_bf16")
+            if sink is None:
+                db = g.to(bias.dtype)
+            elif weight._iper_uses == 0:
+                sink.ready()
+        if ctx.has_add and ctx.needs_input_grad[4]:
+            dadd = dy_cl if co == cop else dy_cl[:, :co]
+        return dx, dw, db, None, dadd
 
 
 def _torch_conv(x, weight, bias, stride=1, padding=0, transposed=False):
-    """The PyTorch side of the step.  Layers with fewer than 8 input or output channels (6-channel stems, the 3- / 1-channel
-    heads, the discriminator's ends) run in fp32: cuDNN has no bf16 channels_last engine for some of their gradients
-    ("GET was unable to find an engine"), and they are a rounding error of the step's FLOPs."""
+    """The PyTorch side of the step (strided / transposed convolutions, the discriminator).  Layers with fewer than 8 input or
+    output channels run in fp32: cuDNN has no bf16 channels_last engine for some of their gradients."""
     tiny = min(weight.shape[0], weight.shape[1]) < 8
     dt = torch.float32 if tiny else x.dtype
     fn = F.conv_transpose2d if transposed else F.conv2d
-    y = fn(x.to(dt), weight.to(dt), None if bias is None else bias.to(dt), stride=stride, padding=padding)
-    return y if tiny else y
+    return fn(x.to(dt), weight.to(dt), None if bias is None else bias.to(dt), stride=stride, padding=padding)
+
+
+def conv(x, weight, bias=None, relu=False, add=None):
+    """Stride-1 "same" convolution [+ residual] [ReLU]: tcgen05 bf16 kernels (forward, dgrad, wgrad, bias grad) when the layer
+    qualifies, torch otherwise."""
+    if _eligible(x, weight):
+        return _Conv.apply(x, weight, bias, relu, add)
+    y = _torch_conv(x, weight, bias, padding=weight.shape[-1] // 2)
+    if add is not None:
+        y = y + add
+    return F.relu(y) if relu else y
 
 
 def conv3x3(x, weight, bias=None):
-    """3x3 / s1 / p1 convolution: tcgen05 bf16 kernels (forward, dgrad, wgrad) when the layer qualifies, torch otherwise."""
-    if _eligible(x, weight):
-        return _Conv3x3.apply(x, weight, bias)
-    return _torch_conv(x, weight, bias, padding=1)
+    return conv(x, weight, bias)
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -123,19 +193,32 @@ class TrainableGenerator(nn.Module):
         mod, attr = name.rsplit(".", 1)
         return getattr(self.net.get_submodule(mod), attr, None)
 
-    def _c(self, name, x, stride=1, padding=0):
+    def _c(self, name, x, stride=1, padding=0, relu=False, add=None):
         w, b = self._p(name + ".weight"), self._p(name + ".bias")
-        if w.shape[-1] == 3 and stride == 1 and padding == 1:
-            return conv3x3(x, w, b)
-        return _torch_conv(x, w, b, stride=stride, padding=padding)
+        if _eligible(x, w, stride, padding):
+            return _Conv.apply(x, w, b, relu, add)
+        y = _torch_conv(x, w, b, stride=stride, padding=padding)
+        if add is not None:
+            y = y + add
+        return F.relu(y) if relu else y
 
     def _ct(self, name, x):
         w, b = self._p(name + ".weight"), self._p(name + ".bias")
         return _torch_conv(x, w, b, stride=2, padding=1, transposed=True)
 
     def _res(self, prefix, x, second):
-        y = F.relu(self._c("%s.main.0" % prefix, x, padding=1))
-        return x + self._c("%s.main.%d" % (prefix, second), y, padding=1)
+        y = self._c("%s.main.0" % prefix, x, padding=1, relu=True)
+        return self._c("%s.main.%d" % (prefix, second), y, padding=1, add=x)
+
+    @staticmethod
+    def native_weight(name, param):
+        """True for the convolution weights that run on csrc/train.cu (stride-1 "same" convolutions): everything 4-D except the
+        stride-2 encoders and the transposed convolutions."""
+        if param.dim() != 4 or param.shape[2] != param.shape[3] or param.shape[2] not in (1, 3, 5, 7):
+            return False
+        if any(t in name for t in ("encoders.", "tsf_net_enc.", "decoders.", "upconvs.")):
+            return False
+        return not any(name.endswith("bg_net.main.%d.weight" % i) for i in (3, 6, 9, 18, 21, 24))
 
     # ---- BGNet (bg_inpaintor.py:24-60) ----
     def forward_bg(self, bg_inputs):
@@ -151,7 +234,7 @@ class TrainableGenerator(nn.Module):
             x = x + inorm(self._c("bg_net.main.%d.main.3" % idx, y, padding=1)); idx += 1
         for _ in range(3):
             x = F.relu(inorm(self._ct("bg_net.main.%d" % idx, x))); idx += 3
-        return torch.tanh(self._c("bg_net.main.%d" % idx, x, padding=3).float()).view(bs, ns, 3, h, w)
+        return torch.tanh(self._c("bg_net.main.%d" % idx, x, padding=3).float()).reshape(bs, ns, 3, h, w)
 
     # ---- SIDNet (attlwb_spade_resunet.py:450-478, ResAutoEncoder) ----
     def forward_src(self, src_inputs, only_enc=False):
@@ -168,8 +251,8 @@ class TrainableGenerator(nn.Module):
         d = x
         for i in range(3):
             d = F.relu(self._ct("src_net.decoders.layers.%d.0" % i, d))
-        img = torch.tanh(self._c("src_net.img_reg.0", d, padding=2).float()).view(bs, ns, 3, h, w)
-        mask = torch.sigmoid(self._c("src_net.att_reg.0", d, padding=2).float()).view(bs, ns, 1, h, w)
+        img = torch.tanh(self._c("src_net.img_reg.0", d, padding=2).float()).reshape(bs, ns, 3, h, w)
+        mask = torch.sigmoid(self._c("src_net.att_reg.0", d, padding=2).float()).reshape(bs, ns, 1, h, w)
         return enc, res, img, mask
 
     # ---- SelfAttentionLWB (attlwb_spade_resunet.py:208-252) ----
@@ -180,13 +263,13 @@ class TrainableGenerator(nn.Module):
         if H != h or W != w:
             T = F.interpolate(T.permute(0, 3, 1, 2), size=(h, w), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
         warp = F.grid_sample(src_x.float(), T.float(), mode="bilinear", padding_mode="zeros", align_corners=False).to(BF16)
-        k = self._c(prefix + ".fk", warp).view(bs, ns, -1, h, w)
-        v = self._c(prefix + ".fv", warp).view(bs, ns, -1, h, w)
+        k = self._c(prefix + ".fk", warp).reshape(bs, ns, -1, h, w)
+        v = self._c(prefix + ".fv", warp).reshape(bs, ns, -1, h, w)
         q = self._c(prefix + ".fq", tsf_x)
         logits = (k.float() * q.float().unsqueeze(1)).sum(dim=2, keepdim=True) / math.sqrt(k.shape[2])
         a = (torch.softmax(logits, dim=1) * v.float()).sum(dim=1).to(BF16)
         normalized = F.instance_norm(tsf_x.float(), eps=1e-5)
-        actv = F.relu(self._c(prefix + ".spade.mlp_shared.0", a, padding=1))
+        actv = self._c(prefix + ".spade.mlp_shared.0", a, padding=1, relu=True)
         gamma = self._c(prefix + ".spade.mlp_gamma", actv, padding=1).float()
         beta = self._c(prefix + ".spade.mlp_beta", actv, padding=1).float()
         return (normalized * (1 + gamma) + beta).to(BF16)
@@ -204,7 +287,7 @@ class TrainableGenerator(nn.Module):
         for i in range(3):
             d = F.relu(self._ct("tsf_net_dec.upconvs.%d.0" % i, d))
             if i != 2:
-                d = F.relu(self._c("tsf_net_dec.skippers.%d.0" % i, torch.cat([enc[1 - i], d], dim=1), padding=1))
+                d = self._c("tsf_net_dec.skippers.%d.0" % i, torch.cat([enc[1 - i], d], dim=1), padding=1, relu=True)
         img = torch.tanh(self._c("tsf_img_reg.0", d, padding=2).float())
         mask = torch.sigmoid(self._c("tsf_att_reg.0", d, padding=2).float())
         return img, mask
@@ -263,7 +346,7 @@ class VGG19Features(nn.Module):
         for hi in self.CUTS:
             for layer in self.features[lo:hi]:
                 # frozen 3x3 convs: the same tcgen05 kernels (forward + data gradient; no weight gradient is requested)
-                x = F.relu(conv3x3(x, layer.weight, layer.bias)).to(BF16) if isinstance(layer, nn.Conv2d) else \
+                x = conv(x, layer.weight, layer.bias, relu=True).to(BF16) if isinstance(layer, nn.Conv2d) else \
                     (x if isinstance(layer, nn.ReLU) else layer(x))
             outs.append(x); lo = hi
         return outs
@@ -286,14 +369,17 @@ def tv_loss(m):
 
 class FlatGradBuckets:
     """Gradient all-reduce of iPERCore/services/train.py:89-95 (DDP) as a few flat NCCL all-reduces overlapped with backward:
-    parameter .grad tensors are views into one flat buffer per bucket (reverse registration order = roughly the order the
-    gradients become ready); when the last gradient of a bucket has been accumulated its all-reduce starts asynchronously."""
+    every parameter's .grad is a view into ONE flat fp32 buffer (reverse registration order = roughly the order the gradients
+    become ready), buckets are contiguous slices of it; when the last gradient of a bucket has been accumulated its all-reduce
+    starts asynchronously.  `offsets[param]` is the parameter's position — ParamStore lays parameters and Adam moments out the
+    same way."""
 
     def __init__(self, params, n_buckets=4, group=None):
         import torch.distributed as dist
         self.dist, self.group = dist, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         params = [p for p in params if p.requires_grad][::-1]
+        self.params = params
         total = sum(p.numel() for p in params)
         per = -(-total // max(1, n_buckets))
         self.buckets, cur, size = [], [], 0
@@ -303,56 +389,148 @@ class FlatGradBuckets:
                 self.buckets.append(cur); cur, size = [], 0
         if cur:
             self.buckets.append(cur)
-        self.flat, self.pending, self.handles = [], [], []
+        self.storage = torch.zeros(total, dtype=torch.float32, device=params[0].device)
+        self.flat, self.pending, self.handles, self.offsets, self.bucket_of = [], [], [], {}, {}
+        off = 0
         for bi, b in enumerate(self.buckets):
-            flat = torch.zeros(sum(p.numel() for p in b), dtype=torch.float32, device=b[0].device)
-            off = 0
+            start = off
             for p in b:
-                p.grad = flat[off:off + p.numel()].view_as(p); off += p.numel()
+                p.grad = self.storage[off:off + p.numel()].view_as(p)
+                self.offsets[p] = off; self.bucket_of[p] = bi
                 p.register_post_accumulate_grad_hook(self._hook(bi))
-            self.flat.append(flat); self.pending.append(len(b))
+                off += p.numel()
+            self.flat.append(self.storage[start:off]); self.pending.append(len(b))
         self.count = [0] * len(self.buckets)
+        self.active = True              # False: gradients that are about to be discarded (D's, during the G step) are not reduced
 
     def _hook(self, bi):
         def fn(_p):
+            if not self.active:
+                return
             self.count[bi] += 1
             if self.count[bi] == self.pending[bi] and self.world > 1:
                 self.handles.append(self.dist.all_reduce(self.flat[bi], op=self.dist.ReduceOp.SUM, group=self.group, async_op=True))
         return fn
 
+    def ready(self, p):
+        """For gradients a kernel accumulated straight into the flat buffer (no autograd accumulation, so no hook)."""
+        self._hook(self.bucket_of[p])(p)
+
     def zero(self):
-        for f in self.flat:
-            f.zero_()
+        self.storage.zero_()
         self.count = [0] * len(self.buckets)
         self.handles = []
 
-    def finish(self):
-        """Wait for the in-flight all-reduces (buckets whose hooks never fired — unused parameters — are reduced now) and average."""
+    def finish(self, average=True):
+        """Wait for the in-flight all-reduces (buckets whose hooks never fired — unused parameters — are reduced now); average
+        unless the caller folds 1/world into its optimizer pass."""
         if self.world > 1:
             for bi, f in enumerate(self.flat):
                 if self.count[bi] != self.pending[bi]:
                     self.handles.append(self.dist.all_reduce(f, op=self.dist.ReduceOp.SUM, group=self.group, async_op=True))
             for h in self.handles:
                 h.wait()
-            for f in self.flat:
-                f.div_(self.world)
+            if average:
+                self.storage.div_(self.world)
+
+
+class _Sink:
+    def __init__(self, grad, buckets, param):
+        self.grad, self._b, self._p = grad, buckets, param
+
+    def ready(self):
+        self._b.ready(self._p)
+
+
+class ParamStore:
+    """Flat fp32 master parameters + Adam moments laid out like the flat gradient of `buckets`, updated by ONE kernel per step
+    (csrc/train.cu adam_pack_kernel = torch.optim.Adam(lr, betas, eps) of lwg_trainer.py's optimizers) that also rewrites the
+    bf16 forward / dgrad packings of the convolution weights `native(name, param)` selects.  Parameters become views of the flat
+    buffer (state_dict names and layouts unchanged: ``personalized.pth`` saves / loads as before; call ``repack()`` after loading)
+    and get ``_iper_pack`` (the packings) and ``_iper_sink`` (their flat-gradient slice, written directly by the wgrad kernels)."""
+    CHUNK = 4096
+
+    def __init__(self, named_params, buckets, native=lambda name, p: False, lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
+        import ctypes
+        from ._lib import AdamSeg
+        self.b, self.lr, self.betas, self.eps = buckets, lr, betas, eps
+        dev = buckets.storage.device
+        total = buckets.storage.numel()
+        self.p = torch.empty(total, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.step_t = torch.zeros(1, dtype=torch.float32, device=dev)
+        named = [(n, p) for n, p in named_params if p.requires_grad]
+        segs, chunks, fwd_total, dg_total, packed = [], [], 0, 0, []
+        for name, p in named:
+            off = buckets.offsets[p]
+            self.p[off:off + p.numel()].copy_(p.detach().reshape(-1))
+            p.data = self.p[off:off + p.numel()].view_as(p)
+            sg = AdamSeg(offset=off, numel=p.numel(), co=0, ci=0, taps=0, co_pad=0, ci_pad=0, reserved=0, fwd_offset=0, dgrad_offset=-1)
+            if native(name, p):
+                co, ci, k, _ = p.shape
+                sg.co, sg.ci, sg.taps, sg.co_pad, sg.ci_pad = co, ci, k * k, _pad64(co), _pad64(ci)
+                sg.fwd_offset, sg.dgrad_offset = fwd_total, dg_total
+                fwd_total += sg.co_pad * sg.taps * sg.ci_pad; dg_total += sg.ci_pad * sg.taps * sg.co_pad
+                packed.append((p, sg))
+                p._iper_sink = _Sink(p.grad, buckets, p)
+            elif p.dim() == 1:
+                p._iper_sink = _Sink(p.grad, buckets, p)         # biases of native layers are reduced by iper_bias_grad_bf16
+            for c0 in range(0, p.numel(), self.CHUNK):
+                chunks.append((len(segs), c0))
+            segs.append(sg)
+        self.pack_fwd = torch.zeros(max(fwd_total, 8), dtype=BF16, device=dev)
+        self.pack_dgrad = torch.zeros(max(dg_total, 8), dtype=BF16, device=dev)
+        for p, sg in packed:
+            p._iper_pack = (self.pack_fwd[sg.fwd_offset:sg.fwd_offset + sg.co_pad * sg.taps * sg.ci_pad].view(sg.co_pad, -1),
+                            self.pack_dgrad[sg.dgrad_offset:sg.dgrad_offset + sg.ci_pad * sg.taps * sg.co_pad].view(sg.ci_pad, -1))
+        arr = (AdamSeg * len(segs))(*segs)
+        self.segs = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        self.chunks = torch.tensor(chunks, dtype=torch.int32).to(dev)
+        self.n_chunks = len(chunks)
+        self.repack()
+
+    def _launch(self, update):
+        check(lib.iper_adam_pack(self.p.data_ptr(), self.b.storage.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), self.segs.data_ptr(),
+                                 self.chunks.data_ptr(), self.n_chunks, self.CHUNK, self.lr, self.betas[0], self.betas[1], self.eps,
+                                 1.0 / self.b.world, self.step_t.data_ptr(), int(update), self.pack_fwd.data_ptr(),
+                                 self.pack_dgrad.data_ptr(), _stream()), "adam_pack")
+
+    def repack(self):
+        self._launch(False)
+
+    def step(self):
+        """One Adam step on the (summed, not yet averaged) flat gradient."""
+        self.step_t += 1
+        self._launch(True)
 
 
 class LWGTrainStep:
     """One optimisation step of LWGTrainer.optimize_parameters (lwg_trainer.py:326-352): G step then D step, Adam lr 1e-4,
-    betas (0.9, 0.999) (deploy.toml [Train]); losses of optimize_G / optimize_D with use_face = false."""
+    betas (0.9, 0.999) (deploy.toml [Train]); losses of optimize_G / optimize_D with use_face = false.  ``graph=True`` captures
+    the whole step (forward, both backward passes, the bucketed all-reduces, both optimizer passes) in one CUDA graph after a
+    few eager warm-up steps: at batch 1 the step is ~3000 small launches and otherwise bound by launch latency."""
 
-    def __init__(self, net, device, lr=1e-4, lambdas=None, distributed=False):
+    def __init__(self, net, device, lr=1e-4, lambdas=None, distributed=False, graph=False, fused_adam=True):
         self.dev = device
         self.G = TrainableGenerator(net).to(device)
         self.D = PatchDiscriminator().to(device)
         self.vgg = VGG19Features().to(device).eval()
         self.lam = dict(rec=10.0, tsf=10.0, mask=5.0, smooth=1.0, adv=1.0)
         self.lam.update(lambdas or {})
-        self.opt_G = torch.optim.Adam(self.G.parameters(), lr=lr, betas=(0.9, 0.999))
-        self.opt_D = torch.optim.Adam(self.D.parameters(), lr=lr, betas=(0.9, 0.999))
-        self.bk_G = FlatGradBuckets(list(self.G.parameters())) if distributed else None
-        self.bk_D = FlatGradBuckets(list(self.D.parameters()), n_buckets=2) if distributed else None
+        self.fused = bool(fused_adam and USE_KERNELS)
+        self.use_graph, self._graph, self._static, self._out, self._eager_steps = bool(graph), None, None, None, 0
+        if self.fused:
+            self.bk_G = FlatGradBuckets(list(self.G.parameters()))
+            self.bk_D = FlatGradBuckets(list(self.D.parameters()), n_buckets=2)
+            self.st_G = ParamStore(list(self.G.named_parameters()), self.bk_G, native=TrainableGenerator.native_weight, lr=lr)
+            self.st_D = ParamStore(list(self.D.named_parameters()), self.bk_D, lr=lr)
+            self.opt_G = self.opt_D = None
+        else:
+            self.opt_G = torch.optim.Adam(self.G.parameters(), lr=lr, betas=(0.9, 0.999), capturable=self.use_graph)
+            self.opt_D = torch.optim.Adam(self.D.parameters(), lr=lr, betas=(0.9, 0.999), capturable=self.use_graph)
+            self.bk_G = FlatGradBuckets(list(self.G.parameters())) if distributed else None
+            self.bk_D = FlatGradBuckets(list(self.D.parameters()), n_buckets=2) if distributed else None
 
     def _zero(self, opt, bk):
         if bk is not None:
@@ -360,13 +538,44 @@ class LWGTrainStep:
         else:
             opt.zero_grad(set_to_none=True)
 
+    def _update(self, opt, bk, store):
+        if store is not None:
+            bk.finish(average=False)          # 1 / world is folded into the Adam pass
+            store.step()
+        else:
+            if bk is not None:
+                bk.finish()
+            opt.step()
+
     def step(self, batch):
         """batch: bg_inputs (bs,1,4,h,w), src_inputs (bs,ns,6,h,w), tsf_inputs (bs,nt,6,h,w), Tst (bs,nt,ns,h,w,2), real_src
         (bs,ns,3,h,w), real_tsf (bs,nt,3,h,w), real_bg (bs,3,h,w), body_mask (bs,ns+nt,1,h,w) -> dict of loss values."""
+        if not self.use_graph:
+            return self._step(batch)
+        if self._graph is None:
+            if self._eager_steps < 2:         # eager warm-up: lazy initialisations (cuDNN plans, NCCL, function attributes)
+                self._eager_steps += 1
+                return self._step(batch)
+            self._static = {k: v.clone() for k, v in batch.items()}
+            torch.cuda.synchronize(self.dev)
+            from ._lib import launch_count
+            n0 = launch_count()
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._out = self._step(self._static)
+            self.launches_per_step = launch_count() - n0       # libiper_b200 launches inside one replay
+        for k, v in batch.items():
+            if v.data_ptr() != self._static[k].data_ptr():
+                self._static[k].copy_(v, non_blocking=True)
+        self._graph.replay()
+        return self._out
+
+    def _step(self, batch):
         b = batch
         bs, nt = b["tsf_inputs"].shape[:2]
         ns = b["src_inputs"].shape[1]
         h, w = b["tsf_inputs"].shape[-2:]
+        st_G, st_D = (self.st_G, self.st_D) if self.fused else (None, None)
         # ---- forward (lwg_trainer.py:699-731) ----
         fake_bg, src_color, src_mask, tsf_color, tsf_mask = self.G(b["bg_inputs"], b["src_inputs"], b["tsf_inputs"], b["Tst"])
         fake_src = src_mask * fake_bg + (1 - src_mask) * src_color
@@ -385,18 +594,18 @@ class LWGTrainStep:
         l_smooth = tv_loss(fm) * self.lam["smooth"]
         loss_G = l_rec + l_tsf + l_adv + l_mask + l_smooth
         self._zero(self.opt_G, self.bk_G)
+        if self.bk_D is not None:
+            self.bk_D.active = False          # the adversarial term back-propagates through D: those gradients are discarded
         loss_G.backward()
-        if self.bk_G is not None:
-            self.bk_G.finish()
-        self.opt_G.step()
+        if self.bk_D is not None:
+            self.bk_D.active = True
+        self._update(self.opt_G, self.bk_G, st_G)
         # ---- D step (optimize_D :797-834) ----
         real_in = torch.cat([r_tsf, tsf_cond], dim=1)
         fake_in = torch.cat([f_tsf.detach(), tsf_cond], dim=1)
         loss_D = lsgan(self.D(real_in), 1.0) + lsgan(self.D(fake_in), -1.0)
         self._zero(self.opt_D, self.bk_D)
         loss_D.backward()
-        if self.bk_D is not None:
-            self.bk_D.finish()
-        self.opt_D.step()
+        self._update(self.opt_D, self.bk_D, st_D)
         return dict(G=loss_G.detach(), D=loss_D.detach(), rec=l_rec.detach(), tsf=l_tsf.detach(), adv=l_adv.detach(),
                     mask=l_mask.detach(), smooth=l_smooth.detach())

@@ -33,6 +33,11 @@ def test_descriptor_struct_matches_header():
     assert ctypes.sizeof(ConvGemmDesc) == 288 and ConvGemmDesc.w_scale_inv.offset == 280 and ConvGemmDesc.cta_pair.offset == 272 and ConvGemmDesc.tiles_m.offset == 260 and ConvGemmDesc.stats_ws.offset == 264 and ConvGemmDesc.max_ctas.offset == 232 and ConvGemmDesc.cross_scale.offset == 256
 
 
+def test_adam_segment_struct_matches_header():
+    from ipercore_b200._lib import AdamSeg
+    assert ctypes.sizeof(AdamSeg) == 56 and AdamSeg.taps.offset == 24 and AdamSeg.fwd_offset.offset == 40 and AdamSeg.dgrad_offset.offset == 48
+
+
 def test_argument_validation_reports_errors():
     from ipercore_b200 import _lib
     d = _lib.ConvGemmDesc()

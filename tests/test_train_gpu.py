@@ -1,6 +1,7 @@
-"""Training-step kernels (csrc/train.cu, ipercore_b200/train.py): the bf16 tcgen05 3x3 convolution — forward, data gradient,
-weight gradient — against torch autograd in fp32 on the same bf16-rounded operands, and one whole G + D optimisation step
-against the all-torch formulation of the same step."""
+"""Training-step kernels (csrc/train.cu, ipercore_b200/train.py): the bf16 tcgen05 stride-1 convolutions (1x1, 3x3, 5x5, 7x7, incl. the
+zero-padded 1/3/4/6-channel ends) — forward with fused bias / residual / ReLU, data gradient, weight gradient (MN-major NHWC
+operands), bias gradient — against torch autograd in fp32 on the same bf16-rounded operands; the fused Adam + repack pass against
+torch.optim.Adam; one whole G + D optimisation step against the all-torch formulation, eager and as a CUDA graph."""
 import numpy as np
 import pytest
 import torch
@@ -39,16 +40,83 @@ def test_conv3x3_bf16_forward_dgrad_wgrad(N, ci, co, H, W):
     assert e_w <= 2e-4 and e_b <= 1e-5            # fp32 accumulation over all pixels, fp32 result
 
 
-def test_conv3x3_falls_back_when_not_eligible():
+@pytest.mark.parametrize("N,ci,co,H,W,k,relu,add", [(1, 64, 64, 32, 48, 1, False, False), (2, 128, 256, 24, 40, 1, True, False),
+                                                    (1, 64, 3, 64, 64, 5, False, False), (1, 64, 1, 40, 72, 5, False, False),
+                                                    (1, 4, 64, 32, 32, 7, False, False), (1, 64, 3, 32, 64, 7, False, False),
+                                                    (1, 6, 64, 16, 16, 3, True, False), (2, 256, 256, 16, 32, 3, False, True),
+                                                    (1, 192, 128, 20, 36, 3, True, True)])
+def test_conv_kxk_padded_ends_fused_epilogue(N, ci, co, H, W, k, relu, add):
+    """Every kernel size of the step, ragged maps (tiles hanging over the border), zero-padded channel ends, fused residual / ReLU."""
     from ipercore_b200 import train
-    x = torch.randn(1, 6, 32, 32, device=DEV).bfloat16()
-    w = torch.randn(64, 6, 3, 3, device=DEV, requires_grad=True)
+    g = torch.Generator(device="cpu").manual_seed(ci * 7 + co + k)
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    x = (rnd(N, ci, H, W) * 0.5).to(DEV).bfloat16().float().requires_grad_(True)
+    w = (rnd(co, ci, k, k) * (1.0 / np.sqrt(k * k * ci))).to(DEV).bfloat16().float().requires_grad_(True)
+    b = (rnd(co) * 0.1).to(DEV).requires_grad_(True)
+    r = (rnd(N, co, H, W) * 0.5).to(DEV).bfloat16().float().requires_grad_(True) if add else None
+    dy = (rnd(N, co, H, W) * 0.5).to(DEV).bfloat16().float()
+    y_ref = F.conv2d(x, w, b, padding=k // 2)
+    if add:
+        y_ref = y_ref + r
+    if relu:
+        y_ref = F.relu(y_ref)
+    ins = (x, w, b) + ((r,) if add else ())
+    g_ref = torch.autograd.grad(y_ref, ins, dy)
+    assert train._eligible(x, w)
+    ins2 = tuple(t.detach().clone().requires_grad_(True) for t in ins)
+    y = train.conv(ins2[0], ins2[1], ins2[2], relu=relu, add=ins2[3] if add else None)
+    assert y.dtype == torch.bfloat16 and y.shape == y_ref.shape
+    g_got = torch.autograd.grad(y, ins2, dy.bfloat16())
+    rel = lambda a, b_: float((a.float() - b_).abs().max()) / max(float(b_.abs().max()), 1e-20)
+    errs = [rel(y, y_ref.detach())] + [rel(a, b_) for a, b_ in zip(g_got, g_ref)]
+    print("conv %dx%d %d->%d %dx%d relu %d add %d: rel err y %.2e dx %.2e dw %.2e db %.2e" % ((k, k, ci, co, H, W, relu, add) + tuple(errs[:4])))
+    assert errs[0] <= 6e-3 and errs[1] <= 6e-3              # bf16 outputs
+    # dY passes through the ReLU mask / bf16 rounding of y only when relu is fused: the mask is taken from the bf16 y (ties at 0)
+    assert errs[2] <= (2e-3 if relu else 2e-4) and errs[3] <= (2e-3 if relu else 1e-5)
+    if add:
+        assert errs[4] <= 6e-3
+
+
+def test_conv_falls_back_when_not_eligible():
+    from ipercore_b200 import train
+    x = torch.randn(1, 64, 4, 8, device=DEV).bfloat16()               # map smaller than one 16x8 tile
+    w = torch.randn(64, 64, 3, 3, device=DEV, requires_grad=True)
     assert not train._eligible(x, w)
-    y = train.conv3x3(x, w)             # 6 input channels: the fp32 torch path (no bf16 cuDNN engine for its gradients)
-    assert y.dtype == torch.float32
-    torch.testing.assert_close(y, F.conv2d(x.float(), w, padding=1), atol=1e-4, rtol=1e-4)
-    frozen = torch.randn(64, 64, 3, 3, device=DEV)                       # frozen layer (VGG): no weight gradient -> eligible at W = 32
+    y = train.conv(x, w)
+    torch.testing.assert_close(y.float(), F.conv2d(x.float(), w.bfloat16().float(), padding=1), atol=5e-2, rtol=5e-2)
+    w4 = torch.randn(64, 64, 4, 4, device=DEV)                        # even kernels (the discriminator's) stay on torch
+    assert not train._eligible(torch.randn(1, 64, 32, 32, device=DEV), w4, 1, 1)
+    assert not train._eligible(torch.randn(1, 64, 32, 32, device=DEV), w, 2, 1)      # strided
+    frozen = torch.randn(64, 64, 3, 3, device=DEV)
     assert train._eligible(torch.randn(1, 64, 32, 32, device=DEV), frozen)
+
+
+def test_pack_weight_matches_the_fused_adam_repack_and_adam_matches_torch():
+    """ParamStore: parameters become views of the flat buffer, the kernel's repacking equals train.pack_weight, and three fused
+    Adam steps equal torch.optim.Adam on the same gradients (fp32, 1e-6)."""
+    from ipercore_b200 import train
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Conv2d(6, 64, 3, padding=1), torch.nn.Conv2d(64, 3, 5, padding=2, bias=False),
+                              torch.nn.Conv2d(64, 128, 1), torch.nn.Conv2d(128, 64, 4, 2, 1)).to(DEV)
+    ref = [p.detach().clone().requires_grad_(True) for p in net.parameters()]
+    opt = torch.optim.Adam(ref, lr=1e-3, betas=(0.9, 0.999))
+    bk = train.FlatGradBuckets(list(net.parameters()), n_buckets=2)
+    store = train.ParamStore(list(net.named_parameters()), bk, native=lambda n, p: p.dim() == 4 and p.shape[-1] in (1, 3, 5, 7), lr=1e-3)
+    for p, r in zip(net.parameters(), ref):
+        assert torch.equal(p.detach(), r.detach())
+        assert store.p.data_ptr() <= p.data_ptr() < store.p.data_ptr() + store.p.numel() * 4
+    for it in range(3):
+        bk.zero()
+        for p, r in zip(net.parameters(), ref):
+            gr = torch.randn_like(r) * (0.1 + it)
+            p.grad.copy_(gr); r.grad = gr.clone()
+        store.step(); opt.step()
+        for p, r in zip(net.parameters(), ref):
+            assert float((p.detach() - r.detach()).abs().max()) <= 1e-6
+    for m in list(net)[:3]:
+        f, d = train.pack_weight(m.weight)
+        assert torch.equal(m.weight._iper_pack[0], f) and torch.equal(m.weight._iper_pack[1], d)
+    assert not hasattr(net[3].weight, "_iper_pack")
 
 
 def _batch(S, seed=0):
@@ -79,7 +147,9 @@ def test_train_step_matches_all_torch_formulation():
             names = ["net.res_blocks.2.main.0.weight", "net.res_attlwbs.1.spade.mlp_gamma.weight", "net.tsf_net_dec.skippers.1.0.weight",
                      "net.src_net.res_blocks.0.main.2.weight", "net.enc_attlwbs.0.spade.mlp_shared.0.weight"]
             params = dict(step.G.named_parameters())
-            grads = torch.autograd.grad(loss, [params[n] for n in names])
+            step._zero(step.opt_G, step.bk_G)             # kernel mode: weight gradients land in the flat buffer behind p.grad
+            loss.backward()
+            grads = [params[n].grad.detach().clone() for n in names]
             out = step.step(_batch(S))
             torch.cuda.synchronize()
             res[use] = (float(loss), [g.float().clone() for g in grads], {k: float(v) for k, v in out.items()})
@@ -93,3 +163,28 @@ def test_train_step_matches_all_torch_formulation():
         assert cos >= 0.95, cos                                   # two bf16 evaluation orders of a 70-layer network (measured 0.976-0.999)
     for k in o0:
         assert np.isfinite(o1[k]) and abs(o1[k] - o0[k]) <= 5e-2 * max(1.0, abs(o0[k])), (k, o1[k], o0[k])
+
+
+def test_train_step_cuda_graph_matches_eager():
+    """The whole step captured in one CUDA graph (forward, both backward passes, both fused Adam passes) follows the eager run:
+    same losses over 4 steps and the same parameters afterwards (bf16 atomics reorder sums: 1e-2 relative on the losses)."""
+    from ipercore_b200 import train
+    from ipercore_b200.generator import AttentionLWBGenerator
+    from oracle.weights import synth_state_dict
+    S = 256
+    hist, params = {}, {}
+    for graph in (False, True):
+        torch.manual_seed(0)
+        net = AttentionLWBGenerator(CFG); net.load_state_dict(synth_state_dict(0))
+        step = train.LWGTrainStep(net, torch.device(DEV), graph=graph)
+        batch = _batch(S)
+        hist[graph] = [{k: float(v) for k, v in step.step(batch).items()} for _ in range(4)]
+        torch.cuda.synchronize()
+        params[graph] = step.G.net.res_blocks[1].main[0].weight.detach().float().clone()
+        if graph:
+            assert step._graph is not None and step.launches_per_step > 100
+    for a, b in zip(hist[False], hist[True]):
+        for k in a:
+            assert np.isfinite(b[k]) and abs(a[k] - b[k]) <= 2e-2 * max(1.0, abs(a[k])), (k, a[k], b[k])
+    moved = float((params[True] - synth_state_dict(0)["res_blocks.1.main.0.weight"].to(DEV)).abs().mean())
+    assert moved > 0 and float((params[True] - params[False]).abs().mean()) <= 0.3 * moved

@@ -14,18 +14,18 @@ from oracle import weights  # noqa: E402
 
 
 def main():
-    out_path = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/train_profile.txt"
+    out_path = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else "gpurun_out/train_profile.txt"
     S, ns = 512, 2
     dev = torch.device("cuda", 0)
     net = AttentionLWBGenerator(CFG)
     net.load_state_dict(weights.synth_state_dict(0), strict=True)
-    step = train.LWGTrainStep(net, dev)
+    step = train.LWGTrainStep(net, dev, graph="--graph" in sys.argv)
     g = torch.Generator().manual_seed(100)
     r = lambda *s: (torch.rand(*s, generator=g) * 2 - 1).to(dev)
     batch = dict(bg_inputs=torch.cat([r(1, 1, 3, S, S), (r(1, 1, 1, S, S) > 0).float()], 2), src_inputs=r(1, ns, 6, S, S),
                  tsf_inputs=r(1, 1, 6, S, S), Tst=r(1, 1, ns, S, S, 2), real_src=r(1, ns, 3, S, S), real_tsf=r(1, 1, 3, S, S),
                  real_bg=r(1, 3, S, S), body_mask=(r(1, ns + 1, 1, S, S) > 0).float())
-    for _ in range(3):
+    for _ in range(5):
         step.step(batch)
     torch.cuda.synchronize()
     from torch.profiler import ProfilerActivity, profile
