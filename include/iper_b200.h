@@ -340,6 +340,34 @@ int iper_adam_pack(float* params, const float* grads, float* exp_avg, float* exp
                    const int* chunks_dev, int n_chunks, int chunk_elems, float lr, float beta1, float beta2, float eps,
                    float grad_scale, const float* step_dev, int update, void* pack_fwd, void* pack_dgrad, iper_stream_t stream);
 
+/* ----------------------------------------------------------------------------------------------------------
+ * Training-step kernels, part 2: the non-GEMM pieces of SelfAttentionLWB and the instance norms, forward and backward, NHWC bf16
+ * (csrc/train_ops.cu).  Reference: attlwb_spade_resunet.py:80-93 (SPADE), 121-139 + 232-240 (softmax over sources), 184-191
+ * (LWB.transform), bg_inpaintor.py / patch_dis.py (InstanceNorm2d + ReLU / LeakyReLU), run by ATen in the reference.
+ *   iper_warp_bf16             out (M,h,w,C) = grid_sample(src (M,h,w,C), T (M,h,w,2) fp32; bilinear, zeros, align_corners=False)
+ *   iper_warp_bwd_bf16         dsrc (M,h,w,C) FP32 (zeroed by the call) += scatter of dout through the same taps
+ *   iper_att_combine_bf16      alpha (bs,ns,HW) fp32 = softmax_s( k_s . q / sqrt(C) ),  a (bs,HW,C) = sum_s alpha_s v_s;
+ *                              k, v (bs*ns,HW,C), q (bs,HW,C); C in {64,128,256}, ns <= 8
+ *   iper_att_combine_bwd_bf16  dk, dv (bs*ns,HW,C), dq (bs,HW,C) from da
+ *   iper_norm_stats_bf16       stats (N,C,2) double = per-(n,c) sum and sum of squares over the HW pixels (zeroed by the call)
+ *   iper_norm_apply_bf16       y = act( IN(x) * (1 + gamma) + beta ) (gamma = beta = NULL: plain instance norm); act 0 none,
+ *                              1 ReLU / LeakyReLU with `slope` for the negative side (0 = ReLU)
+ *   iper_norm_bwd_bf16         dx [, dgamma, dbeta] from dout (y = the saved output, needed when act != 0); sums_ws (N,C,2) double
+ * C %% 8 == 0 everywhere; the norm kernels need C/8 to divide 256 (C = 64, 128, 256, 512).
+ * ---------------------------------------------------------------------------------------------------------- */
+int iper_warp_bf16(const void* src_nhwc, const float* T, int M, int h, int w, int C, void* out_nhwc, iper_stream_t stream);
+int iper_warp_bwd_bf16(const void* dout_nhwc, const float* T, int M, int h, int w, int C, float* dsrc_f32, iper_stream_t stream);
+int iper_att_combine_bf16(const void* k, const void* v, const void* q, int bs, int ns, long long HW, int C, void* a, float* alpha,
+                          iper_stream_t stream);
+int iper_att_combine_bwd_bf16(const void* da, const void* k, const void* v, const void* q, const float* alpha, int bs, int ns,
+                              long long HW, int C, void* dk, void* dv, void* dq, iper_stream_t stream);
+int iper_norm_stats_bf16(const void* x_nhwc, int N, long long HW, int C, double* stats, iper_stream_t stream);
+int iper_norm_apply_bf16(const void* x_nhwc, const double* stats, const void* gamma, const void* beta, int N, long long HW, int C,
+                         float eps, int act, float slope, void* y_nhwc, iper_stream_t stream);
+int iper_norm_bwd_bf16(const void* dout, const void* x, const void* y, const void* gamma, const double* stats, int N, long long HW,
+                       int C, float eps, int act, float slope, double* sums_ws, void* dgamma, void* dbeta, void* dx,
+                       iper_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

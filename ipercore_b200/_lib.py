@@ -85,6 +85,15 @@ SIGNATURES = {
     "iper_bias_grad_bf16": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p],
     "iper_adam_pack": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float,
                        c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
+    "iper_warp_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "iper_warp_bwd_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
+    "iper_att_combine_bf16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p],
+    "iper_att_combine_bwd_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_void_p],
+    "iper_norm_stats_bf16": [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p],
+    "iper_norm_apply_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_int, c_float, c_void_p, c_void_p],
+    "iper_norm_bwd_bf16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_ll, c_int, c_float, c_int, c_float, c_void_p, c_void_p,
+                           c_void_p, c_void_p, c_void_p],
     "iper_gen_create": [c_void_p, c_int, c_int, c_int, c_void_p],
     "iper_gen_load_weight": [c_void_p, ctypes.c_char_p, c_void_p, c_void_p, c_int],
     "iper_gen_pack": [c_void_p, c_void_p, c_size_t, c_void_p],

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INC = os.path.abspath(os.path.join(HERE, "..", "include"))
 SO = os.path.join(HERE, "libiper_b200.so")
-SOURCES = ["api.cu", "raster.cu", "conv_tc.cu", "ops.cu", "lbs.cu", "source.cu", "generator.cu", "train.cu"]
+SOURCES = ["api.cu", "raster.cu", "conv_tc.cu", "ops.cu", "lbs.cu", "source.cu", "generator.cu", "train.cu", "train_ops.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "-I", INC, "-I", CSRC, "--expt-relaxed-constexpr"]

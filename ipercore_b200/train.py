@@ -175,6 +175,109 @@ def conv3x3(x, weight, bias=None):
     return conv(x, weight, bias)
 
 
+class _Warp(torch.autograd.Function):
+    """LWB.transform (attlwb_spade_resunet.py:184-191): grid_sample(src, T) bilinear / zeros / align_corners=False on NHWC bf16;
+    the gradient w.r.t. the source features is scattered with float4 atomics into an fp32 buffer.  T (M,h,w,2) fp32 carries none."""
+
+    @staticmethod
+    def forward(ctx, src, T):
+        m, c, h, w = src.shape
+        src_cl = _to_cl(src, c)
+        T = T.float().contiguous()
+        out = torch.empty_like(src_cl)
+        check(lib.iper_warp_bf16(src_cl.data_ptr(), T.data_ptr(), m, h, w, c, out.data_ptr(), _stream()), "warp_bf16")
+        ctx.save_for_backward(T)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (T,) = ctx.saved_tensors
+        m, c, h, w = dout.shape
+        d_cl = _to_cl(dout, c)
+        ds = torch.empty((m, c, h, w), dtype=torch.float32, device=dout.device, memory_format=CL)
+        check(lib.iper_warp_bwd_bf16(d_cl.data_ptr(), T.data_ptr(), m, h, w, c, ds.data_ptr(), _stream()), "warp_bwd_bf16")
+        return ds.to(BF16), None
+
+
+class _AttCombine(torch.autograd.Function):
+    """a = sum_s softmax_s(K_s . q / sqrt(C)) V_s per pixel (attlwb_spade_resunet.py:121-139, 232-240); k, v (bs*ns,C,h,w), q (bs,C,h,w)."""
+
+    @staticmethod
+    def forward(ctx, k, v, q, ns):
+        bs, c, h, w = q.shape
+        k, v, q = _to_cl(k, c), _to_cl(v, c), _to_cl(q, c)
+        a = torch.empty_like(q)
+        alpha = torch.empty((bs, ns, h * w), dtype=torch.float32, device=q.device)
+        check(lib.iper_att_combine_bf16(k.data_ptr(), v.data_ptr(), q.data_ptr(), bs, ns, h * w, c, a.data_ptr(), alpha.data_ptr(), _stream()),
+              "att_combine_bf16")
+        ctx.save_for_backward(k, v, q, alpha)
+        ctx.ns = ns
+        return a
+
+    @staticmethod
+    def backward(ctx, da):
+        k, v, q, alpha = ctx.saved_tensors
+        bs, c, h, w = q.shape
+        da = _to_cl(da, c)
+        dk, dv, dq = torch.empty_like(k), torch.empty_like(v), torch.empty_like(q)
+        check(lib.iper_att_combine_bwd_bf16(da.data_ptr(), k.data_ptr(), v.data_ptr(), q.data_ptr(), alpha.data_ptr(), bs, ctx.ns, h * w, c,
+                                            dk.data_ptr(), dv.data_ptr(), dq.data_ptr(), _stream()), "att_combine_bwd_bf16")
+        return dk, dv, dq, None
+
+
+class _Norm(torch.autograd.Function):
+    """y = act( InstanceNorm(x) * (1 + gamma) + beta ): SPADE (attlwb_spade_resunet.py:80-93) with gamma / beta, plain
+    InstanceNorm2d(affine=False) [+ ReLU / LeakyReLU] without (bg_inpaintor.py, patch_dis.py).  NHWC bf16, fp64 statistics."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, act, slope, eps):
+        n, c, h, w = x.shape
+        x = _to_cl(x, c)
+        g = None if gamma is None else _to_cl(gamma, c)
+        b = None if beta is None else _to_cl(beta, c)
+        stats = torch.empty((n, c, 2), dtype=torch.float64, device=x.device)
+        st = _stream()
+        check(lib.iper_norm_stats_bf16(x.data_ptr(), n, h * w, c, stats.data_ptr(), st), "norm_stats_bf16")
+        y = torch.empty_like(x)
+        check(lib.iper_norm_apply_bf16(x.data_ptr(), stats.data_ptr(), 0 if g is None else g.data_ptr(), 0 if b is None else b.data_ptr(), n, h * w, c,
+                                       eps, int(act), slope, y.data_ptr(), st), "norm_apply_bf16")
+        ctx.save_for_backward(x, g, y if act else None, stats)
+        ctx.cfg = (int(act), slope, eps)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g, y, stats = ctx.saved_tensors
+        act, slope, eps = ctx.cfg
+        n, c, h, w = x.shape
+        dy = _to_cl(dy, c)
+        sums = torch.empty((n, c, 2), dtype=torch.float64, device=x.device)
+        dx = torch.empty_like(x)
+        dg = db = None
+        if g is not None:
+            dg, db = torch.empty_like(x), torch.empty_like(x)
+        check(lib.iper_norm_bwd_bf16(dy.data_ptr(), x.data_ptr(), 0 if y is None else y.data_ptr(), 0 if g is None else g.data_ptr(), stats.data_ptr(),
+                                     n, h * w, c, eps, act, slope, sums.data_ptr(), 0 if dg is None else dg.data_ptr(),
+                                     0 if db is None else db.data_ptr(), dx.data_ptr(), _stream()), "norm_bwd_bf16")
+        return dx, dg, db, None, None, None
+
+
+def _norm_ok(x):
+    return bool(USE_KERNELS and x.is_cuda and x.shape[1] in (64, 128, 256, 512))
+
+
+def inorm(x, act=False, slope=0.0, gamma=None, beta=None, eps=1e-5):
+    """act( IN(x) [* (1 + gamma) + beta] ) -> bf16."""
+    if _norm_ok(x):
+        return _Norm.apply(x, gamma, beta, act, slope, eps)
+    y = F.instance_norm(x.float(), eps=eps)
+    if gamma is not None:
+        y = y * (1 + gamma.float()) + beta.float()
+    if act:
+        y = F.leaky_relu(y, slope) if slope else F.relu(y)
+    return y.to(BF16)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # generator, training shape (functional over the parameter holders of ipercore_b200.generator.AttentionLWBGenerator)
 # ----------------------------------------------------------------------------------------------------------------------
@@ -224,16 +327,15 @@ class TrainableGenerator(nn.Module):
     def forward_bg(self, bg_inputs):
         bs, ns, _, h, w = bg_inputs.shape
         x = bg_inputs.reshape(bs * ns, -1, h, w).to(BF16)
-        inorm = lambda t: F.instance_norm(t.float(), eps=1e-5).to(BF16)
-        x = F.relu(inorm(self._c("bg_net.main.0", x, padding=3)))       # 4 -> 64 (fp32 conv, see _torch_conv); inorm returns bf16
+        x = inorm(self._c("bg_net.main.0", x, padding=3), act=True)     # 4 -> 64 7x7 (zero-padded to 64 input channels on the kernels)
         idx = 3
         for _ in range(3):
-            x = F.relu(inorm(self._c("bg_net.main.%d" % idx, x, stride=2, padding=1))); idx += 3
+            x = inorm(self._c("bg_net.main.%d" % idx, x, stride=2, padding=1), act=True); idx += 3
         for _ in range(self.n_res):
-            y = F.relu(inorm(self._c("bg_net.main.%d.main.0" % idx, x, padding=1)))
+            y = inorm(self._c("bg_net.main.%d.main.0" % idx, x, padding=1), act=True)
             x = x + inorm(self._c("bg_net.main.%d.main.3" % idx, y, padding=1)); idx += 1
         for _ in range(3):
-            x = F.relu(inorm(self._ct("bg_net.main.%d" % idx, x))); idx += 3
+            x = inorm(self._ct("bg_net.main.%d" % idx, x), act=True); idx += 3
         return torch.tanh(self._c("bg_net.main.%d" % idx, x, padding=3).float()).reshape(bs, ns, 3, h, w)
 
     # ---- SIDNet (attlwb_spade_resunet.py:450-478, ResAutoEncoder) ----
@@ -256,33 +358,49 @@ class TrainableGenerator(nn.Module):
         return enc, res, img, mask
 
     # ---- SelfAttentionLWB (attlwb_spade_resunet.py:208-252) ----
-    def _att(self, prefix, tsf_x, src_x, Tst):
-        bs, ns, H, W, _ = Tst.shape
+    def _flow(self, Tst, h, w, cache):
+        """LWB.resize_trans (attlwb_spade_resunet.py:175-182), once per resolution instead of once per block."""
+        if (h, w) not in cache:
+            bs, ns, H, W, _ = Tst.shape
+            T = Tst.reshape(bs * ns, H, W, 2).float()
+            if H != h or W != w:
+                if USE_KERNELS and T.is_cuda and H == W:
+                    from .ops import flow_resize
+                    T = flow_resize(T, h, w)
+                else:
+                    T = F.interpolate(T.permute(0, 3, 1, 2), size=(h, w), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+            cache[(h, w)] = T.contiguous()
+        return cache[(h, w)]
+
+    def _att(self, prefix, tsf_x, src_x, Tst, cache):
+        bs, ns = Tst.shape[:2]
         h, w = tsf_x.shape[-2:]
-        T = Tst.reshape(bs * ns, H, W, 2)
-        if H != h or W != w:
-            T = F.interpolate(T.permute(0, 3, 1, 2), size=(h, w), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
-        warp = F.grid_sample(src_x.float(), T.float(), mode="bilinear", padding_mode="zeros", align_corners=False).to(BF16)
-        k = self._c(prefix + ".fk", warp).reshape(bs, ns, -1, h, w)
-        v = self._c(prefix + ".fv", warp).reshape(bs, ns, -1, h, w)
-        q = self._c(prefix + ".fq", tsf_x)
-        logits = (k.float() * q.float().unsqueeze(1)).sum(dim=2, keepdim=True) / math.sqrt(k.shape[2])
-        a = (torch.softmax(logits, dim=1) * v.float()).sum(dim=1).to(BF16)
-        normalized = F.instance_norm(tsf_x.float(), eps=1e-5)
+        c = tsf_x.shape[1]
+        T = self._flow(Tst, h, w, cache)
+        if USE_KERNELS and tsf_x.is_cuda and c in (64, 128, 256) and ns <= 8:
+            warp = _Warp.apply(src_x, T)
+            a = _AttCombine.apply(self._c(prefix + ".fk", warp), self._c(prefix + ".fv", warp), self._c(prefix + ".fq", tsf_x), ns)
+        else:
+            warp = F.grid_sample(src_x.float(), T.float(), mode="bilinear", padding_mode="zeros", align_corners=False).to(BF16)
+            k = self._c(prefix + ".fk", warp).reshape(bs, ns, -1, h, w)
+            v = self._c(prefix + ".fv", warp).reshape(bs, ns, -1, h, w)
+            q = self._c(prefix + ".fq", tsf_x)
+            logits = (k.float() * q.float().unsqueeze(1)).sum(dim=2, keepdim=True) / math.sqrt(k.shape[2])
+            a = (torch.softmax(logits, dim=1) * v.float()).sum(dim=1).to(BF16)
         actv = self._c(prefix + ".spade.mlp_shared.0", a, padding=1, relu=True)
-        gamma = self._c(prefix + ".spade.mlp_gamma", actv, padding=1).float()
-        beta = self._c(prefix + ".spade.mlp_beta", actv, padding=1).float()
-        return (normalized * (1 + gamma) + beta).to(BF16)
+        gamma = self._c(prefix + ".spade.mlp_gamma", actv, padding=1)
+        beta = self._c(prefix + ".spade.mlp_beta", actv, padding=1)
+        return inorm(tsf_x, gamma=gamma, beta=beta)
 
     def forward_tsf(self, tsf_inputs, src_enc, src_res, Tst):
         x = tsf_inputs.to(BF16)
-        enc = []
+        enc, cache = [], {}
         for i in range(3):
             x = F.relu(self._c("tsf_net_enc.layers.%d.0" % i, x, stride=2, padding=1)).to(BF16)
-            x = self._att("enc_attlwbs.%d" % i, x, src_enc[i], Tst); enc.append(x)
+            x = self._att("enc_attlwbs.%d" % i, x, src_enc[i], Tst, cache); enc.append(x)
         for i in range(self.n_res):
             x = self._res("res_blocks.%d" % i, x, 2)
-            x = self._att("res_attlwbs.%d" % i, x, src_res[i], Tst)
+            x = self._att("res_attlwbs.%d" % i, x, src_res[i], Tst, cache)
         d = x
         for i in range(3):
             d = F.relu(self._ct("tsf_net_dec.upconvs.%d.0" % i, d))
@@ -320,7 +438,30 @@ class PatchDiscriminator(nn.Module):
         self.model = nn.Sequential(*seq)
 
     def forward(self, x):
-        return self.model(x)
+        """bf16 channels_last with the 6-channel input and the 1-channel output zero-padded to 8 channels: cuDNN has tensor-core
+        engines (forward and both gradients) only for 8-aligned channels; with the true 6 / 1 channels the ends of D fall back to
+        fp32 SIMT kernels that cost more than the rest of D together (measured 4.6 ms of a 39 ms step)."""
+        if not (USE_KERNELS and x.is_cuda):
+            return self.model(x)
+        x = F.pad(x.to(BF16), (0, 0, 0, 0, 0, 2)).contiguous(memory_format=CL)
+        convs = [m for m in self.model if isinstance(m, nn.Conv2d)]
+        skip = False
+        for m in self.model:
+            if isinstance(m, nn.Conv2d):
+                w, b = m.weight.to(BF16), m.bias.to(BF16)
+                if m is convs[0]:
+                    w = F.pad(w, (0, 0, 0, 0, 0, 2))
+                if m is convs[-1]:
+                    w, b = F.pad(w, (0, 0, 0, 0, 0, 0, 0, 7)), F.pad(b, (0, 7))
+                x = F.conv2d(x, w.contiguous(memory_format=CL), b, stride=m.stride, padding=m.padding)
+            elif isinstance(m, nn.InstanceNorm2d):
+                x = inorm(x, act=True, slope=0.2, eps=m.eps)         # InstanceNorm2d + the LeakyReLU(0.2) that follows it
+                skip = True
+                continue
+            elif not skip:
+                x = m(x)
+            skip = False
+        return x[:, :1].float()
 
 
 class VGG19Features(nn.Module):

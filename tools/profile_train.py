@@ -44,7 +44,7 @@ def main():
         f.write("2 training steps: device time %.2f ms total, %.2f ms in iper:: kernels (%.0f%%), %d launches\n"
                 % (tot / 1e3, ours / 1e3, 100 * ours / tot, sum(v[0] for v in rows.values())))
         for k, v in sorted(rows.items(), key=lambda kv: -kv[1][1])[:70]:
-            f.write("%9.1f us %6d x  %5.1f%%  %s\n" % (v[1], v[0], 100 * v[1] / tot, k[:150]))
+            f.write("%9.1f us %6d x  %5.1f%%  %s\n" % (v[1], v[0], 100 * v[1] / tot, k[:150] + (" ... " + k[-260:] if len(k) > 420 else "")))
         f.write("\nCPU-side (self CPU time, top 25):\n")
         f.write(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=25, max_name_column_width=60))
     print(open(out_path).read()[:6000])
