@@ -75,12 +75,15 @@ struct TrainCfg {
     static constexpr int A_BYTES = MODE == 0 ? TR_BOX : 2 * TR_BOX;
     static constexpr int B_BYTES = MODE == 0 ? BN * 128 : (BN / 64) * TR_BOX;
     static constexpr int STAGE = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (200 * 1024) / STAGE > 8 ? 8 : (200 * 1024) / STAGE;
+    // forward / dgrad: <= 96 KB of ring so that TWO CTAs share an SM — at batch 1 the tiles are short (9-49 K steps) and one CTA's
+    // prologue / epilogue hides behind the other's main loop; wgrad keeps the whole SM (64 KB stages)
+    static constexpr int BUDGET = MODE == 0 ? 96 * 1024 : 200 * 1024;
+    static constexpr int STAGES = BUDGET / STAGE > 8 ? 8 : BUDGET / STAGE;
     static constexpr int SMEM = STAGES * STAGE + 1024;
 };
 
 template <int BN, int MODE>
-__global__ void __launch_bounds__(TR_THREADS, 1) train_gemm_kernel(const __grid_constant__ TrainArgs a) {
+__global__ void __launch_bounds__(TR_THREADS, MODE == 0 ? 2 : 1) train_gemm_kernel(const __grid_constant__ TrainArgs a) {
     using Cfg = TrainCfg<BN, MODE>;
     constexpr int STAGES = Cfg::STAGES, STAGE = Cfg::STAGE;
     constexpr int TCOLS = BN < 32 ? 32 : BN;
