@@ -323,9 +323,16 @@ def run_train(args):
                 "gpu_launches": int(args.steps * step.launches_per_step) if step._graph is not None else int(_lib.launch_count() - n0),
                 "clocks": clocks,
                 "losses": {k: float(v) for k, v in out.items()}}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # the captured graph holds NCCL work: tearing the communicator down under it hung the launcher once (2-GPU session);
+        # drop the graph, drain, agree that everyone is done, and leave without running the communicator's destructor
+        step._graph = None
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def config_block(args, launches):
