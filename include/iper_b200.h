@@ -311,14 +311,16 @@ int iper_uv_merge(const float* src_warp, const float* vis_dilated, int bs, int n
  *   iper_conv_wgrad_bf16  dW[co*stride_co + ci*stride_ci + tap*stride_tap] += sum over pixels dY[p, co] * X[p + tap - k/2, ci]
  *                         (fp32 atomics: the caller zeroes dW, or lets several calls accumulate).  Reads both operands in NHWC
  *                         (MN-major tcgen05 operands; no transposed or shifted copies).  Only co < co_valid, ci < ci_valid are
- *                         written (zero-padded ends).  (co, tap, ci) layout: strides (k*k*Cin, 1, Cin); the parameter's own
- *                         (co, ci, ky, kx) layout: strides (Cin_real*k*k, k*k, 1).
+ *                         written (zero-padded ends).  (co, tap, ci) layout: strides (k*k*Cin, 1, Cin) — the fast one: a warp's
+ *                         atomics then fall on consecutive floats; the parameter's own (co, ci, ky, kx) layout: strides
+ *                         (Cin_real*k*k, k*k, 1).
  *   iper_bias_grad_bf16   db[c] += sum over pixels dY[p, c], c < C (fp32 atomics), `pitch` channels per pixel.
  *   iper_adam_pack        torch.optim.Adam's update (betas, eps, no weight decay; bias correction from the device-side step
  *                         counter *step_dev, so the call can be captured in a CUDA graph) over flat fp32 buffers, described by a
  *                         device-resident segment table + chunk table ((segment, first element) pairs of <= chunk_elems elements),
  *                         gradients pre-multiplied by grad_scale (1 / world size); for segments with taps > 0 (convolution weights
- *                         (co, ci, ky, kx)) it also writes the bf16 forward packing (co_pad, taps, ci_pad) at fwd_offset and, when
+ *                         (co, ci, ky, kx), whose GRADIENT is read in the (co, tap, ci) layout iper_conv_wgrad_bf16 writes fastest)
+ *                         it also writes the bf16 forward packing (co_pad, taps, ci_pad) at fwd_offset and, when
  *                         dgrad_offset >= 0, the dgrad packing (ci_pad, taps reversed, co_pad) — padding entries are never written
  *                         (the caller zeroes the pack buffers once).  update = 0 only repacks.
  * H >= 8, W >= 16 for iper_conv_bf16.

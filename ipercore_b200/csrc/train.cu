@@ -282,8 +282,16 @@ __global__ void __launch_bounds__(256) adam_pack_kernel(float* __restrict__ p, c
     for (long long e = (long long)ch.y + threadIdx.x; e < end; e += 256) {
         const long long idx = sg.offset + e;
         float pp = p[idx];
+        int tap = 0, ci = 0, co = 0;
+        long long gidx = idx;
+        if (sg.taps > 0) {                           // convolution weight (co, ci, ky, kx); its gradient is stored (co, tap, ci)
+            tap = (int)(e % sg.taps);
+            const long long cc = e / sg.taps;
+            ci = (int)(cc % sg.ci); co = (int)(cc / sg.ci);
+            gidx = sg.offset + ((long long)co * sg.taps + tap) * sg.ci + ci;
+        }
         if (update) {
-            const float gr = g[idx] * grad_scale;
+            const float gr = g[gidx] * grad_scale;
             const float mm = b1 * m[idx] + (1.f - b1) * gr;
             const float vv = b2 * v[idx] + (1.f - b2) * gr * gr;
             m[idx] = mm; v[idx] = vv;
@@ -291,9 +299,6 @@ __global__ void __launch_bounds__(256) adam_pack_kernel(float* __restrict__ p, c
             p[idx] = pp;
         }
         if (sg.taps > 0) {                           // (co, ci, ky, kx) -> forward (co_pad, tap, ci_pad) and dgrad (ci_pad, taps-1-tap, co_pad)
-            const int tap = (int)(e % sg.taps);
-            const long long cc = e / sg.taps;
-            const int ci = (int)(cc % sg.ci), co = (int)(cc / sg.ci);
             const __nv_bfloat16 h = __float2bfloat16(pp);
             pack_fwd[sg.fwd_offset + ((long long)co * sg.taps + tap) * sg.ci_pad + ci] = h;
             if (sg.dgrad_offset >= 0)
@@ -388,7 +393,9 @@ extern "C" int iper_conv_wgrad_bf16(const void* x_nhwc, const void* dy_nhwc, int
     t.N = N; t.H = H; t.W = W; t.Cin = Cin; t.Cout = Cout; t.ks = ksize; t.pad = ksize / 2; t.taps = ksize * ksize; t.dW = dW;
     t.tiles_x = (W + 15) / 16; t.tiles_y = (H + 7) / 8;
     t.kblocks = t.tiles_x * t.tiles_y * N;
-    t.x_rows = Cin > Cout ? 1 : 0;                          // the wider tensor fills the 128 accumulator rows
+    // accumulator rows = TMEM lanes = the 32 threads of a warp in the epilogue: put the channel index with the SMALLER dW stride
+    // there, so one warp-wide atomic instruction touches consecutive floats (one 128-byte line for stride 1) instead of 32 lines
+    t.x_rows = stride_ci <= stride_co ? 1 : 0;
     const int rowsP = t.x_rows ? Cin : Cout, colsP = t.x_rows ? Cout : Cin;          // padded (tensor) channel counts
     t.rowsC = t.x_rows ? ci_valid : co_valid; t.colsC = t.x_rows ? co_valid : ci_valid;
     t.s_row = t.x_rows ? stride_ci : stride_co; t.s_col = t.x_rows ? stride_co : stride_ci; t.s_tap = stride_tap;

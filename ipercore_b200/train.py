@@ -36,6 +36,15 @@ CL = torch.channels_last
 
 
 USE_KERNELS = True          # tests flip this to compare against the all-torch formulation
+USE_STREAMS = True          # weight / bias gradients on a side stream, parallel to the data gradient
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
 
 
 def _pad64(c):
@@ -124,35 +133,42 @@ class _Conv(torch.autograd.Function):
         if ctx.relu:
             dy_cl = torch.ops.aten.threshold_backward(dy_cl, y, 0).contiguous(memory_format=CL)
         dx = dw = db = dadd = None
-        st = _stream()
         if ctx.needs_input_grad[0]:
             _, wd = _packs(weight)
+        want_w, want_b = ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        weight._iper_uses = getattr(weight, "_iper_uses", 1) - 1
+        # the weight / bias gradients are independent of the data gradient: they run on a side stream (in the captured step: a
+        # parallel branch of the graph) and are joined before this node returns
+        main, side = torch.cuda.current_stream(), (_side_stream(x_cl.device) if USE_STREAMS and (want_w or want_b) else None)
+        if side is not None:
+            side.wait_stream(main)
+        with torch.cuda.stream(side if side is not None else main):
+            st = _stream()
+            if want_w:                                   # (co, tap, ci) layout: a warp's atomics fall on consecutive floats
+                sink = getattr(weight, "_iper_sink", None)
+                g = sink.grad if sink is not None else torch.zeros((co, k * k, ci), dtype=torch.float32, device=x_cl.device)
+                check(lib.iper_conv_wgrad_bf16(x_cl.data_ptr(), dy_cl.data_ptr(), n, h, w, cip, cop, k, g.data_ptr(), k * k * ci, 1, ci, co, ci, st),
+                      "conv_wgrad_bf16")
+                if sink is None:
+                    dw = g.view(co, k, k, ci).permute(0, 3, 1, 2).to(weight.dtype)
+            if want_b:
+                bias = ctx.bias_ref
+                bsink = getattr(bias, "_iper_sink", None)
+                gb = bsink.grad if bsink is not None else torch.zeros((co,), dtype=torch.float32, device=x_cl.device)
+                check(lib.iper_bias_grad_bf16(dy_cl.data_ptr(), n * h * w, co, cop, gb.data_ptr(), st), "bias_grad_bf16")
+                if bsink is None:
+                    db = gb.to(bias.dtype)
+        if ctx.needs_input_grad[0]:
             dx = _conv_call(dy_cl, wd, cip, k)
             if ci != cip:
                 dx = dx[:, :ci]
-        weight._iper_uses = getattr(weight, "_iper_uses", 1) - 1
-        if ctx.needs_input_grad[1]:
-            sink = getattr(weight, "_iper_sink", None)
-            if sink is not None:                         # accumulate into the flat gradient, parameter layout (co, ci, ky, kx)
-                g, strides = sink.grad, (ci * k * k, k * k, 1)
-            else:
-                g = torch.zeros((co, k * k, ci), dtype=torch.float32, device=x_cl.device)
-                strides = (k * k * ci, 1, ci)
-            check(lib.iper_conv_wgrad_bf16(x_cl.data_ptr(), dy_cl.data_ptr(), n, h, w, cip, cop, k, g.data_ptr(), strides[0], strides[1],
-                                           strides[2], co, ci, st), "conv_wgrad_bf16")
-            if sink is None:
-                dw = g.view(co, k, k, ci).permute(0, 3, 1, 2).to(weight.dtype)
-            elif weight._iper_uses == 0:
-                sink.ready()
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            bias = ctx.bias_ref
-            sink = getattr(bias, "_iper_sink", None)
-            g = sink.grad if sink is not None else torch.zeros((co,), dtype=torch.float32, device=x_cl.device)
-            check(lib.iper_bias_grad_bf16(dy_cl.data_ptr(), n * h * w, co, cop, g.data_ptr(), st), "bias_grad_bf16")
-            if sink is None:
-                db = g.to(bias.dtype)
-            elif weight._iper_uses == 0:
-                sink.ready()
+        if side is not None:
+            main.wait_stream(side)
+        if weight._iper_uses == 0:
+            if want_w and getattr(weight, "_iper_sink", None) is not None:
+                weight._iper_sink.ready()
+            if want_b and getattr(ctx.bias_ref, "_iper_sink", None) is not None:
+                ctx.bias_ref._iper_sink.ready()
         if ctx.has_add and ctx.needs_input_grad[4]:
             dadd = dy_cl if co == cop else dy_cl[:, :co]
         return dx, dw, db, None, dadd
@@ -631,7 +647,11 @@ class ParamStore:
                 sg.fwd_offset, sg.dgrad_offset = fwd_total, dg_total
                 fwd_total += sg.co_pad * sg.taps * sg.ci_pad; dg_total += sg.ci_pad * sg.taps * sg.co_pad
                 packed.append((p, sg))
-                p._iper_sink = _Sink(p.grad, buckets, p)
+                # the gradient of a packed weight lives in the flat buffer as (co, tap, ci) — what the wgrad kernel writes fastest
+                # and what the fused Adam pass reads; p.grad is the matching (co, ci, ky, kx) VIEW of it
+                gs = buckets.storage[off:off + p.numel()].view(co, k * k, ci)
+                p.grad = gs.view(co, k, k, ci).permute(0, 3, 1, 2)
+                p._iper_sink = _Sink(gs, buckets, p)
             elif p.dim() == 1:
                 p._iper_sink = _Sink(p.grad, buckets, p)         # biases of native layers are reduced by iper_bias_grad_bf16
             for c0 in range(0, p.numel(), self.CHUNK):
