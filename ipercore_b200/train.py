@@ -725,11 +725,25 @@ class LWGTrainStep:
                 bk.finish()
             opt.step()
 
-    def step(self, batch):
+    def set_lr(self, lr):
+        """Learning rate of both optimizers (lwg_trainer.py:300-324 decays them together).  The rate is a launch argument of the
+        fused Adam pass, so a captured step is dropped and re-captured when it changes."""
+        if self.fused:
+            changed = lr != self.st_G.lr
+            self.st_G.lr = self.st_D.lr = lr
+            if changed:
+                self._graph = None
+        else:
+            for opt in (self.opt_G, self.opt_D):
+                for grp in opt.param_groups:
+                    grp["lr"] = lr
+
+    def step(self, batch, trainable=True):
         """batch: bg_inputs (bs,1,4,h,w), src_inputs (bs,ns,6,h,w), tsf_inputs (bs,nt,6,h,w), Tst (bs,nt,ns,h,w,2), real_src
-        (bs,ns,3,h,w), real_tsf (bs,nt,3,h,w), real_bg (bs,3,h,w), body_mask (bs,ns+nt,1,h,w) -> dict of loss values."""
-        if not self.use_graph:
-            return self._step(batch)
+        (bs,ns,3,h,w), real_tsf (bs,nt,3,h,w), real_bg (bs,3,h,w), body_mask (bs,ns+nt,1,h,w) -> dict of loss values.
+        trainable=False (optimize_parameters' flag, lwg_trainer.py:326-352): only D is updated; such steps run eagerly."""
+        if not self.use_graph or not trainable:
+            return self._step(batch, trainable)
         if self._graph is None:
             if self._eager_steps < 2:         # eager warm-up: lazy initialisations (cuDNN plans, NCCL, function attributes)
                 self._eager_steps += 1
@@ -748,14 +762,17 @@ class LWGTrainStep:
         self._graph.replay()
         return self._out
 
-    def _step(self, batch):
+    def _step(self, batch, trainable=True):
         b = batch
         bs, nt = b["tsf_inputs"].shape[:2]
         ns = b["src_inputs"].shape[1]
         h, w = b["tsf_inputs"].shape[-2:]
         st_G, st_D = (self.st_G, self.st_D) if self.fused else (None, None)
+        for p in self.G.parameters():
+            p._iper_uses = 0                  # forward uses of a weight still waiting for their backward (see _Conv)
         # ---- forward (lwg_trainer.py:699-731) ----
-        fake_bg, src_color, src_mask, tsf_color, tsf_mask = self.G(b["bg_inputs"], b["src_inputs"], b["tsf_inputs"], b["Tst"])
+        with torch.set_grad_enabled(bool(trainable)):
+            fake_bg, src_color, src_mask, tsf_color, tsf_mask = self.G(b["bg_inputs"], b["src_inputs"], b["tsf_inputs"], b["Tst"])
         fake_src = src_mask * fake_bg + (1 - src_mask) * src_color
         fake_tsf = tsf_mask * fake_bg + (1 - tsf_mask) * tsf_color
         fake_masks = torch.cat([src_mask, tsf_mask], dim=1)
@@ -771,13 +788,14 @@ class LWGTrainStep:
         l_mask = F.l1_loss(fm, b["body_mask"].reshape(bs * (ns + nt), 1, h, w)) * self.lam["mask"]
         l_smooth = tv_loss(fm) * self.lam["smooth"]
         loss_G = l_rec + l_tsf + l_adv + l_mask + l_smooth
-        self._zero(self.opt_G, self.bk_G)
-        if self.bk_D is not None:
-            self.bk_D.active = False          # the adversarial term back-propagates through D: those gradients are discarded
-        loss_G.backward()
-        if self.bk_D is not None:
-            self.bk_D.active = True
-        self._update(self.opt_G, self.bk_G, st_G)
+        if trainable:
+            self._zero(self.opt_G, self.bk_G)
+            if self.bk_D is not None:
+                self.bk_D.active = False      # the adversarial term back-propagates through D: those gradients are discarded
+            loss_G.backward()
+            if self.bk_D is not None:
+                self.bk_D.active = True
+            self._update(self.opt_G, self.bk_G, st_G)
         # ---- D step (optimize_D :797-834) ----
         real_in = torch.cat([r_tsf, tsf_cond], dim=1)
         fake_in = torch.cat([f_tsf.detach(), tsf_cond], dim=1)

@@ -253,3 +253,27 @@ def test_train_step_cuda_graph_matches_eager():
             assert np.isfinite(b[k]) and abs(a[k] - b[k]) <= 2e-2 * max(1.0, abs(a[k])), (k, a[k], b[k])
     moved = float((params[True] - synth_state_dict(0)["res_blocks.1.main.0.weight"].to(DEV)).abs().mean())
     assert moved > 0 and float((params[True] - params[False]).abs().mean()) <= 0.3 * moved
+
+
+def test_personalize_loop_writes_a_checkpoint_the_inference_generator_loads(tmp_path):
+    """Personalizer.run's schedule on LWGTrainStep: iterations = (no_decay + decay) * num_videos, G every 2nd batch, lr decay, and the
+    product: personalized.pth under the reference's state_dict names, loaded strictly by the inference generator."""
+    from ipercore_b200 import personalize, train
+    from ipercore_b200.generator import AttentionLWBGenerator
+    from oracle.weights import synth_state_dict
+    sd0 = synth_state_dict(0)
+    net = AttentionLWBGenerator(CFG); net.load_state_dict(sd0)
+    step = train.LWGTrainStep(net, torch.device(DEV), graph=True)
+    batches = [_batch(256, seed=s_) for s_ in (1, 2)]
+    seen = []
+    ckpt = str(tmp_path / "models" / "personalized.pth")
+    hist = personalize.run(step, batches, num_videos=2, niters_no_decay=2, niters_decay=1, train_G_every_n_iterations=2, lr=1e-4,
+                           ckpt_path=ckpt, on_iter=lambda i, out: seen.append(i))
+    torch.cuda.synchronize()
+    assert seen == [1, 2, 3, 4, 5, 6] and len(hist) == 6 and all(np.isfinite(float(h["G"])) for h in hist)
+    assert step.st_G.lr < 1e-4                        # the decay phase ran
+    sd = torch.load(ckpt)
+    assert list(sd.keys()) == list(sd0.keys())
+    moved = max(float((sd[k] - sd0[k]).abs().max()) for k in sd)
+    assert 0 < moved < 1e-2                           # three G updates with Adam at lr 1e-4
+    AttentionLWBGenerator(CFG).load_state_dict(sd, strict=True)
