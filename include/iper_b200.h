@@ -304,11 +304,16 @@ int iper_uv_merge(const float* src_warp, const float* vis_dilated, int bs, int n
  * reference trains these layers through cuDNN and torch.optim.Adam (iPERCore/tools/trainers/lwg_trainer.py:326-352, 699-833 on
  * attlwb_spade_resunet.py:14-25, 80-93, 208-252, 316-357, 605-613; bg_inpaintor.py:24-60).  Everything is NHWC bf16 (= torch
  * channels_last); channel counts are multiples of 64 (callers zero-pad the 1/3/4/6-channel ends).
- *   iper_conv_bf16        y (N,H,W,Cout) = conv_kxk(x (N,H,W,Cin), stride 1, padding k/2; k in {1,3,5,7}) with w_packed (Cout, k*k*Cin)
- *                         bf16, K = (ky*k+kx)*Cin + ci  [+ bias fp32] [+ add_nhwc, a residual of the output's shape] [ReLU].
- *                         dgrad = the same call on dY with the weights rotated by 180 degrees and in/out transposed:
- *                         w'(ci, (k-1-ky, k-1-kx), co) = w(co, ci, ky, kx).
- *   iper_conv_wgrad_bf16  dW[co*stride_co + ci*stride_ci + tap*stride_tap] += sum over pixels dY[p, co] * X[p + tap - k/2, ci]
+ *   iper_conv_bf16        y (N,Ho,Wo,Cout) = conv_kxk(x (N,H,W,Cin), stride 1 | 2, padding pad; k <= 7) with w_packed (Cout, k*k*Cin)
+ *                         bf16, K = (ky*k+kx)*Cin + ci  [+ bias fp32] [+ add_nhwc, a residual of the output's shape] [ReLU].  Stride 2
+ *                         reads x through a 5-D parity view (even H, W).  dgrad of a stride-1 conv = the same call on dY with padding
+ *                         k-1-pad and the weights rotated by 180 degrees, in/out transposed: w'(ci, (k-1-ky, k-1-kx), co) = w(co, ci, ky, kx);
+ *                         dgrad of ConvTranspose2d(k, 2, pad) = this call with stride 2 on dY and the plain (ci_T, tap, co_T) packing.
+ *   iper_conv_transposed_bf16  y (N,2H,2W,Cout) = the stride-2 transposition: ConvTranspose2d(4, 2, 1) forward, and the data gradient
+ *                         of a stride-2 conv (k = 3 or 4, pad 1), as four stride-1 phase convolutions over the input grid with
+ *                         interleaved stores; w_phases = the four K-major blocks (rows Cout, K = (tap in phase, ci)), phases ordered
+ *                         (py,px) = (0,0) (0,1) (1,0) (1,1), taps of a phase = the (ky,kx) with (ky+pad+py), (kx+pad+px) even, ascending.
+ *   iper_conv_wgrad_bf16  dW[co*stride_co + ci*stride_ci + tap*stride_tap] += sum over the pixels p of dY: dY[p, co] * X[stride*p + tap - pad, ci]
  *                         (fp32 atomics: the caller zeroes dW, or lets several calls accumulate).  Reads both operands in NHWC
  *                         (MN-major tcgen05 operands; no transposed or shifted copies).  Only co < co_valid, ci < ci_valid are
  *                         written (zero-padded ends).  (co, tap, ci) layout: strides (k*k*Cin, 1, Cin) — the fast one: a warp's
@@ -323,19 +328,23 @@ int iper_uv_merge(const float* src_warp, const float* vis_dilated, int bs, int n
  *                         it also writes the bf16 forward packing (co_pad, taps, ci_pad) at fwd_offset and, when
  *                         dgrad_offset >= 0, the dgrad packing (ci_pad, taps reversed, co_pad) — padding entries are never written
  *                         (the caller zeroes the pack buffers once).  update = 0 only repacks.
- * H >= 8, W >= 16 for iper_conv_bf16.
+ * Every read tensor must hold one 16 x 8 TMA box: H / stride >= 8, W / stride >= 16.
  * ---------------------------------------------------------------------------------------------------------- */
 typedef struct iper_adam_seg {
     long long offset, numel;        /* position in the flat buffers */
-    int co, ci, taps;               /* convolution weight (co, ci, ky, kx) with taps = k*k; taps = 0: not a packed weight */
-    int co_pad, ci_pad, reserved;   /* channel counts of the packings (multiples of 64) */
+    int co, ci, taps;               /* 4-D weight (co, ci, ky, kx) with taps = k*k (a transposed convolution's (ci_T, co_T, ky, kx) tensor:
+                                       co = ci_T, ci = co_T); taps = 0: not a packed weight */
+    int co_pad, ci_pad;             /* channel counts of the packings (multiples of 64) */
+    int reserved;                   /* kind | k << 8 | pad << 16; kind 1: stride-1 conv, 2: stride-2 conv, 3: ConvTranspose2d(k, 2, pad) */
     long long fwd_offset, dgrad_offset;   /* element offsets into pack_fwd / pack_dgrad (dgrad_offset < 0: none) */
 } iper_adam_seg;
 
-int iper_conv_bf16(const void* x_nhwc, int N, int H, int W, int Cin, const void* w_packed, int Cout, int ksize, const float* bias,
-                   int relu, const void* add_nhwc, void* out_nhwc, iper_stream_t stream);
-int iper_conv_wgrad_bf16(const void* x_nhwc, const void* dy_nhwc, int N, int H, int W, int Cin, int Cout, int ksize, float* dW,
-                         long long stride_co, long long stride_ci, long long stride_tap, int co_valid, int ci_valid,
+int iper_conv_bf16(const void* x_nhwc, int N, int H, int W, int Cin, const void* w_packed, int Cout, int ksize, int stride, int pad,
+                   const float* bias, int relu, const void* add_nhwc, void* out_nhwc, iper_stream_t stream);
+int iper_conv_transposed_bf16(const void* x_nhwc, int N, int H, int W, int Cin, const void* w_phases, int Cout, int ksize, int pad,
+                              const float* bias, int relu, void* out_nhwc, iper_stream_t stream);
+int iper_conv_wgrad_bf16(const void* x_nhwc, const void* dy_nhwc, int N, int H, int W, int Cin, int Cout, int ksize, int stride, int pad,
+                         float* dW, long long stride_co, long long stride_ci, long long stride_tap, int co_valid, int ci_valid,
                          iper_stream_t stream);
 int iper_bias_grad_bf16(const void* dy_nhwc, long long pixels, int C, int pitch, float* db, iper_stream_t stream);
 int iper_adam_pack(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const iper_adam_seg* segs_dev,

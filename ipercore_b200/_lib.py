@@ -79,9 +79,11 @@ SIGNATURES = {
     "iper_nhwc_f32_to_nchw": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "iper_pred_to_u8": [c_void_p, c_int, c_int, c_void_p, c_void_p],
     "iper_morph": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
-    "iper_conv_bf16": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
-    "iper_conv_wgrad_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_ll, c_ll, c_int, c_int,
-                             c_void_p],
+    "iper_conv_bf16": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                       c_void_p],
+    "iper_conv_transposed_bf16": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p],
+    "iper_conv_wgrad_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_ll, c_ll, c_int,
+                             c_int, c_void_p],
     "iper_bias_grad_bf16": [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p],
     "iper_adam_pack": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float,
                        c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p],

@@ -39,17 +39,34 @@ constexpr int TR_BOX = 128 * 128;            // one activation box: 128 pixels x
 
 struct alignas(64) TrainArgs {
     CUtensorMap mapA, mapB;
-    int N, H, W, Cin, Cout, ks, pad;     // conv geometry (forward: Cin -> Cout)
+    int N, H, W;                         // the TILE DOMAIN: forward -> output pixels (or, for a phase of a transposed convolution, the
+                                         // input-resolution grid); wgrad -> the pixels of dY
+    int Cin, Cout;                       // forward: contraction channels and output channels
+    int stride;                          // 1 | 2: the read tensor (forward: x, wgrad: X) is sampled at stride * p + tap offset; stride 2
+                                         // reads through a 5-D view (2C [x parity, c], W/2, 2 [y parity], H/2, N) of the NHWC tensor
+    int ntaps; int8_t tdx[49], tdy[49];  // tap offsets
     int tiles_x, tiles_y, n_tiles;
-    int steps;                           // forward: ks*ks * Cin/64
+    int steps;                           // forward: ntaps * Cin/64
     const float* bias; int relu;
-    const __nv_bfloat16* add;            // residual (same shape and pitch as out) or null
+    const __nv_bfloat16* add;            // residual (same addressing as out) or null
     __nv_bfloat16* out; int out_pitch;
+    int Hout, Wout, osy, osx, ooy, oox;  // output pixel of tile-domain pixel (y, x) = (osy*y + ooy, osx*x + oox) in (N, Hout, Wout, out_pitch)
     // wgrad: mapA = the tensor whose channels are the 128 accumulator rows, mapB = the BN accumulator columns
     int x_rows;                          // 0: rows = dY channels (co), cols = X channels (ci);  1: rows = ci, cols = co
-    int rowsC, colsC, col_tiles, splitk, kblocks, taps;
+    int xC;                              // channel count of X (parity offset of the 5-D view)
+    int rowsC, colsC, col_tiles, splitk, kblocks;
     float* dW; long long s_row, s_col, s_tap;   // element strides of dW for (row channel, column channel, tap)
 };
+
+// activation box at tile origin (x0, y0) of image n, channel chunk c0, shifted by tap offset (dx, dy); stride 2: through the 5-D view
+IPER_DEVINL void load_act(void* smem, const CUtensorMap* map, uint64_t* bar, int stride, int C, int c0, int x0, int y0, int n, int dx, int dy) {
+    if (stride == 1) {
+        tma_load_4d(smem, map, bar, c0, x0 + dx, y0 + dy, n);
+    } else {
+        const int px = dx & 1, py = dy & 1;                 // 2*x0 + dx = 2*(x0 + (dx - px)/2) + px
+        tma_load_5d(smem, map, bar, px * C + c0, x0 + ((dx - px) >> 1), py, y0 + ((dy - py) >> 1), n);
+    }
+}
 
 // [4,6) D fmt = f32, [7,10) A fmt, [10,13) B fmt (1 = bf16), [15] A major, [16] B major (1 = MN-major), [17,23) N>>3, [24,29) M>>4
 IPER_DEVINL constexpr uint32_t umma_idesc_bf16(int M, int N, int mn_major) {
@@ -120,7 +137,7 @@ __global__ void __launch_bounds__(TR_THREADS, MODE == 0 ? 2 : 1) train_gemm_kern
     } else {
         int u = blockIdx.x;
         const int split = u % a.splitk; u /= a.splitk;
-        tap = u % a.taps; u /= a.taps;
+        tap = u % a.ntaps; u /= a.ntaps;
         col0 = (u % a.col_tiles) * BN; row0 = (u / a.col_tiles) * 128;
         const int per = (a.kblocks + a.splitk - 1) / a.splitk;
         k0 = split * per;
@@ -137,19 +154,22 @@ __global__ void __launch_bounds__(TR_THREADS, MODE == 0 ? 2 : 1) train_gemm_kern
                 mbar_arrive_expect_tx(&full_bar[s], STAGE);
                 if (MODE == 0) {
                     const int t = i / cin_chunks, cc = i - t * cin_chunks;
-                    tma_load_4d(sA(s), &a.mapA, &full_bar[s], cc * 64, px0 + t % a.ks - a.pad, py0 + t / a.ks - a.pad, pn);
+                    load_act(sA(s), &a.mapA, &full_bar[s], a.stride, a.Cin, cc * 64, px0, py0, pn, a.tdx[t], a.tdy[t]);
                     tma_load_2d(sB(s), &a.mapB, &full_bar[s], i * 64, n_tile * BN);
                 } else {
                     const int j = k0 + i;
                     const int x0 = (j % a.tiles_x) * 16, y0 = ((j / a.tiles_x) % a.tiles_y) * 8, n = j / (a.tiles_x * a.tiles_y);
-                    const int dx = tap % a.ks - a.pad, dy = tap / a.ks - a.pad;      // X is read at the output pixel + tap offset
-                    const int rx = a.x_rows ? dx : 0, ry = a.x_rows ? dy : 0, cx = a.x_rows ? 0 : dx, cy = a.x_rows ? 0 : dy;
+                    const int dx = a.tdx[tap], dy = a.tdy[tap];                      // X is read at stride * (dY pixel) + tap offset
 #pragma unroll
-                    for (int g = 0; g < 2; g++)        // channels beyond the tensor are zero-filled by TMA (64-channel tensors)
-                        tma_load_4d(sA(s) + g * TR_BOX, &a.mapA, &full_bar[s], row0 + g * 64, x0 + rx, y0 + ry, n);
+                    for (int g = 0; g < 2; g++) {      // channels beyond the tensor are zero-filled by TMA (64-channel tensors)
+                        if (a.x_rows) load_act(sA(s) + g * TR_BOX, &a.mapA, &full_bar[s], a.stride, a.xC, row0 + g * 64, x0, y0, n, dx, dy);
+                        else tma_load_4d(sA(s) + g * TR_BOX, &a.mapA, &full_bar[s], row0 + g * 64, x0, y0, n);
+                    }
 #pragma unroll
-                    for (int g = 0; g < BN / 64; g++)
-                        tma_load_4d(sB(s) + g * TR_BOX, &a.mapB, &full_bar[s], col0 + g * 64, x0 + cx, y0 + cy, n);
+                    for (int g = 0; g < BN / 64; g++) {
+                        if (a.x_rows) tma_load_4d(sB(s) + g * TR_BOX, &a.mapB, &full_bar[s], col0 + g * 64, x0, y0, n);
+                        else load_act(sB(s) + g * TR_BOX, &a.mapB, &full_bar[s], a.stride, a.xC, col0 + g * 64, x0, y0, n, dx, dy);
+                    }
                 }
                 if (++s == STAGES) { s = 0; ph ^= 1; }
             }
@@ -186,7 +206,7 @@ __global__ void __launch_bounds__(TR_THREADS, MODE == 0 ? 2 : 1) train_gemm_kern
         if (MODE == 0) {
             const int x = px0 + row % 16, y = py0 + row / 16;
             const bool valid = x < a.W && y < a.H && pn < a.N;
-            const size_t off = (((size_t)pn * a.H + y) * a.W + x) * a.out_pitch + n_tile * BN;
+            const size_t off = (((size_t)pn * a.Hout + (a.osy * y + a.ooy)) * a.Wout + (a.osx * x + a.oox)) * a.out_pitch + n_tile * BN;
 #pragma unroll 1
             for (int j = 0; j < BN / 32; j++) {
                 uint32_t r[32];
@@ -298,11 +318,29 @@ __global__ void __launch_bounds__(256) adam_pack_kernel(float* __restrict__ p, c
             pp -= lr * inv_bc1 * mm / (sqrtf(vv) * inv_sqrt_bc2 + eps);
             p[idx] = pp;
         }
-        if (sg.taps > 0) {                           // (co, ci, ky, kx) -> forward (co_pad, tap, ci_pad) and dgrad (ci_pad, taps-1-tap, co_pad)
+        if (sg.taps > 0) {
+            // repacking of the (co, ci, ky, kx) tensor (a transposed convolution's weight is (ci_T, co_T, ky, kx): co = ci_T, ci = co_T):
+            //   plain  (co_pad rows, K = (tap, ci))                 forward of kinds 1, 2; data gradient of kind 3
+            //   rev    (ci_pad rows, K = (taps-1-tap, co))          data gradient of kind 1 (rotated by 180 degrees, in/out transposed)
+            //   phases (ci_pad rows, K = (tap in phase, co)) x 4    data gradient of kind 2, forward of kind 3 (stride-2 transposition)
+            const int kind = sg.reserved & 0xff, ks = (sg.reserved >> 8) & 0xff, pad = (sg.reserved >> 16) & 0xff;
             const __nv_bfloat16 h = __float2bfloat16(pp);
-            pack_fwd[sg.fwd_offset + ((long long)co * sg.taps + tap) * sg.ci_pad + ci] = h;
-            if (sg.dgrad_offset >= 0)
-                pack_dgrad[sg.dgrad_offset + ((long long)ci * sg.taps + (sg.taps - 1 - tap)) * sg.co_pad + co] = h;
+            const long long plain = ((long long)co * sg.taps + tap) * sg.ci_pad + ci;
+            if (kind == 1) {
+                pack_fwd[sg.fwd_offset + plain] = h;
+                if (sg.dgrad_offset >= 0)
+                    pack_dgrad[sg.dgrad_offset + ((long long)ci * sg.taps + (sg.taps - 1 - tap)) * sg.co_pad + co] = h;
+            } else {
+                const int ky = tap / ks, kx = tap % ks, py = (ky + pad) & 1, px = (kx + pad) & 1;
+                int n0 = 0;                                   // taps per axis whose phase is 0
+                for (int k = 0; k < ks; k++) n0 += ((k + pad) & 1) == 0;
+                const int n1 = ks - n0, nyp = py ? n1 : n0, nxp = px ? n1 : n0;
+                long long off = 0;                            // blocks of the phases before (py, px) in the order (0,0) (0,1) (1,0) (1,1)
+                for (int ph = 0; ph < py * 2 + px; ph++) off += (long long)sg.ci_pad * ((ph >> 1) ? n1 : n0) * ((ph & 1) ? n1 : n0) * sg.co_pad;
+                const long long pidx = off + ((long long)ci * (nyp * nxp) + (ky >> 1) * nxp + (kx >> 1)) * sg.co_pad + co;
+                if (kind == 2) { pack_fwd[sg.fwd_offset + plain] = h; pack_dgrad[sg.dgrad_offset + pidx] = h; }
+                else { pack_fwd[sg.fwd_offset + pidx] = h; pack_dgrad[sg.dgrad_offset + plain] = h; }
+            }
         }
     }
 }
@@ -351,47 +389,104 @@ static int launch_train(const TrainArgs& t, int grid, cudaStream_t st) {
     return 0;
 }
 
+// the read tensor of a convolution: plain NHWC (stride 1) or the 5-D parity view of it (stride 2; H, W even)
+static int read_map(CUtensorMap* m, const void* base, int N, int H, int W, int C, int stride) {
+    if (stride == 1) return nhwc_map(m, base, N, H, W, C);
+    cuuint64_t d[5] = {(cuuint64_t)2 * C, (cuuint64_t)W / 2, 2, (cuuint64_t)H / 2, (cuuint64_t)N};
+    cuuint64_t st[4] = {(cuuint64_t)2 * C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)2 * W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t b[5] = {64, 16, 1, 8, 1};
+    return bf16_map(m, base, 5, d, st, b);
+}
+static int weight_map(CUtensorMap* m, const void* w, long long K, int rows, int BN) {
+    cuuint64_t bd[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t bs[1] = {(cuuint64_t)K * 2};
+    cuuint32_t bb[2] = {64, (cuuint32_t)BN};
+    return bf16_map(m, w, 2, bd, bs, bb);
+}
+static int launch_fwd(TrainArgs& t, cudaStream_t st) {
+    t.tiles_x = (t.W + 15) / 16; t.tiles_y = (t.H + 7) / 8;
+    const int BN = t.Cout % 128 == 0 ? 128 : 64;
+    t.n_tiles = t.Cout / BN; t.steps = t.ntaps * (t.Cin / 64);
+    const int grid = t.tiles_x * t.tiles_y * t.N * t.n_tiles;
+    return BN == 128 ? launch_train<128, 0>(t, grid, st) : launch_train<64, 0>(t, grid, st);
+}
+
 }  // namespace iper
 
 using namespace iper;
 
-extern "C" int iper_conv_bf16(const void* x_nhwc, int N, int H, int W, int Cin, const void* w_packed, int Cout, int ksize,
-                              const float* bias, int relu, const void* add_nhwc, void* out_nhwc, iper_stream_t stream) {
+#define IPER_A16P(p) (((uintptr_t)(p) & 15) == 0)
+
+extern "C" int iper_conv_bf16(const void* x_nhwc, int N, int H, int W, int Cin, const void* w_packed, int Cout, int ksize, int stride,
+                              int pad, const float* bias, int relu, const void* add_nhwc, void* out_nhwc, iper_stream_t stream) {
     IPER_REQUIRE(x_nhwc && w_packed && out_nhwc, "iper_conv_bf16: null pointer");
-    IPER_REQUIRE(ksize >= 1 && ksize <= 7 && (ksize & 1), "iper_conv_bf16: kernel size %d (odd, <= 7: stride-1 'same' convolutions)", ksize);
-    IPER_REQUIRE(N > 0 && H >= 8 && W >= 16 && Cin % 64 == 0 && Cout % 64 == 0, "iper_conv_bf16: needs H >= 8, W >= 16, Cin %% 64 == 0, Cout %% 64 == 0 "
-                 "(got %dx%d, %d -> %d)", H, W, Cin, Cout);
-    IPER_REQUIRE(((uintptr_t)x_nhwc & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 && ((uintptr_t)out_nhwc & 15) == 0 &&
-                 ((uintptr_t)add_nhwc & 15) == 0, "iper_conv_bf16: 16-byte alignment");
+    IPER_REQUIRE(ksize >= 1 && ksize <= 7 && (stride == 1 || stride == 2) && pad >= 0 && pad < ksize,
+                 "iper_conv_bf16: kernel %d stride %d pad %d unsupported (k <= 7, stride 1 | 2, pad < k)", ksize, stride, pad);
+    IPER_REQUIRE(N > 0 && Cin % 64 == 0 && Cout % 64 == 0 && (stride == 1 || (H % 2 == 0 && W % 2 == 0)),
+                 "iper_conv_bf16: needs Cin %% 64 == 0, Cout %% 64 == 0, even H, W for stride 2 (got %dx%d, %d -> %d)", H, W, Cin, Cout);
+    const int Ho = (H + 2 * pad - ksize) / stride + 1, Wo = (W + 2 * pad - ksize) / stride + 1;
+    IPER_REQUIRE(Ho >= 1 && Wo >= 1 && H / stride >= 8 && W / stride >= 16, "iper_conv_bf16: map %dx%d too small (one 16x8 TMA box per tap)", H, W);
+    IPER_REQUIRE(IPER_A16P(x_nhwc) && IPER_A16P(w_packed) && IPER_A16P(out_nhwc) && IPER_A16P(add_nhwc), "iper_conv_bf16: 16-byte alignment");
     TrainArgs t = {};
-    t.N = N; t.H = H; t.W = W; t.Cin = Cin; t.Cout = Cout; t.ks = ksize; t.pad = ksize / 2;
-    t.tiles_x = (W + 15) / 16; t.tiles_y = (H + 7) / 8;
-    const int BN = Cout % 128 == 0 ? 128 : 64;
-    t.n_tiles = Cout / BN; t.steps = ksize * ksize * (Cin / 64);
+    t.N = N; t.H = Ho; t.W = Wo; t.Cin = Cin; t.Cout = Cout; t.stride = stride; t.ntaps = ksize * ksize;
+    for (int k = 0; k < t.ntaps; k++) { t.tdx[k] = (int8_t)(k % ksize - pad); t.tdy[k] = (int8_t)(k / ksize - pad); }
     t.bias = bias; t.relu = relu; t.add = reinterpret_cast<const __nv_bfloat16*>(add_nhwc);
     t.out = reinterpret_cast<__nv_bfloat16*>(out_nhwc); t.out_pitch = Cout;
-    if (int rc = nhwc_map(&t.mapA, x_nhwc, N, H, W, Cin)) return rc;
-    cuuint64_t bd[2] = {(cuuint64_t)ksize * ksize * Cin, (cuuint64_t)Cout};
-    cuuint64_t bs[1] = {(cuuint64_t)ksize * ksize * Cin * 2};
-    cuuint32_t bb[2] = {64, (cuuint32_t)BN};
-    if (int rc = bf16_map(&t.mapB, w_packed, 2, bd, bs, bb)) return rc;
-    const int grid = t.tiles_x * t.tiles_y * N * t.n_tiles;
-    return BN == 128 ? launch_train<128, 0>(t, grid, (cudaStream_t)stream) : launch_train<64, 0>(t, grid, (cudaStream_t)stream);
+    t.Hout = Ho; t.Wout = Wo; t.osx = t.osy = 1;
+    if (int rc = read_map(&t.mapA, x_nhwc, N, H, W, Cin, stride)) return rc;
+    if (int rc = weight_map(&t.mapB, w_packed, (long long)t.ntaps * Cin, Cout, Cout % 128 == 0 ? 128 : 64)) return rc;
+    return launch_fwd(t, (cudaStream_t)stream);
 }
 
-extern "C" int iper_conv_wgrad_bf16(const void* x_nhwc, const void* dy_nhwc, int N, int H, int W, int Cin, int Cout, int ksize,
-                                    float* dW, long long stride_co, long long stride_ci, long long stride_tap, int co_valid,
+extern "C" int iper_conv_transposed_bf16(const void* x_nhwc, int N, int H, int W, int Cin, const void* w_phases, int Cout, int ksize,
+                                         int pad, const float* bias, int relu, void* out_nhwc, iper_stream_t stream) {
+    IPER_REQUIRE(x_nhwc && w_phases && out_nhwc, "iper_conv_transposed_bf16: null pointer");
+    IPER_REQUIRE((ksize == 3 || ksize == 4) && pad == 1, "iper_conv_transposed_bf16: kernel %d pad %d unsupported (3 or 4, pad 1, stride 2: output 2H x 2W)", ksize, pad);
+    IPER_REQUIRE(N > 0 && H >= 8 && W >= 16 && Cin % 64 == 0 && Cout % 64 == 0,
+                 "iper_conv_transposed_bf16: needs H >= 8, W >= 16, Cin %% 64 == 0, Cout %% 64 == 0 (got %dx%d, %d -> %d)", H, W, Cin, Cout);
+    IPER_REQUIRE(IPER_A16P(x_nhwc) && IPER_A16P(w_phases) && IPER_A16P(out_nhwc), "iper_conv_transposed_bf16: 16-byte alignment");
+    // out[2y + py, 2x + px] = sum over taps with (ky + pad + py) even of x[y + (py + pad - ky)/2, x + (px + pad - kx)/2] w[ky, kx]:
+    // four stride-1 phase convolutions over the input grid, each with its own K-major weight block (rows Cout, K = (tap in phase, ci))
+    long long woff = 0;
+    for (int ph = 0; ph < 4; ph++) {
+        const int py = ph >> 1, px = ph & 1;
+        TrainArgs t = {};
+        t.N = N; t.H = H; t.W = W; t.Cin = Cin; t.Cout = Cout; t.stride = 1;
+        for (int ky = 0; ky < ksize; ky++) {
+            if ((ky + pad + py) & 1) continue;
+            for (int kx = 0; kx < ksize; kx++) {
+                if ((kx + pad + px) & 1) continue;
+                t.tdx[t.ntaps] = (int8_t)((px + pad - kx) / 2); t.tdy[t.ntaps] = (int8_t)((py + pad - ky) / 2); t.ntaps++;
+            }
+        }
+        t.bias = bias; t.relu = relu; t.out = reinterpret_cast<__nv_bfloat16*>(out_nhwc); t.out_pitch = Cout;
+        t.Hout = 2 * H; t.Wout = 2 * W; t.osx = t.osy = 2; t.oox = px; t.ooy = py;
+        if (int rc = nhwc_map(&t.mapA, x_nhwc, N, H, W, Cin)) return rc;
+        if (int rc = weight_map(&t.mapB, reinterpret_cast<const __nv_bfloat16*>(w_phases) + woff, (long long)t.ntaps * Cin, Cout,
+                                Cout % 128 == 0 ? 128 : 64)) return rc;
+        if (int rc = launch_fwd(t, (cudaStream_t)stream)) return rc;
+        woff += (long long)Cout * t.ntaps * Cin;
+    }
+    return 0;
+}
+
+extern "C" int iper_conv_wgrad_bf16(const void* x_nhwc, const void* dy_nhwc, int N, int H, int W, int Cin, int Cout, int ksize, int stride,
+                                    int pad, float* dW, long long stride_co, long long stride_ci, long long stride_tap, int co_valid,
                                     int ci_valid, iper_stream_t stream) {
     IPER_REQUIRE(x_nhwc && dy_nhwc && dW, "iper_conv_wgrad_bf16: null pointer");
-    IPER_REQUIRE(ksize >= 1 && ksize <= 7 && (ksize & 1), "iper_conv_wgrad_bf16: kernel size %d (odd, <= 7)", ksize);
-    IPER_REQUIRE(N > 0 && H > 0 && W > 0 && Cin % 64 == 0 && Cout % 64 == 0,
-                 "iper_conv_wgrad_bf16: needs Cin %% 64 == 0, Cout %% 64 == 0 (got %dx%d, %d -> %d)", H, W, Cin, Cout);
-    IPER_REQUIRE(((uintptr_t)x_nhwc & 15) == 0 && ((uintptr_t)dy_nhwc & 15) == 0, "iper_conv_wgrad_bf16: 16-byte alignment");
+    IPER_REQUIRE(ksize >= 1 && ksize <= 7 && (stride == 1 || stride == 2) && pad >= 0 && pad < ksize,
+                 "iper_conv_wgrad_bf16: kernel %d stride %d pad %d unsupported", ksize, stride, pad);
+    IPER_REQUIRE(N > 0 && H > 0 && W > 0 && Cin % 64 == 0 && Cout % 64 == 0 && (stride == 1 || (H % 2 == 0 && W % 2 == 0)),
+                 "iper_conv_wgrad_bf16: needs Cin %% 64 == 0, Cout %% 64 == 0, even H, W for stride 2 (got %dx%d, %d -> %d)", H, W, Cin, Cout);
+    IPER_REQUIRE(IPER_A16P(x_nhwc) && IPER_A16P(dy_nhwc), "iper_conv_wgrad_bf16: 16-byte alignment");
     IPER_REQUIRE(co_valid > 0 && co_valid <= Cout && ci_valid > 0 && ci_valid <= Cin, "iper_conv_wgrad_bf16: valid channel counts out of range");
+    const int Ho = (H + 2 * pad - ksize) / stride + 1, Wo = (W + 2 * pad - ksize) / stride + 1;      // dY is (N, Ho, Wo, Cout)
+    IPER_REQUIRE(Ho >= 1 && Wo >= 1 && H / stride >= 8 && W / stride >= 16, "iper_conv_wgrad_bf16: map %dx%d too small (one 16x8 TMA box per tap)", H, W);
     cudaStream_t st = (cudaStream_t)stream;
     TrainArgs t = {};
-    t.N = N; t.H = H; t.W = W; t.Cin = Cin; t.Cout = Cout; t.ks = ksize; t.pad = ksize / 2; t.taps = ksize * ksize; t.dW = dW;
-    t.tiles_x = (W + 15) / 16; t.tiles_y = (H + 7) / 8;
+    t.N = N; t.H = Ho; t.W = Wo; t.Cin = Cin; t.Cout = Cout; t.stride = stride; t.ntaps = ksize * ksize; t.dW = dW; t.xC = Cin;
+    for (int k = 0; k < t.ntaps; k++) { t.tdx[k] = (int8_t)(k % ksize - pad); t.tdy[k] = (int8_t)(k / ksize - pad); }
+    t.tiles_x = (Wo + 15) / 16; t.tiles_y = (Ho + 7) / 8;
     t.kblocks = t.tiles_x * t.tiles_y * N;
     // accumulator rows = TMEM lanes = the 32 threads of a warp in the epilogue: put the channel index with the SMALLER dW stride
     // there, so one warp-wide atomic instruction touches consecutive floats (one 128-byte line for stride 1) instead of 32 lines
@@ -402,13 +497,15 @@ extern "C" int iper_conv_wgrad_bf16(const void* x_nhwc, const void* dy_nhwc, int
     const int BN = colsP % 128 == 0 ? 128 : 64;
     const int row_tiles = (rowsP + 127) / 128;
     t.col_tiles = colsP / BN;
-    const int items = row_tiles * t.col_tiles * t.taps;
+    const int items = row_tiles * t.col_tiles * t.ntaps;
     int sk = (148 * 2 + items - 1) / items;                // fill the machine about twice over
     if (sk > t.kblocks) sk = t.kblocks;
     if (sk < 1) sk = 1;
     t.splitk = sk;
-    if (int rc = nhwc_map(&t.mapA, t.x_rows ? x_nhwc : dy_nhwc, N, H, W, rowsP)) return rc;
-    if (int rc = nhwc_map(&t.mapB, t.x_rows ? dy_nhwc : x_nhwc, N, H, W, colsP)) return rc;
+    CUtensorMap mx, my;
+    if (int rc = read_map(&mx, x_nhwc, N, H, W, Cin, stride)) return rc;
+    if (int rc = nhwc_map(&my, dy_nhwc, N, Ho, Wo, Cout)) return rc;
+    t.mapA = t.x_rows ? mx : my; t.mapB = t.x_rows ? my : mx;
     const int grid = items * sk;
     return BN == 128 ? launch_train<128, 1>(t, grid, st) : launch_train<64, 1>(t, grid, st);
 }

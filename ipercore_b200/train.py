@@ -51,36 +51,74 @@ def _pad64(c):
     return (c + 63) // 64 * 64
 
 
-def _eligible(x, weight, stride=1, padding=None):
-    """Stride-1 "same" convolutions with an odd kernel <= 7 on maps of at least 8x16 run on the tcgen05 kernels; channel counts
-    that are not multiples of 64 (the 1/3/4/6-channel ends) are zero-padded by the caller below."""
-    co, ci, kh, kw = weight.shape
+S1, S2, CT = 1, 2, 3        # kinds of convolution the kernels run: stride 1, stride 2, ConvTranspose2d(k, 2, 1)
+
+
+def _kind(x, weight, stride=1, padding=None, transposed=False):
+    """0 = not on the kernels, else S1 / S2 / CT.  Every tensor a kernel reads must hold one 16x8 TMA box at its (possibly halved)
+    resolution; channel counts that are not multiples of 64 (the 1/3/4/6-channel ends) are zero-padded by the caller below."""
+    kh, kw = weight.shape[2:]
     h, w = x.shape[-2:]
     if padding is None:
         padding = kh // 2
-    return bool(USE_KERNELS and x.is_cuda and kh == kw and kh in (1, 3, 5, 7) and stride == 1 and padding == kh // 2 and h >= 8 and w >= 16)
+    if not (USE_KERNELS and x.is_cuda and kh == kw and 1 <= kh <= 7 and 0 <= padding < kh):
+        return 0
+    if transposed:
+        return CT if (stride == 2 and kh == 4 and padding == 1 and h >= 8 and w >= 16) else 0
+    if stride == 1:
+        ho, wo = h + 2 * padding - kh + 1, w + 2 * padding - kw + 1
+        return S1 if (h >= 8 and w >= 16 and ho >= 8 and wo >= 16) else 0            # dgrad reads dY (ho x wo)
+    if stride == 2:
+        return S2 if (kh in (3, 4) and padding == 1 and h % 2 == 0 and w % 2 == 0 and h >= 16 and w >= 32) else 0
+    return 0
 
 
-def pack_weight(weight):
-    """(co, ci, k, k) fp32 -> (forward (co_pad, k*k*ci_pad), dgrad (ci_pad, k*k*co_pad)) bf16, K = (tap, channel); the dgrad
-    packing holds the 180-degree-rotated, in/out-transposed filter.  The torch formulation of csrc/train.cu adam_pack_kernel's
-    repacking (used for frozen weights and by the tests; trainable weights are repacked by the fused Adam pass)."""
+def _eligible(x, weight, stride=1, padding=None, transposed=False):
+    return _kind(x, weight, stride, padding, transposed) != 0
+
+
+def _phase_taps(k, pad):
+    """Taps of the four output phases (py, px) of a stride-2 transposition: those with (ky + pad + py), (kx + pad + px) even."""
+    out = []
+    for py in (0, 1):
+        for px in (0, 1):
+            out.append([(ky, kx) for ky in range(k) if (ky + pad + py) % 2 == 0 for kx in range(k) if (kx + pad + px) % 2 == 0])
+    return out
+
+
+def pack_weight(weight, kind=S1, pad=None):
+    """4-D weight -> (forward packing, dgrad packing) in bf16, K-major rows, channels zero-padded to multiples of 64 — the torch
+    formulation of csrc/train.cu adam_pack_kernel's repacking (frozen weights and tests; trainable weights are repacked by the
+    fused Adam pass).  With (co, ci) = the first two dims (a transposed convolution's weight is (ci_T, co_T, k, k)):
+      plain  (co_pad, K = (tap, ci))                 forward of S1 / S2, data gradient of CT
+      rev    (ci_pad, K = (taps-1-tap, co))          data gradient of S1
+      phases 4 x (ci_pad, K = (tap in phase, co))    data gradient of S2, forward of CT"""
     co, ci, k, _ = weight.shape
+    pad = k // 2 if pad is None else pad
     cop, cip = _pad64(co), _pad64(ci)
     w = weight.detach()
-    f = torch.zeros((cop, k * k, cip), dtype=BF16, device=w.device)
-    f[:co, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, k * k, ci)
-    d = torch.zeros((cip, k * k, cop), dtype=BF16, device=w.device)
-    d[:ci, :, :co] = w.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, k * k, co)
-    return f.view(cop, -1), d.view(cip, -1)
+    plain = torch.zeros((cop, k * k, cip), dtype=BF16, device=w.device)
+    plain[:co, :, :ci] = w.permute(0, 2, 3, 1).reshape(co, k * k, ci)
+    if kind == S1:
+        rev = torch.zeros((cip, k * k, cop), dtype=BF16, device=w.device)
+        rev[:ci, :, :co] = w.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, k * k, co)
+        return plain.view(cop, -1), rev.view(cip, -1)
+    blocks = []
+    for taps in _phase_taps(k, pad):
+        b = torch.zeros((cip, len(taps), cop), dtype=BF16, device=w.device)
+        for t, (ky, kx) in enumerate(taps):
+            b[:ci, t, :co] = w[:, :, ky, kx].t()
+        blocks.append(b.reshape(-1))
+    phases = torch.cat(blocks)
+    return (plain.view(cop, -1), phases) if kind == S2 else (phases, plain.view(cop, -1))
 
 
-def _packs(weight):
+def _packs(weight, kind, pad):
     pk = getattr(weight, "_iper_pack", None)            # maintained by ParamStore (trainable) ...
     if pk is None:
         if weight.requires_grad:
-            return pack_weight(weight)
-        pk = weight._iper_pack = pack_weight(weight)    # ... or packed once (frozen weights: VGG)
+            return pack_weight(weight, kind, pad)
+        pk = weight._iper_pack = pack_weight(weight, kind, pad)    # ... or packed once (frozen weights: VGG)
     return pk
 
 
@@ -92,50 +130,66 @@ def _to_cl(x, cpad):
     return x.contiguous(memory_format=CL)
 
 
-def _conv_call(x_cl, w_packed, cout, ksize, bias=None, relu=False, add=None):
+def _conv_call(x_cl, w_packed, cout, ksize, stride=1, pad=None, bias=None, relu=False, add=None):
     n, cin, h, w = x_cl.shape
-    y = torch.empty((n, cout, h, w), dtype=BF16, device=x_cl.device, memory_format=CL)
-    check(lib.iper_conv_bf16(x_cl.data_ptr(), n, h, w, cin, w_packed.data_ptr(), cout, ksize, 0 if bias is None else bias.data_ptr(),
+    pad = ksize // 2 if pad is None else pad
+    ho, wo = (h + 2 * pad - ksize) // stride + 1, (w + 2 * pad - ksize) // stride + 1
+    y = torch.empty((n, cout, ho, wo), dtype=BF16, device=x_cl.device, memory_format=CL)
+    check(lib.iper_conv_bf16(x_cl.data_ptr(), n, h, w, cin, w_packed.data_ptr(), cout, ksize, stride, pad, 0 if bias is None else bias.data_ptr(),
                              int(relu), 0 if add is None else add.data_ptr(), y.data_ptr(), _stream()), "conv_bf16")
     return y
 
 
+def _convT_call(x_cl, w_phases, cout, ksize, pad, bias=None, relu=False):
+    n, cin, h, w = x_cl.shape
+    y = torch.empty((n, cout, 2 * h, 2 * w), dtype=BF16, device=x_cl.device, memory_format=CL)
+    check(lib.iper_conv_transposed_bf16(x_cl.data_ptr(), n, h, w, cin, w_phases.data_ptr(), cout, ksize, pad,
+                                        0 if bias is None else bias.data_ptr(), int(relu), y.data_ptr(), _stream()), "conv_transposed_bf16")
+    return y
+
+
 class _Conv(torch.autograd.Function):
-    """y = [relu]( conv2d(x, weight, bias, stride 1, padding k/2) [+ add] ) in bf16 on the tcgen05 kernels; x any layout, y
-    channels_last.  Weight / bias gradients go straight into the parameter's flat fp32 gradient when the parameter has a sink
-    (ParamStore), otherwise they are returned to autograd."""
+    """y = [relu]( conv(x, weight, bias) [+ add] ) in bf16 on the tcgen05 kernels — stride-1 (any k <= 7 / padding), stride-2
+    (k = 3 | 4, pad 1) and ConvTranspose2d(4, 2, 1); x any layout, y channels_last.  Weight / bias gradients go straight into the
+    parameter's flat fp32 gradient when the parameter has a sink (ParamStore), otherwise they are returned to autograd."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, relu, add):
-        co, ci, k, _ = weight.shape
-        cop, cip = _pad64(co), _pad64(ci)
-        x_cl = _to_cl(x, cip)
-        wf, _ = _packs(weight)
+    def forward(ctx, x, weight, bias, relu, add, kind, pad):
+        k = weight.shape[2]
+        cin, cout = (weight.shape[0], weight.shape[1]) if kind == CT else (weight.shape[1], weight.shape[0])
+        cinp, coutp = _pad64(cin), _pad64(cout)
+        x_cl = _to_cl(x, cinp)
+        wf, _ = _packs(weight, kind, pad)
         b = None
         if bias is not None:
             b = bias.detach().float()
-            b = (F.pad(b, (0, cop - co)) if co != cop else b).contiguous()
-        a = None if add is None else _to_cl(add, cop)
-        y = _conv_call(x_cl, wf, cop, k, b, relu, a)
+            b = (F.pad(b, (0, coutp - cout)) if cout != coutp else b).contiguous()
+        if kind == CT:
+            y = _convT_call(x_cl, wf, coutp, k, pad, b, relu)
+        else:
+            a = None if add is None else _to_cl(add, coutp)
+            y = _conv_call(x_cl, wf, coutp, k, 2 if kind == S2 else 1, pad, b, relu, a)
         ctx.save_for_backward(x_cl, weight, y if relu else None)
-        ctx.has_bias, ctx.relu, ctx.has_add, ctx.bias_ref = bias is not None, relu, add is not None, bias
+        ctx.cfg = (bias is not None, relu, add is not None, kind, pad, cin, cout)
+        ctx.bias_ref = bias
         if weight.requires_grad and torch.is_grad_enabled():
             weight._iper_uses = getattr(weight, "_iper_uses", 0) + 1
-        return y if co == cop else y[:, :co]
+        return y if cout == coutp else y[:, :cout]
 
     @staticmethod
     def backward(ctx, dy):
         x_cl, weight, y = ctx.saved_tensors
-        co, ci, k, _ = weight.shape
-        cop, cip = _pad64(co), _pad64(ci)
+        has_bias, relu, has_add, kind, pad, cin, cout = ctx.cfg
+        k = weight.shape[2]
+        cinp, coutp = _pad64(cin), _pad64(cout)
         n, _, h, w = x_cl.shape
-        dy_cl = _to_cl(dy, cop)
-        if ctx.relu:
+        dy_cl = _to_cl(dy, coutp)
+        if relu:
             dy_cl = torch.ops.aten.threshold_backward(dy_cl, y, 0).contiguous(memory_format=CL)
         dx = dw = db = dadd = None
         if ctx.needs_input_grad[0]:
-            _, wd = _packs(weight)
-        want_w, want_b = ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+            _, wd = _packs(weight, kind, pad)
+        want_w, want_b = ctx.needs_input_grad[1], has_bias and ctx.needs_input_grad[2]
         weight._iper_uses = getattr(weight, "_iper_uses", 1) - 1
         # the weight / bias gradients are independent of the data gradient: they run on a side stream (in the captured step: a
         # parallel branch of the graph) and are joined before this node returns
@@ -144,24 +198,35 @@ class _Conv(torch.autograd.Function):
             side.wait_stream(main)
         with torch.cuda.stream(side if side is not None else main):
             st = _stream()
-            if want_w:                                   # (co, tap, ci) layout: a warp's atomics fall on consecutive floats
+            if want_w:        # gradient layout (d0, tap, d1) of the (d0, d1, k, k) tensor: a warp's atomics fall on consecutive floats
+                d0, d1 = weight.shape[:2]
                 sink = getattr(weight, "_iper_sink", None)
-                g = sink.grad if sink is not None else torch.zeros((co, k * k, ci), dtype=torch.float32, device=x_cl.device)
-                check(lib.iper_conv_wgrad_bf16(x_cl.data_ptr(), dy_cl.data_ptr(), n, h, w, cip, cop, k, g.data_ptr(), k * k * ci, 1, ci, co, ci, st),
-                      "conv_wgrad_bf16")
+                g = sink.grad if sink is not None else torch.zeros((d0, k * k, d1), dtype=torch.float32, device=x_cl.device)
+                if kind == CT:    # dWt[ci, co, tap] = sum_p x[p, ci] dY[2p + tap - pad, co]: the strided read runs over dY
+                    check(lib.iper_conv_wgrad_bf16(dy_cl.data_ptr(), x_cl.data_ptr(), n, 2 * h, 2 * w, coutp, cinp, k, 2, pad, g.data_ptr(),
+                                                   k * k * d1, 1, d1, cin, cout, st), "conv_wgrad_bf16")
+                else:
+                    check(lib.iper_conv_wgrad_bf16(x_cl.data_ptr(), dy_cl.data_ptr(), n, h, w, cinp, coutp, k, 2 if kind == S2 else 1, pad,
+                                                   g.data_ptr(), k * k * d1, 1, d1, cout, cin, st), "conv_wgrad_bf16")
                 if sink is None:
-                    dw = g.view(co, k, k, ci).permute(0, 3, 1, 2).to(weight.dtype)
+                    dw = g.view(d0, k, k, d1).permute(0, 3, 1, 2).to(weight.dtype)
             if want_b:
                 bias = ctx.bias_ref
                 bsink = getattr(bias, "_iper_sink", None)
-                gb = bsink.grad if bsink is not None else torch.zeros((co,), dtype=torch.float32, device=x_cl.device)
-                check(lib.iper_bias_grad_bf16(dy_cl.data_ptr(), n * h * w, co, cop, gb.data_ptr(), st), "bias_grad_bf16")
+                gb = bsink.grad if bsink is not None else torch.zeros((cout,), dtype=torch.float32, device=x_cl.device)
+                check(lib.iper_bias_grad_bf16(dy_cl.data_ptr(), dy_cl.shape[0] * dy_cl.shape[2] * dy_cl.shape[3], cout, coutp, gb.data_ptr(), st),
+                      "bias_grad_bf16")
                 if bsink is None:
                     db = gb.to(bias.dtype)
         if ctx.needs_input_grad[0]:
-            dx = _conv_call(dy_cl, wd, cip, k)
-            if ci != cip:
-                dx = dx[:, :ci]
+            if kind == S1:
+                dx = _conv_call(dy_cl, wd, cinp, k, 1, k - 1 - pad)
+            elif kind == S2:
+                dx = _convT_call(dy_cl, wd, cinp, k, pad)
+            else:
+                dx = _conv_call(dy_cl, wd, cinp, k, 2, pad)
+            if cin != cinp:
+                dx = dx[:, :cin]
         if side is not None:
             main.wait_stream(side)
         if weight._iper_uses == 0:
@@ -169,9 +234,9 @@ class _Conv(torch.autograd.Function):
                 weight._iper_sink.ready()
             if want_b and getattr(ctx.bias_ref, "_iper_sink", None) is not None:
                 ctx.bias_ref._iper_sink.ready()
-        if ctx.has_add and ctx.needs_input_grad[4]:
-            dadd = dy_cl if co == cop else dy_cl[:, :co]
-        return dx, dw, db, None, dadd
+        if has_add and ctx.needs_input_grad[4]:
+            dadd = dy_cl if cout == coutp else dy_cl[:, :cout]
+        return dx, dw, db, None, dadd, None, None
 
 
 def _torch_conv(x, weight, bias, stride=1, padding=0, transposed=False):
@@ -193,12 +258,14 @@ def _torch_conv(x, weight, bias, stride=1, padding=0, transposed=False):
     return fn(x.contiguous(memory_format=CL), w.contiguous(memory_format=CL), None if bias is None else bias.to(BF16), stride=stride, padding=padding)
 
 
-def conv(x, weight, bias=None, relu=False, add=None):
-    """Stride-1 "same" convolution [+ residual] [ReLU]: tcgen05 bf16 kernels (forward, dgrad, wgrad, bias grad) when the layer
-    qualifies, torch otherwise."""
-    if _eligible(x, weight):
-        return _Conv.apply(x, weight, bias, relu, add)
-    y = _torch_conv(x, weight, bias, padding=weight.shape[-1] // 2)
+def conv(x, weight, bias=None, relu=False, add=None, stride=1, padding=None, transposed=False):
+    """Convolution [+ residual] [ReLU]: tcgen05 bf16 kernels (forward, dgrad, wgrad, bias grad) when the layer qualifies (see
+    _kind), torch otherwise."""
+    padding = weight.shape[-1] // 2 if padding is None else padding
+    kind = _kind(x, weight, stride, padding, transposed)
+    if kind and not (kind != S1 and add is not None):
+        return _Conv.apply(x, weight, bias, relu, add, kind, padding)
+    y = _torch_conv(x, weight, bias, stride=stride, padding=padding, transposed=transposed)
     if add is not None:
         y = y + add
     return F.relu(y) if relu else y
@@ -330,17 +397,10 @@ class TrainableGenerator(nn.Module):
         return getattr(self.net.get_submodule(mod), attr, None)
 
     def _c(self, name, x, stride=1, padding=0, relu=False, add=None):
-        w, b = self._p(name + ".weight"), self._p(name + ".bias")
-        if _eligible(x, w, stride, padding):
-            return _Conv.apply(x, w, b, relu, add)
-        y = _torch_conv(x, w, b, stride=stride, padding=padding)
-        if add is not None:
-            y = y + add
-        return F.relu(y) if relu else y
+        return conv(x, self._p(name + ".weight"), self._p(name + ".bias"), relu=relu, add=add, stride=stride, padding=padding)
 
-    def _ct(self, name, x):
-        w, b = self._p(name + ".weight"), self._p(name + ".bias")
-        return _torch_conv(x, w, b, stride=2, padding=1, transposed=True)
+    def _ct(self, name, x, relu=False):
+        return conv(x, self._p(name + ".weight"), self._p(name + ".bias"), relu=relu, stride=2, padding=1, transposed=True)
 
     def _res(self, prefix, x, second):
         y = self._c("%s.main.0" % prefix, x, padding=1, relu=True)
@@ -348,13 +408,16 @@ class TrainableGenerator(nn.Module):
 
     @staticmethod
     def native_weight(name, param):
-        """True for the convolution weights that run on csrc/train.cu (stride-1 "same" convolutions): everything 4-D except the
-        stride-2 encoders and the transposed convolutions."""
-        if param.dim() != 4 or param.shape[2] != param.shape[3] or param.shape[2] not in (1, 3, 5, 7):
-            return False
-        if any(t in name for t in ("encoders.", "tsf_net_enc.", "decoders.", "upconvs.")):
-            return False
-        return not any(name.endswith("bg_net.main.%d.weight" % i) for i in (3, 6, 9, 18, 21, 24))
+        """(kind, pad) of the convolution a 4-D weight belongs to — which packings the fused Adam pass maintains for it — or None.
+        Mirrors the layer calls below: stride-2 encoders (3x3, pad 1), transposed decoders (4x4, pad 1), everything else stride 1."""
+        if param.dim() != 4 or param.shape[2] != param.shape[3] or not 1 <= param.shape[2] <= 7:
+            return None
+        k = param.shape[2]
+        if any(t in name for t in ("decoders.", "upconvs.")) or any(name.endswith("bg_net.main.%d.weight" % i) for i in (18, 21, 24)):
+            return (CT, 1) if k == 4 else None
+        if any(t in name for t in ("encoders.", "tsf_net_enc.")) or any(name.endswith("bg_net.main.%d.weight" % i) for i in (3, 6, 9)):
+            return (S2, 1) if k in (3, 4) else None
+        return (S1, k // 2) if k % 2 else None
 
     # ---- BGNet (bg_inpaintor.py:24-60) ----
     def forward_bg(self, bg_inputs):
@@ -377,7 +440,7 @@ class TrainableGenerator(nn.Module):
         x = src_inputs.reshape(bs * ns, -1, h, w).to(BF16)
         enc = []
         for i in range(3):
-            x = F.relu(self._c("src_net.encoders.layers.%d.0" % i, x, stride=2, padding=1)).to(BF16); enc.append(x)
+            x = self._c("src_net.encoders.layers.%d.0" % i, x, stride=2, padding=1, relu=True).to(BF16); enc.append(x)
         res = []
         for i in range(self.n_res):
             x = self._res("src_net.res_blocks.%d" % i, x, 2); res.append(x)
@@ -385,7 +448,7 @@ class TrainableGenerator(nn.Module):
             return enc, res
         d = x
         for i in range(3):
-            d = F.relu(self._ct("src_net.decoders.layers.%d.0" % i, d))
+            d = self._ct("src_net.decoders.layers.%d.0" % i, d, relu=True)
         img = torch.tanh(self._c("src_net.img_reg.0", d, padding=2).float()).reshape(bs, ns, 3, h, w)
         mask = torch.sigmoid(self._c("src_net.att_reg.0", d, padding=2).float()).reshape(bs, ns, 1, h, w)
         return enc, res, img, mask
@@ -429,14 +492,14 @@ class TrainableGenerator(nn.Module):
         x = tsf_inputs.to(BF16)
         enc, cache = [], {}
         for i in range(3):
-            x = F.relu(self._c("tsf_net_enc.layers.%d.0" % i, x, stride=2, padding=1)).to(BF16)
+            x = self._c("tsf_net_enc.layers.%d.0" % i, x, stride=2, padding=1, relu=True).to(BF16)
             x = self._att("enc_attlwbs.%d" % i, x, src_enc[i], Tst, cache); enc.append(x)
         for i in range(self.n_res):
             x = self._res("res_blocks.%d" % i, x, 2)
             x = self._att("res_attlwbs.%d" % i, x, src_res[i], Tst, cache)
         d = x
         for i in range(3):
-            d = F.relu(self._ct("tsf_net_dec.upconvs.%d.0" % i, d))
+            d = self._ct("tsf_net_dec.upconvs.%d.0" % i, d, relu=True)
             if i != 2:
                 d = self._c("tsf_net_dec.skippers.%d.0" % i, torch.cat([enc[1 - i], d], dim=1), padding=1, relu=True)
         img = torch.tanh(self._c("tsf_img_reg.0", d, padding=2).float())
@@ -471,22 +534,14 @@ class PatchDiscriminator(nn.Module):
         self.model = nn.Sequential(*seq)
 
     def forward(self, x):
-        """bf16 channels_last with the 6-channel input and the 1-channel output zero-padded to 8 channels: cuDNN has tensor-core
-        engines (forward and both gradients) only for 8-aligned channels; with the true 6 / 1 channels the ends of D fall back to
-        fp32 SIMT kernels that cost more than the rest of D together (measured 4.6 ms of a 39 ms step)."""
+        """The 4x4 convolutions (stride 2 / stride 1, pad 1; the 6-channel input and the 1-channel output zero-padded to 64) on the
+        tcgen05 kernels, InstanceNorm2d + LeakyReLU(0.2) fused (``inorm``)."""
         if not (USE_KERNELS and x.is_cuda):
             return self.model(x)
-        x = F.pad(x.to(BF16), (0, 0, 0, 0, 0, 2)).contiguous(memory_format=CL)
-        convs = [m for m in self.model if isinstance(m, nn.Conv2d)]
         skip = False
         for m in self.model:
             if isinstance(m, nn.Conv2d):
-                w, b = m.weight.to(BF16), m.bias.to(BF16)
-                if m is convs[0]:
-                    w = F.pad(w, (0, 0, 0, 0, 0, 2))
-                if m is convs[-1]:
-                    w, b = F.pad(w, (0, 0, 0, 0, 0, 0, 0, 7)), F.pad(b, (0, 7))
-                x = F.conv2d(x, w.contiguous(memory_format=CL), b, stride=m.stride, padding=m.padding)
+                x = conv(x, m.weight, m.bias, stride=m.stride[0], padding=m.padding[0])
             elif isinstance(m, nn.InstanceNorm2d):
                 x = inorm(x, act=True, slope=0.2, eps=m.eps)         # InstanceNorm2d + the LeakyReLU(0.2) that follows it
                 skip = True
@@ -494,7 +549,11 @@ class PatchDiscriminator(nn.Module):
             elif not skip:
                 x = m(x)
             skip = False
-        return x[:, :1].float()
+        return x.float()
+
+    def native_weight(self):
+        """{parameter: (kind, pad)} for ParamStore."""
+        return {m.weight: (S2 if m.stride[0] == 2 else S1, m.padding[0]) for m in self.model if isinstance(m, nn.Conv2d)}
 
 
 class VGG19Features(nn.Module):
@@ -624,7 +683,7 @@ class ParamStore:
     and get ``_iper_pack`` (the packings) and ``_iper_sink`` (their flat-gradient slice, written directly by the wgrad kernels)."""
     CHUNK = 4096
 
-    def __init__(self, named_params, buckets, native=lambda name, p: False, lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, named_params, buckets, native=lambda name, p: None, lr=1e-4, betas=(0.9, 0.999), eps=1e-8):
         import ctypes
         from ._lib import AdamSeg
         self.b, self.lr, self.betas, self.eps = buckets, lr, betas, eps
@@ -641,9 +700,11 @@ class ParamStore:
             self.p[off:off + p.numel()].copy_(p.detach().reshape(-1))
             p.data = self.p[off:off + p.numel()].view_as(p)
             sg = AdamSeg(offset=off, numel=p.numel(), co=0, ci=0, taps=0, co_pad=0, ci_pad=0, reserved=0, fwd_offset=0, dgrad_offset=-1)
-            if native(name, p):
+            kp = native(name, p)
+            if kp:
                 co, ci, k, _ = p.shape
                 sg.co, sg.ci, sg.taps, sg.co_pad, sg.ci_pad = co, ci, k * k, _pad64(co), _pad64(ci)
+                sg.reserved = kp[0] | (k << 8) | (kp[1] << 16)
                 sg.fwd_offset, sg.dgrad_offset = fwd_total, dg_total
                 fwd_total += sg.co_pad * sg.taps * sg.ci_pad; dg_total += sg.ci_pad * sg.taps * sg.co_pad
                 packed.append((p, sg))
@@ -659,9 +720,9 @@ class ParamStore:
             segs.append(sg)
         self.pack_fwd = torch.zeros(max(fwd_total, 8), dtype=BF16, device=dev)
         self.pack_dgrad = torch.zeros(max(dg_total, 8), dtype=BF16, device=dev)
-        for p, sg in packed:
-            p._iper_pack = (self.pack_fwd[sg.fwd_offset:sg.fwd_offset + sg.co_pad * sg.taps * sg.ci_pad].view(sg.co_pad, -1),
-                            self.pack_dgrad[sg.dgrad_offset:sg.dgrad_offset + sg.ci_pad * sg.taps * sg.co_pad].view(sg.ci_pad, -1))
+        for p, sg in packed:         # flat slices (the kernels take pointers; see pack_weight for the three layouts)
+            size = sg.co_pad * sg.taps * sg.ci_pad
+            p._iper_pack = (self.pack_fwd[sg.fwd_offset:sg.fwd_offset + size], self.pack_dgrad[sg.dgrad_offset:sg.dgrad_offset + size])
         arr = (AdamSeg * len(segs))(*segs)
         self.segs = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
         self.chunks = torch.tensor(chunks, dtype=torch.int32).to(dev)
@@ -702,7 +763,8 @@ class LWGTrainStep:
             self.bk_G = FlatGradBuckets(list(self.G.parameters()))
             self.bk_D = FlatGradBuckets(list(self.D.parameters()), n_buckets=2)
             self.st_G = ParamStore(list(self.G.named_parameters()), self.bk_G, native=TrainableGenerator.native_weight, lr=lr)
-            self.st_D = ParamStore(list(self.D.named_parameters()), self.bk_D, lr=lr)
+            dmap = self.D.native_weight()
+            self.st_D = ParamStore(list(self.D.named_parameters()), self.bk_D, native=lambda n, p: dmap.get(p), lr=lr)
             self.opt_G = self.opt_D = None
         else:
             self.opt_G = torch.optim.Adam(self.G.parameters(), lr=lr, betas=(0.9, 0.999), capturable=self.use_graph)

@@ -44,3 +44,76 @@ def test_flat_grad_buckets_gloo_world2():
     out = mgr.dict()
     mp.spawn(_worker, args=(2, 29541, out), nprocs=2, join=True)
     assert dict(out) == {0: True, 1: True}
+
+
+def _unpack(rows_by_k, rows, taps, cols):
+    return rows_by_k.float().reshape(rows, taps, cols)
+
+
+def _emulate_transposed(x, phases, cout, k, pad):
+    """csrc/train.cu iper_conv_transposed_bf16 in torch: four stride-1 phase convolutions over the input grid, tap offsets
+    ((px + pad - kx) / 2, (py + pad - ky) / 2), weight blocks (rows cout_pad, K = (tap in phase, ci_pad)), interleaved stores."""
+    import torch.nn.functional as F
+    from ipercore_b200.train import _pad64, _phase_taps
+    n, cin, h, w = x.shape
+    cinp, coutp = _pad64(cin), _pad64(cout)
+    out = torch.zeros(n, cout, 2 * h, 2 * w)
+    off = 0
+    for ph, taps in enumerate(_phase_taps(k, pad)):
+        py, px = ph >> 1, ph & 1
+        blk = phases[off:off + coutp * len(taps) * cinp].float().reshape(coutp, len(taps), cinp); off += blk.numel()
+        acc = torch.zeros(n, cout, h, w)
+        for t, (ky, kx) in enumerate(taps):
+            dy, dx = (py + pad - ky) // 2, (px + pad - kx) // 2
+            assert (py + pad - ky) % 2 == 0 and (px + pad - kx) % 2 == 0
+            xs = F.pad(x, (2, 2, 2, 2))[:, :, 2 + dy:2 + dy + h, 2 + dx:2 + dx + w]          # x[y + dy, x + dx], zero outside
+            acc += torch.einsum("nchw,oc->nohw", xs, blk[:cout, t, :cin])
+        out[:, :, py::2, px::2] = acc
+    return out
+
+
+def test_phase_packing_reproduces_transposed_convolutions():
+    """Index algebra of the stride-2 transposition (host side of csrc/train.cu + train.pack_weight): ConvTranspose2d(4,2,1) forward
+    from the CT forward packing, and the data gradients of stride-2 convolutions (k = 3, 4) from the S2 dgrad packing."""
+    import torch.nn.functional as F
+    from ipercore_b200 import train
+    torch.manual_seed(0)
+    bf = lambda t: t.bfloat16().float()
+    x = bf(torch.randn(2, 5, 6, 7))
+    wt = bf(torch.randn(5, 3, 4, 4))                                   # ConvTranspose2d weight (ci, co, k, k)
+    fwd, dg = train.pack_weight(wt, train.CT, 1)
+    assert torch.allclose(_emulate_transposed(x, fwd, 3, 4, 1), F.conv_transpose2d(x, wt, stride=2, padding=1), atol=1e-5)
+    # its data gradient = a stride-2 conv of dY with the plain (ci_T rows, K = (tap, co_T)) packing
+    dy = bf(torch.randn(2, 3, 12, 14))
+    plain = dg.float().reshape(64, 16, 64)[:5, :, :3]                  # (ci_T, tap, co_T)
+    ref = F.conv2d(dy, wt.permute(0, 1, 2, 3), stride=2, padding=1)    # conv with weight (out = ci_T, in = co_T, k, k)
+    assert torch.allclose(ref, F.conv2d(dy, plain.permute(0, 2, 1).reshape(5, 3, 4, 4), stride=2, padding=1), atol=1e-5)
+    xg = x.clone().requires_grad_(True)
+    (gx,) = torch.autograd.grad(F.conv_transpose2d(xg, wt, stride=2, padding=1), xg, dy)
+    assert torch.allclose(gx, ref, atol=1e-4)
+    for k in (3, 4):                                                    # stride-2 conv (co, ci, k, k): dX from the phase packing
+        w = bf(torch.randn(4, 6, k, k))
+        xin = bf(torch.randn(1, 6, 8, 10)).requires_grad_(True)
+        y = F.conv2d(xin, w, stride=2, padding=1)
+        dyy = bf(torch.randn_like(y))
+        (gxin,) = torch.autograd.grad(y, xin, dyy)
+        f2, d2 = train.pack_weight(w, train.S2, 1)
+        assert torch.equal(f2.float().reshape(64, k * k, 64)[:4, :, :6], w.permute(0, 2, 3, 1).reshape(4, k * k, 6))
+        assert torch.allclose(_emulate_transposed(dyy, d2, 6, k, 1), gxin, atol=1e-4), k
+
+
+def test_rev_packing_gives_the_data_gradient_of_non_same_convolutions():
+    """S1 with k = 4, pad 1 (the discriminator's last layers): dX = conv(dY, rev packing, padding k-1-pad)."""
+    import torch.nn.functional as F
+    from ipercore_b200 import train
+    torch.manual_seed(1)
+    bf = lambda t: t.bfloat16().float()
+    for k, pad in ((4, 1), (3, 1), (5, 2), (1, 0)):
+        w = bf(torch.randn(3, 5, k, k))
+        x = bf(torch.randn(1, 5, 9, 11)).requires_grad_(True)
+        y = F.conv2d(x, w, padding=pad)
+        dy = bf(torch.randn_like(y))
+        (gx,) = torch.autograd.grad(y, x, dy)
+        _, rev = train.pack_weight(w, train.S1, pad)
+        wr = rev.float().reshape(64, k * k, 64)[:5, :, :3].permute(0, 2, 1).reshape(5, 3, k, k)
+        assert torch.allclose(F.conv2d(dy, wr, padding=k - 1 - pad), gx, atol=1e-4), (k, pad)

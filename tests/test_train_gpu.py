@@ -8,6 +8,10 @@ import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).abs().max()) / max(float(b.float().abs().max()), 1e-20)
 DEV = "cuda:0"
 CFG = dict(name="AttLWB-SPADE", BGNet=dict(cond_nc=4, n_res_block=6, num_filters=[64, 128, 128, 256]),
            SIDNet=dict(cond_nc=6, n_res_block=6, num_filters=[64, 128, 256]),
@@ -77,6 +81,34 @@ def test_conv_kxk_padded_ends_fused_epilogue(N, ci, co, H, W, k, relu, add):
         assert errs[4] <= 6e-3
 
 
+@pytest.mark.parametrize("mode,N,ci,co,H,W,k", [("s2", 1, 64, 128, 32, 64, 3), ("s2", 2, 6, 64, 48, 64, 3), ("s2", 1, 128, 256, 16, 32, 3),
+                                                ("s2", 1, 6, 64, 32, 64, 4), ("s2", 1, 128, 256, 32, 32, 4),
+                                                ("ct", 1, 256, 128, 16, 16, 4), ("ct", 2, 128, 64, 8, 24, 4), ("ct", 1, 64, 64, 24, 40, 4),
+                                                ("k4", 1, 256, 256, 31, 31, 4), ("k4", 1, 128, 1, 20, 24, 4)])
+def test_strided_transposed_and_non_same_convolutions(mode, N, ci, co, H, W, k):
+    """Stride-2 convolutions (5-D parity view), ConvTranspose2d(4,2,1) (four phase convolutions) and the discriminator's 4x4 stride-1
+    pad-1 layers: forward, data gradient, weight gradient, bias gradient against torch autograd in fp32."""
+    from ipercore_b200 import train
+    g = torch.Generator(device="cpu").manual_seed(ci * 3 + co + H)
+    rnd = lambda *s: torch.randn(*s, generator=g)
+    x = (rnd(N, ci, H, W) * 0.5).to(DEV).bfloat16().float().requires_grad_(True)
+    wshape = (ci, co, k, k) if mode == "ct" else (co, ci, k, k)
+    w = (rnd(*wshape) * (1.0 / np.sqrt(k * k * ci))).to(DEV).bfloat16().float().requires_grad_(True)
+    b = (rnd(co) * 0.1).to(DEV).requires_grad_(True)
+    kw = dict(stride=2, padding=1, transposed=True) if mode == "ct" else dict(stride=2 if mode == "s2" else 1, padding=1)
+    y_ref = F.conv_transpose2d(x, w, b, stride=2, padding=1) if mode == "ct" else F.conv2d(x, w, b, stride=kw["stride"], padding=1)
+    dy = (rnd(*y_ref.shape) * 0.5).to(DEV).bfloat16().float()
+    g_ref = torch.autograd.grad(y_ref, (x, w, b), dy)
+    assert train._kind(x, w, **kw) == {"s2": train.S2, "ct": train.CT, "k4": train.S1}[mode]
+    x2, w2, b2 = (t.detach().clone().requires_grad_(True) for t in (x, w, b))
+    y = train.conv(x2, w2, b2, **kw)
+    assert y.dtype == torch.bfloat16 and y.shape == y_ref.shape
+    g_got = torch.autograd.grad(y, (x2, w2, b2), dy.bfloat16())
+    errs = [_rel(y, y_ref.detach())] + [_rel(a, b_) for a, b_ in zip(g_got, g_ref)]
+    print("%s %dx%d %d->%d %dx%d: rel err y %.2e dx %.2e dw %.2e db %.2e" % ((mode, k, k, ci, co, H, W) + tuple(errs)))
+    assert errs[0] <= 6e-3 and errs[1] <= 6e-3 and errs[2] <= 2e-4 and errs[3] <= 1e-5
+
+
 def test_conv_falls_back_when_not_eligible():
     from ipercore_b200 import train
     x = torch.randn(1, 64, 4, 8, device=DEV).bfloat16()               # map smaller than one 16x8 tile
@@ -84,9 +116,10 @@ def test_conv_falls_back_when_not_eligible():
     assert not train._eligible(x, w)
     y = train.conv(x, w)
     torch.testing.assert_close(y.float(), F.conv2d(x.float(), w.bfloat16().float(), padding=1), atol=5e-2, rtol=5e-2)
-    w4 = torch.randn(64, 64, 4, 4, device=DEV)                        # even kernels (the discriminator's) stay on torch
-    assert not train._eligible(torch.randn(1, 64, 32, 32, device=DEV), w4, 1, 1)
-    assert not train._eligible(torch.randn(1, 64, 32, 32, device=DEV), w, 2, 1)      # strided
+    w4 = torch.randn(64, 64, 4, 4, device=DEV)                        # the discriminator's 4x4 / pad 1: output 15x15 is below one box
+    assert not train._eligible(torch.randn(1, 64, 16, 16, device=DEV), w4, 1, 1)
+    assert not train._eligible(torch.randn(1, 64, 16, 16, device=DEV), w, 2, 1)      # strided: the half-resolution map is below one box
+    assert not train._eligible(torch.randn(1, 64, 32, 32, device=DEV), torch.randn(64, 64, 6, 6, device=DEV), 2, 2)
     frozen = torch.randn(64, 64, 3, 3, device=DEV)
     assert train._eligible(torch.randn(1, 64, 32, 32, device=DEV), frozen)
 
@@ -97,11 +130,14 @@ def test_pack_weight_matches_the_fused_adam_repack_and_adam_matches_torch():
     from ipercore_b200 import train
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Conv2d(6, 64, 3, padding=1), torch.nn.Conv2d(64, 3, 5, padding=2, bias=False),
-                              torch.nn.Conv2d(64, 128, 1), torch.nn.Conv2d(128, 64, 4, 2, 1)).to(DEV)
+                              torch.nn.Conv2d(64, 128, 1), torch.nn.Conv2d(128, 64, 4, 2, 1), torch.nn.ConvTranspose2d(64, 32, 4, 2, 1),
+                              torch.nn.Conv2d(32, 8, 3, 2, 1), torch.nn.Conv2d(8, 8, 2)).to(DEV)
+    kinds = {net[0].weight: (train.S1, 1), net[1].weight: (train.S1, 2), net[2].weight: (train.S1, 0), net[3].weight: (train.S2, 1),
+             net[4].weight: (train.CT, 1), net[5].weight: (train.S2, 1)}
     ref = [p.detach().clone().requires_grad_(True) for p in net.parameters()]
     opt = torch.optim.Adam(ref, lr=1e-3, betas=(0.9, 0.999))
     bk = train.FlatGradBuckets(list(net.parameters()), n_buckets=2)
-    store = train.ParamStore(list(net.named_parameters()), bk, native=lambda n, p: p.dim() == 4 and p.shape[-1] in (1, 3, 5, 7), lr=1e-3)
+    store = train.ParamStore(list(net.named_parameters()), bk, native=lambda n, p: kinds.get(p), lr=1e-3)
     for p, r in zip(net.parameters(), ref):
         assert torch.equal(p.detach(), r.detach())
         assert store.p.data_ptr() <= p.data_ptr() < store.p.data_ptr() + store.p.numel() * 4
@@ -113,75 +149,10 @@ def test_pack_weight_matches_the_fused_adam_repack_and_adam_matches_torch():
         store.step(); opt.step()
         for p, r in zip(net.parameters(), ref):
             assert float((p.detach() - r.detach()).abs().max()) <= 1e-6
-    for m in list(net)[:3]:
-        f, d = train.pack_weight(m.weight)
-        assert torch.equal(m.weight._iper_pack[0], f) and torch.equal(m.weight._iper_pack[1], d)
-    assert not hasattr(net[3].weight, "_iper_pack")
-
-
-def _rel(a, b):
-    return float((a.float() - b.float()).abs().max()) / max(float(b.float().abs().max()), 1e-20)
-
-
-@pytest.mark.parametrize("M,C,h,w", [(2, 64, 32, 48), (4, 256, 16, 16), (1, 128, 40, 24)])
-def test_warp_bf16_forward_backward(M, C, h, w):
-    """LWB.transform on NHWC bf16 vs F.grid_sample in fp32 (flows partly outside [-1, 1] and the -2 background value)."""
-    from ipercore_b200 import train
-    g = torch.Generator().manual_seed(M * 100 + C)
-    src = torch.randn(M, C, h, w, generator=g).to(DEV).bfloat16().float().requires_grad_(True)
-    T = (torch.rand(M, h, w, 2, generator=g) * 2.6 - 1.3).to(DEV)
-    T[:, : h // 4] = -2.0
-    dy = torch.randn(M, C, h, w, generator=g).to(DEV).bfloat16().float()
-    ref = F.grid_sample(src, T, mode="bilinear", padding_mode="zeros", align_corners=False)
-    (gref,) = torch.autograd.grad(ref, src, dy)
-    s2 = src.detach().clone().requires_grad_(True)
-    out = train._Warp.apply(s2, T)
-    (gs,) = torch.autograd.grad(out, s2, dy.bfloat16())
-    print("warp %dx%dx%dx%d: out %.2e dsrc %.2e" % (M, C, h, w, _rel(out, ref), _rel(gs, gref)))
-    assert out.dtype == torch.bfloat16 and _rel(out, ref) <= 5e-3 and _rel(gs, gref) <= 5e-3       # bf16 rounding of the results
-
-
-@pytest.mark.parametrize("bs,ns,C,h,w", [(1, 2, 64, 16, 32), (2, 3, 256, 8, 16), (1, 2, 128, 24, 24)])
-def test_att_combine_forward_backward(bs, ns, C, h, w):
-    from ipercore_b200 import train
-    g = torch.Generator().manual_seed(bs + ns + C)
-    mk = lambda *s: torch.randn(*s, generator=g).to(DEV).bfloat16().float().requires_grad_(True)
-    k, v, q = mk(bs * ns, C, h, w), mk(bs * ns, C, h, w), mk(bs, C, h, w)
-    da = torch.randn(bs, C, h, w, generator=g).to(DEV).bfloat16().float()
-    kk, vv = k.view(bs, ns, C, h, w), v.view(bs, ns, C, h, w)
-    logits = (kk * q.unsqueeze(1)).sum(dim=2, keepdim=True) / np.sqrt(C)
-    ref = (torch.softmax(logits, dim=1) * vv).sum(dim=1)
-    gref = torch.autograd.grad(ref, (k, v, q), da)
-    ins = tuple(t.detach().clone().requires_grad_(True) for t in (k, v, q))
-    a = train._AttCombine.apply(*ins, ns)
-    got = torch.autograd.grad(a, ins, da.bfloat16())
-    errs = [_rel(a, ref)] + [_rel(x, y) for x, y in zip(got, gref)]
-    print("att_combine bs %d ns %d C %d: a %.2e dk %.2e dv %.2e dq %.2e" % ((bs, ns, C) + tuple(errs)))
-    assert max(errs) <= 6e-3
-
-
-@pytest.mark.parametrize("N,C,h,w,spade,act,slope", [(2, 64, 32, 32, True, False, 0.0), (1, 256, 16, 24, True, False, 0.0),
-                                                     (2, 128, 16, 16, False, True, 0.0), (1, 512, 12, 12, False, True, 0.2),
-                                                     (1, 64, 40, 40, False, False, 0.0)])
-def test_norm_spade_forward_backward(N, C, h, w, spade, act, slope):
-    from ipercore_b200 import train
-    g = torch.Generator().manual_seed(N + C + h)
-    mk = lambda sc=1.0: (torch.randn(N, C, h, w, generator=g) * sc + 0.3).to(DEV).bfloat16().float().requires_grad_(True)
-    x, gm, bt = mk(2.0), mk(0.5), mk(0.5)
-    dy = torch.randn(N, C, h, w, generator=g).to(DEV).bfloat16().float()
-    ref = F.instance_norm(x, eps=1e-5)
-    if spade:
-        ref = ref * (1 + gm) + bt
-    if act:
-        ref = F.leaky_relu(ref, slope) if slope else F.relu(ref)
-    ins = (x, gm, bt) if spade else (x,)
-    gref = torch.autograd.grad(ref, ins, dy)
-    ins2 = tuple(t.detach().clone().requires_grad_(True) for t in ins)
-    y = train.inorm(ins2[0], act=act, slope=slope, gamma=ins2[1] if spade else None, beta=ins2[2] if spade else None)
-    got = torch.autograd.grad(y, ins2, dy.bfloat16())
-    errs = [_rel(y, ref)] + [_rel(a, b) for a, b in zip(got, gref)]
-    print("norm N %d C %d %dx%d spade %d act %d: %s" % (N, C, h, w, spade, act, " ".join("%.2e" % e for e in errs)))
-    assert y.dtype == torch.bfloat16 and max(errs) <= 8e-3          # bf16 stores; the activation mask is taken from the bf16 output
+    for m in list(net)[:6]:                      # the kernel's repacking after the last update == the torch formulation, all three kinds
+        f, d = train.pack_weight(m.weight, *kinds[m.weight])
+        assert torch.equal(m.weight._iper_pack[0], f.reshape(-1)) and torch.equal(m.weight._iper_pack[1], d.reshape(-1)), m
+    assert not hasattr(net[6].weight, "_iper_pack")
 
 
 def _batch(S, seed=0):
