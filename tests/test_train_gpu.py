@@ -155,6 +155,67 @@ def test_pack_weight_matches_the_fused_adam_repack_and_adam_matches_torch():
     assert not hasattr(net[6].weight, "_iper_pack")
 
 
+@pytest.mark.parametrize("M,C,h,w", [(2, 64, 32, 48), (4, 256, 16, 16), (1, 128, 40, 24)])
+def test_warp_bf16_forward_backward(M, C, h, w):
+    """LWB.transform on NHWC bf16 vs F.grid_sample in fp32 (flows partly outside [-1, 1] and the -2 background value)."""
+    from ipercore_b200 import train
+    g = torch.Generator().manual_seed(M * 100 + C)
+    src = torch.randn(M, C, h, w, generator=g).to(DEV).bfloat16().float().requires_grad_(True)
+    T = (torch.rand(M, h, w, 2, generator=g) * 2.6 - 1.3).to(DEV)
+    T[:, : h // 4] = -2.0
+    dy = torch.randn(M, C, h, w, generator=g).to(DEV).bfloat16().float()
+    ref = F.grid_sample(src, T, mode="bilinear", padding_mode="zeros", align_corners=False)
+    (gref,) = torch.autograd.grad(ref, src, dy)
+    s2 = src.detach().clone().requires_grad_(True)
+    out = train._Warp.apply(s2, T)
+    (gs,) = torch.autograd.grad(out, s2, dy.bfloat16())
+    print("warp %dx%dx%dx%d: out %.2e dsrc %.2e" % (M, C, h, w, _rel(out, ref), _rel(gs, gref)))
+    assert out.dtype == torch.bfloat16 and _rel(out, ref) <= 5e-3 and _rel(gs, gref) <= 5e-3       # bf16 rounding of the results
+
+
+@pytest.mark.parametrize("bs,ns,C,h,w", [(1, 2, 64, 16, 32), (2, 3, 256, 8, 16), (1, 2, 128, 24, 24)])
+def test_att_combine_forward_backward(bs, ns, C, h, w):
+    from ipercore_b200 import train
+    g = torch.Generator().manual_seed(bs + ns + C)
+    mk = lambda *s: torch.randn(*s, generator=g).to(DEV).bfloat16().float().requires_grad_(True)
+    k, v, q = mk(bs * ns, C, h, w), mk(bs * ns, C, h, w), mk(bs, C, h, w)
+    da = torch.randn(bs, C, h, w, generator=g).to(DEV).bfloat16().float()
+    kk, vv = k.view(bs, ns, C, h, w), v.view(bs, ns, C, h, w)
+    logits = (kk * q.unsqueeze(1)).sum(dim=2, keepdim=True) / np.sqrt(C)
+    ref = (torch.softmax(logits, dim=1) * vv).sum(dim=1)
+    gref = torch.autograd.grad(ref, (k, v, q), da)
+    ins = tuple(t.detach().clone().requires_grad_(True) for t in (k, v, q))
+    a = train._AttCombine.apply(*ins, ns)
+    got = torch.autograd.grad(a, ins, da.bfloat16())
+    errs = [_rel(a, ref)] + [_rel(x, y) for x, y in zip(got, gref)]
+    print("att_combine bs %d ns %d C %d: a %.2e dk %.2e dv %.2e dq %.2e" % ((bs, ns, C) + tuple(errs)))
+    assert max(errs) <= 6e-3
+
+
+@pytest.mark.parametrize("N,C,h,w,spade,act,slope", [(2, 64, 32, 32, True, False, 0.0), (1, 256, 16, 24, True, False, 0.0),
+                                                     (2, 128, 16, 16, False, True, 0.0), (1, 512, 12, 12, False, True, 0.2),
+                                                     (1, 64, 40, 40, False, False, 0.0)])
+def test_norm_spade_forward_backward(N, C, h, w, spade, act, slope):
+    from ipercore_b200 import train
+    g = torch.Generator().manual_seed(N + C + h)
+    mk = lambda sc=1.0: (torch.randn(N, C, h, w, generator=g) * sc + 0.3).to(DEV).bfloat16().float().requires_grad_(True)
+    x, gm, bt = mk(2.0), mk(0.5), mk(0.5)
+    dy = torch.randn(N, C, h, w, generator=g).to(DEV).bfloat16().float()
+    ref = F.instance_norm(x, eps=1e-5)
+    if spade:
+        ref = ref * (1 + gm) + bt
+    if act:
+        ref = F.leaky_relu(ref, slope) if slope else F.relu(ref)
+    ins = (x, gm, bt) if spade else (x,)
+    gref = torch.autograd.grad(ref, ins, dy)
+    ins2 = tuple(t.detach().clone().requires_grad_(True) for t in ins)
+    y = train.inorm(ins2[0], act=act, slope=slope, gamma=ins2[1] if spade else None, beta=ins2[2] if spade else None)
+    got = torch.autograd.grad(y, ins2, dy.bfloat16())
+    errs = [_rel(y, ref)] + [_rel(a, b) for a, b in zip(got, gref)]
+    print("norm N %d C %d %dx%d spade %d act %d: %s" % (N, C, h, w, spade, act, " ".join("%.2e" % e for e in errs)))
+    assert y.dtype == torch.bfloat16 and max(errs) <= 8e-3          # bf16 stores; the activation mask is taken from the bf16 output
+
+
 def _batch(S, seed=0):
     g = torch.Generator().manual_seed(seed)
     r = lambda *s: (torch.rand(*s, generator=g) * 2 - 1).to(DEV)
