@@ -316,8 +316,8 @@ def run_train(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "LWG training step %dx%d: G (AttLWB-SPADE) + D (patch_global) + VGG19 perceptual, batch 1 per GPU, "
                                        "ns=%d, nt=1 (BASELINE.json configs[4])" % (S, S, ns),
-                           "kernels": "every stride-1 convolution of G and VGG19 (1x1, 3x3, 5x5, 7x7: fwd, dgrad, wgrad, bias grad) on tcgen05 bf16, "
-                                      "fused Adam + weight repack; strided / transposed convs, D, norms, warp, losses are PyTorch",
+                           "kernels": "every convolution of G, D and VGG19 (stride 1 / 2 / transposed: fwd, dgrad, wgrad, bias grad) on tcgen05 bf16, "
+                                      "warp, attention combine, instance norm / SPADE fwd + bwd, fused Adam + weight repack; pooling and losses are ATen",
                            "cuda_graph": not args.no_graph,
                            "allreduce": "bucketed flat NCCL all-reduce of %d G + %d D gradients, overlapped with backward" % (n_g, n_d)},
                 "gpu_launches": int(args.steps * step.launches_per_step) if step._graph is not None else int(_lib.launch_count() - n0),

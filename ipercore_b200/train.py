@@ -2,18 +2,18 @@
 perceptual, bf16, NCCL gradient all-reduce) — see DESIGN.md §8b for what is and is not on hand-written kernels.
 
 On the kernels of csrc/train.cu / csrc/train_ops.cu (everything NHWC bf16 = torch channels_last, no layout conversions):
-  * every stride-1 "same" convolution of the generator and of VGG19 — 1x1 (fq / fk / fv), 3x3 (ResidualBlocks, SPADE, skip
-    convs, BGNet, VGG), 5x5 (heads), 7x7 (BGNet ends), the 1/3/4/6-channel ends zero-padded to 64 — forward with fused bias /
-    residual / ReLU, data gradient, weight gradient (MN-major tcgen05 operands straight from NHWC) and bias gradient, the last
-    two accumulated straight into the flat fp32 gradient buffer the all-reduce and the optimizer work on (``_Conv``);
+  * every convolution of the generator, the discriminator and VGG19 — stride 1 (1x1 fq / fk / fv, 3x3, 5x5 heads, 7x7 BGNet
+    ends, D's 4x4 pad-1 layers), stride 2 (encoders, D) and ConvTranspose2d(4, 2, 1) (decoders), the 1/3/4/6-channel ends
+    zero-padded to 64 — forward with fused bias / residual / ReLU, data gradient, weight gradient (MN-major tcgen05 operands
+    straight from NHWC) and bias gradient, the last two accumulated straight into the flat fp32 gradient buffer the all-reduce
+    and the optimizer work on (``_Conv``);
   * LWB.transform (grid_sample) and its gradient (``_Warp``), the softmax over sources + weighted sum of SelfAttentionLWB
     (``_AttCombine``), InstanceNorm / SPADE modulation / ReLU / LeakyReLU with their backward (``_Norm``);
   * Adam for G and D as one pass each over flat fp32 parameter / moment buffers that also rewrites the bf16 forward and dgrad
     packings of every convolution weight (``ParamStore``);
   * the whole step (forward, both backward passes, bucketed NCCL all-reduces, both optimizer passes) replayed as ONE CUDA graph
-    (``LWGTrainStep(graph=True)``): at batch 1 the step is ~1650 launches of 5-50 us each.
-Still PyTorch (bf16 channels_last cuDNN / ATen): the stride-2 encoder convolutions and the transposed convolutions (12 + 9
-layers), the discriminator's 4x4 convolutions, max-pooling, tanh / sigmoid, the loss reductions.
+    (``LWGTrainStep(graph=True)``): at batch 1 the step is ~1370 launches of 5-50 us each.
+Still ATen: channel-padding copies of the tiny ends, max-pooling, tanh / sigmoid, the loss reductions.
 
 Mirrors ``LWGTrainer`` (iPERCore/tools/trainers/lwg_trainer.py: forward :699-731, optimize_G :733-795, optimize_D :797-834,
 optimize_parameters :326-352) with the generator's training-shape forward
