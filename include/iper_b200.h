@@ -366,6 +366,10 @@ int iper_adam_pack(float* params, const float* grads, float* exp_avg, float* exp
  *   iper_norm_bwd_bf16         dx [, dgamma, dbeta] from dout (y = the saved output, needed when act != 0); sums_ws (N,C,2) double
  * C %% 8 == 0 everywhere; the norm kernels need C/8 to divide 256 (C = 64, 128, 256, 512).
  * ---------------------------------------------------------------------------------------------------------- */
+/* (N,C,H,W) fp32 (is_bf16 = 0) or bf16 with arbitrary element strides -> dense NHWC bf16, channels zero-padded to Cpad (multiple of 8):
+ * the cast + pad + channels_last copy of the 1/3/4/6-channel ends of the training step in one pass. */
+int iper_pad_nhwc_bf16(const void* x, int is_bf16, int N, int C, int H, int W, long long stride_n, long long stride_c, long long stride_h,
+                       long long stride_w, int Cpad, void* out_nhwc, iper_stream_t stream);
 int iper_warp_bf16(const void* src_nhwc, const float* T, int M, int h, int w, int C, void* out_nhwc, iper_stream_t stream);
 int iper_warp_bwd_bf16(const void* dout_nhwc, const float* T, int M, int h, int w, int C, float* dsrc_f32, iper_stream_t stream);
 int iper_att_combine_bf16(const void* k, const void* v, const void* q, int bs, int ns, long long HW, int C, void* a, float* alpha,

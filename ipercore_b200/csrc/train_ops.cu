@@ -305,6 +305,32 @@ __global__ void __launch_bounds__(256) norm_bwd_kernel(const __nv_bfloat16* __re
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// (N, C, H, W) fp32 | bf16 with ANY element strides -> dense NHWC bf16 with the channels zero-padded to Cpad (a multiple of 8):
+// the cast + F.pad + channels_last copy of the 1/3/4/6-channel ends of the step in one pass (16-byte stores)
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) pad_nhwc_kernel(const T* __restrict__ x, int N, int C, int H, int W, long long sn, long long sc,
+                                                       long long sh, long long sw, int Cpad, __nv_bfloat16* __restrict__ out) {
+    const int groups = Cpad / 8;
+    const long long total = (long long)N * H * W * groups;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cg = (int)(i % groups);
+        const long long pix = i / groups;
+        Vec8 v;
+#pragma unroll
+        for (int c = 0; c < 8; c++) v.v[c] = 0.f;
+        if (cg * 8 < C) {
+            const int xw = (int)(pix % W), yh = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+            const T* src = x + n * sn + yh * sh + xw * sw;
+#pragma unroll
+            for (int c = 0; c < 8; c++)
+                if (cg * 8 + c < C) v.v[c] = (float)src[(long long)(cg * 8 + c) * sc];
+        }
+        st8(out + pix * Cpad + cg * 8, v);
+    }
+}
+
 static int grid_for(long long work_items, int per_block) {
     long long b = (work_items + per_block - 1) / per_block;
     if (b > 148 * 8) b = 148 * 8;
@@ -409,6 +435,22 @@ extern "C" int iper_norm_bwd_bf16(const void* dout, const void* x, const void* y
     auto Bm = [](void* p) { return reinterpret_cast<__nv_bfloat16*>(p); };
     norm_bwd_kernel<0><<<grid, 256, 0, st>>>(B(dout), B(x), B(y), B(gamma), stats, sums_ws, HW, C, eps, act, slope, Bm(dgamma), Bm(dbeta), nullptr);
     norm_bwd_kernel<1><<<grid, 256, 0, st>>>(B(dout), B(x), B(y), B(gamma), stats, sums_ws, HW, C, eps, act, slope, nullptr, nullptr, Bm(dx));
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int iper_pad_nhwc_bf16(const void* x, int is_bf16, int N, int C, int H, int W, long long stride_n, long long stride_c,
+                                  long long stride_h, long long stride_w, int Cpad, void* out_nhwc, iper_stream_t stream) {
+    IPER_REQUIRE(x && out_nhwc && IPER_A16(out_nhwc) && N > 0 && C > 0 && H > 0 && W > 0 && Cpad >= C && Cpad % 8 == 0,
+                 "iper_pad_nhwc_bf16: null / unaligned pointer or Cpad %d not a multiple of 8 >= C %d", Cpad, C);
+    const long long total = (long long)N * H * W * (Cpad / 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (is_bf16)
+        pad_nhwc_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x), N, C, H, W, stride_n, stride_c,
+                                                                            stride_h, stride_w, Cpad, reinterpret_cast<__nv_bfloat16*>(out_nhwc));
+    else
+        pad_nhwc_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const float*>(x), N, C, H, W, stride_n, stride_c, stride_h,
+                                                                    stride_w, Cpad, reinterpret_cast<__nv_bfloat16*>(out_nhwc));
     IPER_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -122,8 +122,28 @@ def _packs(weight, kind, pad):
     return pk
 
 
+class _PadCL(torch.autograd.Function):
+    """(N,C,H,W) fp32 | bf16, any strides -> bf16 channels_last with the channels zero-padded to cpad, in one kernel (instead of a
+    cast, an F.pad and a layout copy: 45 us each on a 512x512 map).  Backward = the slice of the first C channels."""
+
+    @staticmethod
+    def forward(ctx, x, cpad):
+        n, c, h, w = x.shape
+        out = torch.empty((n, cpad, h, w), dtype=BF16, device=x.device, memory_format=CL)
+        sn, sc, sh, sw = x.stride()
+        check(lib.iper_pad_nhwc_bf16(x.data_ptr(), int(x.dtype == BF16), n, c, h, w, sn, sc, sh, sw, cpad, out.data_ptr(), _stream()), "pad_nhwc_bf16")
+        ctx.c, ctx.dt = c, x.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g[:, :ctx.c].to(ctx.dt), None
+
+
 def _to_cl(x, cpad):
     """-> bf16 channels_last with the channel count zero-padded to cpad."""
+    if x.shape[1] != cpad and USE_KERNELS and x.is_cuda and x.dtype in (BF16, torch.float32):
+        return _PadCL.apply(x, cpad)
     x = x.to(BF16)
     if x.shape[1] != cpad:
         x = F.pad(x, (0, 0, 0, 0, 0, cpad - x.shape[1]))
@@ -842,7 +862,11 @@ class LWGTrainStep:
         tsf_cond = b["tsf_inputs"][:, :, -3:].reshape(bs * nt, 3, h, w)
         f_tsf = fake_tsf.reshape(bs * nt, 3, h, w)
         r_tsf = b["real_tsf"].reshape(bs * nt, 3, h, w)
-        d_fake = self.D(torch.cat([f_tsf, tsf_cond], dim=1))       # D runs in fp32/TF32: its ends have 6 and 1 channels (see _torch_conv)
+        for p in self.D.parameters():         # the adversarial term back-propagates THROUGH D: no gradients for D's own parameters
+            p.requires_grad_(False)
+        d_fake = self.D(torch.cat([f_tsf, tsf_cond], dim=1))
+        for p in self.D.parameters():
+            p.requires_grad_(True)
         l_adv = lsgan(d_fake, 0.0) * self.lam["adv"]
         l_rec = (F.l1_loss(fake_src, b["real_src"]) + F.l1_loss(fake_bg.reshape(-1, 3, h, w), b["real_bg"])) / 2 * self.lam["rec"]
         l_tsf = vgg_loss(self.vgg, f_tsf, r_tsf) * self.lam["tsf"]

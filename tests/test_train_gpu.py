@@ -109,6 +109,23 @@ def test_strided_transposed_and_non_same_convolutions(mode, N, ci, co, H, W, k):
     assert errs[0] <= 6e-3 and errs[1] <= 6e-3 and errs[2] <= 2e-4 and errs[3] <= 1e-5
 
 
+def test_pad_to_channels_last_kernel():
+    """The fused cast + zero-pad + channels_last copy of the tiny-channel ends: fp32 NCHW input, a bf16 channel slice of a
+    channels_last tensor (the layout autograd hands the heads' gradients back in), and its backward."""
+    from ipercore_b200 import train
+    x = torch.randn(2, 6, 24, 40, device=DEV, requires_grad=True)
+    y = train._to_cl(x, 64)
+    ref = F.pad(x.detach().bfloat16(), (0, 0, 0, 0, 0, 58))
+    assert y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=torch.channels_last) and torch.equal(y, ref)
+    g = torch.randn_like(y)
+    (gx,) = torch.autograd.grad(y, x, g)
+    assert gx.dtype == torch.float32 and torch.equal(gx, g[:, :6].float())
+    big = torch.randn(1, 64, 16, 32, device=DEV).bfloat16().contiguous(memory_format=torch.channels_last)
+    sl = big[:, 5:8]                                                   # strided view: 3 of 64 channels
+    assert torch.equal(train._to_cl(sl, 64), F.pad(sl, (0, 0, 0, 0, 0, 61)))
+    assert torch.equal(train._to_cl(big, 64), big)                    # nothing to pad: no copy semantics change
+
+
 def test_conv_falls_back_when_not_eligible():
     from ipercore_b200 import train
     x = torch.randn(1, 64, 4, 8, device=DEV).bfloat16()               # map smaller than one 16x8 tile
