@@ -37,14 +37,60 @@ CL = torch.channels_last
 
 USE_KERNELS = True          # tests flip this to compare against the all-torch formulation
 USE_STREAMS = True          # weight / bias gradients on a side stream, parallel to the data gradient
-_SIDE = {}
+USE_BRANCHES = True         # independent sub-networks (BGNet, VGG of the target) on their own streams = parallel branches of the graph
+_SIDE, _BRANCH = {}, {}
 
 
 def _side_stream(device):
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    """The side stream paired with the CURRENT stream (each branch of the step has its own)."""
+    dev = torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(dev).cuda_stream)
     if key not in _SIDE:
-        _SIDE[key] = torch.cuda.Stream(device=device)
+        _SIDE[key] = torch.cuda.Stream(device=dev)
     return _SIDE[key]
+
+
+def _branch_stream(device, idx):
+    dev = torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), idx)
+    if key not in _BRANCH:
+        _BRANCH[key] = torch.cuda.Stream(device=dev)
+    return _BRANCH[key]
+
+
+def _all_streams(device):
+    dev = torch.device(device)
+    d = dev.index if dev.index is not None else torch.cuda.current_device()
+    return [s for (k, _), s in list(_SIDE.items()) + list(_BRANCH.items()) if k == d]
+
+
+class _Branch:
+    """``with _Branch(device, idx) as b: y = f(x)`` runs f on branch stream idx, forked from the current stream; ``b.join(y...)`` makes
+    the current stream wait for it (autograd replays the backward of those ops on the same stream, i.e. in parallel too)."""
+
+    def __init__(self, device, idx):
+        self.on = bool(USE_BRANCHES and USE_KERNELS and torch.device(device).type == "cuda")
+        self.main = torch.cuda.current_stream(device) if self.on else None
+        self.s = _branch_stream(device, idx) if self.on else None
+        self.ctx = None
+
+    def __enter__(self):
+        if self.on:
+            self.s.wait_stream(self.main)
+            self.ctx = torch.cuda.stream(self.s)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.on:
+            self.ctx.__exit__(*exc)
+        return False
+
+    def join(self, *tensors):
+        if self.on:
+            self.main.wait_stream(self.s)
+            for t in tensors:
+                t.record_stream(self.main)
 
 
 def _pad64(c):
@@ -528,12 +574,14 @@ class TrainableGenerator(nn.Module):
 
     def forward(self, bg_inputs, src_inputs, tsf_inputs, Tst):
         """-> bg_img (bs,.,3,h,w), src_imgs (bs,ns,3,h,w), src_masks (bs,ns,1,h,w), tsf_imgs (bs,nt,3,h,w), tsf_masks (bs,nt,1,h,w)."""
-        bg_img = self.forward_bg(bg_inputs)
+        with _Branch(bg_inputs.device, 1) as br:          # BGNet does not depend on SIDNet / TSFNet: its own branch, forward and backward
+            bg_img = self.forward_bg(bg_inputs)
         enc, res, src_imgs, src_masks = self.forward_src(src_inputs, only_enc=False)
         imgs, masks = [], []
         for t in range(tsf_inputs.shape[1]):
             i, m = self.forward_tsf(tsf_inputs[:, t], enc, res, Tst[:, t].contiguous())
             imgs.append(i); masks.append(m)
+        br.join(bg_img)
         return bg_img, src_imgs, src_masks, torch.stack(imgs, 1), torch.stack(masks, 1)
 
 
@@ -605,10 +653,16 @@ class VGG19Features(nn.Module):
         return outs
 
 
-def vgg_loss(vgg, x, y, weights=(1 / 32, 1 / 16, 1 / 8, 1 / 4, 1.0)):
-    fx = vgg(x.to(BF16))
+def vgg_target(vgg, y):
+    """VGG features of the real image: no gradient, depends only on the batch -> computed on its own branch at the top of the step."""
     with torch.no_grad():
-        fy = vgg(y.to(BF16))
+        return vgg(y.to(BF16))
+
+
+def vgg_loss(vgg, x, y, weights=(1 / 32, 1 / 16, 1 / 8, 1 / 4, 1.0), fy=None):
+    fx = vgg(x.to(BF16))
+    if fy is None:
+        fy = vgg_target(vgg, y)
     return sum(w * F.l1_loss(a.float(), b.float().detach()) for w, a, b in zip(weights, fx, fy))
 
 
@@ -662,6 +716,11 @@ class FlatGradBuckets:
                 return
             self.count[bi] += 1
             if self.count[bi] == self.pending[bi] and self.world > 1:
+                if self.storage.is_cuda:                    # gradients of this bucket may have been produced on other branches
+                    cur = torch.cuda.current_stream(self.storage.device)
+                    for s_ in _all_streams(self.storage.device):
+                        if s_ != cur:
+                            cur.wait_stream(s_)
                 self.handles.append(self.dist.all_reduce(self.flat[bi], op=self.dist.ReduceOp.SUM, group=self.group, async_op=True))
         return fn
 
@@ -852,6 +911,9 @@ class LWGTrainStep:
         st_G, st_D = (self.st_G, self.st_D) if self.fused else (None, None)
         for p in self.G.parameters():
             p._iper_uses = 0                  # forward uses of a weight still waiting for their backward (see _Conv)
+        r_tsf = b["real_tsf"].reshape(bs * nt, 3, h, w)
+        with _Branch(self.dev, 2) as br_vgg:
+            fy = vgg_target(self.vgg, r_tsf) if trainable else None
         # ---- forward (lwg_trainer.py:699-731) ----
         with torch.set_grad_enabled(bool(trainable)):
             fake_bg, src_color, src_mask, tsf_color, tsf_mask = self.G(b["bg_inputs"], b["src_inputs"], b["tsf_inputs"], b["Tst"])
@@ -861,7 +923,6 @@ class LWGTrainStep:
         # ---- G step (optimize_G :733-795) ----
         tsf_cond = b["tsf_inputs"][:, :, -3:].reshape(bs * nt, 3, h, w)
         f_tsf = fake_tsf.reshape(bs * nt, 3, h, w)
-        r_tsf = b["real_tsf"].reshape(bs * nt, 3, h, w)
         for p in self.D.parameters():         # the adversarial term back-propagates THROUGH D: no gradients for D's own parameters
             p.requires_grad_(False)
         d_fake = self.D(torch.cat([f_tsf, tsf_cond], dim=1))
@@ -869,7 +930,8 @@ class LWGTrainStep:
             p.requires_grad_(True)
         l_adv = lsgan(d_fake, 0.0) * self.lam["adv"]
         l_rec = (F.l1_loss(fake_src, b["real_src"]) + F.l1_loss(fake_bg.reshape(-1, 3, h, w), b["real_bg"])) / 2 * self.lam["rec"]
-        l_tsf = vgg_loss(self.vgg, f_tsf, r_tsf) * self.lam["tsf"]
+        br_vgg.join(*(fy or ()))
+        l_tsf = vgg_loss(self.vgg, f_tsf, r_tsf, fy=fy) * self.lam["tsf"]
         fm = fake_masks.reshape(bs * (ns + nt), 1, h, w)
         l_mask = F.l1_loss(fm, b["body_mask"].reshape(bs * (ns + nt), 1, h, w)) * self.lam["mask"]
         l_smooth = tv_loss(fm) * self.lam["smooth"]
