@@ -512,11 +512,15 @@ class TrainableGenerator(nn.Module):
             x = self._res("src_net.res_blocks.%d" % i, x, 2); res.append(x)
         if only_enc:
             return enc, res
-        d = x
-        for i in range(3):
-            d = self._ct("src_net.decoders.layers.%d.0" % i, d, relu=True)
-        img = torch.tanh(self._c("src_net.img_reg.0", d, padding=2).float()).reshape(bs, ns, 3, h, w)
-        mask = torch.sigmoid(self._c("src_net.att_reg.0", d, padding=2).float()).reshape(bs, ns, 1, h, w)
+        # the source decoder + heads only feed the reconstruction loss: TSFNet needs enc / res alone, so they run as a branch
+        # parallel to forward_tsf (joined by the caller through self._src_branch)
+        with _Branch(x.device, 3) as br:
+            d = x
+            for i in range(3):
+                d = self._ct("src_net.decoders.layers.%d.0" % i, d, relu=True)
+            img = torch.tanh(self._c("src_net.img_reg.0", d, padding=2).float()).reshape(bs, ns, 3, h, w)
+            mask = torch.sigmoid(self._c("src_net.att_reg.0", d, padding=2).float()).reshape(bs, ns, 1, h, w)
+        self._src_branch = (br, img, mask)
         return enc, res, img, mask
 
     # ---- SelfAttentionLWB (attlwb_spade_resunet.py:208-252) ----
@@ -582,6 +586,8 @@ class TrainableGenerator(nn.Module):
             i, m = self.forward_tsf(tsf_inputs[:, t], enc, res, Tst[:, t].contiguous())
             imgs.append(i); masks.append(m)
         br.join(bg_img)
+        sb, self._src_branch = self._src_branch, None
+        sb[0].join(sb[1], sb[2])
         return bg_img, src_imgs, src_masks, torch.stack(imgs, 1), torch.stack(masks, 1)
 
 
@@ -947,7 +953,9 @@ class LWGTrainStep:
         # ---- D step (optimize_D :797-834) ----
         real_in = torch.cat([r_tsf, tsf_cond], dim=1)
         fake_in = torch.cat([f_tsf.detach(), tsf_cond], dim=1)
-        loss_D = lsgan(self.D(real_in), 1.0) + lsgan(self.D(fake_in), -1.0)
+        d_out = self.D(torch.cat([real_in, fake_in], dim=0))      # one pass over both (instance norm is per sample: same result)
+        nb = real_in.shape[0]
+        loss_D = lsgan(d_out[:nb], 1.0) + lsgan(d_out[nb:], -1.0)
         self._zero(self.opt_D, self.bk_D)
         loss_D.backward()
         self._update(self.opt_D, self.bk_D, st_D)
