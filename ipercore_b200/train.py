@@ -47,7 +47,7 @@ def _side_stream(device):
     key = (dev.index if dev.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(dev).cuda_stream)
     if key not in _SIDE:
         _SIDE[key] = torch.cuda.Stream(device=dev)
-    return _SIDE[key]
+    return _note(_SIDE[key])
 
 
 def _branch_stream(device, idx):
@@ -55,13 +55,22 @@ def _branch_stream(device, idx):
     key = (dev.index if dev.index is not None else torch.cuda.current_device(), idx)
     if key not in _BRANCH:
         _BRANCH[key] = torch.cuda.Stream(device=dev)
-    return _BRANCH[key]
+    return _note(_BRANCH[key])
+
+
+_USED = []          # streams the CURRENT step has forked work onto (cleared at the top of every step; inside a capture they are all capturing)
+
+
+def _note(stream):
+    if all(stream != s for s in _USED):
+        _USED.append(stream)
+    return stream
 
 
 def _all_streams(device):
     dev = torch.device(device)
     d = dev.index if dev.index is not None else torch.cuda.current_device()
-    return [s for (k, _), s in list(_SIDE.items()) + list(_BRANCH.items()) if k == d]
+    return [s for s in _USED if s.device.index == d]
 
 
 class _Branch:
@@ -917,6 +926,7 @@ class LWGTrainStep:
         st_G, st_D = (self.st_G, self.st_D) if self.fused else (None, None)
         for p in self.G.parameters():
             p._iper_uses = 0                  # forward uses of a weight still waiting for their backward (see _Conv)
+        _USED.clear()
         r_tsf = b["real_tsf"].reshape(bs * nt, 3, h, w)
         with _Branch(self.dev, 2) as br_vgg:
             fy = vgg_target(self.vgg, r_tsf) if trainable else None
