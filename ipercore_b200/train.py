@@ -12,7 +12,8 @@ On the kernels of csrc/train.cu / csrc/train_ops.cu (everything NHWC bf16 = torc
   * Adam for G and D as one pass each over flat fp32 parameter / moment buffers that also rewrites the bf16 forward and dgrad
     packings of every convolution weight (``ParamStore``);
   * the whole step (forward, both backward passes, bucketed NCCL all-reduces, both optimizer passes) replayed as ONE CUDA graph
-    (``LWGTrainStep(graph=True)``): at batch 1 the step is ~1370 launches of 5-50 us each.
+    (``LWGTrainStep(graph=True)``): at batch 1 the step is ~1370 launches of 5-50 us each, so the graph is made wide — weight /
+    bias gradients on a side stream next to the data gradient, BGNet / the VGG target features / the source decoder as branches.
 Still ATen: channel-padding copies of the tiny ends, max-pooling, tanh / sigmoid, the loss reductions.
 
 Mirrors ``LWGTrainer`` (iPERCore/tools/trainers/lwg_trainer.py: forward :699-731, optimize_G :733-795, optimize_D :797-834,
