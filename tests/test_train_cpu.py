@@ -117,3 +117,29 @@ def test_rev_packing_gives_the_data_gradient_of_non_same_convolutions():
         _, rev = train.pack_weight(w, train.S1, pad)
         wr = rev.float().reshape(64, k * k, 64)[:5, :, :3].permute(0, 2, 1).reshape(5, 3, k, k)
         assert torch.allclose(F.conv2d(dy, wr, padding=k - 1 - pad), gx, atol=1e-4), (k, pad)
+
+
+def test_native_weight_classification_covers_every_convolution_of_the_generator():
+    """ParamStore keeps one forward + one dgrad packing per convolution weight; which layouts depends on how the layer is CALLED
+    (TrainableGenerator.native_weight mirrors the layer code): 9 stride-2 encoder convs, 9 transposed decoder convs, the rest
+    stride 1 with 'same' padding — and no 4-D parameter of the 221-tensor checkpoint is left unclassified."""
+    from ipercore_b200 import train
+    from ipercore_b200.generator import AttentionLWBGenerator
+    cfg = dict(name="AttLWB-SPADE", BGNet=dict(cond_nc=4, n_res_block=6, num_filters=[64, 128, 128, 256]),
+               SIDNet=dict(cond_nc=6, n_res_block=6, num_filters=[64, 128, 256]),
+               TSFNet=dict(cond_nc=6, n_res_block=6, num_filters=[64, 128, 256]))
+    G = train.TrainableGenerator(AttentionLWBGenerator(cfg))
+    kinds = {n: train.TrainableGenerator.native_weight(n, p) for n, p in G.named_parameters() if p.dim() == 4}
+    assert all(v is not None for v in kinds.values()), [n for n, v in kinds.items() if v is None]
+    by = {k: [n for n, v in kinds.items() if v[0] == k] for k in (train.S1, train.S2, train.CT)}
+    assert len(by[train.S2]) == 9 and all(G.net.get_parameter(n[4:]).shape[2] == 3 for n in by[train.S2])
+    assert len(by[train.CT]) == 9 and all(G.net.get_parameter(n[4:]).shape[2] == 4 for n in by[train.CT])
+    assert len(by[train.S1]) == len(kinds) - 18
+    for n in by[train.S1]:
+        k = G.net.get_parameter(n[4:]).shape[2]
+        assert kinds[n] == (train.S1, k // 2) and k in (1, 3, 5, 7), n
+    assert kinds["net.bg_net.main.0.weight"] == (train.S1, 3) and kinds["net.tsf_img_reg.0.weight"] == (train.S1, 2)
+    assert kinds["net.tsf_net_dec.upconvs.0.0.weight"] == (train.CT, 1) and kinds["net.src_net.encoders.layers.1.0.weight"] == (train.S2, 1)
+    # the discriminator: four stride-2 4x4 convs, two stride-1 4x4 / pad-1 convs
+    dk = sorted(v for v in train.PatchDiscriminator().native_weight().values())
+    assert dk == [(train.S1, 1)] * 2 + [(train.S2, 1)] * 4
