@@ -843,7 +843,7 @@ class LWGTrainStep:
     """One optimisation step of LWGTrainer.optimize_parameters (lwg_trainer.py:326-352): G step then D step, Adam lr 1e-4,
     betas (0.9, 0.999) (deploy.toml [Train]); losses of optimize_G / optimize_D with use_face = false.  ``graph=True`` captures
     the whole step (forward, both backward passes, the bucketed all-reduces, both optimizer passes) in one CUDA graph after a
-    few eager warm-up steps: at batch 1 the step is ~3000 small launches and otherwise bound by launch latency."""
+    few eager warm-up steps: at batch 1 the step is ~1400 small launches and otherwise bound by launch latency."""
 
     def __init__(self, net, device, lr=1e-4, lambdas=None, distributed=False, graph=False, fused_adam=True):
         self.dev = device
