@@ -370,6 +370,13 @@ int iper_adam_pack(float* params, const float* grads, float* exp_avg, float* exp
  * the cast + pad + channels_last copy of the 1/3/4/6-channel ends of the training step in one pass. */
 int iper_pad_nhwc_bf16(const void* x, int is_bf16, int N, int C, int H, int W, long long stride_n, long long stride_c, long long stride_h,
                        long long stride_w, int Cpad, void* out_nhwc, iper_stream_t stream);
+/* Weight gradient of the THIN ends (one side has <= 4 real channels: the 5x5 heads, the 7x7 BGNet ends), stride 1, on CUDA cores:
+ *   sign +1, thin = dY (N,H,W,thin_pitch; Ct real), wide = X (N,H,W,Cw):  dW[ct*stride_thin + tap*stride_tap + cw*stride_wide] += sum_p dY[p,ct] X[p + tap - pad, cw]
+ *   sign -1, thin = X, wide = dY:                                          dW[...] += sum_q dY[q - (tap - pad), cw] X[q, ct]
+ * (the tensor-core wgrad streams a 64-channel zero-padded operand for these layers: 410-470 us per launch at 512x512). */
+int iper_thin_wgrad_bf16(const void* wide_nhwc, const void* thin_nhwc, int N, int H, int W, int Cw, int thin_pitch, int Ct, int ksize,
+                         int pad, int sign, float* dW, long long stride_thin, long long stride_wide, long long stride_tap,
+                         iper_stream_t stream);
 int iper_warp_bf16(const void* src_nhwc, const float* T, int M, int h, int w, int C, void* out_nhwc, iper_stream_t stream);
 int iper_warp_bwd_bf16(const void* dout_nhwc, const float* T, int M, int h, int w, int C, float* dsrc_f32, iper_stream_t stream);
 int iper_att_combine_bf16(const void* k, const void* v, const void* q, int bs, int ns, long long HW, int C, void* a, float* alpha,

@@ -88,6 +88,8 @@ SIGNATURES = {
     "iper_adam_pack": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_float, c_float, c_float,
                        c_float, c_void_p, c_int, c_void_p, c_void_p, c_void_p],
     "iper_pad_nhwc_bf16": [c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_ll, c_int, c_void_p, c_void_p],
+    "iper_thin_wgrad_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_ll, c_ll, c_ll,
+                             c_void_p],
     "iper_warp_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "iper_warp_bwd_bf16": [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p],
     "iper_att_combine_bf16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p],

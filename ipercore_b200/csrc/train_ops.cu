@@ -331,6 +331,96 @@ __global__ void __launch_bounds__(256) pad_nhwc_kernel(const T* __restrict__ x, 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// weight gradient of the THIN ends (5x5 heads 64 -> 3 / 1, 7x7 BGNet ends 4 -> 64 / 64 -> 3) on CUDA cores.  Through the tensor-core
+// wgrad these layers stream 25-49 taps x 262 144 pixels of a 64-channel operand of which 1-4 channels are real (measured 410-470 us
+// per launch, the slowest launches of the step); here the wide tensor's halo tile sits in shared memory once per tap group and
+// every thread owns one wide channel: acc[tap][ct] += thin[p][ct] * wide[p + sign * (tap - pad)][cw] over the tile's pixels.
+//   thin = dY (co <= 4):  dW[co, tap, ci] = sum_p dY[p, co] X[p + (tap - pad), ci]        sign +1, wide = X
+//   thin = X  (ci <= 4):  dW[co, tap, ci] = sum_q dY[q - (tap - pad), co] X[q, ci]        sign -1, wide = dY
+// grid (tiles [persistent], tap groups of <= 16, 64-channel chunks of the wide tensor); 256 threads = 64 channels x 4 pixel groups.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int THIN_TG = 16;
+
+struct ThinArgs {
+    const __nv_bfloat16* wide; const __nv_bfloat16* thin;
+    int N, H, W, wide_pitch, thin_pitch, Ct, ks, pad, sign;
+    float* dW; long long s_t, s_w, s_tap;
+};
+
+__global__ void __launch_bounds__(256) thin_wgrad_kernel(const ThinArgs a) {
+    extern __shared__ __align__(16) uint8_t thin_smem[];
+    const int P = max(a.pad, a.ks - 1 - a.pad), TW = 16 + 2 * P, TH = 8 + 2 * P;
+    __nv_bfloat16* sw = reinterpret_cast<__nv_bfloat16*>(thin_smem);                       // [TH][TW][64]
+    float* st = reinterpret_cast<float*>(thin_smem + (size_t)TH * TW * 128);                 // [128][4]
+    float* sacc = st + 128 * 4;                                                              // [THIN_TG * 4][64]
+    const int cw = threadIdx.x & 63, g = threadIdx.x >> 6;
+    const int taps = a.ks * a.ks, tap0 = blockIdx.y * THIN_TG, nt = min(THIN_TG, taps - tap0), chunk = blockIdx.z;
+    float acc[THIN_TG][4];
+#pragma unroll
+    for (int t = 0; t < THIN_TG; t++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[t][c] = 0.f;
+    int toff[THIN_TG];                       // offset of tap t inside the halo tile, in pixels, relative to the thin pixel's halo position
+#pragma unroll
+    for (int t = 0; t < THIN_TG; t++) {
+        const int tt = min(tap0 + t, taps - 1);
+        toff[t] = (a.sign * (tt / a.ks - a.pad)) * TW + a.sign * (tt % a.ks - a.pad);
+    }
+    const int tiles_x = (a.W + 15) / 16, tiles_y = (a.H + 7) / 8, n_tiles = tiles_x * tiles_y * a.N;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int x0 = (tile % tiles_x) * 16, y0 = ((tile / tiles_x) % tiles_y) * 8, n = tile / (tiles_x * tiles_y);
+        __syncthreads();                     // the previous tile's readers are done
+        for (int i = threadIdx.x; i < TH * TW * 8; i += 256) {          // wide halo tile, 16 bytes per thread, zero outside the image
+            const int c8 = i & 7, hp = i >> 3, hx = hp % TW, hy = hp / TW;
+            const int gx = x0 - P + hx, gy = y0 - P + hy;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (gx >= 0 && gx < a.W && gy >= 0 && gy < a.H)
+                v = __ldg(reinterpret_cast<const uint4*>(a.wide + (((size_t)n * a.H + gy) * a.W + gx) * a.wide_pitch + chunk * 64 + c8 * 8));
+            *reinterpret_cast<uint4*>(sw + (size_t)hp * 64 + c8 * 8) = v;
+        }
+        if (threadIdx.x < 128) {                                          // thin tile: the first 4 channels of each pixel as floats
+            const int px = threadIdx.x & 15, py = threadIdx.x >> 4, gx = x0 + px, gy = y0 + py;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gx < a.W && gy < a.H) {
+                const uint2 u = __ldg(reinterpret_cast<const uint2*>(a.thin + (((size_t)n * a.H + gy) * a.W + gx) * a.thin_pitch));
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+                const float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]);
+                v = make_float4(f0.x, a.Ct > 1 ? f0.y : 0.f, a.Ct > 2 ? f1.x : 0.f, a.Ct > 3 ? f1.y : 0.f);
+            }
+            reinterpret_cast<float4*>(st)[threadIdx.x] = v;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int q = 0; q < 32; q++) {                                    // this thread's 32 pixels: rows 2g, 2g + 1 of the tile
+            const int py = 2 * g + (q >> 4), px = q & 15;
+            const float4 th = reinterpret_cast<const float4*>(st)[py * 16 + px];
+            const __nv_bfloat16* base = sw + ((size_t)(py + P) * TW + (px + P)) * 64 + cw;
+#pragma unroll
+            for (int t = 0; t < THIN_TG; t++) {
+                if (t < nt) {
+                    const float x = __bfloat162float(base[toff[t] * 64]);
+                    acc[t][0] += th.x * x; acc[t][1] += th.y * x; acc[t][2] += th.z * x; acc[t][3] += th.w * x;
+                }
+            }
+        }
+    }
+    // combine the four pixel groups in shared memory, then one atomic per (tap, thin channel, wide channel)
+    __syncthreads();
+    for (int i = threadIdx.x; i < THIN_TG * 4 * 64; i += 256) sacc[i] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < THIN_TG; t++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) atomicAdd(&sacc[(t * 4 + c) * 64 + cw], acc[t][c]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < THIN_TG * 4 * 64; i += 256) {
+        const int w = i & 63, c = (i >> 6) & 3, t = i >> 8;
+        if (t < nt && c < a.Ct)
+            atomicAdd(a.dW + (long long)c * a.s_t + (long long)(tap0 + t) * a.s_tap + (long long)(chunk * 64 + w) * a.s_w, sacc[i]);
+    }
+}
+
 static int grid_for(long long work_items, int per_block) {
     long long b = (work_items + per_block - 1) / per_block;
     if (b > 148 * 8) b = 148 * 8;
@@ -451,6 +541,35 @@ extern "C" int iper_pad_nhwc_bf16(const void* x, int is_bf16, int N, int C, int 
     else
         pad_nhwc_kernel<float><<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const float*>(x), N, C, H, W, stride_n, stride_c, stride_h,
                                                                     stride_w, Cpad, reinterpret_cast<__nv_bfloat16*>(out_nhwc));
+    IPER_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int iper_thin_wgrad_bf16(const void* wide_nhwc, const void* thin_nhwc, int N, int H, int W, int Cw, int thin_pitch, int Ct,
+                                    int ksize, int pad, int sign, float* dW, long long stride_thin, long long stride_wide,
+                                    long long stride_tap, iper_stream_t stream) {
+    IPER_REQUIRE(wide_nhwc && thin_nhwc && dW && IPER_A16(wide_nhwc) && (((uintptr_t)thin_nhwc) & 7) == 0, "iper_thin_wgrad_bf16: null / unaligned pointer");
+    IPER_REQUIRE(N > 0 && H > 0 && W > 0 && Cw > 0 && Cw % 64 == 0 && Ct >= 1 && Ct <= 4 && thin_pitch >= 4 && thin_pitch % 4 == 0 &&
+                 ksize >= 1 && ksize <= 7 && pad >= 0 && pad < ksize && (sign == 1 || sign == -1),
+                 "iper_thin_wgrad_bf16: needs Cw %% 64 == 0, 1 <= Ct <= 4, thin_pitch %% 4 == 0, k <= 7, sign +-1 (got Cw %d Ct %d k %d)", Cw, Ct, ksize);
+    const int P = pad > ksize - 1 - pad ? pad : ksize - 1 - pad;
+    const int smem = (8 + 2 * P) * (16 + 2 * P) * 128 + 128 * 16 + THIN_TG * 4 * 64 * 4;
+    static int have[64] = {};
+    int dev = 0;
+    IPER_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && have[dev] < smem) {
+        IPER_CHECK_CUDA(cudaFuncSetAttribute(thin_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        have[dev] = smem;
+    }
+    ThinArgs a;
+    a.wide = reinterpret_cast<const __nv_bfloat16*>(wide_nhwc); a.thin = reinterpret_cast<const __nv_bfloat16*>(thin_nhwc);
+    a.N = N; a.H = H; a.W = W; a.wide_pitch = Cw; a.thin_pitch = thin_pitch; a.Ct = Ct; a.ks = ksize; a.pad = pad; a.sign = sign;
+    a.dW = dW; a.s_t = stride_thin; a.s_w = stride_wide; a.s_tap = stride_tap;
+    const int n_tiles = ((W + 15) / 16) * ((H + 7) / 8) * N, groups = (ksize * ksize + THIN_TG - 1) / THIN_TG, chunks = Cw / 64;
+    int bx = (148 * 2) / (groups * chunks);
+    if (bx < 1) bx = 1;
+    if (bx > n_tiles) bx = n_tiles;
+    thin_wgrad_kernel<<<dim3(bx, groups, chunks), 256, smem, (cudaStream_t)stream>>>(a);
     IPER_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

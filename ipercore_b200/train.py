@@ -38,6 +38,7 @@ CL = torch.channels_last
 
 USE_KERNELS = True          # tests flip this to compare against the all-torch formulation
 USE_STREAMS = True          # weight / bias gradients on a side stream, parallel to the data gradient
+USE_THIN = True             # weight gradients of the layers with <= 4 channels on one side on the CUDA-core kernel (not zero-padded MMAs)
 USE_BRANCHES = True         # independent sub-networks (BGNet, VGG of the target) on their own streams = parallel branches of the graph
 _SIDE, _BRANCH = {}, {}
 
@@ -278,7 +279,14 @@ class _Conv(torch.autograd.Function):
                 d0, d1 = weight.shape[:2]
                 sink = getattr(weight, "_iper_sink", None)
                 g = sink.grad if sink is not None else torch.zeros((d0, k * k, d1), dtype=torch.float32, device=x_cl.device)
-                if kind == CT:    # dWt[ci, co, tap] = sum_p x[p, ci] dY[2p + tap - pad, co]: the strided read runs over dY
+                same = kind == S1 and k % 2 == 1 and pad == k // 2
+                if USE_THIN and same and cout <= 4 and cin % 64 == 0:         # thin = dY (heads, BGNet's 64 -> 3 end): CUDA-core kernel
+                    check(lib.iper_thin_wgrad_bf16(x_cl.data_ptr(), dy_cl.data_ptr(), n, h, w, cin, coutp, cout, k, pad, 1, g.data_ptr(),
+                                                   k * k * d1, 1, d1, st), "thin_wgrad_bf16")
+                elif USE_THIN and same and cin <= 4 and cout % 64 == 0:       # thin = X (BGNet's 4 -> 64 stem)
+                    check(lib.iper_thin_wgrad_bf16(dy_cl.data_ptr(), x_cl.data_ptr(), n, h, w, cout, cinp, cin, k, pad, -1, g.data_ptr(),
+                                                   1, k * k * d1, d1, st), "thin_wgrad_bf16")
+                elif kind == CT:  # dWt[ci, co, tap] = sum_p x[p, ci] dY[2p + tap - pad, co]: the strided read runs over dY
                     check(lib.iper_conv_wgrad_bf16(dy_cl.data_ptr(), x_cl.data_ptr(), n, 2 * h, 2 * w, coutp, cinp, k, 2, pad, g.data_ptr(),
                                                    k * k * d1, 1, d1, cin, cout, st), "conv_wgrad_bf16")
                 else:
