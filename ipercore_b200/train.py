@@ -38,7 +38,10 @@ CL = torch.channels_last
 
 USE_KERNELS = True          # tests flip this to compare against the all-torch formulation
 USE_STREAMS = True          # weight / bias gradients on a side stream, parallel to the data gradient
-USE_THIN = True             # weight gradients of the layers with <= 4 channels on one side on the CUDA-core kernel (not zero-padded MMAs)
+USE_THIN = False            # opt-in: weight gradients of the layers with <= 4 channels on one side on the CUDA-core kernel instead of
+                            # zero-padded MMAs.  Correct (tests), but measured SLOWER inside the wide graph (16.4 vs 15.5 ms per step):
+                            # its CUDA-core work competes with the epilogues of the branches that run next to it, whereas the
+                            # tensor-core version idles the SIMT pipes.
 USE_BRANCHES = True         # independent sub-networks (BGNet, VGG of the target) on their own streams = parallel branches of the graph
 _SIDE, _BRANCH = {}, {}
 

@@ -126,6 +126,24 @@ def test_pad_to_channels_last_kernel():
     assert torch.equal(train._to_cl(big, 64), big)                    # nothing to pad: no copy semantics change
 
 
+@pytest.mark.parametrize("ci,co,H,W,k", [(64, 3, 40, 48, 5), (64, 1, 24, 40, 5), (4, 64, 32, 32, 7), (64, 3, 16, 32, 7)])
+def test_thin_end_weight_gradient_kernel(ci, co, H, W, k):
+    """The opt-in CUDA-core weight gradient of the layers with <= 4 channels on one side (train.USE_THIN) against torch autograd."""
+    from ipercore_b200 import train
+    g = torch.Generator(device="cpu").manual_seed(ci + co + k)
+    x = (torch.randn(2, ci, H, W, generator=g) * 0.5).to(DEV).bfloat16().float().requires_grad_(True)
+    w = (torch.randn(co, ci, k, k, generator=g) * (1.0 / np.sqrt(k * k * ci))).to(DEV).bfloat16().float().requires_grad_(True)
+    dy = (torch.randn(2, co, H, W, generator=g) * 0.5).to(DEV).bfloat16().float()
+    (gw_ref,) = torch.autograd.grad(F.conv2d(x, w, padding=k // 2), w, dy)
+    w2 = w.detach().clone().requires_grad_(True)
+    train.USE_THIN = True
+    try:
+        (gw,) = torch.autograd.grad(train.conv(x.detach(), w2), w2, dy.bfloat16())
+    finally:
+        train.USE_THIN = False
+    assert _rel(gw, gw_ref) <= 2e-4
+
+
 def test_conv_falls_back_when_not_eligible():
     from ipercore_b200 import train
     x = torch.randn(1, 64, 4, 8, device=DEV).bfloat16()               # map smaller than one 16x8 tile
