@@ -47,6 +47,26 @@ def test_argument_validation_reports_errors():
         _lib.check(_lib.lib.iper_rasterize_faces(None, 1, 1, 8, 0.1, 100.0, None, None, None, 0, None), "rasterize_faces")
 
 
+def test_training_entry_points_validate_arguments():
+    """The training-step entry points reject bad arguments with a status and a message before touching the device."""
+    from ipercore_b200 import _lib
+    L = _lib.lib
+    assert L.iper_conv_bf16(None, 1, 64, 64, 64, None, 64, 3, 1, 1, None, 0, None, None, None) != 0 and b"null" in L.iper_last_error()
+    assert L.iper_conv_bf16(16, 1, 64, 64, 64, 16, 64, 9, 1, 1, None, 0, None, 16, None) != 0 and b"kernel 9" in L.iper_last_error()
+    assert L.iper_conv_bf16(16, 1, 64, 64, 60, 16, 64, 3, 1, 1, None, 0, None, 16, None) != 0 and b"Cin" in L.iper_last_error()
+    assert L.iper_conv_bf16(16, 1, 63, 64, 64, 16, 64, 3, 2, 1, None, 0, None, 16, None) != 0 and b"even" in L.iper_last_error()
+    assert L.iper_conv_bf16(16, 1, 4, 64, 64, 16, 64, 3, 1, 1, None, 0, None, 16, None) != 0 and b"too small" in L.iper_last_error()
+    assert L.iper_conv_transposed_bf16(16, 1, 16, 16, 64, 16, 64, 5, 1, None, 0, 16, None) != 0 and b"kernel 5" in L.iper_last_error()
+    assert L.iper_conv_wgrad_bf16(16, 16, 1, 64, 64, 64, 64, 3, 1, 1, None, 1, 1, 1, 64, 64, None) != 0 and b"null" in L.iper_last_error()
+    assert L.iper_conv_wgrad_bf16(16, 16, 1, 64, 64, 64, 64, 3, 1, 1, 16, 1, 1, 1, 65, 64, None) != 0 and b"valid channel" in L.iper_last_error()
+    assert L.iper_bias_grad_bf16(16, 10, 70, 64, 16, None) != 0 and b"pitch" in L.iper_last_error()
+    assert L.iper_thin_wgrad_bf16(16, 16, 1, 64, 64, 64, 64, 5, 5, 2, 1, 16, 1, 1, 1, None) != 0 and b"Ct" in L.iper_last_error()
+    assert L.iper_att_combine_bf16(16, 16, 16, 1, 9, 64, 64, 16, 16, None) != 0 and b"ns" in L.iper_last_error()
+    assert L.iper_norm_stats_bf16(16, 1, 64, 72, 16, None) != 0 and b"unsupported C" in L.iper_last_error()
+    assert L.iper_pad_nhwc_bf16(16, 0, 1, 6, 8, 8, 384, 64, 8, 1, 60, 16, None) != 0 and b"Cpad" in L.iper_last_error()
+    assert L.iper_adam_pack(None, None, None, None, None, None, 0, 0, 1e-4, 0.9, 0.999, 1e-8, 1.0, None, 1, None, None, None) != 0
+
+
 def test_generator_loads_reference_checkpoint_layout():
     from ipercore_b200.generator import AttentionLWBGenerator
     from oracle.weights import synth_state_dict
