@@ -296,6 +296,7 @@ class _Conv(torch.autograd.Function):
                     check(lib.iper_conv_wgrad_bf16(x_cl.data_ptr(), dy_cl.data_ptr(), n, h, w, cinp, coutp, k, 2 if kind == S2 else 1, pad,
                                                    g.data_ptr(), k * k * d1, 1, d1, cout, cin, st), "conv_wgrad_bf16")
                 if sink is None:
+                    g.record_stream(main)            # allocated under the side stream, consumed by autograd on the main one
                     dw = g.view(d0, k, k, d1).permute(0, 3, 1, 2).to(weight.dtype)
             if want_b:
                 bias = ctx.bias_ref
@@ -304,6 +305,7 @@ class _Conv(torch.autograd.Function):
                 check(lib.iper_bias_grad_bf16(dy_cl.data_ptr(), dy_cl.shape[0] * dy_cl.shape[2] * dy_cl.shape[3], cout, coutp, gb.data_ptr(), st),
                       "bias_grad_bf16")
                 if bsink is None:
+                    gb.record_stream(main)
                     db = gb.to(bias.dtype)
         if ctx.needs_input_grad[0]:
             if kind == S1:
