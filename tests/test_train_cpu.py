@@ -143,3 +143,64 @@ def test_native_weight_classification_covers_every_convolution_of_the_generator(
     # the discriminator: four stride-2 4x4 convs, two stride-1 4x4 / pad-1 convs
     dk = sorted(v for v in train.PatchDiscriminator().native_weight().values())
     assert dk == [(train.S1, 1)] * 2 + [(train.S2, 1)] * 4
+
+
+def test_personalize_schedule_with_a_mock_step():
+    """Host logic of ipercore_b200.personalize.run (Personalizer.run, personalization.py:95-151): iteration count, the
+    train_G_every_n_iterations pattern over each pass of the loader, the linear decay phase, the checkpoint."""
+    import tempfile
+    from ipercore_b200 import personalize
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.ones(3))
+
+    class G:
+        net = Net()
+
+    class Step:
+        def __init__(self):
+            self.G, self.calls, self.lrs = G(), [], []
+
+        def set_lr(self, lr):
+            self.lrs.append(lr)
+
+        def step(self, batch, trainable=True):
+            self.calls.append((batch, trainable))
+            return {"G": torch.tensor(float(len(self.calls)))}
+
+    st = Step()
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "models", "m", "personalized.pth")
+        hist = personalize.run(st, ["a", "b", "c"], num_videos=2, niters_no_decay=2, niters_decay=2, train_G_every_n_iterations=2, lr=1e-3,
+                               final_lr=1e-5, ckpt_path=path)
+        assert list(torch.load(path).keys()) == ["w"]
+    assert len(hist) == 8 and [b for b, _ in st.calls] == ["a", "b", "c", "a", "b", "c", "a", "b"]
+    assert [t for _, t in st.calls] == [False, True, False] * 2 + [False, True]          # G on every 2nd batch of each pass
+    assert st.lrs[0] == 1e-3 and len(st.lrs) == 1 + 4                                     # constant for 4 iterations, then 4 decay steps
+    assert abs(st.lrs[-1] - 1e-5) < 1e-9 and all(a > b for a, b in zip(st.lrs[1:], st.lrs[2:]))
+    try:
+        personalize.run(Step(), [], niters_no_decay=1)
+        assert False, "an empty loader must raise"
+    except ValueError:
+        pass
+
+
+def test_conv_falls_back_to_torch_on_cpu():
+    """Without a GPU tensor nothing is routed to the kernels (_kind == 0) and train.conv is the plain bf16 torch formulation,
+    tiny channel ends included (they are zero-padded to 8 for cuDNN's sake; on CPU that must not change the result)."""
+    import torch.nn.functional as F
+    from ipercore_b200 import train
+    torch.manual_seed(0)
+    x = torch.randn(1, 6, 20, 24)
+    w = torch.randn(16, 6, 3, 3) * 0.2
+    b = torch.randn(16) * 0.1
+    assert train._kind(x, w, 2, 1) == 0 and train._kind(x, w) == 0
+    for kw, ref in ((dict(stride=2, padding=1), F.conv2d(x, w, b, stride=2, padding=1)), (dict(), F.conv2d(x, w, b, padding=1))):
+        y = train.conv(x, w, b, relu=True, **kw)
+        assert y.dtype == torch.bfloat16 and float((y.float() - F.relu(ref)).abs().max()) <= 0.06 * float(ref.abs().max())
+    wt = torch.randn(6, 8, 4, 4) * 0.2
+    yt = train.conv(x, wt, None, stride=2, padding=1, transposed=True)
+    rt = F.conv_transpose2d(x, wt, stride=2, padding=1)
+    assert yt.shape == rt.shape and float((yt.float() - rt).abs().max()) <= 0.06 * float(rt.abs().max())
